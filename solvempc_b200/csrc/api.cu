@@ -1,0 +1,726 @@
+// api.cu -- the C ABI of include/solvempc_b200.h: handles, device memory, launches.
+// No CPU fallback: every compute entry point needs a CUDA device and returns SMPC_ERR_CUDA otherwise.
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/solvempc_b200.h"
+#include "json_min.hpp"
+#include "kernels.cuh"
+#include "plan.hpp"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string &msg) { g_err = msg; return code; }
+int cuda_fail(cudaError_t e, const char *what) {
+  g_err = std::string(what) + ": " + cudaGetErrorString(e);
+  return SMPC_ERR_CUDA;
+}
+#define CK(call)                                         \
+  do {                                                   \
+    cudaError_t e__ = (call);                            \
+    if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+  } while (0)
+
+struct DeviceBuf {   // one cudaMalloc carved into aligned pieces
+  char *base = nullptr;
+  size_t size = 0, used = 0;
+  cudaError_t alloc(size_t bytes) { size = bytes; used = 0; return cudaMalloc((void **)&base, bytes ? bytes : 256); }
+  template <typename T> T *take(size_t count) {
+    size_t off = (used + 255) & ~size_t(255);
+    used = off + count * sizeof(T);
+    return used <= size ? reinterpret_cast<T *>(base + off) : nullptr;
+  }
+  static size_t need(size_t bytes) { return ((bytes + 255) & ~size_t(255)) + 256; }
+  void release() { if (base) cudaFree(base); base = nullptr; }
+};
+
+}  // namespace
+
+struct smpc_solver {
+  int device = 0, n = 0, m = 0, B = 0;
+  int regime = 0;  // 0 shared-factor, 1 per-instance
+  smpc_settings st{};
+  cudaStream_t stream = nullptr;
+  smpc::SharedPlan plan;
+  DeviceBuf planbuf, batchbuf;
+  smpc::SharedPlanDev dplan{};
+  double *d_q = nullptr, *d_l = nullptr, *d_u = nullptr;
+  bool have_q = false, have_l = false, have_u = false;
+  double *d_xi = nullptr, *d_z = nullptr, *d_y = nullptr, *d_rho = nullptr;
+  double *d_x = nullptr, *d_yout = nullptr, *d_obj = nullptr, *d_pri = nullptr, *d_dua = nullptr;
+  int *d_status = nullptr, *d_iter = nullptr, *d_rhoup = nullptr;
+  double *d_stage_x = nullptr, *d_stage_y = nullptr;  // warm-start staging
+  DeviceBuf packbuf;                                  // small-kernel operator pack + work queue
+  smpc::SmallPackDev dpack{};
+  int *d_queue = nullptr;
+  int num_sms = 148;
+  long long launches = 0;
+  int kernel = 1;
+  bool solved_once = false;
+  bool cold_solves = false, timing = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;   // pending kernel timings
+  double timed_ms = 0.0;
+  int timed_launches = 0;
+};
+
+struct smpc_mpc {
+  int device = 0, B = 0, plants = 1;
+  smpc::MpcDims dims{};
+  int per_instance = 0;
+  double xref = 0.0;
+  cudaStream_t stream = nullptr;
+  DeviceBuf buf;
+  double *d_Ad = nullptr, *d_Bd = nullptr, *d_Cd = nullptr, *d_K = nullptr;
+  smpc::MpcMatsDev mats{};
+  double *d_X = nullptr, *d_U = nullptr, *d_ref = nullptr;
+  smpc_solver *solver = nullptr;
+  long long launches = 0;
+};
+
+namespace {
+
+smpc::SettingsDev to_dev(const smpc_settings &s) {
+  smpc::SettingsDev d;
+  d.rho0 = s.rho; d.sigma = s.sigma; d.alpha = s.alpha; d.eps_abs = s.eps_abs; d.eps_rel = s.eps_rel;
+  d.eps_prim_inf = s.eps_prim_inf; d.eps_dual_inf = s.eps_dual_inf; d.rho_tol = s.adaptive_rho_tolerance;
+  d.max_iter = s.max_iter; d.check_every = s.check_termination; d.adaptive_rho = s.adaptive_rho;
+  d.rho_interval = s.adaptive_rho_interval; d.warm_start = s.warm_start; d.scaled_termination = s.scaled_termination;
+  return d;
+}
+
+int check_settings(const smpc_settings &s) {
+  if (!(s.rho > 0) || !(s.sigma > 0) || !(s.alpha > 0 && s.alpha < 2)) return fail(SMPC_ERR_ARG, "rho, sigma must be > 0 and 0 < alpha < 2");
+  if (s.eps_abs < 0 || s.eps_rel < 0 || (s.eps_abs == 0 && s.eps_rel == 0)) return fail(SMPC_ERR_ARG, "eps_abs/eps_rel must be >= 0 and not both 0");
+  if (s.max_iter <= 0 || s.check_termination < 0 || s.scaling < 0 || s.adaptive_rho_interval < 0) return fail(SMPC_ERR_ARG, "max_iter > 0; check_termination, scaling, adaptive_rho_interval >= 0");
+  if (s.adaptive_rho && !(s.adaptive_rho_tolerance >= 1.0)) return fail(SMPC_ERR_ARG, "adaptive_rho_tolerance must be >= 1");
+  return SMPC_OK;
+}
+
+int select_device(int device) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    g_err = "no CUDA device available (this library has no CPU fallback)";
+    if (e != cudaSuccess) { g_err += std::string(": ") + cudaGetErrorString(e); cudaGetLastError(); }
+    return SMPC_ERR_CUDA;
+  }
+  if (device < 0 || device >= count) return fail(SMPC_ERR_ARG, "device index out of range");
+  CK(cudaSetDevice(device));
+  return SMPC_OK;
+}
+
+int upload_plan(smpc_solver *s) {
+  const smpc::SharedPlan &p = s->plan;
+  const size_t n = p.n, m = p.m;
+  size_t bytes = 0;
+  for (size_t c : {n * n, m * n, n * m, n * n, n * n, n * n, n * n, m * n, n, n, n, m, m, m, m}) bytes += DeviceBuf::need(c * sizeof(double));
+  bytes += DeviceBuf::need(m);
+  CK(s->planbuf.alloc(bytes));
+  auto put = [&](const std::vector<double> &v, size_t count, const double **dst) -> cudaError_t {
+    double *d = s->planbuf.take<double>(count ? count : 1);
+    *dst = d;
+    if (!count) return cudaSuccess;
+    return cudaMemcpy(d, v.data(), count * sizeof(double), cudaMemcpyHostToDevice);
+  };
+  smpc::SharedPlanDev &d = s->dplan;
+  d.n = p.n; d.m = p.m; d.c = p.c; d.cinv = p.cinv;
+  CK(put(p.SG, n * n, &d.SG)); CK(put(p.W, m * n, &d.W)); CK(put(p.WT, n * m, &d.WT));
+  CK(put(p.V, n * n, &d.V)); CK(put(p.VT, n * n, &d.VT)); CK(put(p.PVT, n * n, &d.PVT));
+  CK(put(p.VinvT, n * n, &d.VinvT)); CK(put(p.Abar, m * n, &d.Abar));
+  CK(put(p.lam, n, &d.lam)); CK(put(p.D, n, &d.D)); CK(put(p.Dinv, n, &d.Dinv));
+  CK(put(p.E, m, &d.E)); CK(put(p.Einv, m, &d.Einv));
+  std::vector<double> l0(m), u0(m);   // unscaled setup bounds
+  for (size_t i = 0; i < m; ++i) { l0[i] = p.l0bar[i] * p.Einv[i]; u0[i] = p.u0bar[i] * p.Einv[i]; }
+  CK(put(l0, m, &d.l0)); CK(put(u0, m, &d.u0));
+  signed char *ct = s->planbuf.take<signed char>(m ? m : 1);
+  if (m) CK(cudaMemcpy(ct, p.ctype.data(), m, cudaMemcpyHostToDevice));
+  d.ctype = ct;
+  return SMPC_OK;
+}
+
+// zero-padded k-major packs for admm_shared_small_kernel
+int upload_small_pack(smpc_solver *s) {
+  const smpc::SharedPlan &p = s->plan;
+  const int n = p.n, m = p.m, NP = 16, MP = 32;
+  std::vector<double> M1T((NP + MP) * NP, 0.0), WT(NP * MP, 0.0), VT(NP * NP, 0.0), PVT(NP * NP, 0.0), Ab(MP * NP, 0.0),
+      V(NP * NP, 0.0), lam(NP, 0.0), D(NP, 1.0), Dinv(NP, 1.0), E(MP, 1.0), Einv(MP, 1.0);
+  std::vector<int> ct(MP, 0);
+  for (int i = 0; i < n; ++i) {
+    for (int k = 0; k < n; ++k) {
+      M1T[k * NP + i] = p.SG[(size_t)i * n + k];
+      VT[k * NP + i] = p.V[(size_t)i * n + k];
+      PVT[k * NP + i] = p.PVT[(size_t)k * n + i];
+      V[k * NP + i] = p.V[(size_t)k * n + i];
+    }
+    lam[i] = p.lam[i]; D[i] = p.D[i]; Dinv[i] = p.Dinv[i];
+  }
+  for (int r = 0; r < m; ++r) {
+    for (int k = 0; k < n; ++k) {
+      M1T[(NP + r) * NP + k] = p.W[(size_t)r * n + k];   // [sigma G | W'](i=k, NP+r) = W(r,k)
+      WT[k * MP + r] = p.W[(size_t)r * n + k];
+      Ab[r * NP + k] = p.Abar[(size_t)r * n + k];
+    }
+    E[r] = p.E[r]; Einv[r] = p.Einv[r]; ct[r] = p.ctype[r];
+  }
+  size_t bytes = 0;
+  for (size_t c : {M1T.size(), WT.size(), VT.size(), PVT.size(), Ab.size(), V.size(), lam.size(), D.size(), Dinv.size(), E.size(), Einv.size()})
+    bytes += DeviceBuf::need(c * sizeof(double));
+  bytes += DeviceBuf::need(MP * sizeof(int)) + DeviceBuf::need(sizeof(int));
+  CK(s->packbuf.alloc(bytes));
+  auto put = [&](const std::vector<double> &v, const double **dst) -> cudaError_t {
+    double *d = s->packbuf.take<double>(v.size());
+    *dst = d;
+    return cudaMemcpy(d, v.data(), v.size() * sizeof(double), cudaMemcpyHostToDevice);
+  };
+  smpc::SmallPackDev &k = s->dpack;
+  CK(put(M1T, &k.M1T)); CK(put(WT, &k.WT)); CK(put(VT, &k.VT)); CK(put(PVT, &k.PVT)); CK(put(Ab, &k.Ab)); CK(put(V, &k.V));
+  CK(put(lam, &k.lam)); CK(put(D, &k.D)); CK(put(Dinv, &k.Dinv)); CK(put(E, &k.E)); CK(put(Einv, &k.Einv));
+  int *dct = s->packbuf.take<int>(MP);
+  CK(cudaMemcpy(dct, ct.data(), MP * sizeof(int), cudaMemcpyHostToDevice));
+  k.ctype = dct;
+  s->d_queue = s->packbuf.take<int>(1);
+  if (!s->d_queue) return fail(SMPC_ERR_CUDA, "internal: pack buffer carve-out overflow");
+  CK(cudaMemset(s->d_queue, 0, sizeof(int)));
+  int sms = 0;
+  CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
+  s->num_sms = sms > 0 ? sms : 148;
+  return SMPC_OK;
+}
+
+int alloc_batch(smpc_solver *s) {
+  const size_t n = s->n, m = s->m, B = s->B;
+  size_t bytes = 0;
+  for (size_t c : {B * n, B * m, B * m, B * n, B * m, B * m, B, B * n, B * m, B, B, B, B * n, B * m}) bytes += DeviceBuf::need(c * sizeof(double));
+  bytes += 3 * DeviceBuf::need(B * sizeof(int));
+  CK(s->batchbuf.alloc(bytes));
+  DeviceBuf &b = s->batchbuf;
+  s->d_q = b.take<double>(B * n); s->d_l = b.take<double>(B * m); s->d_u = b.take<double>(B * m);
+  s->d_xi = b.take<double>(B * n); s->d_z = b.take<double>(B * m); s->d_y = b.take<double>(B * m);
+  s->d_rho = b.take<double>(B); s->d_x = b.take<double>(B * n); s->d_yout = b.take<double>(B * m);
+  s->d_obj = b.take<double>(B); s->d_pri = b.take<double>(B); s->d_dua = b.take<double>(B);
+  s->d_stage_x = b.take<double>(B * n); s->d_stage_y = b.take<double>(B * m);
+  s->d_status = b.take<int>(B); s->d_iter = b.take<int>(B); s->d_rhoup = b.take<int>(B);
+  if (!s->d_rhoup) return fail(SMPC_ERR_CUDA, "internal: batch buffer carve-out overflow");
+  CK(cudaMemset(b.base, 0, b.size));
+  return SMPC_OK;
+}
+
+int reset_state(smpc_solver *s, bool reset_rho) {
+  const size_t n = s->n, m = s->m, B = s->B;
+  CK(cudaMemsetAsync(s->d_xi, 0, B * n * sizeof(double), s->stream));
+  CK(cudaMemsetAsync(s->d_z, 0, B * m * sizeof(double), s->stream));
+  CK(cudaMemsetAsync(s->d_y, 0, B * m * sizeof(double), s->stream));
+  if (reset_rho) {
+    double rho = std::min(std::max(s->st.rho, smpc::kRhoMin), smpc::kRhoMax);
+    CK(smpc::launch_fill(s->d_rho, rho, B, s->stream));
+    s->launches++;
+  }
+  return SMPC_OK;
+}
+
+int copy_in(smpc_solver *s, double *dst, const double *src, size_t count, int loc) {
+  if (!src) return fail(SMPC_ERR_ARG, "null input pointer");
+  if (loc != SMPC_HOST && loc != SMPC_DEVICE) return fail(SMPC_ERR_ARG, "loc must be SMPC_HOST or SMPC_DEVICE");
+  CK(cudaMemcpyAsync(dst, src, count * sizeof(double), loc == SMPC_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, s->stream));
+  return SMPC_OK;
+}
+template <typename T>
+int copy_out(smpc_solver *s, T *dst, const T *src, size_t count, int loc) {
+  if (!dst) return SMPC_OK;
+  CK(cudaMemcpyAsync(dst, src, count * sizeof(T), loc == SMPC_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, s->stream));
+  return SMPC_OK;
+}
+
+int create_shared_common(smpc_solver **out, int device, int n, int m, int batch, const double *P, const double *A,
+                         const double *q0, const double *l0, const double *u0, const smpc_settings *settings) {
+  if (!out) return fail(SMPC_ERR_ARG, "out is null");
+  *out = nullptr;
+  if (!P || (!A && m > 0) || !settings) return fail(SMPC_ERR_ARG, "P, A and settings must not be null");
+  if (n <= 0 || m < 0 || batch <= 0) return fail(SMPC_ERR_ARG, "need n > 0, m >= 0, batch > 0");
+  if (int rc = check_settings(*settings)) return rc;
+  smpc_solver *s = new smpc_solver;
+  s->device = device; s->n = n; s->m = m; s->B = batch; s->st = *settings; s->regime = 0;
+  std::string err;
+  int rc = smpc::build_shared_plan(n, m, P, A, q0, l0, u0, s->st, s->plan, err);   // host maths, no device needed
+  if (rc != SMPC_OK) { delete s; return fail(rc, err); }
+  rc = select_device(device);
+  if (rc == SMPC_OK) rc = upload_plan(s);
+  if (rc == SMPC_OK) rc = alloc_batch(s);
+  if (rc == SMPC_OK) rc = reset_state(s, true);
+  if (rc == SMPC_OK && q0) {   // until updateGradient is called every instance keeps the setup gradient
+    bool nz = false;
+    for (int j = 0; j < n; ++j) nz = nz || q0[j] != 0.0;
+    if (nz) {
+      std::vector<double> rep((size_t)batch * n);
+      for (int b = 0; b < batch; ++b) std::memcpy(&rep[(size_t)b * n], q0, sizeof(double) * n);
+      cudaError_t e = cudaMemcpy(s->d_q, rep.data(), rep.size() * sizeof(double), cudaMemcpyHostToDevice);
+      if (e != cudaSuccess) rc = cuda_fail(e, "setup gradient upload"); else s->have_q = true;
+    }
+  }
+  if (rc == SMPC_OK) { cudaError_t e = cudaStreamSynchronize(s->stream); if (e != cudaSuccess) rc = cuda_fail(e, "setup sync"); }
+  s->kernel = 1;
+  if (rc == SMPC_OK && (settings->kernel == 2 || (settings->kernel == 0 && smpc::small_kernel_supports(n, m)))) {
+    if (!smpc::small_kernel_supports(n, m)) rc = fail(SMPC_ERR_ARG, "kernel 2 (register-resident) supports n <= 16, m <= 32 only");
+    else { s->kernel = 2; rc = upload_small_pack(s); }
+  }
+  if (rc != SMPC_OK) { s->planbuf.release(); s->batchbuf.release(); s->packbuf.release(); delete s; return rc; }
+  *out = s;
+  return SMPC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+void smpc_default_settings(smpc_settings *s) {
+  if (!s) return;
+  s->rho = 0.1; s->sigma = 1e-6; s->alpha = 1.6;
+  s->eps_abs = 1e-3; s->eps_rel = 1e-3; s->eps_prim_inf = 1e-4; s->eps_dual_inf = 1e-4;
+  s->adaptive_rho_tolerance = 5.0;
+  s->max_iter = 4000; s->check_termination = 25; s->scaling = 10;
+  s->adaptive_rho = 1; s->adaptive_rho_interval = 25;
+  s->warm_start = 1; s->scaled_termination = 0; s->kernel = 0;
+}
+
+const char *smpc_last_error(void) { return g_err.c_str(); }
+const char *smpc_version(void) { return "solvempc_b200 0.1 (sm_100a)"; }
+
+int smpc_device_count(void) {
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return count;
+}
+
+int smpc_solver_create_shared(smpc_solver **out, int device, int n, int m, int batch, const double *P, const double *A,
+                              const double *q0, const double *l0, const double *u0, const smpc_settings *settings) {
+  return create_shared_common(out, device, n, m, batch, P, A, q0, l0, u0, settings);
+}
+
+int smpc_solver_create_shared_csc(smpc_solver **out, int device, int n, int m, int batch, const int *Pp, const int *Pi,
+                                  const double *Px, const int *Ap, const int *Ai, const double *Ax, const double *q0,
+                                  const double *l0, const double *u0, const smpc_settings *settings) {
+  if (!Pp || !Pi || !Px || (m > 0 && (!Ap || !Ai || !Ax))) return fail(SMPC_ERR_ARG, "null CSC array");
+  if (n <= 0 || m < 0) return fail(SMPC_ERR_ARG, "need n > 0, m >= 0");
+  std::vector<double> P((size_t)n * n, 0.0), A((size_t)m * n, 0.0);
+  for (int j = 0; j < n; ++j)
+    for (int k = Pp[j]; k < Pp[j + 1]; ++k) {
+      int i = Pi[k];
+      if (i < 0 || i >= n) return fail(SMPC_ERR_ARG, "P row index out of range");
+      if (i <= j) P[(size_t)i * n + j] = Px[k];   // upper triangle only, as osqp-eigen passes
+    }
+  for (int j = 0; j < n && m > 0; ++j)
+    for (int k = Ap[j]; k < Ap[j + 1]; ++k) {
+      int i = Ai[k];
+      if (i < 0 || i >= m) return fail(SMPC_ERR_ARG, "A row index out of range");
+      A[(size_t)i * n + j] = Ax[k];
+    }
+  return create_shared_common(out, device, n, m, batch, P.data(), A.data(), q0, l0, u0, settings);
+}
+
+int smpc_solver_create_batched(smpc_solver **out, int, int, int, int, const double *, const double *, int,
+                               const double *, const double *, const smpc_settings *) {
+  if (out) *out = nullptr;
+  return fail(SMPC_ERR_STATE, "per-instance regime is not built yet (SURVEY 8 'next')");
+}
+
+int smpc_solver_destroy(smpc_solver *s) {
+  if (!s) return SMPC_OK;
+  cudaSetDevice(s->device);
+  cudaStreamSynchronize(s->stream);
+  s->planbuf.release(); s->batchbuf.release(); s->packbuf.release();
+  delete s;
+  return SMPC_OK;
+}
+
+int smpc_solver_set_stream(smpc_solver *s, void *stream) {
+  if (!s) return fail(SMPC_ERR_ARG, "null handle");
+  s->stream = (cudaStream_t)stream;
+  return SMPC_OK;
+}
+
+int smpc_solver_dims(const smpc_solver *s, int *n, int *m, int *batch) {
+  if (!s) return fail(SMPC_ERR_ARG, "null handle");
+  if (n) *n = s->n; if (m) *m = s->m; if (batch) *batch = s->B;
+  return SMPC_OK;
+}
+
+int smpc_solver_update_lin_cost(smpc_solver *s, const double *q, int loc) {
+  if (!s) return fail(SMPC_ERR_ARG, "null handle");
+  CK(cudaSetDevice(s->device));
+  if (int rc = copy_in(s, s->d_q, q, (size_t)s->B * s->n, loc)) return rc;
+  s->have_q = true;
+  return SMPC_OK;
+}
+int smpc_solver_update_upper_bound(smpc_solver *s, const double *u, int loc) {
+  if (!s) return fail(SMPC_ERR_ARG, "null handle");
+  CK(cudaSetDevice(s->device));
+  if (int rc = copy_in(s, s->d_u, u, (size_t)s->B * s->m, loc)) return rc;
+  s->have_u = true;
+  return SMPC_OK;
+}
+int smpc_solver_update_lower_bound(smpc_solver *s, const double *l, int loc) {
+  if (!s) return fail(SMPC_ERR_ARG, "null handle");
+  CK(cudaSetDevice(s->device));
+  if (int rc = copy_in(s, s->d_l, l, (size_t)s->B * s->m, loc)) return rc;
+  s->have_l = true;
+  return SMPC_OK;
+}
+int smpc_solver_update_bounds(smpc_solver *s, const double *l, const double *u, int loc) {
+  if (int rc = smpc_solver_update_lower_bound(s, l, loc)) return rc;
+  return smpc_solver_update_upper_bound(s, u, loc);
+}
+
+int smpc_solver_warm_start(smpc_solver *s, const double *x, const double *y, int loc) {
+  if (!s) return fail(SMPC_ERR_ARG, "null handle");
+  CK(cudaSetDevice(s->device));
+  if (int rc = copy_in(s, s->d_stage_x, x, (size_t)s->B * s->n, loc)) return rc;
+  if (int rc = copy_in(s, s->d_stage_y, y, (size_t)s->B * s->m, loc)) return rc;
+  CK(smpc::launch_warm_start(s->dplan, s->B, s->d_stage_x, s->d_stage_y, s->d_xi, s->d_z, s->d_y, s->stream));
+  s->launches++;
+  return SMPC_OK;
+}
+int smpc_solver_cold_start(smpc_solver *s) {
+  if (!s) return fail(SMPC_ERR_ARG, "null handle");
+  CK(cudaSetDevice(s->device));
+  return reset_state(s, false);
+}
+int smpc_solver_reset(smpc_solver *s) {
+  if (!s) return fail(SMPC_ERR_ARG, "null handle");
+  CK(cudaSetDevice(s->device));
+  return reset_state(s, true);
+}
+
+int smpc_solver_solve(smpc_solver *s) {
+  if (!s) return fail(SMPC_ERR_ARG, "null handle");
+  CK(cudaSetDevice(s->device));
+  smpc::BatchDev b{};
+  b.B = s->B;
+  b.q = s->have_q ? s->d_q : nullptr; b.l = s->have_l ? s->d_l : nullptr; b.u = s->have_u ? s->d_u : nullptr;
+  b.xi = s->d_xi; b.z = s->d_z; b.y = s->d_y; b.rho = s->d_rho;
+  b.x_out = s->d_x; b.y_out = s->d_yout; b.status = s->d_status; b.iter = s->d_iter; b.rho_updates = s->d_rhoup;
+  b.obj = s->d_obj; b.pri_res = s->d_pri; b.dua_res = s->d_dua;
+  b.fresh = s->cold_solves ? 1 : 0;
+  smpc::SettingsDev sd = to_dev(s->st);
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  if (s->timing) {
+    CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
+    CK(cudaEventRecord(ev0, s->stream));
+  }
+  cudaError_t e = s->kernel == 2 ? smpc::launch_admm_shared_small(s->dpack, s->dplan, b, sd, s->d_queue, s->num_sms, s->stream)
+                                 : smpc::launch_admm_shared_generic(s->dplan, b, sd, s->stream);
+  if (e != cudaSuccess) return cuda_fail(e, "ADMM kernel launch");
+  if (s->timing) { CK(cudaEventRecord(ev1, s->stream)); s->events.emplace_back(ev0, ev1); }
+  s->launches++;
+  s->solved_once = true;
+  return SMPC_OK;
+}
+
+int smpc_solver_set_cold_solves(smpc_solver *s, int on) {
+  if (!s) return fail(SMPC_ERR_ARG, "null handle");
+  s->cold_solves = on != 0;
+  return SMPC_OK;
+}
+int smpc_solver_enable_timing(smpc_solver *s, int on) {
+  if (!s) return fail(SMPC_ERR_ARG, "null handle");
+  s->timing = on != 0;
+  return SMPC_OK;
+}
+int smpc_solver_kernel_ms(smpc_solver *s, double *total_ms, int *launches, int reset) {
+  if (!s) return fail(SMPC_ERR_ARG, "null handle");
+  CK(cudaSetDevice(s->device));
+  for (auto &ev : s->events) {
+    CK(cudaEventSynchronize(ev.second));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, ev.first, ev.second));
+    s->timed_ms += ms; s->timed_launches++;
+    cudaEventDestroy(ev.first); cudaEventDestroy(ev.second);
+  }
+  s->events.clear();
+  if (total_ms) *total_ms = s->timed_ms;
+  if (launches) *launches = s->timed_launches;
+  if (reset) { s->timed_ms = 0.0; s->timed_launches = 0; }
+  return SMPC_OK;
+}
+
+int smpc_solver_get_solution(smpc_solver *s, double *x, double *y, int loc) {
+  if (!s) return fail(SMPC_ERR_ARG, "null handle");
+  if (!s->solved_once) return fail(SMPC_ERR_STATE, "get_solution before solve");
+  CK(cudaSetDevice(s->device));
+  if (int rc = copy_out(s, x, s->d_x, (size_t)s->B * s->n, loc)) return rc;
+  if (int rc = copy_out(s, y, s->d_yout, (size_t)s->B * s->m, loc)) return rc;
+  if (loc == SMPC_HOST) CK(cudaStreamSynchronize(s->stream));
+  return SMPC_OK;
+}
+
+int smpc_solver_get_info(smpc_solver *s, int *status, int *iter, double *obj, double *pri_res, double *dua_res,
+                         double *rho, int *rho_updates, int loc) {
+  if (!s) return fail(SMPC_ERR_ARG, "null handle");
+  if (!s->solved_once) return fail(SMPC_ERR_STATE, "get_info before solve");
+  CK(cudaSetDevice(s->device));
+  const size_t B = s->B;
+  if (int rc = copy_out(s, status, s->d_status, B, loc)) return rc;
+  if (int rc = copy_out(s, iter, s->d_iter, B, loc)) return rc;
+  if (int rc = copy_out(s, obj, s->d_obj, B, loc)) return rc;
+  if (int rc = copy_out(s, pri_res, s->d_pri, B, loc)) return rc;
+  if (int rc = copy_out(s, dua_res, s->d_dua, B, loc)) return rc;
+  if (int rc = copy_out(s, rho, s->d_rho, B, loc)) return rc;
+  if (int rc = copy_out(s, rho_updates, s->d_rhoup, B, loc)) return rc;
+  if (loc == SMPC_HOST) CK(cudaStreamSynchronize(s->stream));
+  return SMPC_OK;
+}
+
+int smpc_solver_count_solved(smpc_solver *s, int *count) {
+  if (!s || !count) return fail(SMPC_ERR_ARG, "null argument");
+  if (!s->solved_once) return fail(SMPC_ERR_STATE, "count_solved before solve");
+  std::vector<int> st(s->B);
+  CK(cudaSetDevice(s->device));
+  CK(cudaMemcpyAsync(st.data(), s->d_status, sizeof(int) * s->B, cudaMemcpyDeviceToHost, s->stream));
+  CK(cudaStreamSynchronize(s->stream));
+  int c = 0;
+  for (int v : st) c += (v == SMPC_SOLVED);
+  *count = c;
+  return SMPC_OK;
+}
+
+int smpc_solver_sync(smpc_solver *s) {
+  if (!s) return fail(SMPC_ERR_ARG, "null handle");
+  CK(cudaSetDevice(s->device));
+  CK(cudaStreamSynchronize(s->stream));
+  return SMPC_OK;
+}
+
+int smpc_solver_get_scaling(smpc_solver *s, double *D, double *E, double *c) {
+  if (!s) return fail(SMPC_ERR_ARG, "null handle");
+  if (D) std::memcpy(D, s->plan.D.data(), sizeof(double) * s->n);
+  if (E) std::memcpy(E, s->plan.E.data(), sizeof(double) * s->m);
+  if (c) *c = s->plan.c;
+  return SMPC_OK;
+}
+
+long long smpc_solver_launch_count(const smpc_solver *s) { return s ? s->launches : 0; }
+const char *smpc_solver_kernel_name(const smpc_solver *s) {
+  if (!s) return "";
+  return s->kernel == 2 ? "admm_shared_small_kernel" : "admm_shared_generic_kernel";
+}
+
+/* host-only inspection of the shared plan (no device needed): used by the CPU tests of the host logic */
+int smpc_shared_plan_inspect(int n, int m, const double *P, const double *A, const double *q0, const double *l0, const double *u0,
+                             const smpc_settings *settings, double *D, double *E, double *c, double *lam, double *V,
+                             double *SG, double *W, double *PVT, double *VinvT, signed char *ctype) {
+  if (!P || !settings || (!A && m > 0)) return fail(SMPC_ERR_ARG, "null argument");
+  if (int rc = check_settings(*settings)) return rc;
+  smpc::SharedPlan pl; std::string err;
+  int rc = smpc::build_shared_plan(n, m, P, A, q0, l0, u0, *settings, pl, err);
+  if (rc != SMPC_OK) return fail(rc, err);
+  auto cp = [](double *dst, const std::vector<double> &v) { if (dst) std::memcpy(dst, v.data(), v.size() * sizeof(double)); };
+  cp(D, pl.D); cp(E, pl.E); if (c) *c = pl.c; cp(lam, pl.lam); cp(V, pl.V); cp(SG, pl.SG); cp(W, pl.W); cp(PVT, pl.PVT); cp(VinvT, pl.VinvT);
+  if (ctype) std::memcpy(ctype, pl.ctype.data(), pl.ctype.size());
+  return SMPC_OK;
+}
+
+/* ------------------------------------------------------------------------------------ MPC layer */
+static int mpc_alloc(smpc_mpc *M, const smpc_mpc_config *cfg) {
+  const size_t N = M->dims.N, nx = M->dims.nx, P = M->plants, B = M->B;
+  size_t bytes = 0;
+  for (size_t c : {P * nx * nx, P * nx, nx, nx, P * N * N, P * 2 * N * N, P * N * nx, P * N, P * N * N, P * 2 * N * nx, P * 2 * N,
+                   P * 2 * N, P * N * nx, P * N * N, P * N, B * nx, B, B}) bytes += DeviceBuf::need(c * sizeof(double));
+  CK(M->buf.alloc(bytes));
+  DeviceBuf &b = M->buf;
+  M->d_Ad = b.take<double>(P * nx * nx); M->d_Bd = b.take<double>(P * nx); M->d_Cd = b.take<double>(nx); M->d_K = b.take<double>(nx);
+  smpc::MpcMatsDev &t = M->mats;
+  t.H = b.take<double>(P * N * N); t.Gbar = b.take<double>(P * 2 * N * N); t.Fx = b.take<double>(P * N * nx); t.Fu = b.take<double>(P * N);
+  t.Fr = b.take<double>(P * N * N); t.Sbar = b.take<double>(P * 2 * N * nx); t.Ku = b.take<double>(P * 2 * N); t.W0 = b.take<double>(P * 2 * N);
+  t.Sx = b.take<double>(P * N * nx); t.Su = b.take<double>(P * N * N); t.CAB = b.take<double>(P * N);
+  M->d_X = b.take<double>(B * nx); M->d_U = b.take<double>(B); M->d_ref = b.take<double>(B);
+  if (!M->d_ref) return fail(SMPC_ERR_CUDA, "internal: mpc buffer carve-out overflow");
+  CK(cudaMemset(b.base, 0, b.size));
+  CK(cudaMemcpy(M->d_Ad, cfg->Ad, P * nx * nx * sizeof(double), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(M->d_Bd, cfg->Bd, P * nx * sizeof(double), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(M->d_Cd, cfg->Cd, nx * sizeof(double), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(M->d_K, cfg->K, nx * sizeof(double), cudaMemcpyHostToDevice));
+  return SMPC_OK;
+}
+
+int smpc_mpc_create(smpc_mpc **out, int device, const smpc_mpc_config *cfg, int batch, const smpc_settings *settings) {
+  if (!out) return fail(SMPC_ERR_ARG, "out is null");
+  *out = nullptr;
+  if (!cfg || !settings || !cfg->Ad || !cfg->Bd || !cfg->Cd || !cfg->K) return fail(SMPC_ERR_ARG, "null config field");
+  if (cfg->horizon < 1 || cfg->nx < 1 || cfg->nx > 16 || batch < 1) return fail(SMPC_ERR_ARG, "need horizon >= 1, 1 <= nx <= 16, batch >= 1");
+  if (cfg->per_instance) return fail(SMPC_ERR_STATE, "per-instance plants are not built yet (SURVEY 8 'next')");
+  if (int rc = check_settings(*settings)) return rc;
+  if (int rc = select_device(device)) return rc;
+  smpc_mpc *M = new smpc_mpc;
+  M->device = device; M->B = batch; M->per_instance = cfg->per_instance; M->plants = cfg->per_instance ? batch : 1;
+  M->dims.N = cfg->horizon; M->dims.nx = cfg->nx; M->dims.n_state_rows = cfg->n_state_rows; M->dims.Q = cfg->Q; M->dims.R = cfg->R;
+  M->dims.RD = cfg->RD; M->dims.u_limit = cfg->u_limit; M->xref = cfg->xref;
+  int rc = mpc_alloc(M, cfg);
+  if (rc == SMPC_OK) {
+    cudaError_t e = smpc::launch_mpc_assemble(M->dims, M->plants, M->d_Ad, M->d_Bd, M->d_Cd, M->d_K, M->mats, nullptr);
+    if (e != cudaSuccess) rc = cuda_fail(e, "mpc_assemble launch"); else M->launches++;
+  }
+  const int N = cfg->horizon;
+  std::vector<double> H((size_t)N * N), G((size_t)2 * N * N), W0(2 * N), lb(2 * N, -DBL_MAX);
+  if (rc == SMPC_OK) {
+    cudaError_t e = cudaMemcpy(H.data(), M->mats.H, H.size() * sizeof(double), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(G.data(), M->mats.Gbar, G.size() * sizeof(double), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(W0.data(), M->mats.W0, W0.size() * sizeof(double), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) rc = cuda_fail(e, "assembly readback");
+  }
+  // cpp:42-43,54-64: n = N, m = 2N, q = f(X=U=ref=0) = 0, l = -DBL_MAX, u = W0 (X = U = 0)
+  if (rc == SMPC_OK) rc = smpc_solver_create_shared(&M->solver, device, N, 2 * N, batch, H.data(), G.data(), nullptr, lb.data(), W0.data(), settings);
+  if (rc == SMPC_OK) {
+    std::vector<double> ref(batch, cfg->xref);
+    cudaError_t e = cudaMemcpy(M->d_ref, ref.data(), sizeof(double) * batch, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) rc = cuda_fail(e, "ref upload");
+  }
+  if (rc != SMPC_OK) { std::string keep = g_err; smpc_mpc_destroy(M); g_err = keep; return rc; }
+  *out = M;
+  return SMPC_OK;
+}
+
+int smpc_mpc_create_from_json(smpc_mpc **out, int device, const char *path, int batch, const smpc_settings *settings) {
+  if (!out) return fail(SMPC_ERR_ARG, "out is null");
+  *out = nullptr;
+  if (!path) return fail(SMPC_ERR_ARG, "null path");
+  std::ifstream f(path);
+  if (!f) return fail(SMPC_ERR_IO, std::string("cannot open config '") + path + "'");
+  std::stringstream ss; ss << f.rdbuf();
+  std::vector<double> Ad, Bd, Cd, K, tmp;
+  smpc_mpc_config cfg{};
+  try {
+    const std::string text = ss.str();
+    smpc::JsonParser parser(text);
+    smpc::JsonValue j = parser.parse();
+    int r, c;
+    j.at("Ad").flatten(Ad, r, c);
+    if (r != c) throw std::runtime_error("Ad must be square");
+    cfg.nx = r;
+    // shape checks as the reference's from_json does (cpp:465-472)
+    j.at("Bd").flatten(Bd, r, c); if (r * c != cfg.nx) throw std::runtime_error("Bd must have nx entries");
+    j.at("Cd").flatten(Cd, r, c); if (r * c != cfg.nx) throw std::runtime_error("Cd must be 1 x nx");
+    j.at("K").flatten(K, r, c); if (r * c != cfg.nx) throw std::runtime_error("K must be 1 x nx");
+    j.at("Dd").flatten(tmp, r, c); if (r * c != 1) throw std::runtime_error("Dd must be 1 x 1");   // loaded, never used (cpp:116)
+    j.at("Q").flatten(tmp, r, c); if (r * c != 1) throw std::runtime_error("Q must be 1 x 1"); cfg.Q = tmp[0];
+    j.at("R").flatten(tmp, r, c); if (r * c != 1) throw std::runtime_error("R must be 1 x 1"); cfg.R = tmp[0];
+    j.at("RD").flatten(tmp, r, c); if (r * c != 1) throw std::runtime_error("RD must be 1 x 1"); cfg.RD = tmp[0];
+    if (j.at("xref").kind != smpc::JsonValue::Number) throw std::runtime_error("xref must be a number");
+    cfg.xref = j.at("xref").num;
+    cfg.horizon = j.has("horizon") ? (int)j.at("horizon").num : 15;            // mpcWindow, h:26
+    cfg.n_state_rows = j.has("n_state_rows") ? (int)j.at("n_state_rows").num : 10;  // literal at cpp:185
+    cfg.u_limit = j.has("u_limit") ? j.at("u_limit").num : 255.0;              // literal at cpp:368
+  } catch (const std::exception &e) {
+    return fail(SMPC_ERR_IO, std::string("config '") + path + "': " + e.what());
+  }
+  cfg.Ad = Ad.data(); cfg.Bd = Bd.data(); cfg.Cd = Cd.data(); cfg.K = K.data(); cfg.per_instance = 0;
+  return smpc_mpc_create(out, device, &cfg, batch, settings);
+}
+
+int smpc_mpc_destroy(smpc_mpc *M) {
+  if (!M) return SMPC_OK;
+  cudaSetDevice(M->device);
+  if (M->solver) smpc_solver_destroy(M->solver);
+  cudaStreamSynchronize(M->stream);
+  M->buf.release();
+  delete M;
+  return SMPC_OK;
+}
+
+int smpc_mpc_set_stream(smpc_mpc *M, void *stream) {
+  if (!M) return fail(SMPC_ERR_ARG, "null handle");
+  M->stream = (cudaStream_t)stream;
+  return smpc_solver_set_stream(M->solver, stream);
+}
+
+int smpc_mpc_dims(const smpc_mpc *M, int *horizon, int *nx, int *n, int *mrows, int *batch) {
+  if (!M) return fail(SMPC_ERR_ARG, "null handle");
+  if (horizon) *horizon = M->dims.N; if (nx) *nx = M->dims.nx; if (n) *n = M->dims.N; if (mrows) *mrows = 2 * M->dims.N; if (batch) *batch = M->B;
+  return SMPC_OK;
+}
+
+smpc_solver *smpc_mpc_solver(smpc_mpc *M) { return M ? M->solver : nullptr; }
+
+int smpc_mpc_get_matrix(smpc_mpc *M, const char *name, int index, double *out, int capacity) {
+  if (!M || !name || !out) return fail(SMPC_ERR_ARG, "null argument");
+  if (index < 0 || index >= M->plants) return fail(SMPC_ERR_ARG, "plant index out of range");
+  const size_t N = M->dims.N, nx = M->dims.nx;
+  struct { const char *nm; const double *p; size_t count; } tab[] = {
+      {"H", M->mats.H, N * N}, {"Gbar", M->mats.Gbar, 2 * N * N}, {"Fx", M->mats.Fx, N * nx}, {"Fu", M->mats.Fu, N},
+      {"Fr", M->mats.Fr, N * N}, {"Sbar", M->mats.Sbar, 2 * N * nx}, {"Ku", M->mats.Ku, 2 * N}, {"W0", M->mats.W0, 2 * N},
+      {"Sx", M->mats.Sx, N * nx}, {"Su", M->mats.Su, N * N}, {"CAB", M->mats.CAB, N}};
+  for (auto &t : tab)
+    if (!std::strcmp(name, t.nm)) {
+      if ((size_t)capacity < t.count) return fail(SMPC_ERR_ARG, "output capacity too small");
+      CK(cudaSetDevice(M->device));
+      CK(cudaStreamSynchronize(M->stream));
+      CK(cudaMemcpy(out, t.p + (size_t)index * t.count, t.count * sizeof(double), cudaMemcpyDeviceToHost));
+      return SMPC_OK;
+    }
+  return fail(SMPC_ERR_ARG, std::string("unknown matrix '") + name + "'");
+}
+
+int smpc_mpc_set_state(smpc_mpc *M, const double *X, const double *U, const double *ref, int loc) {
+  if (!M) return fail(SMPC_ERR_ARG, "null handle");
+  if (loc != SMPC_HOST && loc != SMPC_DEVICE) return fail(SMPC_ERR_ARG, "loc must be SMPC_HOST or SMPC_DEVICE");
+  CK(cudaSetDevice(M->device));
+  cudaMemcpyKind k = loc == SMPC_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+  if (X) CK(cudaMemcpyAsync(M->d_X, X, sizeof(double) * M->B * M->dims.nx, k, M->stream));
+  if (U) CK(cudaMemcpyAsync(M->d_U, U, sizeof(double) * M->B, k, M->stream));
+  if (ref) CK(cudaMemcpyAsync(M->d_ref, ref, sizeof(double) * M->B, k, M->stream));
+  return SMPC_OK;
+}
+
+int smpc_mpc_controller_step(smpc_mpc *M) {
+  if (!M) return fail(SMPC_ERR_ARG, "null handle");
+  CK(cudaSetDevice(M->device));
+  smpc_solver *s = M->solver;
+  // setF (cpp:90), W0 + Sbar X + Ku U (cpp:99) written straight into the solver's q / u (updateGradient, updateUpperBound)
+  CK(smpc::launch_mpc_step_vectors(M->dims, M->B, M->per_instance, M->mats, M->d_X, M->d_U, M->d_ref, s->d_q, s->d_u, M->stream));
+  M->launches++;
+  s->have_q = true; s->have_u = true;
+  if (int rc = smpc_solver_solve(s)) return rc;                                            // cpp:102
+  CK(smpc::launch_mpc_apply_control(M->B, s->n, s->d_x, s->d_status, M->d_U, M->stream));  // cpp:105
+  M->launches++;
+  return SMPC_OK;
+}
+
+int smpc_mpc_plant_step(smpc_mpc *M) {
+  if (!M) return fail(SMPC_ERR_ARG, "null handle");
+  CK(cudaSetDevice(M->device));
+  CK(smpc::launch_mpc_plant_step(M->B, M->dims.nx, M->per_instance, M->d_Ad, M->d_Bd, M->d_X, M->d_U, M->stream));
+  M->launches++;
+  return SMPC_OK;
+}
+
+int smpc_mpc_get_state(smpc_mpc *M, double *X, double *U, int loc) {
+  if (!M) return fail(SMPC_ERR_ARG, "null handle");
+  CK(cudaSetDevice(M->device));
+  cudaMemcpyKind k = loc == SMPC_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+  if (X) CK(cudaMemcpyAsync(X, M->d_X, sizeof(double) * M->B * M->dims.nx, k, M->stream));
+  if (U) CK(cudaMemcpyAsync(U, M->d_U, sizeof(double) * M->B, k, M->stream));
+  if (loc == SMPC_HOST) CK(cudaStreamSynchronize(M->stream));
+  return SMPC_OK;
+}
+
+int smpc_mpc_get_step_vectors(smpc_mpc *M, double *f, double *ub, int loc) {
+  if (!M) return fail(SMPC_ERR_ARG, "null handle");
+  CK(cudaSetDevice(M->device));
+  cudaMemcpyKind k = loc == SMPC_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+  smpc_solver *s = M->solver;
+  if (f) CK(cudaMemcpyAsync(f, s->d_q, sizeof(double) * M->B * s->n, k, M->stream));
+  if (ub) CK(cudaMemcpyAsync(ub, s->d_u, sizeof(double) * M->B * s->m, k, M->stream));
+  if (loc == SMPC_HOST) CK(cudaStreamSynchronize(M->stream));
+  return SMPC_OK;
+}
+
+long long smpc_mpc_launch_count(const smpc_mpc *M) { return M ? M->launches + (M->solver ? M->solver->launches : 0) : 0; }
+
+}  // extern "C"

@@ -1,0 +1,59 @@
+// device_types.cuh -- POD views handed to the kernels (all pointers are device pointers).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace smpc {
+
+constexpr double kRhoMin = 1e-6, kRhoMax = 1e6, kRhoEqOverIneq = 1e3;
+constexpr double kInfty = 1e30, kMinScaling = 1e-4, kDivTol = 1e-10, kRhoTolRow = 1e-4;
+
+struct SettingsDev {
+  double rho0, sigma, alpha, eps_abs, eps_rel, eps_prim_inf, eps_dual_inf, rho_tol;
+  int max_iter, check_every, adaptive_rho, rho_interval, warm_start, scaled_termination;
+};
+
+// shared-factor plan (see plan.hpp); matrices are stored so that lane = output row reads coalesced
+struct SharedPlanDev {
+  int n, m;
+  double c, cinv;
+  const double *SG;     // n*n   sigma*V'V (symmetric)
+  const double *W;      // m*n   A̅V, row-major:  t-phase reads W[r*n+i]
+  const double *WT;     // n*m   (A̅V)':          z-phase reads WT[k*m+r]
+  const double *V;      // n*n   row-major:       qhat_i = sum_k V[k*n+i] qbar_k
+  const double *VT;     // n*n                    xbar_i = sum_k VT[k*n+i] xi_k
+  const double *PVT;    // n*n                    (P̄x)_i = sum_k PVT[k*n+i] xi_k
+  const double *VinvT;  // n*n                    xi_i = sum_k VinvT[k*n+i] xbar_k
+  const double *Abar;   // m*n   row-major:       (A̅'y)_i = sum_r Abar[r*n+i] y_r
+  const double *lam, *D, *Dinv, *E, *Einv;
+  const double *l0, *u0;        // UNSCALED setup bounds (used when the batch has none of its own)
+  const signed char *ctype;     // m
+};
+
+// zero-padded, k-major packs of the plan for the register-resident small-QP kernel (n<=16, m<=32)
+struct SmallPackDev {
+  const double *M1T;   // [48][16]  M1T[k][i] = [sigma*G | W'](i,k)
+  const double *WT;    // [16][32]  WT[k][r]  = W(r,k)
+  const double *VT;    // [16][16]  VT[k][i]  = V(i,k)
+  const double *PVT;   // [16][16]  PVT[k][i] = (P̄V)(i,k)
+  const double *Ab;    // [32][16]  A̅ row-major
+  const double *V;     // [16][16]  V row-major
+  const double *lam, *D, *Dinv;   // [16]
+  const double *E, *Einv;         // [32]
+  const int *ctype;               // [32]
+};
+
+// per-instance data and state, [B][len] contiguous
+struct BatchDev {
+  int B;
+  int fresh;            // 1: ignore stored iterates and rho (x = z = y = 0, rho = rho0)
+  const double *q;      // [B][n] unscaled gradient (NULL = 0)
+  const double *l, *u;  // [B][m] unscaled bounds (NULL = plan.l0 / plan.u0)
+  double *xi;           // [B][n] warm-start state in plan coordinates
+  double *z, *y;        // [B][m] scaled z, y
+  double *rho;          // [B]
+  double *x_out, *y_out;                 // [B][n], [B][m] unscaled solution
+  int *status, *iter, *rho_updates;      // [B]
+  double *obj, *pri_res, *dua_res;       // [B]
+};
+
+}  // namespace smpc

@@ -1,0 +1,40 @@
+// kernels.cuh -- launchers of the CUDA kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "../../include/solvempc_b200.h"
+#include "device_types.cuh"
+
+namespace smpc {
+
+// admm_shared_generic.cu
+cudaError_t launch_admm_shared_generic(const SharedPlanDev &P, const BatchDev &Bt, const SettingsDev &S,
+                                       cudaStream_t stream);
+cudaError_t launch_fill(double *p, double v, size_t count, cudaStream_t stream);
+cudaError_t launch_warm_start(const SharedPlanDev &P, int B, const double *x, const double *y, double *xi,
+                              double *z, double *ys, cudaStream_t stream);
+
+// admm_shared_small.cu : register-resident kernel for small QPs (n <= 16, m <= 32)
+bool small_kernel_supports(int n, int m);
+size_t small_pack_doubles();
+cudaError_t launch_admm_shared_small(const SmallPackDev &K, const SharedPlanDev &P, const BatchDev &Bt,
+                                     const SettingsDev &S, int *queue, int num_sms, cudaStream_t stream);
+
+// mpc_assembly.cu
+struct MpcDims { int N, nx, n_state_rows; double Q, R, RD, u_limit; };
+struct MpcMatsDev {   // per plant (index p): all row-major
+  double *H, *Gbar, *Fx, *Fu, *Fr, *Sbar, *Ku, *W0, *Sx, *Su, *CAB;
+};
+cudaError_t launch_mpc_assemble(const MpcDims &d, int plants, const double *Ad, const double *Bd,
+                                const double *Cd, const double *K, const MpcMatsDev &out, cudaStream_t stream);
+// f = Fx X + Fu U + Fr ref ; ub = W0 + Sbar X + Ku U  for the whole batch (mats shared when stride 0)
+cudaError_t launch_mpc_step_vectors(const MpcDims &d, int B, int per_instance, const MpcMatsDev &mats,
+                                    const double *X, const double *U, const double *ref, double *f,
+                                    double *ub, cudaStream_t stream);
+// U += dU[0]
+cudaError_t launch_mpc_apply_control(int B, int n, const double *x, const int *status, double *U, cudaStream_t stream);
+// X <- Ad X + Bd U
+cudaError_t launch_mpc_plant_step(int B, int nx, int per_instance, const double *Ad, const double *Bd,
+                                  double *X, const double *U, cudaStream_t stream);
+
+}  // namespace smpc

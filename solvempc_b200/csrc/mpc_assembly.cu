@@ -1,0 +1,144 @@
+// mpc_assembly.cu -- on-device condensed-QP assembly and per-step vectors of the MPC layer.
+//
+// Device restatement of the reference builders (src/ModelPredictiveControlAPI.cpp):
+//   setTransformations (cpp:180-208), setH (cpp:247-263), setFVars (cpp:303-307),
+//   setLinearConstraints (cpp:326-347), setUpperBound (cpp:360-369), setF (cpp:372-375) and the
+//   upper bound sent at cpp:99 -- with mpcWindow / N_S (h:26-30) as run-time N / nx.
+// One CTA assembles one plant, so the same kernel serves the shared plant (1 CTA) and per-instance
+// linearised plants (one CTA each, BASELINE config 4).
+// Reference quirks kept: S carries K in its first n_state_rows rows only;
+// Su strictly-upper = 0; Fu uses diag(LL' Rbar') = R.
+#include "kernels.cuh"
+
+namespace smpc {
+
+constexpr int kMaxNx = 16;
+
+__global__ void __launch_bounds__(256) mpc_assemble_kernel(MpcDims d, int plants, const double *__restrict__ Ad_all,
+                                                           const double *__restrict__ Bd_all,
+                                                           const double *__restrict__ Cd,
+                                                           const double *__restrict__ K, MpcMatsDev o) {
+  const int p = blockIdx.x;
+  if (p >= plants) return;
+  const int N = d.N, nx = d.nx, tid = threadIdx.x, nt = blockDim.x;
+  __shared__ double Ak[kMaxNx * kMaxNx], An[kMaxNx * kMaxNx], Ad[kMaxNx * kMaxNx], Bd[kMaxNx], row[kMaxNx];
+  extern __shared__ double pc[];  // N prefix sums of CAB
+  double *H = o.H + (size_t)p * N * N, *Gbar = o.Gbar + (size_t)p * 2 * N * N, *Fx = o.Fx + (size_t)p * N * nx;
+  double *Fu = o.Fu + (size_t)p * N, *Fr = o.Fr + (size_t)p * N * N, *Sbar = o.Sbar + (size_t)p * 2 * N * nx;
+  double *Ku = o.Ku + (size_t)p * 2 * N, *W0 = o.W0 + (size_t)p * 2 * N, *Sx = o.Sx + (size_t)p * N * nx;
+  double *Su = o.Su + (size_t)p * N * N, *CAB = o.CAB + (size_t)p * N;
+  for (int e = tid; e < nx * nx; e += nt) { Ad[e] = Ad_all[(size_t)p * nx * nx + e]; Ak[e] = (e / nx == e % nx) ? 1.0 : 0.0; }
+  for (int e = tid; e < nx; e += nt) Bd[e] = Bd_all[(size_t)p * nx + e];
+  __syncthreads();
+  // cpp:187-190: CAB[i] = Cd Ad^i Bd ; Sx[i] = Cd Ad^(i+1)
+  for (int i = 0; i < N; ++i) {
+    if (tid < nx) { double s = 0; for (int k = 0; k < nx; ++k) s += Cd[k] * Ak[k * nx + tid]; row[tid] = s; }
+    for (int e = tid; e < nx * nx; e += nt) { int r = e / nx, c = e % nx; double s = 0; for (int k = 0; k < nx; ++k) s += Ak[r * nx + k] * Ad[k * nx + c]; An[e] = s; }
+    __syncthreads();
+    if (tid == 0) { double s = 0; for (int k = 0; k < nx; ++k) s += row[k] * Bd[k]; CAB[i] = s; pc[i] = (i ? pc[i - 1] : 0.0) + s; }
+    for (int e = tid; e < nx * nx; e += nt) Ak[e] = An[e];
+    __syncthreads();
+    if (tid < nx) { double s = 0; for (int k = 0; k < nx; ++k) s += Cd[k] * Ak[k * nx + tid]; Sx[i * nx + tid] = s; }
+    __syncthreads();
+  }
+  // cpp:197-201: Su(i,j) = sum_{k<=i-j} CAB[k] (j<=i), 0 above the diagonal
+  for (int e = tid; e < N * N; e += nt) { int i = e / N, j = e % N; Su[e] = j <= i ? pc[i - j] : 0.0; }
+  // cpp:185,208: Sbar = [S; -S], S rows < n_state_rows = K ; cpp:332-335: Gbar = [K0 LL; -K0 LL] ; cpp:364-368
+  const int ns = d.n_state_rows < N ? d.n_state_rows : N;
+  for (int e = tid; e < N * nx; e += nt) { int i = e / nx, c = e % nx; double v = i < ns ? K[c] : 0.0; Sbar[e] = v; Sbar[(size_t)N * nx + e] = -v; }
+  for (int e = tid; e < N * N; e += nt) { int i = e / N, j = e % N; double v = j <= i ? K[0] : 0.0; Gbar[e] = v; Gbar[(size_t)N * N + e] = -v; }
+  for (int i = tid; i < N; i += nt) { Ku[i] = -K[0]; Ku[N + i] = K[0]; W0[i] = d.u_limit; W0[N + i] = d.u_limit; }
+  __syncthreads();
+  // cpp:250-251: H = sym(2 (LL' Rbar LL + RbarD + Su' Qbar Su)), (LL'LL)(i,j) = N - max(i,j)
+  for (int e = tid; e < N * N; e += nt) {
+    int i = e / N, j = e % N;
+    if (j < i) continue;
+    double s = 0;
+    for (int k = j; k < N; ++k) s += Su[(size_t)k * N + i] * Su[(size_t)k * N + j];  // rows k < max(i,j) contribute 0
+    double v = 2.0 * (d.R * (double)(N - j) + (i == j ? d.RD : 0.0) + d.Q * s);
+    H[(size_t)i * N + j] = v; H[(size_t)j * N + i] = v;
+  }
+  // cpp:305-307: Fu = 2 (R 1 + Q Su' Su(:,0)) ; Fr = -2 Q Su' ; Fx = 2 Q Su' Sx
+  for (int i = tid; i < N; i += nt) {
+    double s = 0;
+    for (int k = i; k < N; ++k) s += Su[(size_t)k * N + 0] * Su[(size_t)k * N + i];
+    Fu[i] = 2.0 * (d.R + d.Q * s);
+  }
+  for (int e = tid; e < N * N; e += nt) { int i = e / N, j = e % N; Fr[e] = -2.0 * d.Q * Su[(size_t)j * N + i]; }
+  for (int e = tid; e < N * nx; e += nt) {
+    int i = e / nx, c = e % nx; double s = 0;
+    for (int k = i; k < N; ++k) s += Su[(size_t)k * N + i] * Sx[k * nx + c];
+    Fx[e] = 2.0 * d.Q * s;
+  }
+}
+
+// One warp per instance: f (cpp:374) and ub (cpp:99).
+__global__ void mpc_step_vectors_kernel(MpcDims d, int B, int per_instance, MpcMatsDev mt, const double *__restrict__ X,
+                                        const double *__restrict__ U, const double *__restrict__ ref,
+                                        double *__restrict__ f, double *__restrict__ ub) {
+  const int lane = threadIdx.x & 31, b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const int N = d.N, nx = d.nx;
+  const size_t p = per_instance ? (size_t)b : 0;
+  const double *Fx = mt.Fx + p * N * nx, *Fu = mt.Fu + p * N, *Fr = mt.Fr + p * N * N;
+  const double *Sbar = mt.Sbar + p * 2 * N * nx, *Ku = mt.Ku + p * 2 * N, *W0 = mt.W0 + p * 2 * N;
+  const double *x = X + (size_t)b * nx;
+  const double u = U[b], r = ref[b];
+  for (int i = lane; i < N; i += 32) {
+    double s = 0;
+    for (int c = 0; c < nx; ++c) s += Fx[i * nx + c] * x[c];
+    s += Fu[i] * u;
+    double rr = 0;
+    for (int j = i; j < N; ++j) rr += Fr[(size_t)i * N + j] * r;   // Fr(i,j) = 0 for j < i
+    f[(size_t)b * N + i] = s + rr;
+  }
+  for (int i = lane; i < 2 * N; i += 32) {
+    double s = 0;
+    for (int c = 0; c < nx; ++c) s += Sbar[i * nx + c] * x[c];
+    ub[(size_t)b * 2 * N + i] = (W0[i] + s) + Ku[i] * u;
+  }
+}
+
+// cpp:105: U += dU*[0] -- the reference returns before this line unless the status is SOLVED (cpp:102)
+__global__ void mpc_apply_control_kernel(int B, int n, const double *__restrict__ x, const int *__restrict__ status,
+                                         double *__restrict__ U) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B && status[b] == SMPC_SOLVED) U[b] += x[(size_t)b * n];
+}
+
+__global__ void mpc_plant_step_kernel(int B, int nx, int per_instance, const double *__restrict__ Ad,
+                                      const double *__restrict__ Bd, double *__restrict__ X,
+                                      const double *__restrict__ U) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const double *A = Ad + (per_instance ? (size_t)b * nx * nx : 0), *Bv = Bd + (per_instance ? (size_t)b * nx : 0);
+  double xo[kMaxNx], xn[kMaxNx];
+  for (int c = 0; c < nx; ++c) xo[c] = X[(size_t)b * nx + c];
+  for (int r = 0; r < nx; ++r) { double s = 0; for (int c = 0; c < nx; ++c) s += A[r * nx + c] * xo[c]; xn[r] = s + Bv[r] * U[b]; }
+  for (int c = 0; c < nx; ++c) X[(size_t)b * nx + c] = xn[c];
+}
+
+cudaError_t launch_mpc_assemble(const MpcDims &d, int plants, const double *Ad, const double *Bd, const double *Cd,
+                                const double *K, const MpcMatsDev &out, cudaStream_t stream) {
+  if (d.nx > kMaxNx || d.nx < 1 || d.N < 1) return cudaErrorInvalidValue;
+  mpc_assemble_kernel<<<plants, 256, d.N * sizeof(double), stream>>>(d, plants, Ad, Bd, Cd, K, out);
+  return cudaGetLastError();
+}
+cudaError_t launch_mpc_step_vectors(const MpcDims &d, int B, int per_instance, const MpcMatsDev &mats, const double *X,
+                                    const double *U, const double *ref, double *f, double *ub, cudaStream_t stream) {
+  const int wpc = 8;
+  mpc_step_vectors_kernel<<<(B + wpc - 1) / wpc, wpc * 32, 0, stream>>>(d, B, per_instance, mats, X, U, ref, f, ub);
+  return cudaGetLastError();
+}
+cudaError_t launch_mpc_apply_control(int B, int n, const double *x, const int *status, double *U, cudaStream_t stream) {
+  mpc_apply_control_kernel<<<(B + 255) / 256, 256, 0, stream>>>(B, n, x, status, U);
+  return cudaGetLastError();
+}
+cudaError_t launch_mpc_plant_step(int B, int nx, int per_instance, const double *Ad, const double *Bd, double *X,
+                                  const double *U, cudaStream_t stream) {
+  if (nx > kMaxNx) return cudaErrorInvalidValue;
+  mpc_plant_step_kernel<<<(B + 127) / 128, 128, 0, stream>>>(B, nx, per_instance, Ad, Bd, X, U);
+  return cudaGetLastError();
+}
+
+}  // namespace smpc

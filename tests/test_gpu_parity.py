@@ -1,0 +1,329 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs,
+against the committed golden fixtures, and -- at BASELINE sizes -- through solver-independent KKT properties.
+
+Tolerance (north star): u0 and the whole trajectory within 1e-4 relative (to ||x||_inf of the instance), same
+status, same active set; additionally the iteration counts must agree because both sides run the same algorithm.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+import solvempc_b200 as sm
+from problems import KNOWN_CASES, c2_batch, random_qp
+
+pytestmark = pytest.mark.gpu
+
+EPS = dict(eps_abs=1e-5, eps_rel=1e-5)
+REL = 1e-4          # north-star tolerance
+TIGHT = 1e-7        # what two implementations of the same iteration actually achieve
+
+
+def rel_err(x, xo):
+    scale = np.maximum(np.abs(xo).max(axis=-1), 1e-9)
+    return (np.abs(x - xo).max(axis=-1) / scale).max()
+
+
+def active_set(A, x, y, u):
+    Ax = x @ A.T
+    return (y > 1e-6 * np.abs(y).max(axis=-1, keepdims=True) + 1e-300) | (u - Ax < 1e-6 * np.maximum(1.0, np.abs(u)))
+
+
+@pytest.fixture(scope="module")
+def cfg_path(repo_root):
+    return os.path.join(repo_root, "config", "MPC_API.json")
+
+
+@pytest.mark.parametrize("kernel", [1, 2])
+def test_c1_reference_cases_through_mpc_api(cfg_path, golden, ref_mats, kernel):
+    """Config 1: shipped plant + horizon, the four known-answer states, one controller each (B=1) and batched."""
+    m, _ = ref_mats
+    for batch in (1, 4):
+        for k0 in range(0, 4, batch):
+            cases = golden["cases"][k0:k0 + batch]
+            mpc = sm.BatchedModelPredictiveControlAPI(cfg_path, batch=batch, kernel=kernel, **EPS)
+            assert (mpc.mpcWindow, mpc.N_S, mpc.n_variables, mpc.n_constraints) == (15, 4, 15, 30)
+            for name in ("H", "Gbar", "Fx", "Fu", "Fr", "Sbar", "Ku", "W0", "Sx", "Su", "CAB"):
+                g = np.array(golden[name], dtype=float).reshape(mpc.matrix(name).shape)
+                assert np.abs(mpc.matrix(name) - g).max() <= 1e-12 * max(np.abs(g).max(), 1e-300), name
+            mpc.set_state(X=np.array([c["X"] for c in cases]), U=np.array([c["U"] for c in cases]),
+                          ref=np.array([c["xref"] for c in cases]))
+            assert mpc.controllerStep()
+            f, ub = mpc.step_vectors()
+            x, y = mpc.solver.solution()
+            info = mpc.solver.info()
+            _, U = mpc.state()
+            for j, c in enumerate(cases):
+                assert np.abs(f[j] - c["q"]).max() <= 1e-12 * np.abs(c["q"]).max()
+                assert np.abs(ub[j] - c["u"]).max() <= 1e-12 * np.abs(c["u"]).max()
+                assert info["status"][j] == c["status"] == 1 and info["iter"][j] == c["iter"]
+                assert rel_err(x[j], np.array(c["x"])) < TIGHT
+                assert abs(U[j] - c["U_after"]) < 1e-9
+            mpc.close()
+    # and against the exact KKT answers (solver independent)
+    mpc = sm.BatchedModelPredictiveControlAPI(cfg_path, batch=4, kernel=kernel, **EPS)
+    mpc.set_state(X=np.array([c["X"] for c in KNOWN_CASES]), U=np.array([c["U"] for c in KNOWN_CASES]),
+                  ref=np.array([c["ref"] for c in KNOWN_CASES]))
+    assert mpc.controllerStep()
+    x, y = mpc.solver.solution()
+    f, ub = mpc.step_vectors()
+    for j, c in enumerate(KNOWN_CASES):
+        xs, ys = oracle.exact_qp_active_set(m["H"], f[j], m["Gbar"], ub[j], c["active"])
+        assert np.abs(x[j] - xs).max() < 5e-6 and abs(x[j][0] - c["du0"]) < 1e-6
+        assert set(np.nonzero(active_set(m["Gbar"], x[j], y[j], ub[j]))[0]) == set(c["active"])
+
+
+@pytest.mark.parametrize("kernel", [1, 2])
+def test_c2_batch_4096_matches_oracle(ref_mats, kernel):
+    """Config 2: 4096 random x0 / references sharing P and A, cold solves."""
+    m, _ = ref_mats
+    B = 4096
+    X, U, ref = c2_batch(B, seed=0)
+    f, ub = oracle.mpc_batch_vectors(m, X, U, ref)
+    ora = oracle.solve_batch(m["H"], m["Gbar"], m["lb"], m["W0"], f, ub, nthreads=os.cpu_count() or 1, **EPS)
+    s = sm.BatchedSolver(m["H"], m["Gbar"], m["lb"], m["W0"], batch=B, kernel=kernel, **EPS)
+    assert s.kernel_name == ("admm_shared_small_kernel" if kernel == 2 else "admm_shared_generic_kernel")
+    s.update_gradient(f)
+    s.update_upper_bound(ub)
+    s.solve()
+    x, y = s.solution()
+    info = s.info()
+    assert np.array_equal(info["status"], ora["status"]) and (info["status"] == 1).all()
+    assert np.array_equal(info["iter"], ora["iter"])
+    assert rel_err(x, ora["x"]) < TIGHT < REL
+    assert rel_err(x[:, :1], ora["x"][:, :1]) < REL        # u0 increment
+    assert np.abs(y - ora["y"]).max() < 1e-7 * max(1.0, np.abs(ora["y"]).max())
+    assert np.array_equal(active_set(m["Gbar"], x, y, ub), active_set(m["Gbar"], ora["x"], ora["y"], ub))
+    assert s.count_solved() == B
+    # second solve on the same handle is warm started and rho persists (cpp:52): oracle does the same per instance
+    s.solve()
+    info2 = s.info()
+    assert (info2["iter"] == 25).all() and (info2["status"] == 1).all()
+    # cold-solve mode reproduces the first solve bit for bit
+    s.set_cold_solves(True)
+    s.solve()
+    x3, _ = s.solution()
+    assert np.array_equal(x3, x) and np.array_equal(s.info()["iter"], info["iter"])
+    s.close()
+
+
+def test_generic_and_small_kernels_agree_bitwise_on_status(ref_mats):
+    m, _ = ref_mats
+    X, U, ref = c2_batch(512, seed=5)
+    f, ub = oracle.mpc_batch_vectors(m, X, U, ref)
+    out = []
+    for kernel in (1, 2):
+        s = sm.BatchedSolver(m["H"], m["Gbar"], m["lb"], m["W0"], batch=512, kernel=kernel, **EPS)
+        s.update_gradient(f); s.update_upper_bound(ub); s.solve()
+        out.append((s.solution()[0], s.info()))
+        s.close()
+    assert np.array_equal(out[0][1]["iter"], out[1][1]["iter"])
+    assert rel_err(out[0][0], out[1][0]) < 1e-9
+
+
+@pytest.mark.parametrize("n,m,B", [(3, 0, 8), (12, 20, 64), (16, 32, 64), (17, 33, 32), (40, 70, 32), (100, 200, 8)])
+def test_random_qps_generic_shapes(n, m, B):
+    """Two-sided bounds, equality rows and a free row; every instance gets its own q, l, u."""
+    P, q0, A, l0, u0 = random_qp(n, max(m, 1), seed=n * 7 + m)
+    if m == 0:
+        A, l0, u0 = np.zeros((0, n)), np.zeros(0), np.zeros(0)
+    else:
+        l0[: m // 5] = u0[: m // 5]
+        l0[m // 5], u0[m // 5] = -np.inf, np.inf
+    rng = np.random.default_rng(n + m)
+    q = q0[None, :] + 0.3 * rng.standard_normal((B, n))
+    sh = 0.2 * rng.standard_normal((B, m)) if m else np.zeros((B, 0))
+    l, u = l0[None, :] + sh, u0[None, :] + sh
+    xs, ys, st, it = [], [], [], []
+    for b in range(B):
+        so = oracle.Solver(P, np.zeros(n), A, l0, u0, **EPS)
+        so.update_lin_cost(q[b])
+        if m:
+            so.update_bounds(l[b], u[b])
+        r = so.solve()
+        xs.append(r["x"]); ys.append(r["y"]); st.append(r["status"]); it.append(r["iter"])
+    s = sm.BatchedSolver(P, A, l0, u0, batch=B, **EPS)
+    s.update_gradient(q)
+    if m:
+        s.update_bounds(l, u)
+    s.solve()
+    x, y = s.solution()
+    info = s.info()
+    assert np.array_equal(info["status"], np.array(st)) and np.array_equal(info["iter"], np.array(it))
+    assert rel_err(x, np.array(xs)) < TIGHT
+    if m:
+        assert np.abs(y - np.array(ys)).max() < 1e-6 * max(1.0, np.abs(np.array(ys)).max())
+    s.close()
+
+
+@pytest.mark.parametrize("kernel", [1, 2])
+@pytest.mark.parametrize("opts", [dict(adaptive_rho=0), dict(scaling=0), dict(scaled_termination=1),
+                                  dict(adaptive_rho_interval=50), dict(check_termination=10, adaptive_rho_interval=30),
+                                  dict(max_iter=30), dict(alpha=1.0, rho=1.0, eps_abs=1e-3, eps_rel=1e-3)])
+def test_settings_follow_the_oracle(ref_mats, kernel, opts):
+    m, _ = ref_mats
+    kw = {**EPS, **opts}
+    X, U, ref = c2_batch(96, seed=11)
+    f, ub = oracle.mpc_batch_vectors(m, X, U, ref)
+    ora = oracle.solve_batch(m["H"], m["Gbar"], m["lb"], m["W0"], f, ub, nthreads=4, **kw)
+    s = sm.BatchedSolver(m["H"], m["Gbar"], m["lb"], m["W0"], batch=96, kernel=kernel, **kw)
+    s.update_gradient(f); s.update_upper_bound(ub); s.solve()
+    x, y = s.solution()
+    info = s.info()
+    assert np.array_equal(info["status"], ora["status"]) and np.array_equal(info["iter"], ora["iter"])
+    assert rel_err(x, ora["x"]) < 1e-6
+    s.close()
+
+
+@pytest.mark.parametrize("kernel", [1, 2])
+def test_infeasible_unbounded_and_bad_bounds(kernel):
+    P = np.eye(2); A = np.array([[1.0, 0.0], [1.0, 0.0]])
+    l = np.array([[1.0, -np.inf], [-2.0, -np.inf], [0.5, -np.inf]]); u = np.array([[np.inf, -1.0], [np.inf, 3.0], [np.inf, 0.25]])
+    s = sm.BatchedSolver(P, A, np.array([-1.0, -np.inf]), np.array([np.inf, 1.0]), batch=3, kernel=kernel)
+    s.update_gradient(np.zeros((3, 2))); s.update_bounds(l, u); s.solve()
+    x, _ = s.solution(); info = s.info()
+    exp = []
+    for b in range(3):
+        so = oracle.Solver(P, np.zeros(2), A, np.array([-1.0, -np.inf]), np.array([np.inf, 1.0]))
+        so.update_bounds(l[b], u[b]); exp.append(so.solve())
+    assert [e["status"] for e in exp] == [sm.PRIMAL_INFEASIBLE, sm.SOLVED, sm.PRIMAL_INFEASIBLE]
+    assert list(info["status"]) == [e["status"] for e in exp] and list(info["iter"]) == [e["iter"] for e in exp]
+    assert np.isnan(x[0]).all() and np.isnan(x[2]).all() and np.abs(x[1] - exp[1]["x"]).max() < 1e-9
+    s.close()
+    P = np.diag([1.0, 0.0]); A = np.array([[1.0, 0.0]])
+    s = sm.BatchedSolver(P, A, np.array([-1.0]), np.array([1.0]), batch=2, kernel=kernel)
+    s.update_gradient(np.array([[0.0, -1.0], [0.3, 0.0]])); s.solve()
+    info = s.info(); x, _ = s.solution()
+    so = oracle.Solver(P, np.zeros(2), A, np.array([-1.0]), np.array([1.0])); so.update_lin_cost(np.array([0.0, -1.0]))
+    r0 = so.solve()
+    assert r0["status"] == sm.DUAL_INFEASIBLE and info["status"][0] == sm.DUAL_INFEASIBLE and info["iter"][0] == r0["iter"]
+    assert np.isnan(x[0]).all() and info["status"][1] == sm.SOLVED
+    s.close()
+    # l > u for one instance: that instance stays UNSOLVED, the others are solved
+    P, q, A, l0, u0 = random_qp(6, 8, 2)
+    s = sm.BatchedSolver(P, A, l0, u0, batch=2, kernel=kernel)
+    lb = np.stack([l0, l0]); ubd = np.stack([u0, u0]); lb[1, 3] = ubd[1, 3] + 1.0
+    s.update_gradient(np.stack([q, q])); s.update_bounds(lb, ubd); s.solve()
+    info = s.info()
+    assert info["status"][0] == sm.SOLVED and info["status"][1] == sm.UNSOLVED and info["iter"][1] == 0
+    s.close()
+
+
+@pytest.mark.parametrize("kernel", [1, 2])
+def test_closed_loop_warm_start_matches_reference_run(cfg_path, golden, ref_mats, kernel):
+    """40 warm-started controllerStep + plant steps: the golden trajectory came from the reference's own class."""
+    m, cfg = ref_mats
+    cl = golden["closed_loop"]
+    B = 5
+    rng = np.random.default_rng(4)
+    X0 = np.vstack([cl["X0"], rng.standard_normal((B - 1, 4)) * np.array([0.05, 0.2, 0.05, 0.3])])
+    U0 = np.r_[cl["U0"], rng.standard_normal(B - 1)]
+    ref = np.r_[cl["xref"], 0.2 * rng.standard_normal(B - 1)]
+    mpc = sm.BatchedModelPredictiveControlAPI(cfg_path, batch=B, kernel=kernel, **EPS)
+    mpc.set_state(X=X0, U=U0, ref=ref)
+    solvers = [oracle.Solver(m["H"], np.zeros(15), m["Gbar"], m["lb"], m["W0"], **EPS) for _ in range(B)]
+    Xo, Uo = X0.copy(), U0.copy()
+    for k in range(cl["steps"]):
+        assert mpc.controllerStep()
+        mpc.plant_step()
+        X, U = mpc.state()
+        info = mpc.solver.info()
+        for b in range(B):
+            f, ub = oracle.mpc_step_vectors(m, Xo[b], Uo[b], ref[b])
+            solvers[b].update_lin_cost(f); solvers[b].update_upper_bound(ub)
+            r = solvers[b].solve()
+            Uo[b] += r["x"][0]
+            Xo[b] = cfg["Ad"] @ Xo[b] + cfg["Bd"] * Uo[b]
+            assert info["iter"][b] == r["iter"] and info["status"][b] == 1
+        assert info["iter"][0] == cl["iters"][k]
+        assert abs(U[0] - cl["U"][k]) < 1e-8 and np.abs(X[0] - np.array(cl["X"][k])).max() < 1e-8
+        assert np.abs(U - Uo).max() < 1e-7 * max(1.0, np.abs(Uo).max())
+        assert np.abs(X - Xo).max() < 1e-7 * max(1.0, np.abs(Xo).max())
+    mpc.close()
+
+
+def test_user_warm_start_and_device_buffers(ref_mats):
+    import torch
+    m, _ = ref_mats
+    B = 64
+    X, U, ref = c2_batch(B, seed=21)
+    f, ub = oracle.mpc_batch_vectors(m, X, U, ref)
+    s = sm.BatchedSolver(m["H"], m["Gbar"], m["lb"], m["W0"], batch=B, **EPS)
+    fd, ud = torch.from_numpy(f).cuda(), torch.from_numpy(ub).cuda()
+    s.set_stream(torch.cuda.current_stream().cuda_stream)
+    s.update_gradient(fd); s.update_upper_bound(ud); s.solve()
+    xd = torch.empty(B, 15, dtype=torch.float64, device="cuda"); yd = torch.empty(B, 30, dtype=torch.float64, device="cuda")
+    s.solution_into(xd, yd)
+    torch.cuda.synchronize()
+    x, y = s.solution()
+    assert np.array_equal(xd.cpu().numpy(), x)
+    it0 = s.info()["iter"].copy()
+    # osqp_warm_start with the solution on a fresh handle: same path as the oracle's warm start
+    s2 = sm.BatchedSolver(m["H"], m["Gbar"], m["lb"], m["W0"], batch=B, **EPS)
+    s2.update_gradient(f); s2.update_upper_bound(ub); s2.warm_start(x, y); s2.solve()
+    it2 = s2.info()["iter"]
+    x2, _ = s2.solution()
+    for b in range(0, B, 7):
+        so = oracle.Solver(m["H"], np.zeros(15), m["Gbar"], m["lb"], m["W0"], **EPS)
+        so.update_lin_cost(f[b]); so.update_upper_bound(ub[b]); so.warm_start(x[b], y[b])
+        r = so.solve()
+        assert r["iter"] == it2[b] and rel_err(x2[b], r["x"]) < 1e-6
+    assert (it2 <= it0).all()
+    s.close(); s2.close()
+
+
+def test_full_size_properties_and_sharding(ref_mats):
+    """BASELINE-size batch (65 536 instances) checked through size-independent properties: every instance
+    satisfies OSQP's stopping rule recomputed independently in unscaled space, iterations are multiples of 25,
+    and a shard of the batch solved on its own handle gives bitwise the same answers."""
+    m, _ = ref_mats
+    B = 65536
+    X, U, ref = c2_batch(B, seed=123)
+    f, ub = oracle.mpc_batch_vectors(m, X, U, ref)
+    s = sm.BatchedSolver(m["H"], m["Gbar"], m["lb"], m["W0"], batch=B, **EPS)
+    s.update_gradient(f); s.update_upper_bound(ub); s.solve()
+    x, y = s.solution(); info = s.info()
+    assert (info["status"] == 1).all() and (info["iter"] % 25 == 0).all() and info["iter"].max() <= 400
+    H, G = m["H"], m["Gbar"]
+    Ax, Px, Aty = x @ G.T, x @ H.T, y @ G
+    rd = np.abs(Px + f + Aty).max(axis=1)
+    tol_d = 1e-5 + 1e-5 * np.maximum(np.maximum(np.abs(Px).max(1), np.abs(Aty).max(1)), np.abs(f).max(1))
+    assert (rd < tol_d * 1.0000001).all()
+    assert ((Ax - ub).max(axis=1) < 1e-5 + 1e-5 * np.abs(Ax).max(axis=1)).all()
+    assert (y > -1e-9).all()                                   # one-sided rows: duals >= 0
+    assert np.abs(np.minimum(y, 1.0) * np.minimum(ub - Ax, 1.0)).max() < 1e-3   # complementarity
+    assert 0.3 < (np.abs(y).max(axis=1) > 1e-7).mean() < 0.6   # ~43 % of instances saturate
+    lo, hi = 3 * B // 8, 5 * B // 8
+    s2 = sm.BatchedSolver(m["H"], m["Gbar"], m["lb"], m["W0"], batch=hi - lo, **EPS)
+    s2.update_gradient(f[lo:hi]); s2.update_upper_bound(ub[lo:hi]); s2.solve()
+    x2, y2 = s2.solution()
+    assert np.array_equal(x2, x[lo:hi]) and np.array_equal(y2, y[lo:hi])
+    # a 2 048-instance sample against the oracle
+    idx = np.arange(0, B, 32)
+    ora = oracle.solve_batch(m["H"], m["Gbar"], m["lb"], m["W0"], f[idx], ub[idx], nthreads=os.cpu_count() or 1, **EPS)
+    assert np.array_equal(info["iter"][idx], ora["iter"]) and rel_err(x[idx], ora["x"]) < TIGHT
+    s.close(); s2.close()
+
+
+def test_horizon_100_config5_shape(ref_mats, repo_root):
+    """Config 5 shape (N = 100 -> n = 100, m = 200) through the MPC API on the generic kernel."""
+    _, cfg = ref_mats
+    N, B = 100, 16
+    mats = oracle.mpc_build(**{**cfg, "N": N})
+    conf = dict(Ad=cfg["Ad"], Bd=cfg["Bd"], Cd=cfg["Cd"], K=cfg["K"], Q=cfg["Q"], R=cfg["R"], RD=cfg["RD"], horizon=N)
+    mpc = sm.BatchedModelPredictiveControlAPI(conf, batch=B, **EPS)
+    for name in ("H", "Gbar", "Fx", "Fu", "Fr", "Sbar"):
+        assert np.abs(mpc.matrix(name) - mats[name]).max() <= 1e-11 * np.abs(mats[name]).max(), name
+    X, U, ref = c2_batch(B, seed=9)
+    mpc.set_state(X=X, U=U, ref=ref)
+    ok = mpc.controllerStep()
+    f, ub = oracle.mpc_batch_vectors(mats, X, U, ref)
+    fd, ubd = mpc.step_vectors()
+    assert np.abs(fd - f).max() < 1e-11 * np.abs(f).max() and np.abs(ubd - ub).max() < 1e-11 * np.abs(ub).max()
+    ora = oracle.solve_batch(mats["H"], mats["Gbar"], mats["lb"], mats["W0"], f, ub, nthreads=4, **EPS)
+    x, _ = mpc.solver.solution(); info = mpc.solver.info()
+    assert ok == bool((ora["status"] == 1).all())
+    assert np.array_equal(info["status"], ora["status"]) and np.array_equal(info["iter"], ora["iter"])
+    assert rel_err(x, ora["x"]) < 1e-6
+    mpc.close()
