@@ -7,10 +7,16 @@
 //   lane r      = lane                    keeps  wr[i] = W(r, i), i < 16                      (z-phase)
 //   and its rows of xi, q̂, 1/(1+rho*lambda), z, y, l̄, ū.
 // Per iteration (OSQP 0.6.x osqp_solve in plan coordinates, see admm_shared_generic.cu / plan.hpp):
-//   24 DFMA + 1 shuffle-add for t, 16 DFMA for z̃, ~13 FP64 element-wise ops, two 512-byte shared-memory
+//   24 DFMA + 1 shuffle-add for t, 16 DFMA for z̃, ~12 FP64 element-wise ops, two 512-byte shared-memory
 //   broadcasts ([xi; w] and t).  HBM is touched once per solve (q, u in; x, y, status out), so the kernel is
-//   bound by the FP64 pipe, not by HBM.
-// Termination checks / rho adaptation (every 25 iterations) read their operators from shared memory.
+//   bound by the FP64 pipe and by the latency of the dependent chain of one iteration, not by HBM.
+// The element-wise tail is arranged so that only   v = alpha*z̃ + base,  z = clip(v),  w' = rho*(2z - v)
+// sit on the critical path (base = (1-alpha) z + y/rho and y' = rho (v - z) are OSQP's update_z / update_y
+// re-associated; y' is exactly 0 on rows that are not clipped).
+// Termination checks / rho adaptation (every check_termination / adaptive_rho_interval iterations) are an
+// out-of-line routine that reads its operators from shared memory.
+#include <cstdint>
+
 #include "device_types.cuh"
 #include "kernels.cuh"
 
@@ -19,268 +25,332 @@ namespace smpc {
 namespace {
 
 constexpr int NP = 16, MP = 32, KH = (NP + MP) / 2;   // padded sizes; 24 concatenated entries per half-warp
+constexpr unsigned kFull = 0xffffffffu;
 
-__device__ __forceinline__ double wmax(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+__device__ __forceinline__ double2 lds128(uint32_t addr) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr) : "memory");
   return v;
+}
+__device__ __forceinline__ void sts64(uint32_t addr, double v) {
+  asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
+// exact max over the warp of NON-NEGATIVE doubles: compare the IEEE bit patterns as two 32-bit halves (REDUX)
+__device__ __forceinline__ double wmax_nn(double v) {
+  const unsigned hi = (unsigned)__double2hiint(v);
+  const unsigned mh = __reduce_max_sync(kFull, hi);
+  const unsigned lo = hi == mh ? (unsigned)__double2loint(v) : 0u;
+  const unsigned ml = __reduce_max_sync(kFull, lo);
+  return __hiloint2double((int)mh, (int)ml);
 }
 __device__ __forceinline__ double wsum(double v) {
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
   return v;
 }
 __device__ __forceinline__ double rho_row(int ct, double rho) {
   return ct == 0 ? rho : (ct == 1 ? kRhoEqOverIneq * rho : kRhoMin);
 }
 
-struct Info {
-  double pri_res, dua_res, nEz, nEAx, nDq, nDAty, nDPx;
-  double s_rp, s_rd, s_z, s_Ax, s_q, s_Aty, s_Px;
-  double obj;
+// CTA-shared operator block (doubles): VT[16][16] PVT[16][16] Ab[32][16] V[16][16] AbT[16][32]
+constexpr int kCtaMatDoubles = NP * NP * 3 + 2 * MP * NP;
+// per-warp block (doubles): cbuf[48] = [xi; w], tbuf[16], sbuf[32]
+constexpr int kWarpDoubles = NP + MP + NP + MP;
+
+struct CheckOut {
+  double rho;              // possibly adapted
+  double obj, pri_res, dua_res;
+  double xbar;             // lane's entry of x̄ = V xi
+  int status;              // SMPC_UNSOLVED while running
+  int rho_changed;
 };
 
-}  // namespace
+struct LaneConst {          // per-lane constants of the plan
+  double D, Dinv, E, Einv;
+  int ct;
+};
 
-// CTA-shared operator block (doubles): VT[16][16] PVT[16][16] AbP[32][16] V[16][16]
-constexpr int kCtaMatDoubles = NP * NP * 3 + MP * NP;
-// per-warp block (doubles): cbuf[48] tbuf[16] sbuf[32]
-constexpr int kWarpDoubles = NP + MP + NP + MP;
+// OSQP update_info + check_termination (+ is_primal_infeasible / is_dual_infeasible) + adapt_rho for one QP.
+// Everything it returns except xbar is uniform across the warp.  cbuf[0..15] must hold the current xi.
+__device__ __noinline__ CheckOut check_step(const double *sm, double *cbuf, double *sbuf, const SettingsDev &S, int n, int m,
+                                            double c, double cinv, LaneConst L, double rho, double qb_i, double z_r,
+                                            double y_r, double dy_r, double dxi_i, double lb_r, double ub_r,
+                                            bool do_check, bool approx, bool do_adapt) {
+  const double *sVT = sm, *sPVT = sVT + NP * NP, *sAb = sPVT + NP * NP, *sAbT = sAb + MP * NP + NP * NP;
+  const int lane = threadIdx.x & 31, h = lane >> 4, i = lane & 15, r = lane;
+  const bool unscale = !S.scaled_termination;
+  CheckOut o;
+  o.rho = rho; o.status = SMPC_UNSOLVED; o.rho_changed = 0;
+  sbuf[r] = y_r;
+  __syncwarp();
+  double ax = 0.0, apx = 0.0, aty = 0.0;
+#pragma unroll
+  for (int k = 0; k < NP / 2; ++k) {
+    const double xk = cbuf[8 * h + k];
+    ax = fma(sVT[(8 * h + k) * NP + i], xk, ax);
+    apx = fma(sPVT[(8 * h + k) * NP + i], xk, apx);
+  }
+#pragma unroll
+  for (int k = 0; k < MP / 2; ++k) aty = fma(sAb[(16 * h + k) * NP + i], sbuf[16 * h + k], aty);
+  ax += __shfl_xor_sync(kFull, ax, 16);
+  apx += __shfl_xor_sync(kFull, apx, 16);
+  aty += __shfl_xor_sync(kFull, aty, 16);
+  o.xbar = ax;
+  __syncwarp();
+  if (h == 0) sbuf[i] = ax;          // x̄ for A̅ x̄
+  __syncwarp();
+  double Ax_r = 0.0;
+#pragma unroll
+  for (int k = 0; k < NP; ++k) Ax_r = fma(sAbT[k * MP + r], sbuf[k], Ax_r);
+  __syncwarp();
+  const double rp = Ax_r - z_r, rd = (qb_i + apx) + aty;
+  const double s_rp = wmax_nn(fabs(rp)), s_z = wmax_nn(fabs(z_r)), s_Ax = wmax_nn(fabs(Ax_r));
+  const double s_rd = wmax_nn(fabs(rd)), s_q = wmax_nn(fabs(qb_i)), s_Aty = wmax_nn(fabs(aty)), s_Px = wmax_nn(fabs(apx));
+  double pri_res, dua_res, nEz, nEAx, nDq, nDAty, nDPx, obj;
+  const double ob = h == 0 ? 0.5 * ax * apx + qb_i * ax : 0.0;
+  if (unscale) {
+    pri_res = wmax_nn(fabs(L.Einv * rp)); nEz = wmax_nn(fabs(L.Einv * z_r)); nEAx = wmax_nn(fabs(L.Einv * Ax_r));
+    dua_res = cinv * wmax_nn(fabs(L.Dinv * rd)); nDq = wmax_nn(fabs(L.Dinv * qb_i));
+    nDAty = wmax_nn(fabs(L.Dinv * aty)); nDPx = wmax_nn(fabs(L.Dinv * apx));
+    obj = cinv * wsum(ob);
+  } else {
+    pri_res = s_rp; nEz = s_z; nEAx = s_Ax; dua_res = s_rd; nDq = s_q; nDAty = s_Aty; nDPx = s_Px;
+    obj = wsum(ob);
+  }
+  if (m == 0) pri_res = 0.0;
+  o.obj = obj; o.pri_res = pri_res; o.dua_res = dua_res;
+
+  if (do_check) {
+    double ea = S.eps_abs, er = S.eps_rel, epi = S.eps_prim_inf, edi = S.eps_dual_inf;
+    if (approx) { ea *= 10; er *= 10; epi *= 10; edi *= 10; }
+    bool prim_ok = false, dual_ok = false, prim_inf = false, dual_inf = false;
+    if (m == 0) prim_ok = true;
+    else if (pri_res < ea + er * fmax(nEz, nEAx)) prim_ok = true;
+    else {
+      // is_primal_infeasible: project delta_y on the polar of the recession cone of [l, u]
+      double d = dy_r;
+      const bool uinf = ub_r > kInfty * kMinScaling, linf = lb_r < -kInfty * kMinScaling;
+      if (uinf) d = linf ? 0.0 : fmin(d, 0.0); else if (linf) d = fmax(d, 0.0);
+      const double nd = wmax_nn(fabs(unscale ? L.E * d : d));
+      if (nd > epi) {
+        double lhs = 0.0;
+        const double dp = fmax(d, 0.0), dm = fmin(d, 0.0);
+        if (dp != 0.0) lhs += ub_r * dp;
+        if (dm != 0.0) lhs += lb_r * dm;
+        lhs = wsum(lhs);
+        if (lhs < -epi * nd) {
+          sbuf[r] = d;
+          __syncwarp();
+          double a = 0.0;
+#pragma unroll
+          for (int k = 0; k < MP / 2; ++k) a = fma(sAb[(16 * h + k) * NP + i], sbuf[16 * h + k], a);
+          a += __shfl_xor_sync(kFull, a, 16);
+          __syncwarp();
+          prim_inf = wmax_nn(fabs(unscale ? L.Dinv * a : a)) < epi * nd;
+        }
+      }
+    }
+    if (dua_res < ea + er * (unscale ? cinv : 1.0) * fmax(fmax(nDq, nDAty), nDPx)) dual_ok = true;
+    else {
+      // is_dual_infeasible on delta_x = V delta_xi
+      if (h == 0) sbuf[i] = dxi_i;
+      __syncwarp();
+      double dx = 0.0, pd = 0.0;
+#pragma unroll
+      for (int k = 0; k < NP / 2; ++k) {
+        const double dk = sbuf[8 * h + k];
+        dx = fma(sVT[(8 * h + k) * NP + i], dk, dx);
+        pd = fma(sPVT[(8 * h + k) * NP + i], dk, pd);
+      }
+      dx += __shfl_xor_sync(kFull, dx, 16);
+      pd += __shfl_xor_sync(kFull, pd, 16);
+      __syncwarp();
+      if (h == 0) sbuf[i] = dx;
+      __syncwarp();
+      double ad = 0.0;
+#pragma unroll
+      for (int k = 0; k < NP; ++k) ad = fma(sAbT[k * MP + r], sbuf[k], ad);
+      __syncwarp();
+      const double nd = wmax_nn(fabs(unscale ? L.D * dx : dx));
+      const double qd = wsum(h == 0 ? qb_i * dx : 0.0);
+      const double cs = unscale ? c : 1.0;
+      if (nd > edi && qd < -cs * edi * nd && wmax_nn(fabs(unscale ? L.Dinv * pd : pd)) < cs * edi * nd) {
+        if (unscale) ad *= L.Einv;
+        const int bad = ((ub_r < kInfty * kMinScaling) && (ad > edi * nd)) || ((lb_r > -kInfty * kMinScaling) && (ad < -edi * nd));
+        dual_inf = !__any_sync(kFull, bad && r < m);
+      }
+    }
+    if (prim_ok && dual_ok) o.status = approx ? SMPC_SOLVED_INACCURATE : SMPC_SOLVED;
+    else if (prim_inf) { o.status = approx ? SMPC_PRIMAL_INFEASIBLE_INACCURATE : SMPC_PRIMAL_INFEASIBLE; o.obj = kInfty; }
+    else if (dual_inf) { o.status = approx ? SMPC_DUAL_INFEASIBLE_INACCURATE : SMPC_DUAL_INFEASIBLE; o.obj = -kInfty; }
+  }
+  if (do_adapt && o.status == SMPC_UNSOLVED) {
+    // compute_rho_estimate / adapt_rho on the SCALED residual norms
+    const double pr = s_rp / (fmax(s_z, s_Ax) + kDivTol);
+    const double dr = s_rd / (fmax(fmax(s_q, s_Aty), s_Px) + kDivTol);
+    const double rn = fmin(fmax(rho * sqrt(pr / (dr + kDivTol)), kRhoMin), kRhoMax);
+    if (rn > rho * S.rho_tol || rn < rho / S.rho_tol) { o.rho = rn; o.rho_changed = 1; }
+  }
+  return o;
+}
+
+}  // namespace
 
 __global__ void __launch_bounds__(128, 3)
 admm_shared_small_kernel(SmallPackDev K, SharedPlanDev P, BatchDev Bt, SettingsDev S, int *queue) {
   extern __shared__ __align__(16) double smem[];
-  double *sVT = smem, *sPVT = sVT + NP * NP, *sAb = sPVT + NP * NP, *sV = sAb + MP * NP;
+  double *sV = smem + NP * NP * 2 + MP * NP;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double *cbuf = smem + kCtaMatDoubles + warp * kWarpDoubles, *tbuf = cbuf + NP + MP, *sbuf = tbuf + NP;
   const int h = lane >> 4, i = lane & 15, r = lane;
   const int n = P.n, m = P.m;
 
-  for (int e = threadIdx.x; e < NP * NP; e += blockDim.x) { sVT[e] = K.VT[e]; sPVT[e] = K.PVT[e]; sV[e] = K.V[e]; }
-  for (int e = threadIdx.x; e < MP * NP; e += blockDim.x) sAb[e] = K.Ab[e];
+  for (int e = threadIdx.x; e < NP * NP; e += blockDim.x) {
+    smem[e] = K.VT[e]; smem[NP * NP + e] = K.PVT[e]; sV[e] = K.V[e];
+  }
+  for (int e = threadIdx.x; e < MP * NP; e += blockDim.x) {
+    smem[2 * NP * NP + e] = K.Ab[e];
+    const int rr = e / NP, kk = e % NP;
+    smem[3 * NP * NP + MP * NP + kk * MP + rr] = K.Ab[e];   // AbT[k][r]
+  }
 
-  // shared operators -> registers (coalesced: the packs are stored k-major)
-  double m1[KH], wr[NP];
-#pragma unroll
-  for (int j = 0; j < KH; ++j) m1[j] = K.M1T[(KH * h + j) * NP + i];
-#pragma unroll
-  for (int k = 0; k < NP; ++k) wr[k] = K.WT[k * MP + r];
-  const double lam_i = K.lam[i], D_i = K.D[i], Dinv_i = K.Dinv[i];
-  const double E_r = K.E[r], Einv_r = K.Einv[r];
-  const int ct_r = K.ctype[r];
-  const double alpha = S.alpha, c = P.c, cinv = P.cinv;
-  const bool unscale = !S.scaled_termination;
+  const double lam_i = K.lam[i];
+  LaneConst LC;
+  LC.D = K.D[i]; LC.Dinv = K.Dinv[i]; LC.E = K.E[r]; LC.Einv = K.Einv[r]; LC.ct = K.ctype[r];
+  const double alpha = S.alpha, oma = 1.0 - S.alpha, c = P.c, cinv = P.cinv;
   const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+  const uint32_t a_cv = (uint32_t)__cvta_generic_to_shared(cbuf + KH * h);   // this half-warp's 24 entries of [xi; w]
+  const uint32_t a_tv = (uint32_t)__cvta_generic_to_shared(tbuf);
+  const uint32_t a_xi = (uint32_t)__cvta_generic_to_shared(cbuf + i);
+  const uint32_t a_w = (uint32_t)__cvta_generic_to_shared(cbuf + NP + r);
+  const uint32_t a_t = (uint32_t)__cvta_generic_to_shared(tbuf + i);
+  const int check_every = S.check_every > 0 ? S.check_every : 0x7fffffff;
+  const int adapt_every = (S.adaptive_rho && S.rho_interval > 0) ? S.rho_interval : 0x7fffffff;
   __syncthreads();
 
   for (;;) {
     int b = 0;
     if (lane == 0) b = atomicAdd(queue, 1);
-    b = __shfl_sync(0xffffffffu, b, 0);
+    b = __shfl_sync(kFull, b, 0);
     if (b >= Bt.B) break;
 
     // ---- load the instance (osqp_update_lin_cost / osqp_update_bounds scaling)
-    double qb_i = (i < n && Bt.q) ? c * (D_i * Bt.q[(size_t)b * n + i]) : 0.0;
-    double xi_i = (i < n && S.warm_start && !Bt.fresh) ? Bt.xi[(size_t)b * n + i] : 0.0;
+    const bool warm = S.warm_start && !Bt.fresh;
+    const double qb_i = (i < n && Bt.q) ? c * (LC.D * Bt.q[(size_t)b * n + i]) : 0.0;
+    double xi_i = (i < n && warm) ? Bt.xi[(size_t)b * n + i] : 0.0;
     double lb_r = -1.0, ub_r = 1.0, z_r = 0.0, y_r = 0.0;   // padded rows: A row = 0, never active
     if (r < m) {
-      lb_r = E_r * (Bt.l ? Bt.l[(size_t)b * m + r] : P.l0[r]);
-      ub_r = E_r * (Bt.u ? Bt.u[(size_t)b * m + r] : P.u0[r]);
-      if (S.warm_start && !Bt.fresh) { z_r = Bt.z[(size_t)b * m + r]; y_r = Bt.y[(size_t)b * m + r]; }
+      lb_r = LC.E * (Bt.l ? Bt.l[(size_t)b * m + r] : P.l0[r]);
+      ub_r = LC.E * (Bt.u ? Bt.u[(size_t)b * m + r] : P.u0[r]);
+      if (warm) { z_r = Bt.z[(size_t)b * m + r]; y_r = Bt.y[(size_t)b * m + r]; }
     }
     double rho = Bt.fresh ? fmin(fmax(S.rho0, kRhoMin), kRhoMax) : Bt.rho[b];
     int rho_updates = 0;
     // l > u (osqp_update_bounds refuses it) or a row whose class (equality / inequality / free) differs from the
     // shared plan's: the instance is left UNSOLVED (see admm_shared_generic.cu)
     const int ct_now = (lb_r < -kInfty * kMinScaling && ub_r > kInfty * kMinScaling) ? -1 : ((ub_r - lb_r < kRhoTolRow) ? 1 : 0);
-    const bool bad_bounds = __any_sync(0xffffffffu, r < m && (lb_r > ub_r || ct_now != ct_r));
-    // q̂ = V' q̄
+    const bool bad_bounds = __any_sync(kFull, r < m && (lb_r > ub_r || ct_now != LC.ct));
+    // q̂ = V' q̄ ; lanes of the upper half-warp start their partial sum at 0, the lower half at -q̂
     if (h == 0) sbuf[i] = qb_i;
     __syncwarp();
-    double qh_i;
+    double nqh_i;
     {
       double a = 0.0;
 #pragma unroll
       for (int k = 0; k < NP / 2; ++k) a = fma(sV[(8 * h + k) * NP + i], sbuf[8 * h + k], a);
-      qh_i = a + __shfl_xor_sync(0xffffffffu, a, 16);
+      a += __shfl_xor_sync(kFull, a, 16);
+      nqh_i = h == 0 ? -a : 0.0;
     }
-    double rv = rho_row(ct_r, rho), rinv = 1.0 / rv;
+    double rv = rho_row(LC.ct, rho), rinv = 1.0 / rv;
     double dinv_i = 1.0 / (1.0 + rho * lam_i);
-    double dxi_i = 0.0, dy_r = 0.0, t_i = 0.0;
+    double dxi_i = 0.0, dy_r = 0.0;
+    double base_r = fma(rinv, y_r, oma * z_r), om_xi = oma * xi_i;
     __syncwarp();
-    if (h == 0) cbuf[i] = xi_i;
-    cbuf[NP + r] = rv * z_r - y_r;
+    if (h == 0) sts64(a_xi, xi_i);
+    sts64(a_w, rv * z_r - y_r);
     __syncwarp();
 
     int status = SMPC_UNSOLVED, iter = 0;
-    bool can_check = false;
-    Info I = {};
-    double xbar_i = 0.0;
-
-    // OSQP update_info.  cbuf[0..15] holds the current xi.
-    auto update_info = [&]() {
-      sbuf[r] = y_r;
-      __syncwarp();
-      double ax = 0.0, apx = 0.0, aty = 0.0, Ax_r = 0.0;
-#pragma unroll
-      for (int k = 0; k < NP / 2; ++k) {
-        double xk = cbuf[8 * h + k];
-        ax = fma(sVT[(8 * h + k) * NP + i], xk, ax);
-        apx = fma(sPVT[(8 * h + k) * NP + i], xk, apx);
-      }
-#pragma unroll
-      for (int k = 0; k < MP / 2; ++k) aty = fma(sAb[(16 * h + k) * NP + i], sbuf[16 * h + k], aty);
-#pragma unroll
-      for (int k = 0; k < NP; ++k) Ax_r = fma(wr[k], cbuf[k], Ax_r);
-      ax += __shfl_xor_sync(0xffffffffu, ax, 16);
-      apx += __shfl_xor_sync(0xffffffffu, apx, 16);
-      aty += __shfl_xor_sync(0xffffffffu, aty, 16);
-      xbar_i = ax;
-      const double rp = Ax_r - z_r, rd = (qb_i + apx) + aty;
-      I.s_rp = wmax(fabs(rp)); I.s_z = wmax(fabs(z_r)); I.s_Ax = wmax(fabs(Ax_r));
-      I.s_rd = wmax(fabs(rd)); I.s_q = wmax(fabs(qb_i)); I.s_Aty = wmax(fabs(aty)); I.s_Px = wmax(fabs(apx));
-      double ob = h == 0 ? 0.5 * ax * apx + qb_i * ax : 0.0;
-      if (unscale) {
-        I.pri_res = wmax(fabs(Einv_r * rp)); I.nEz = wmax(fabs(Einv_r * z_r)); I.nEAx = wmax(fabs(Einv_r * Ax_r));
-        I.dua_res = cinv * wmax(fabs(Dinv_i * rd)); I.nDq = wmax(fabs(Dinv_i * qb_i));
-        I.nDAty = wmax(fabs(Dinv_i * aty)); I.nDPx = wmax(fabs(Dinv_i * apx));
-        I.obj = cinv * wsum(ob);
-      } else {
-        I.pri_res = I.s_rp; I.nEz = I.s_z; I.nEAx = I.s_Ax;
-        I.dua_res = I.s_rd; I.nDq = I.s_q; I.nDAty = I.s_Aty; I.nDPx = I.s_Px;
-        I.obj = wsum(ob);
-      }
-      if (m == 0) I.pri_res = 0.0;
-      __syncwarp();
-    };
-
-    auto primal_infeasible = [&](double eps) -> bool {
-      double d = dy_r;
-      const bool uinf = ub_r > kInfty * kMinScaling, linf = lb_r < -kInfty * kMinScaling;
-      if (uinf) d = linf ? 0.0 : fmin(d, 0.0); else if (linf) d = fmax(d, 0.0);
-      dy_r = d;
-      const double nd = wmax(fabs(unscale ? E_r * d : d));
-      if (!(nd > eps)) return false;
-      double lhs = 0.0;
-      const double dp = fmax(d, 0.0), dm = fmin(d, 0.0);
-      if (dp != 0.0) lhs += ub_r * dp;
-      if (dm != 0.0) lhs += lb_r * dm;
-      lhs = wsum(lhs);
-      if (!(lhs < -eps * nd)) return false;
-      sbuf[r] = d;
-      __syncwarp();
-      double a = 0.0;
-#pragma unroll
-      for (int k = 0; k < MP / 2; ++k) a = fma(sAb[(16 * h + k) * NP + i], sbuf[16 * h + k], a);
-      a += __shfl_xor_sync(0xffffffffu, a, 16);
-      __syncwarp();
-      return wmax(fabs(unscale ? Dinv_i * a : a)) < eps * nd;
-    };
-
-    auto dual_infeasible = [&](double eps) -> bool {
-      if (h == 0) sbuf[i] = dxi_i;
-      __syncwarp();
-      double dx = 0.0, pd = 0.0, ad = 0.0;
-#pragma unroll
-      for (int k = 0; k < NP / 2; ++k) {
-        double dk = sbuf[8 * h + k];
-        dx = fma(sVT[(8 * h + k) * NP + i], dk, dx);
-        pd = fma(sPVT[(8 * h + k) * NP + i], dk, pd);
-      }
-#pragma unroll
-      for (int k = 0; k < NP; ++k) ad = fma(wr[k], sbuf[k], ad);
-      dx += __shfl_xor_sync(0xffffffffu, dx, 16);
-      pd += __shfl_xor_sync(0xffffffffu, pd, 16);
-      __syncwarp();
-      const double nd = wmax(fabs(unscale ? D_i * dx : dx));
-      const double qd = wsum(h == 0 ? qb_i * dx : 0.0);
-      const double cs = unscale ? c : 1.0;
-      if (!(nd > eps)) return false;
-      if (!(qd < -cs * eps * nd)) return false;
-      if (!(wmax(fabs(unscale ? Dinv_i * pd : pd)) < cs * eps * nd)) return false;
-      if (unscale) ad *= Einv_r;
-      const int bad = ((ub_r < kInfty * kMinScaling) && (ad > eps * nd)) || ((lb_r > -kInfty * kMinScaling) && (ad < -eps * nd));
-      return !__any_sync(0xffffffffu, bad && r < m);
-    };
-
-    auto check_termination = [&](bool approx) -> bool {
-      double ea = S.eps_abs, er = S.eps_rel, epi = S.eps_prim_inf, edi = S.eps_dual_inf;
-      if (approx) { ea *= 10; er *= 10; epi *= 10; edi *= 10; }
-      bool prim_ok = false, dual_ok = false, prim_inf = false, dual_inf = false;
-      if (m == 0) prim_ok = true;
-      else {
-        const double ep = ea + er * fmax(I.nEz, I.nEAx);
-        if (I.pri_res < ep) prim_ok = true; else prim_inf = primal_infeasible(epi);
-      }
-      const double ed = ea + er * (unscale ? cinv : 1.0) * fmax(fmax(I.nDq, I.nDAty), I.nDPx);
-      if (I.dua_res < ed) dual_ok = true; else dual_inf = dual_infeasible(edi);
-      if (prim_ok && dual_ok) { status = approx ? SMPC_SOLVED_INACCURATE : SMPC_SOLVED; return true; }
-      if (prim_inf) { status = approx ? SMPC_PRIMAL_INFEASIBLE_INACCURATE : SMPC_PRIMAL_INFEASIBLE; I.obj = kInfty; return true; }
-      if (dual_inf) { status = approx ? SMPC_DUAL_INFEASIBLE_INACCURATE : SMPC_DUAL_INFEASIBLE; I.obj = -kInfty; return true; }
-      return false;
-    };
+    int to_check = check_every, to_adapt = adapt_every;
+    bool checked_last = false;
+    CheckOut co;
+    co.obj = 0.0; co.pri_res = 0.0; co.dua_res = 0.0; co.xbar = 0.0;
 
     if (!bad_bounds) {
-      for (iter = 1; iter <= S.max_iter; ++iter) {
-        // t = (sigma G xi + W' w - q̂) ./ (1 + rho lambda): each half-warp sums 24 of the 48 concatenated terms
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-        const double2 *cv = reinterpret_cast<const double2 *>(cbuf + KH * h);
+      while (iter < S.max_iter) {
+        // iterations until the next termination check / rho adaptation: a call-free inner loop, so the shared
+        // operators stay in registers; they are (re)loaded from L1/L2 here because check_step is out of line
+        int steps = to_check < to_adapt ? to_check : to_adapt;
+        if (steps > S.max_iter - iter) steps = S.max_iter - iter;
+        double m1[KH], wr[NP];
 #pragma unroll
-        for (int j = 0; j < KH / 4; ++j) {
-          const double2 u0 = cv[2 * j], u1 = cv[2 * j + 1];
-          a0 = fma(m1[4 * j + 0], u0.x, a0); a1 = fma(m1[4 * j + 1], u0.y, a1);
-          a2 = fma(m1[4 * j + 2], u1.x, a2); a3 = fma(m1[4 * j + 3], u1.y, a3);
-        }
-        double acc = (a0 + a1) + (a2 + a3);
-        acc += __shfl_xor_sync(0xffffffffu, acc, 16);
-        t_i = (acc - qh_i) * dinv_i;
-        if (h == 0) tbuf[i] = t_i;
-        __syncwarp();
-        // z̃ = W t
-        const double2 *tv = reinterpret_cast<const double2 *>(tbuf);
-        double b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
+        for (int j = 0; j < KH; ++j) m1[j] = __ldg(K.M1T + (KH * h + j) * NP + i);
 #pragma unroll
-        for (int j = 0; j < NP / 4; ++j) {
-          const double2 u0 = tv[2 * j], u1 = tv[2 * j + 1];
-          b0 = fma(wr[4 * j + 0], u0.x, b0); b1 = fma(wr[4 * j + 1], u0.y, b1);
-          b2 = fma(wr[4 * j + 2], u1.x, b2); b3 = fma(wr[4 * j + 3], u1.y, b3);
-        }
-        const double zt = (b0 + b1) + (b2 + b3);
-        // x, z, y updates (OSQP update_x / update_z / update_y)
-        const double xn = alpha * t_i + (1.0 - alpha) * xi_i;
-        dxi_i = xn - xi_i; xi_i = xn;
-        const double zr = alpha * zt + (1.0 - alpha) * z_r;
-        const double zn = fmin(fmax(zr + rinv * y_r, lb_r), ub_r);
-        dy_r = rv * (zr - zn);
-        z_r = zn; y_r += dy_r;
-        can_check = S.check_every && (iter % S.check_every == 0);
-        const bool adapt = S.adaptive_rho && S.rho_interval && (iter % S.rho_interval == 0);
-        if (can_check || adapt) {
-          if (h == 0) cbuf[i] = xi_i;
-          __syncwarp();
-          update_info();
-          if (can_check && check_termination(false)) break;
-          if (adapt) {
-            const double pr = I.s_rp / (fmax(I.s_z, I.s_Ax) + kDivTol);
-            const double dr = I.s_rd / (fmax(fmax(I.s_q, I.s_Aty), I.s_Px) + kDivTol);
-            const double rn = fmin(fmax(rho * sqrt(pr / (dr + kDivTol)), kRhoMin), kRhoMax);
-            if (rn > rho * S.rho_tol || rn < rho / S.rho_tol) {
-              rho = rn; ++rho_updates;
-              rv = rho_row(ct_r, rho); rinv = 1.0 / rv; dinv_i = 1.0 / (1.0 + rho * lam_i);
-            }
+        for (int k = 0; k < NP; ++k) wr[k] = __ldg(K.WT + k * MP + r);
+        for (int s = 0; s < steps; ++s) {
+          // ---- t = (sigma G xi + W' w - q̂) ./ (1 + rho lambda): each half-warp sums 24 of the 48 concatenated terms
+          double a0 = nqh_i, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+          for (int j = 0; j < KH / 4; ++j) {
+            const double2 u0 = lds128(a_cv + 32 * j), u1 = lds128(a_cv + 32 * j + 16);
+            a0 = fma(m1[4 * j + 0], u0.x, a0); a1 = fma(m1[4 * j + 1], u0.y, a1);
+            a2 = fma(m1[4 * j + 2], u1.x, a2); a3 = fma(m1[4 * j + 3], u1.y, a3);
           }
-        } else if (h == 0) cbuf[i] = xi_i;
-        cbuf[NP + r] = rv * z_r - y_r;
-        __syncwarp();
+          double acc = (a0 + a1) + (a2 + a3);
+          acc += __shfl_xor_sync(kFull, acc, 16);
+          const double t_i = acc * dinv_i;
+          if (h == 0) sts64(a_t, t_i);
+          __syncwarp();
+          // x update (off the critical path of z̃)
+          const double xn = fma(alpha, t_i, om_xi);
+          dxi_i = xn - xi_i; xi_i = xn; om_xi = oma * xn;
+          if (h == 0) sts64(a_xi, xn);
+          // ---- z̃ = W t
+          double b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
+#pragma unroll
+          for (int j = 0; j < NP / 4; ++j) {
+            const double2 u0 = lds128(a_tv + 32 * j), u1 = lds128(a_tv + 32 * j + 16);
+            b0 = fma(wr[4 * j + 0], u0.x, b0); b1 = fma(wr[4 * j + 1], u0.y, b1);
+            b2 = fma(wr[4 * j + 2], u1.x, b2); b3 = fma(wr[4 * j + 3], u1.y, b3);
+          }
+          const double zt = (b0 + b1) + (b2 + b3);
+          // ---- z, y updates (OSQP update_z / update_y re-associated, see the file header)
+          const double v = fma(alpha, zt, base_r);
+          const double zn = v < lb_r ? lb_r : (v > ub_r ? ub_r : v);
+          const double yn = rv * (v - zn);
+          sts64(a_w, rv * fma(2.0, zn, -v));   // w' = rho z - y'
+          dy_r = yn - y_r; y_r = yn; z_r = zn;
+          base_r = fma(rinv, yn, oma * zn);
+          __syncwarp();
+        }
+        iter += steps; to_check -= steps; to_adapt -= steps;
+        const bool do_check = to_check == 0, do_adapt = to_adapt == 0;
+        checked_last = do_check;
+        if (do_check) to_check = check_every;
+        if (do_adapt) to_adapt = adapt_every;
+        if (do_check || do_adapt) {
+          co = check_step(smem, cbuf, sbuf, S, n, m, c, cinv, LC, rho, qb_i, z_r, y_r, dy_r, dxi_i, lb_r, ub_r, do_check, false, do_adapt);
+          if (co.status != SMPC_UNSOLVED) { status = co.status; break; }
+          if (co.rho_changed) {
+            rho = co.rho; ++rho_updates;
+            rv = rho_row(LC.ct, rho); rinv = 1.0 / rv; dinv_i = 1.0 / (1.0 + rho * lam_i);
+            base_r = fma(rinv, y_r, oma * z_r);
+            sts64(a_w, rv * z_r - y_r);
+            __syncwarp();
+          }
+        }
       }
-      if (iter > S.max_iter) iter = S.max_iter;
-      if (!can_check) {
-        if (h == 0) cbuf[i] = xi_i;
-        __syncwarp();
-        update_info();
-        check_termination(false);
+      if (status == SMPC_UNSOLVED) {
+        if (!checked_last) {
+          co = check_step(smem, cbuf, sbuf, S, n, m, c, cinv, LC, rho, qb_i, z_r, y_r, dy_r, dxi_i, lb_r, ub_r, true, false, false);
+          status = co.status;
+        }
+        if (status == SMPC_UNSOLVED) {
+          const CheckOut ca = check_step(smem, cbuf, sbuf, S, n, m, c, cinv, LC, rho, qb_i, z_r, y_r, dy_r, dxi_i, lb_r, ub_r, true, true, false);
+          status = ca.status == SMPC_UNSOLVED ? SMPC_MAX_ITER_REACHED : ca.status;
+          if (ca.status != SMPC_UNSOLVED) co.obj = ca.obj;
+        }
       }
-      if (status == SMPC_UNSOLVED) { if (!check_termination(true)) status = SMPC_MAX_ITER_REACHED; }
     }
     __syncwarp();
 
@@ -288,18 +358,18 @@ admm_shared_small_kernel(SmallPackDev K, SharedPlanDev P, BatchDev Bt, SettingsD
     const bool has_sol = !bad_bounds && !(status == SMPC_PRIMAL_INFEASIBLE || status == SMPC_PRIMAL_INFEASIBLE_INACCURATE ||
                                           status == SMPC_DUAL_INFEASIBLE || status == SMPC_DUAL_INFEASIBLE_INACCURATE);
     if (h == 0 && i < n) {
-      if (Bt.x_out) Bt.x_out[(size_t)b * n + i] = has_sol ? D_i * xbar_i : qnan;
+      if (Bt.x_out) Bt.x_out[(size_t)b * n + i] = has_sol ? LC.D * co.xbar : qnan;
       Bt.xi[(size_t)b * n + i] = has_sol ? xi_i : 0.0;
     }
     if (r < m) {
-      if (Bt.y_out) Bt.y_out[(size_t)b * m + r] = has_sol ? cinv * (E_r * y_r) : qnan;
+      if (Bt.y_out) Bt.y_out[(size_t)b * m + r] = has_sol ? cinv * (LC.E * y_r) : qnan;
       Bt.z[(size_t)b * m + r] = has_sol ? z_r : 0.0;
       Bt.y[(size_t)b * m + r] = has_sol ? y_r : 0.0;
     }
     if (lane == 0) {
       Bt.rho[b] = rho;
       Bt.status[b] = status; Bt.iter[b] = iter; Bt.rho_updates[b] = rho_updates;
-      Bt.obj[b] = I.obj; Bt.pri_res[b] = I.pri_res; Bt.dua_res[b] = I.dua_res;
+      Bt.obj[b] = co.obj; Bt.pri_res[b] = co.pri_res; Bt.dua_res[b] = co.dua_res;
     }
   }
 }
@@ -315,7 +385,7 @@ cudaError_t launch_admm_shared_small(const SmallPackDev &K, const SharedPlanDev 
   cudaError_t e = cudaMemsetAsync(queue, 0, sizeof(int), stream);
   if (e != cudaSuccess) return e;
   int grid = (Bt.B + wpc - 1) / wpc;
-  const int resident = num_sms * 4;   // __launch_bounds__(128, 3): four CTAs per SM
+  const int resident = num_sms * 3;   // __launch_bounds__(128, 3): three CTAs (12 warps) per SM
   if (grid > resident) grid = resident;
   admm_shared_small_kernel<<<grid, wpc * 32, smem, stream>>>(K, P, Bt, S, queue);
   return cudaGetLastError();

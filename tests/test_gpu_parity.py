@@ -21,13 +21,26 @@ TIGHT = 1e-7        # what two implementations of the same iteration actually ac
 
 
 def rel_err(x, xo):
+    """max over instances of ||x - xo||_inf / ||xo||_inf; NaN solutions (infeasible instances) must coincide."""
+    x, xo = np.asarray(x, dtype=float), np.asarray(xo, dtype=float)
+    assert np.array_equal(np.isnan(x), np.isnan(xo)), "NaN pattern differs"
+    x, xo = np.nan_to_num(x), np.nan_to_num(xo)
     scale = np.maximum(np.abs(xo).max(axis=-1), 1e-9)
     return (np.abs(x - xo).max(axis=-1) / scale).max()
 
 
-def active_set(A, x, y, u):
+def active_set(A, x, y, u, thr=1e-6):
+    """a row is active if its dual is non-negligible or its slack is ~0."""
     Ax = x @ A.T
-    return (y > 1e-6 * np.abs(y).max(axis=-1, keepdims=True) + 1e-300) | (u - Ax < 1e-6 * np.maximum(1.0, np.abs(u)))
+    return (y > thr * np.abs(y).max(axis=-1, keepdims=True) + 1e-9) | (u - Ax < thr * np.maximum(1.0, np.abs(u)))
+
+
+def same_active_set(A, x, y, xo, yo, u):
+    """Same active set, with hysteresis on the two thresholds so that rows sitting exactly at a threshold
+    (duals ~1e-6 relative) cannot flip the comparison: clearly-active rows of one side must be active on the other."""
+    lo_a, lo_b = active_set(A, x, y, u, 5e-7), active_set(A, xo, yo, u, 5e-7)
+    hi_a, hi_b = active_set(A, x, y, u, 2e-6), active_set(A, xo, yo, u, 2e-6)
+    return bool((hi_a <= lo_b).all() and (hi_b <= lo_a).all())
 
 
 @pytest.fixture(scope="module")
@@ -94,7 +107,7 @@ def test_c2_batch_4096_matches_oracle(ref_mats, kernel):
     assert rel_err(x, ora["x"]) < TIGHT < REL
     assert rel_err(x[:, :1], ora["x"][:, :1]) < REL        # u0 increment
     assert np.abs(y - ora["y"]).max() < 1e-7 * max(1.0, np.abs(ora["y"]).max())
-    assert np.array_equal(active_set(m["Gbar"], x, y, ub), active_set(m["Gbar"], ora["x"], ora["y"], ub))
+    assert same_active_set(m["Gbar"], x, y, ora["x"], ora["y"], ub)
     assert s.count_solved() == B
     # second solve on the same handle is warm started and rho persists (cpp:52): oracle does the same per instance
     s.solve()
@@ -153,7 +166,8 @@ def test_random_qps_generic_shapes(n, m, B):
     assert np.array_equal(info["status"], np.array(st)) and np.array_equal(info["iter"], np.array(it))
     assert rel_err(x, np.array(xs)) < TIGHT
     if m:
-        assert np.abs(y - np.array(ys)).max() < 1e-6 * max(1.0, np.abs(np.array(ys)).max())
+        assert rel_err(y, np.array(ys)) < 1e-5
+    assert (np.array(st) == 1).sum() >= 1          # (the shifted bounds make some instances infeasible: NaN parity above)
     s.close()
 
 
@@ -292,7 +306,10 @@ def test_full_size_properties_and_sharding(ref_mats):
     assert (rd < tol_d * 1.0000001).all()
     assert ((Ax - ub).max(axis=1) < 1e-5 + 1e-5 * np.abs(Ax).max(axis=1)).all()
     assert (y > -1e-9).all()                                   # one-sided rows: duals >= 0
-    assert np.abs(np.minimum(y, 1.0) * np.minimum(ub - Ax, 1.0)).max() < 1e-3   # complementarity
+    tol_p = (1e-5 + 1e-5 * np.abs(Ax).max(axis=1))[:, None]
+    slack = ub - Ax
+    assert (slack[y > 1e-12] <= (3 * tol_p * np.ones_like(y))[y > 1e-12]).all()      # y_i > 0  =>  row at its bound
+    assert (y[slack > 3 * tol_p * np.ones_like(y)] <= 1e-12).all()                   # slack   =>  y_i = 0
     assert 0.3 < (np.abs(y).max(axis=1) > 1e-7).mean() < 0.6   # ~43 % of instances saturate
     lo, hi = 3 * B // 8, 5 * B // 8
     s2 = sm.BatchedSolver(m["H"], m["Gbar"], m["lb"], m["W0"], batch=hi - lo, **EPS)
