@@ -1,0 +1,473 @@
+// admm_instance.cu -- per-instance regime: every QP carries its OWN P_i and A_i (per-instance linearised
+// plants, BASELINE config 4), so nothing of the KKT system is shared.  One warp owns one QP for its whole solve:
+//   setup  (ruiz_instance_kernel): OSQP scale_data (10 Ruiz passes + cost scaling) on (P_i, A_i) in shared memory
+//   solve  (admm_instance_kernel): A̅_i and the factor live in the warp's shared-memory slice;
+//          M = P̄ + sigma I + A̅' diag(rho_vec) A̅  ->  Cholesky  ->  M^-1 = L^-T L^-1   (refactored whenever rho changes,
+//          exactly when OSQP refactors its KKT matrix),  then the OSQP iteration in x-space:
+//          x̃ = M^-1 (sigma x - q̄ + A̅'(rho_vec.*z - y)),  z̃ = A̅ x̃,  relaxation, clip to [l̄, ū], dual update,
+//          residual norms / termination / infeasibility / rho adaptation every check interval.
+// Restates OSQP 0.6.x -- the arithmetic the reference reaches through solver.initSolver() /
+// solver.solve() (src/ModelPredictiveControlAPI.cpp:64,102).  Shared-memory rows are padded to an odd number of
+// doubles so that "lane = row" and "lane = column" sweeps are both bank-conflict free.
+#include "device_types.cuh"
+#include "kernels.cuh"
+
+namespace smpc {
+
+namespace {
+
+constexpr unsigned kFull = 0xffffffffu;
+constexpr double kMaxScaling = 1e4;
+
+__device__ __forceinline__ double wmax(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(kFull, v, o));
+  return v;
+}
+__device__ __forceinline__ double wsum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+__device__ __forceinline__ double limit_scaling(double v) {
+  v = v < kMinScaling ? 1.0 : v;
+  return v > kMaxScaling ? kMaxScaling : v;
+}
+__host__ __device__ __forceinline__ int odd_ld(int n) { return n | 1; }
+// per-warp shared-memory doubles of admm_instance_kernel: A̅ (m x ld), M^-1 and scratch (n x ld each), 8 n-vectors, 10 m-vectors
+__host__ __device__ __forceinline__ size_t instance_warp_doubles(int n, int m) {
+  return (size_t)m * odd_ld(n) + 2 * (size_t)n * odd_ld(n) + 8 * (size_t)n + 10 * (size_t)m;
+}
+
+// sum_r A[r*ld + i] * vec[r]   (lane = column i)
+__device__ __forceinline__ double col_dot_s(const double *A, int ld, int rows, int i, const double *vec) {
+  double a0 = 0.0, a1 = 0.0;
+  int r = 0;
+  for (; r + 2 <= rows; r += 2) { a0 = fma(A[r * ld + i], vec[r], a0); a1 = fma(A[(r + 1) * ld + i], vec[r + 1], a1); }
+  if (r < rows) a0 = fma(A[r * ld + i], vec[r], a0);
+  return a0 + a1;
+}
+// sum_k A[r*ld + k] * vec[k]   (lane = row r)
+__device__ __forceinline__ double row_dot_s(const double *A, int ld, int cols, int r, const double *vec) {
+  double a0 = 0.0, a1 = 0.0;
+  int k = 0;
+  for (; k + 2 <= cols; k += 2) { a0 = fma(A[r * ld + k], vec[k], a0); a1 = fma(A[r * ld + k + 1], vec[k + 1], a1); }
+  if (k < cols) a0 = fma(A[r * ld + k], vec[k], a0);
+  return a0 + a1;
+}
+
+struct Info {
+  double pri_res, dua_res, nEz, nEAx, nDq, nDAty, nDPx;
+  double s_rp, s_rd, s_z, s_Ax, s_q, s_Aty, s_Px;
+  double obj;
+};
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------- setup
+// In-place OSQP scale_data on instance b: P[b] (n*n, upper triangle mirrored first), A[b] (m*n); writes D, E, c.
+__global__ void ruiz_instance_kernel(InstanceDataDev I, int iters, int warps_per_cta) {
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.x * warps_per_cta + warp;
+  if (b >= I.B) return;
+  const int n = I.n, m = I.m, ldP = odd_ld(n), ldA = odd_ld(n);
+  double *P = smem + (size_t)warp * ((n + m) * ldP + 2 * n + 2 * m);
+  double *A = P + n * ldP, *D = A + m * ldA, *dt = D + n, *E = dt + n, *et = E + m;
+  double *gP = I.P + (size_t)b * n * n, *gA = I.A + (size_t)b * m * n;
+  for (int e = lane; e < n * n; e += 32) { int i = e / n, j = e % n; P[i * ldP + j] = i <= j ? gP[i * n + j] : gP[j * n + i]; }
+  for (int e = lane; e < m * n; e += 32) A[(e / n) * ldA + e % n] = gA[e];
+  for (int j = lane; j < n; j += 32) D[j] = 1.0;
+  for (int i = lane; i < m; i += 32) E[i] = 1.0;
+  double c = 1.0;
+  __syncwarp();
+  for (int it = 0; it < iters; ++it) {
+    for (int j = lane; j < n; j += 32) {
+      double r = 0.0;
+      for (int i = 0; i < n; ++i) r = fmax(r, fabs(P[i * ldP + j]));
+      for (int i = 0; i < m; ++i) r = fmax(r, fabs(A[i * ldA + j]));
+      dt[j] = 1.0 / sqrt(limit_scaling(r));
+    }
+    for (int i = lane; i < m; i += 32) {
+      double r = 0.0;
+      for (int j = 0; j < n; ++j) r = fmax(r, fabs(A[i * ldA + j]));
+      et[i] = 1.0 / sqrt(limit_scaling(r));
+    }
+    __syncwarp();
+    for (int e = lane; e < n * n; e += 32) { int i = e / n, j = e % n; P[i * ldP + j] = (dt[i] * P[i * ldP + j]) * dt[j]; }
+    for (int e = lane; e < m * n; e += 32) { int i = e / n, j = e % n; A[i * ldA + j] = (et[i] * A[i * ldA + j]) * dt[j]; }
+    for (int j = lane; j < n; j += 32) D[j] *= dt[j];
+    for (int i = lane; i < m; i += 32) E[i] *= et[i];
+    __syncwarp();
+    // cost scaling: mean column norm of P̄ (the setup gradient is 0: its norm counts as 1)
+    for (int j = lane; j < n; j += 32) {
+      double r = 0.0;
+      for (int i = 0; i < n; ++i) r = fmax(r, fabs(P[i * ldP + j]));
+      dt[j] = r;
+    }
+    __syncwarp();
+    double mean = 0.0;
+    for (int j = 0; j < n; ++j) mean += dt[j];   // same summation order as the oracle
+    mean /= n;
+    double ct = limit_scaling(fmax(mean, 1.0));
+    ct = 1.0 / ct;
+    __syncwarp();
+    for (int e = lane; e < n * n; e += 32) { int i = e / n, j = e % n; P[i * ldP + j] *= ct; }
+    c *= ct;
+    __syncwarp();
+  }
+  for (int e = lane; e < n * n; e += 32) gP[e] = P[(e / n) * ldP + e % n];
+  for (int e = lane; e < m * n; e += 32) gA[e] = A[(e / n) * ldA + e % n];
+  for (int j = lane; j < n; j += 32) I.D[(size_t)b * n + j] = D[j];
+  for (int i = lane; i < m; i += 32) I.E[(size_t)b * m + i] = E[i];
+  if (lane == 0) I.c[b] = c;
+}
+
+// ---------------------------------------------------------------------------------------------- solve
+__global__ void __launch_bounds__(256) admm_instance_kernel(InstanceDataDev I, BatchDev Bt, SettingsDev S, int warps_per_cta) {
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.x * warps_per_cta + warp;
+  if (b >= Bt.B) return;
+  const int n = I.n, m = I.m, ldA = odd_ld(n), ldM = odd_ld(n);
+  double *base = smem + (size_t)warp * instance_warp_doubles(n, m);
+  double *Ab = base, *Mi = Ab + m * ldA, *Sc = Mi + n * ldM;
+  double *x = Sc + n * ldM, *dx = x + n, *qb = dx + n, *xt = qb + n, *sPx = xt + n, *sAty = sPx + n, *Dv = sAty + n, *Dinv = Dv + n;
+  double *z = Dinv + n, *y = z + m, *lb = y + m, *ub = lb + m, *w = ub + m, *zt = w + m, *dy = zt + m, *rv = dy + m, *Ev = rv + m, *Einv = Ev + m;
+  const double *gP = I.P + (size_t)b * n * n, *gA = I.A + (size_t)b * m * n;
+  const double alpha = S.alpha, c = I.c[b], cinv = 1.0 / c;
+  const bool unscale = !S.scaled_termination;
+  const bool warm = S.warm_start && !Bt.fresh;
+
+  // ---- load the instance
+  for (int e = lane; e < m * n; e += 32) Ab[(e / n) * ldA + e % n] = gA[e];
+  for (int i = lane; i < n; i += 32) {
+    const double d = I.D[(size_t)b * n + i];
+    Dv[i] = d; Dinv[i] = 1.0 / d;
+    qb[i] = Bt.q ? c * (d * Bt.q[(size_t)b * n + i]) : 0.0;
+    x[i] = warm ? Bt.xi[(size_t)b * n + i] : 0.0;
+    dx[i] = 0.0;
+  }
+  double rho = Bt.fresh ? fmin(fmax(S.rho0, kRhoMin), kRhoMax) : Bt.rho[b];
+  int bad_rows = 0;
+  for (int r = lane; r < m; r += 32) {
+    const double e = I.E[(size_t)b * m + r];
+    Ev[r] = e; Einv[r] = 1.0 / e;
+    lb[r] = e * (Bt.l ? Bt.l[(size_t)b * m + r] : I.l0[r]);
+    ub[r] = e * (Bt.u ? Bt.u[(size_t)b * m + r] : I.u0[r]);
+    z[r] = warm ? Bt.z[(size_t)b * m + r] : 0.0;
+    y[r] = warm ? Bt.y[(size_t)b * m + r] : 0.0;
+    dy[r] = 0.0;
+    bad_rows |= lb[r] > ub[r];
+  }
+  const bool bad_bounds = __any_sync(kFull, bad_rows);
+  int rho_updates = 0;
+  __syncwarp();
+
+  // rho_vec from the instance's own (scaled) bounds: OSQP set_rho_vec / update_rho_vec
+  auto set_rho_vec = [&]() {
+    for (int r = lane; r < m; r += 32) {
+      const bool fr = lb[r] < -kInfty * kMinScaling && ub[r] > kInfty * kMinScaling;
+      rv[r] = fr ? kRhoMin : ((ub[r] - lb[r] < kRhoTolRow) ? kRhoEqOverIneq * rho : rho);
+    }
+    __syncwarp();
+  };
+
+  // M = P̄ + sigma I + A̅' diag(rho_vec) A̅ ;  M = L L' ;  Mi = M^-1 = L^-T L^-1.   Returns false if M is not PD.
+  auto refactor = [&]() -> bool {
+    for (int e = lane; e < n * n; e += 32) {
+      const int i = e / n, j = e % n;
+      if (j > i) continue;
+      double s0 = gP[i * n + j] + (i == j ? S.sigma : 0.0), s1 = 0.0;
+      int r = 0;
+      for (; r + 2 <= m; r += 2) {
+        s0 = fma(rv[r] * Ab[r * ldA + i], Ab[r * ldA + j], s0);
+        s1 = fma(rv[r + 1] * Ab[(r + 1) * ldA + i], Ab[(r + 1) * ldA + j], s1);
+      }
+      if (r < m) s0 = fma(rv[r] * Ab[r * ldA + i], Ab[r * ldA + j], s0);
+      Sc[i * ldM + j] = s0 + s1;
+    }
+    __syncwarp();
+    // left-looking Cholesky, lower triangle of Sc in place
+    int ok = 1;
+    for (int j = 0; j < n; ++j) {
+      for (int i = j + lane; i < n; i += 32) {
+        double s = Sc[i * ldM + j];
+        for (int k = 0; k < j; ++k) s = fma(-Sc[i * ldM + k], Sc[j * ldM + k], s);
+        xt[i] = s;    // column j before scaling (xt is free here)
+      }
+      __syncwarp();
+      const double d = xt[j];
+      if (!(d > 0.0)) { ok = 0; break; }
+      const double sd = sqrt(d);
+      for (int i = j + lane; i < n; i += 32) Sc[i * ldM + j] = i == j ? sd : xt[i] / sd;
+      __syncwarp();
+    }
+    if (!ok) return false;
+    // Linv (lower) into Mi: lane c solves L v = e_c by forward substitution, column by column
+    for (int cc = lane; cc < n; cc += 32) {
+      Mi[cc * ldM + cc] = 1.0 / Sc[cc * ldM + cc];
+      for (int i = cc + 1; i < n; ++i) {
+        double s = 0.0;
+        for (int k = cc; k < i; ++k) s = fma(Sc[i * ldM + k], Mi[k * ldM + cc], s);
+        Mi[i * ldM + cc] = -s / Sc[i * ldM + i];
+      }
+    }
+    __syncwarp();
+    // M^-1 = Linv' Linv (full symmetric) into Sc
+    for (int e = lane; e < n * n; e += 32) {
+      const int i = e / n, j = e % n;
+      if (j > i) continue;
+      double s = 0.0;
+      for (int k = i; k < n; ++k) s = fma(Mi[k * ldM + i], Mi[k * ldM + j], s);
+      Sc[i * ldM + j] = s;
+    }
+    __syncwarp();
+    for (int e = lane; e < n * n; e += 32) { const int i = e / n, j = e % n; if (j > i) Sc[i * ldM + j] = Sc[j * ldM + i]; }
+    __syncwarp();
+    double *t = Mi; Mi = Sc; Sc = t;
+    return true;
+  };
+
+  int status = SMPC_UNSOLVED, iter = 0;
+  bool can_check = false;
+  Info F = {};
+
+  auto update_info = [&]() {
+    for (int i = lane; i < n; i += 32) {
+      double s = 0.0;
+      for (int k = 0; k < n; ++k) s = fma(gP[i * n + k], x[k], s);   // P̄ x (P̄ symmetric, read from L2 at checks only)
+      sPx[i] = s;
+      sAty[i] = col_dot_s(Ab, ldA, m, i, y);
+    }
+    for (int r = lane; r < m; r += 32) w[r] = row_dot_s(Ab, ldA, n, r, x);
+    __syncwarp();
+    double a_rp = 0, a_z = 0, a_Ax = 0, u_rp = 0, u_z = 0, u_Ax = 0;
+    for (int r = lane; r < m; r += 32) {
+      const double rp = w[r] - z[r], ei = Einv[r];
+      a_rp = fmax(a_rp, fabs(rp)); a_z = fmax(a_z, fabs(z[r])); a_Ax = fmax(a_Ax, fabs(w[r]));
+      u_rp = fmax(u_rp, fabs(ei * rp)); u_z = fmax(u_z, fabs(ei * z[r])); u_Ax = fmax(u_Ax, fabs(ei * w[r]));
+    }
+    double a_rd = 0, a_q = 0, a_Aty = 0, a_Px = 0, u_rd = 0, u_q = 0, u_Aty = 0, u_Px = 0, ob = 0;
+    for (int i = lane; i < n; i += 32) {
+      const double rd = (qb[i] + sPx[i]) + sAty[i], di = Dinv[i];
+      a_rd = fmax(a_rd, fabs(rd)); a_q = fmax(a_q, fabs(qb[i])); a_Aty = fmax(a_Aty, fabs(sAty[i])); a_Px = fmax(a_Px, fabs(sPx[i]));
+      u_rd = fmax(u_rd, fabs(di * rd)); u_q = fmax(u_q, fabs(di * qb[i])); u_Aty = fmax(u_Aty, fabs(di * sAty[i])); u_Px = fmax(u_Px, fabs(di * sPx[i]));
+      ob += 0.5 * x[i] * sPx[i] + qb[i] * x[i];
+    }
+    F.s_rp = wmax(a_rp); F.s_z = wmax(a_z); F.s_Ax = wmax(a_Ax);
+    F.s_rd = wmax(a_rd); F.s_q = wmax(a_q); F.s_Aty = wmax(a_Aty); F.s_Px = wmax(a_Px);
+    if (unscale) {
+      F.pri_res = wmax(u_rp); F.nEz = wmax(u_z); F.nEAx = wmax(u_Ax);
+      F.dua_res = cinv * wmax(u_rd); F.nDq = wmax(u_q); F.nDAty = wmax(u_Aty); F.nDPx = wmax(u_Px);
+      F.obj = cinv * wsum(ob);
+    } else {
+      F.pri_res = F.s_rp; F.nEz = F.s_z; F.nEAx = F.s_Ax;
+      F.dua_res = F.s_rd; F.nDq = F.s_q; F.nDAty = F.s_Aty; F.nDPx = F.s_Px;
+      F.obj = wsum(ob);
+    }
+    if (m == 0) F.pri_res = 0.0;
+  };
+
+  auto primal_infeasible = [&](double eps) -> bool {
+    double nd = 0.0;
+    for (int r = lane; r < m; r += 32) {
+      double d = dy[r];
+      const bool uinf = ub[r] > kInfty * kMinScaling, linf = lb[r] < -kInfty * kMinScaling;
+      if (uinf) d = linf ? 0.0 : fmin(d, 0.0); else if (linf) d = fmax(d, 0.0);
+      dy[r] = d;
+      nd = fmax(nd, fabs(unscale ? Ev[r] * d : d));
+    }
+    nd = wmax(nd);
+    __syncwarp();
+    if (!(nd > eps)) return false;
+    double lhs = 0.0;
+    for (int r = lane; r < m; r += 32) {
+      const double dp = fmax(dy[r], 0.0), dm = fmin(dy[r], 0.0);
+      if (dp != 0.0) lhs += ub[r] * dp;
+      if (dm != 0.0) lhs += lb[r] * dm;
+    }
+    lhs = wsum(lhs);
+    if (!(lhs < -eps * nd)) return false;
+    double na = 0.0;
+    for (int i = lane; i < n; i += 32) {
+      const double v = col_dot_s(Ab, ldA, m, i, dy);
+      na = fmax(na, fabs(unscale ? Dinv[i] * v : v));
+    }
+    return wmax(na) < eps * nd;
+  };
+
+  auto dual_infeasible = [&](double eps) -> bool {
+    double nd = 0.0, qd = 0.0;
+    for (int i = lane; i < n; i += 32) {
+      nd = fmax(nd, fabs(unscale ? Dv[i] * dx[i] : dx[i]));
+      qd += qb[i] * dx[i];
+    }
+    nd = wmax(nd); qd = wsum(qd);
+    const double cs = unscale ? c : 1.0;
+    if (!(nd > eps)) return false;
+    if (!(qd < -cs * eps * nd)) return false;
+    double np = 0.0;
+    for (int i = lane; i < n; i += 32) {
+      double s = 0.0;
+      for (int k = 0; k < n; ++k) s = fma(gP[i * n + k], dx[k], s);
+      np = fmax(np, fabs(unscale ? Dinv[i] * s : s));
+    }
+    if (!(wmax(np) < cs * eps * nd)) return false;
+    int bad = 0;
+    for (int r = lane; r < m; r += 32) {
+      double v = row_dot_s(Ab, ldA, n, r, dx);
+      if (unscale) v *= Einv[r];
+      if (((ub[r] < kInfty * kMinScaling) && (v > eps * nd)) || ((lb[r] > -kInfty * kMinScaling) && (v < -eps * nd))) bad = 1;
+    }
+    return !__any_sync(kFull, bad);
+  };
+
+  auto check_termination = [&](bool approx) -> bool {
+    double ea = S.eps_abs, er = S.eps_rel, epi = S.eps_prim_inf, edi = S.eps_dual_inf;
+    if (approx) { ea *= 10; er *= 10; epi *= 10; edi *= 10; }
+    bool prim_ok = false, dual_ok = false, prim_inf = false, dual_inf = false;
+    if (m == 0) prim_ok = true;
+    else if (F.pri_res < ea + er * fmax(F.nEz, F.nEAx)) prim_ok = true;
+    else prim_inf = primal_infeasible(epi);
+    if (F.dua_res < ea + er * (unscale ? cinv : 1.0) * fmax(fmax(F.nDq, F.nDAty), F.nDPx)) dual_ok = true;
+    else dual_inf = dual_infeasible(edi);
+    if (prim_ok && dual_ok) { status = approx ? SMPC_SOLVED_INACCURATE : SMPC_SOLVED; return true; }
+    if (prim_inf) { status = approx ? SMPC_PRIMAL_INFEASIBLE_INACCURATE : SMPC_PRIMAL_INFEASIBLE; F.obj = kInfty; return true; }
+    if (dual_inf) { status = approx ? SMPC_DUAL_INFEASIBLE_INACCURATE : SMPC_DUAL_INFEASIBLE; F.obj = -kInfty; return true; }
+    return false;
+  };
+
+  bool factor_ok = true;
+  if (!bad_bounds) {
+    set_rho_vec();
+    factor_ok = refactor();
+  }
+  for (iter = 1; iter <= S.max_iter && !bad_bounds && factor_ok; ++iter) {
+    for (int r = lane; r < m; r += 32) w[r] = rv[r] * z[r] - y[r];
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) sAty[i] = (S.sigma * x[i] - qb[i]) + col_dot_s(Ab, ldA, m, i, w);   // rhs
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) xt[i] = row_dot_s(Mi, ldM, n, i, sAty);                              // x̃ = M^-1 rhs
+    __syncwarp();
+    for (int r = lane; r < m; r += 32) {
+      const double ztl = row_dot_s(Ab, ldA, n, r, xt);
+      const double rr = rv[r], rinv = 1.0 / rr;
+      const double zr = alpha * ztl + (1.0 - alpha) * z[r];
+      const double zn = fmin(fmax(zr + rinv * y[r], lb[r]), ub[r]);
+      const double d = rr * (zr - zn);
+      z[r] = zn; y[r] += d; dy[r] = d;
+    }
+    for (int i = lane; i < n; i += 32) {
+      const double xn = alpha * xt[i] + (1.0 - alpha) * x[i];
+      dx[i] = xn - x[i];
+      x[i] = xn;
+    }
+    __syncwarp();
+    can_check = S.check_every && (iter % S.check_every == 0);
+    if (can_check) {
+      update_info();
+      if (check_termination(false)) break;
+    }
+    if (S.adaptive_rho && S.rho_interval && (iter % S.rho_interval == 0)) {
+      if (!can_check) update_info();
+      const double pr = F.s_rp / (fmax(F.s_z, F.s_Ax) + kDivTol);
+      const double dr = F.s_rd / (fmax(fmax(F.s_q, F.s_Aty), F.s_Px) + kDivTol);
+      const double rn = fmin(fmax(rho * sqrt(pr / (dr + kDivTol)), kRhoMin), kRhoMax);
+      if (rn > rho * S.rho_tol || rn < rho / S.rho_tol) {
+        rho = rn; ++rho_updates;
+        __syncwarp();
+        set_rho_vec();
+        if (!refactor()) { factor_ok = false; break; }
+      }
+    }
+    __syncwarp();
+  }
+  if (iter > S.max_iter) iter = S.max_iter;
+  if (bad_bounds || !factor_ok) iter = 0;
+  else {
+    if (!can_check) { update_info(); check_termination(false); }
+    if (status == SMPC_UNSOLVED) { if (!check_termination(true)) status = SMPC_MAX_ITER_REACHED; }
+  }
+
+  const bool has_sol = !bad_bounds && factor_ok && !(status == SMPC_PRIMAL_INFEASIBLE || status == SMPC_PRIMAL_INFEASIBLE_INACCURATE ||
+                                                     status == SMPC_DUAL_INFEASIBLE || status == SMPC_DUAL_INFEASIBLE_INACCURATE);
+  const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+  __syncwarp();
+  for (int i = lane; i < n; i += 32) {
+    if (Bt.x_out) Bt.x_out[(size_t)b * n + i] = has_sol ? Dv[i] * x[i] : qnan;
+    Bt.xi[(size_t)b * n + i] = has_sol ? x[i] : 0.0;
+  }
+  for (int r = lane; r < m; r += 32) {
+    if (Bt.y_out) Bt.y_out[(size_t)b * m + r] = has_sol ? cinv * (Ev[r] * y[r]) : qnan;
+    Bt.z[(size_t)b * m + r] = has_sol ? z[r] : 0.0;
+    Bt.y[(size_t)b * m + r] = has_sol ? y[r] : 0.0;
+  }
+  if (lane == 0) {
+    Bt.rho[b] = rho;
+    Bt.status[b] = status; Bt.iter[b] = iter; Bt.rho_updates[b] = rho_updates;
+    Bt.obj[b] = F.obj; Bt.pri_res[b] = F.pri_res; Bt.dua_res[b] = F.dua_res;
+  }
+}
+
+// osqp_warm_start in the per-instance regime: x̄ = D^-1 x, z = A̅ x̄, ȳ = c E^-1 y
+__global__ void warm_start_instance_kernel(InstanceDataDev I, const double *x, const double *y, double *xs, double *z, double *ys) {
+  const int lane = threadIdx.x & 31, b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= I.B) return;
+  const int n = I.n, m = I.m;
+  const double c = I.c[b];
+  for (int i = lane; i < n; i += 32) xs[(size_t)b * n + i] = x[(size_t)b * n + i] / I.D[(size_t)b * n + i];
+  __syncwarp();
+  for (int r = lane; r < m; r += 32) {
+    double s = 0.0;
+    for (int k = 0; k < n; ++k) s = fma(I.A[((size_t)b * m + r) * n + k], xs[(size_t)b * n + k], s);
+    z[(size_t)b * m + r] = s;
+    ys[(size_t)b * m + r] = c * (y[(size_t)b * m + r] / I.E[(size_t)b * m + r]);
+  }
+}
+
+static int pick_wpc(size_t per_warp_bytes) {
+  int wpc = 8;
+  while (wpc > 1 && wpc * per_warp_bytes > 200 * 1024) --wpc;
+  return wpc;
+}
+
+bool instance_kernel_supports(int n, int m) {
+  return n >= 1 && m >= 0 && instance_warp_doubles(n, m) * sizeof(double) <= 227 * 1024 &&
+         ((size_t)(n + m) * odd_ld(n) + 2 * n + 2 * m) * sizeof(double) <= 227 * 1024;
+}
+
+cudaError_t launch_ruiz_instance(const InstanceDataDev &I, int iters, cudaStream_t stream) {
+  const size_t per = ((size_t)(I.n + I.m) * odd_ld(I.n) + 2 * I.n + 2 * I.m) * sizeof(double);
+  const int wpc = pick_wpc(per);
+  const size_t smem = wpc * per;
+  if (smem > 227 * 1024) return cudaErrorInvalidValue;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(ruiz_instance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  ruiz_instance_kernel<<<(I.B + wpc - 1) / wpc, wpc * 32, smem, stream>>>(I, iters, wpc);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_admm_instance(const InstanceDataDev &I, const BatchDev &Bt, const SettingsDev &S, cudaStream_t stream) {
+  const size_t per = instance_warp_doubles(I.n, I.m) * sizeof(double);
+  const int wpc = pick_wpc(per);
+  const size_t smem = wpc * per;
+  if (smem > 227 * 1024) return cudaErrorInvalidValue;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(admm_instance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  admm_instance_kernel<<<(Bt.B + wpc - 1) / wpc, wpc * 32, smem, stream>>>(I, Bt, S, wpc);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_warm_start_instance(const InstanceDataDev &I, const double *x, const double *y, double *xs, double *z,
+                                       double *ys, cudaStream_t stream) {
+  const int wpc = 4;
+  warm_start_instance_kernel<<<(I.B + wpc - 1) / wpc, wpc * 32, 0, stream>>>(I, x, y, xs, z, ys);
+  return cudaGetLastError();
+}
+
+}  // namespace smpc

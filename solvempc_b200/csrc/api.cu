@@ -59,6 +59,8 @@ struct smpc_solver {
   double *d_x = nullptr, *d_yout = nullptr, *d_obj = nullptr, *d_pri = nullptr, *d_dua = nullptr;
   int *d_status = nullptr, *d_iter = nullptr, *d_rhoup = nullptr;
   double *d_stage_x = nullptr, *d_stage_y = nullptr;  // warm-start staging
+  DeviceBuf instbuf;                                  // per-instance regime: P̄, A̅, D, E, c
+  smpc::InstanceDataDev dinst{};
   DeviceBuf packbuf;                                  // small-kernel operator pack + work queue
   smpc::SmallPackDev dpack{};
   int *d_queue = nullptr;
@@ -326,17 +328,61 @@ int smpc_solver_create_shared_csc(smpc_solver **out, int device, int n, int m, i
   return create_shared_common(out, device, n, m, batch, P.data(), A.data(), q0, l0, u0, settings);
 }
 
-int smpc_solver_create_batched(smpc_solver **out, int, int, int, int, const double *, const double *, int,
-                               const double *, const double *, const smpc_settings *) {
-  if (out) *out = nullptr;
-  return fail(SMPC_ERR_STATE, "per-instance regime is not built yet (SURVEY 8 'next')");
+int smpc_solver_create_batched(smpc_solver **out, int device, int n, int m, int batch, const double *P, const double *A, int loc,
+                               const double *l0, const double *u0, const smpc_settings *settings) {
+  if (!out) return fail(SMPC_ERR_ARG, "out is null");
+  *out = nullptr;
+  if (!P || (!A && m > 0) || !settings) return fail(SMPC_ERR_ARG, "P, A and settings must not be null");
+  if (n <= 0 || m < 0 || batch <= 0) return fail(SMPC_ERR_ARG, "need n > 0, m >= 0, batch > 0");
+  if (loc != SMPC_HOST && loc != SMPC_DEVICE) return fail(SMPC_ERR_ARG, "loc must be SMPC_HOST or SMPC_DEVICE");
+  if (int rc = check_settings(*settings)) return rc;
+  if (!smpc::instance_kernel_supports(n, m)) return fail(SMPC_ERR_ARG, "per-instance regime: n, m too large for one warp's shared memory");
+  for (int i = 0; i < m; ++i) {
+    double lo = l0 ? l0[i] : -INFINITY, hi = u0 ? u0[i] : INFINITY;
+    if (lo > hi) return fail(SMPC_ERR_DATA, "lower bound greater than upper bound");
+  }
+  if (int rc = select_device(device)) return rc;
+  smpc_solver *s = new smpc_solver;
+  s->device = device; s->n = n; s->m = m; s->B = batch; s->st = *settings; s->regime = 1; s->kernel = 3;
+  s->plan.n = n; s->plan.m = m;
+  auto body = [&]() -> int {
+    const size_t N = n, M = m, B = batch;
+    size_t bytes = 0;
+    for (size_t c : {B * N * N, B * M * N, B * N, B * M, B, M, M}) bytes += DeviceBuf::need(c * sizeof(double));
+    CK(s->instbuf.alloc(bytes));
+    smpc::InstanceDataDev &d = s->dinst;
+    d.n = n; d.m = m; d.B = batch;
+    d.P = s->instbuf.take<double>(B * N * N); d.A = s->instbuf.take<double>(B * M * N ? B * M * N : 1);
+    d.D = s->instbuf.take<double>(B * N); d.E = s->instbuf.take<double>(B * M ? B * M : 1); d.c = s->instbuf.take<double>(B);
+    double *dl0 = s->instbuf.take<double>(M ? M : 1), *du0 = s->instbuf.take<double>(M ? M : 1);
+    if (!du0) return fail(SMPC_ERR_CUDA, "internal: instance buffer carve-out overflow");
+    std::vector<double> hl(M), hu(M);
+    for (size_t i = 0; i < M; ++i) { hl[i] = l0 ? l0[i] : -INFINITY; hu[i] = u0 ? u0[i] : INFINITY; }
+    if (M) { CK(cudaMemcpy(dl0, hl.data(), M * sizeof(double), cudaMemcpyHostToDevice)); CK(cudaMemcpy(du0, hu.data(), M * sizeof(double), cudaMemcpyHostToDevice)); }
+    d.l0 = dl0; d.u0 = du0;
+    cudaMemcpyKind k = loc == SMPC_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    CK(cudaMemcpy(d.P, P, B * N * N * sizeof(double), k));
+    if (M) CK(cudaMemcpy(d.A, A, B * M * N * sizeof(double), k));
+    if (s->st.scaling > 0) { CK(smpc::launch_ruiz_instance(d, s->st.scaling, nullptr)); s->launches++; }
+    else {
+      CK(smpc::launch_ruiz_instance(d, 0, nullptr)); s->launches++;   // zero passes: mirrors P's upper triangle, D = E = c = 1
+    }
+    if (int rc = alloc_batch(s)) return rc;
+    if (int rc = reset_state(s, true)) return rc;
+    CK(cudaDeviceSynchronize());
+    return SMPC_OK;
+  };
+  int rc = body();
+  if (rc != SMPC_OK) { s->instbuf.release(); s->batchbuf.release(); delete s; return rc; }
+  *out = s;
+  return SMPC_OK;
 }
 
 int smpc_solver_destroy(smpc_solver *s) {
   if (!s) return SMPC_OK;
   cudaSetDevice(s->device);
   cudaStreamSynchronize(s->stream);
-  s->planbuf.release(); s->batchbuf.release(); s->packbuf.release();
+  s->planbuf.release(); s->batchbuf.release(); s->packbuf.release(); s->instbuf.release();
   delete s;
   return SMPC_OK;
 }
@@ -384,7 +430,8 @@ int smpc_solver_warm_start(smpc_solver *s, const double *x, const double *y, int
   CK(cudaSetDevice(s->device));
   if (int rc = copy_in(s, s->d_stage_x, x, (size_t)s->B * s->n, loc)) return rc;
   if (int rc = copy_in(s, s->d_stage_y, y, (size_t)s->B * s->m, loc)) return rc;
-  CK(smpc::launch_warm_start(s->dplan, s->B, s->d_stage_x, s->d_stage_y, s->d_xi, s->d_z, s->d_y, s->stream));
+  if (s->regime == 1) CK(smpc::launch_warm_start_instance(s->dinst, s->d_stage_x, s->d_stage_y, s->d_xi, s->d_z, s->d_y, s->stream));
+  else CK(smpc::launch_warm_start(s->dplan, s->B, s->d_stage_x, s->d_stage_y, s->d_xi, s->d_z, s->d_y, s->stream));
   s->launches++;
   return SMPC_OK;
 }
@@ -415,8 +462,9 @@ int smpc_solver_solve(smpc_solver *s) {
     CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
     CK(cudaEventRecord(ev0, s->stream));
   }
-  cudaError_t e = s->kernel == 2 ? smpc::launch_admm_shared_small(s->dpack, s->dplan, b, sd, s->d_queue, s->num_sms, s->stream)
-                                 : smpc::launch_admm_shared_generic(s->dplan, b, sd, s->stream);
+  cudaError_t e = s->regime == 1 ? smpc::launch_admm_instance(s->dinst, b, sd, s->stream)
+                  : s->kernel == 2 ? smpc::launch_admm_shared_small(s->dpack, s->dplan, b, sd, s->d_queue, s->num_sms, s->stream)
+                                   : smpc::launch_admm_shared_generic(s->dplan, b, sd, s->stream);
   if (e != cudaSuccess) return cuda_fail(e, "ADMM kernel launch");
   if (s->timing) { CK(cudaEventRecord(ev1, s->stream)); s->events.emplace_back(ev0, ev1); }
   s->launches++;
@@ -500,6 +548,14 @@ int smpc_solver_sync(smpc_solver *s) {
 
 int smpc_solver_get_scaling(smpc_solver *s, double *D, double *E, double *c) {
   if (!s) return fail(SMPC_ERR_ARG, "null handle");
+  if (s->regime == 1) {   // per-instance regime: the scaling of instance 0
+    CK(cudaSetDevice(s->device));
+    CK(cudaStreamSynchronize(s->stream));
+    if (D) CK(cudaMemcpy(D, s->dinst.D, sizeof(double) * s->n, cudaMemcpyDeviceToHost));
+    if (E && s->m) CK(cudaMemcpy(E, s->dinst.E, sizeof(double) * s->m, cudaMemcpyDeviceToHost));
+    if (c) CK(cudaMemcpy(c, s->dinst.c, sizeof(double), cudaMemcpyDeviceToHost));
+    return SMPC_OK;
+  }
   if (D) std::memcpy(D, s->plan.D.data(), sizeof(double) * s->n);
   if (E) std::memcpy(E, s->plan.E.data(), sizeof(double) * s->m);
   if (c) *c = s->plan.c;
@@ -509,7 +565,7 @@ int smpc_solver_get_scaling(smpc_solver *s, double *D, double *E, double *c) {
 long long smpc_solver_launch_count(const smpc_solver *s) { return s ? s->launches : 0; }
 const char *smpc_solver_kernel_name(const smpc_solver *s) {
   if (!s) return "";
-  return s->kernel == 2 ? "admm_shared_small_kernel" : "admm_shared_generic_kernel";
+  return s->regime == 1 ? "admm_instance_kernel" : s->kernel == 2 ? "admm_shared_small_kernel" : "admm_shared_generic_kernel";
 }
 
 /* host-only inspection of the shared plan (no device needed): used by the CPU tests of the host logic */
@@ -555,7 +611,6 @@ int smpc_mpc_create(smpc_mpc **out, int device, const smpc_mpc_config *cfg, int 
   *out = nullptr;
   if (!cfg || !settings || !cfg->Ad || !cfg->Bd || !cfg->Cd || !cfg->K) return fail(SMPC_ERR_ARG, "null config field");
   if (cfg->horizon < 1 || cfg->nx < 1 || cfg->nx > 16 || batch < 1) return fail(SMPC_ERR_ARG, "need horizon >= 1, 1 <= nx <= 16, batch >= 1");
-  if (cfg->per_instance) return fail(SMPC_ERR_STATE, "per-instance plants are not built yet (SURVEY 8 'next')");
   if (int rc = check_settings(*settings)) return rc;
   if (int rc = select_device(device)) return rc;
   smpc_mpc *M = new smpc_mpc;
@@ -576,7 +631,10 @@ int smpc_mpc_create(smpc_mpc **out, int device, const smpc_mpc_config *cfg, int 
     if (e != cudaSuccess) rc = cuda_fail(e, "assembly readback");
   }
   // cpp:42-43,54-64: n = N, m = 2N, q = f(X=U=ref=0) = 0, l = -DBL_MAX, u = W0 (X = U = 0)
-  if (rc == SMPC_OK) rc = smpc_solver_create_shared(&M->solver, device, N, 2 * N, batch, H.data(), G.data(), nullptr, lb.data(), W0.data(), settings);
+  if (rc == SMPC_OK) {
+    if (M->per_instance) rc = smpc_solver_create_batched(&M->solver, device, N, 2 * N, batch, M->mats.H, M->mats.Gbar, SMPC_DEVICE, lb.data(), W0.data(), settings);
+    else rc = smpc_solver_create_shared(&M->solver, device, N, 2 * N, batch, H.data(), G.data(), nullptr, lb.data(), W0.data(), settings);
+  }
   if (rc == SMPC_OK) {
     std::vector<double> ref(batch, cfg->xref);
     cudaError_t e = cudaMemcpy(M->d_ref, ref.data(), sizeof(double) * batch, cudaMemcpyHostToDevice);

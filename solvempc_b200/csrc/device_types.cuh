@@ -42,6 +42,15 @@ struct SmallPackDev {
   const int *ctype;               // [32]
 };
 
+// per-instance regime: every QP has its own (scaled) P̄_i, A̅_i and scaling
+struct InstanceDataDev {
+  int n, m, B;
+  double *P;            // [B][n][n]  P̄ (full symmetric) after ruiz_instance_kernel
+  double *A;            // [B][m][n]  A̅
+  double *D, *E, *c;    // [B][n], [B][m], [B]
+  const double *l0, *u0;   // shared UNSCALED setup bounds (m)
+};
+
 // per-instance data and state, [B][len] contiguous
 struct BatchDev {
   int B;

@@ -20,6 +20,13 @@ size_t small_pack_doubles();
 cudaError_t launch_admm_shared_small(const SmallPackDev &K, const SharedPlanDev &P, const BatchDev &Bt,
                                      const SettingsDev &S, int *queue, int num_sms, cudaStream_t stream);
 
+// admm_instance.cu : per-instance regime (own P_i, A_i per QP; batched Cholesky in shared memory)
+cudaError_t launch_ruiz_instance(const InstanceDataDev &I, int iters, cudaStream_t stream);
+cudaError_t launch_admm_instance(const InstanceDataDev &I, const BatchDev &Bt, const SettingsDev &S, cudaStream_t stream);
+cudaError_t launch_warm_start_instance(const InstanceDataDev &I, const double *x, const double *y, double *xs, double *z,
+                                       double *ys, cudaStream_t stream);
+bool instance_kernel_supports(int n, int m);
+
 // mpc_assembly.cu
 struct MpcDims { int N, nx, n_state_rows; double Q, R, RD, u_limit; };
 struct MpcMatsDev {   // per plant (index p): all row-major

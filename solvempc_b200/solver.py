@@ -57,6 +57,24 @@ class BatchedSolver:
         L.check(L.lib().smpc_solver_dims(self._h, C.byref(n), C.byref(m), C.byref(b)))
         self.n, self.m, self.batch = n.value, m.value, b.value
 
+    @classmethod
+    def batched(cls, P, A, l0=None, u0=None, device=0, settings=None, **kw):
+        """Per-instance regime: P [B][n][n] and A [B][m][n] differ per instance (numpy or CUDA tensors)."""
+        st = settings if settings is not None else L.default_settings(**kw)
+        B, n = P.shape[0], P.shape[1]
+        m = A.shape[1]
+        pp, lp, _k1 = _loc_ptr(P, B * n * n, "P")
+        pa, la, _k2 = _loc_ptr(A, B * m * n, "A") if m else (None, lp, None)
+        if m and lp != la:
+            raise ValueError("P and A must live in the same place")
+        l0 = None if l0 is None else np.ascontiguousarray(l0, dtype=np.float64)
+        u0 = None if u0 is None else np.ascontiguousarray(u0, dtype=np.float64)
+        h = C.c_void_p()
+        L.check(L.lib().smpc_solver_create_batched(C.byref(h), device, n, m, B, pp, pa, lp, _np_ptr(l0), _np_ptr(u0), C.byref(st)))
+        obj = cls(None, None, _handle=h.value, settings=st)
+        obj._own = True
+        return obj
+
     def close(self):
         if getattr(self, "_h", None) and self._own:
             L.lib().smpc_solver_destroy(self._h)

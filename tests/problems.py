@@ -39,3 +39,19 @@ def random_qp(n, m, seed, density=1.0, active_frac=0.3):
     u = Ax + w * 0.5 - shift
     l = u - w - 1.0
     return P, q, A, l, u
+
+
+def c4_plants(B, cfg, seed=0):
+    """Config 4 inputs: Ad_i = Ad + 0.01 |Ad| o N(0,1), Bd_i = -(Ad_i - I) e1, rejected if rho(Ad_i) >= 1."""
+    rng = np.random.default_rng(seed)
+    Ad, nx = cfg["Ad"], cfg["Ad"].shape[0]
+    out_A, out_B = np.empty((B, nx, nx)), np.empty((B, nx))
+    k = 0
+    while k < B:
+        Ai = Ad + 0.01 * np.abs(Ad) * rng.standard_normal((nx, nx))
+        if np.abs(np.linalg.eigvals(Ai)).max() >= 1.0:
+            continue
+        out_A[k] = Ai
+        out_B[k] = -(Ai - np.eye(nx))[:, 0]
+        k += 1
+    return out_A, out_B

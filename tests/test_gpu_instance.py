@@ -1,0 +1,82 @@
+"""GPU parity of the per-instance regime (every QP has its own P_i, A_i: batched Cholesky path, BASELINE config 4)."""
+import numpy as np
+import pytest
+
+import oracle
+import solvempc_b200 as sm
+from problems import c2_batch, c4_plants, random_qp
+from test_gpu_parity import EPS, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("n,m,B", [(6, 9, 16), (30, 60, 48), (33, 40, 8)])
+def test_random_per_instance_qps(n, m, B):
+    Ps, As, qs, ls, us = [], [], [], [], []
+    P0, q0, A0, l0, u0 = random_qp(n, m, seed=100)
+    rng = np.random.default_rng(n)
+    for b in range(B):
+        P, q, A, _, _ = random_qp(n, m, seed=1000 + b)
+        Ps.append(P); As.append(A); qs.append(q)
+        sh = 0.1 * rng.standard_normal(m)
+        ls.append(l0 + sh); us.append(u0 + sh)
+    Ps, As, qs, ls, us = map(np.array, (Ps, As, qs, ls, us))
+    ls[:, 0] = us[:, 0]                                   # an equality row everywhere
+    l0 = l0.copy(); l0[0] = u0[0]
+    s = sm.BatchedSolver.batched(Ps, As, l0, u0, **EPS)
+    assert s.kernel_name == "admm_instance_kernel" and (s.n, s.m, s.batch) == (n, m, B)
+    s.update_gradient(qs); s.update_bounds(ls, us); s.solve()
+    x, y = s.solution(); info = s.info()
+    xs, ys, st, it, ru = [], [], [], [], []
+    for b in range(B):
+        so = oracle.Solver(Ps[b], np.zeros(n), As[b], l0, u0, **EPS)
+        if b == 0:
+            D, E, c = so.scaling()
+            Dd, Ed, cd = s.scaling()
+            assert np.abs(Dd - D).max() <= 1e-15 * D.max() and np.abs(Ed - E).max() <= 1e-15 * E.max() and abs(cd - c) <= 1e-15 * c
+        so.update_lin_cost(qs[b]); so.update_bounds(ls[b], us[b])
+        r = so.solve()
+        xs.append(r["x"]); ys.append(r["y"]); st.append(r["status"]); it.append(r["iter"]); ru.append(r["rho_updates"])
+    assert np.array_equal(info["status"], np.array(st)) and np.array_equal(info["iter"], np.array(it))
+    assert np.array_equal(info["rho_updates"], np.array(ru))
+    assert rel_err(x, np.array(xs)) < 1e-6 and rel_err(y, np.array(ys)) < 1e-5
+    # warm second solve (rho and iterates persist), as the oracle does per instance
+    s.solve()
+    assert (s.info()["iter"][np.array(st) == 1] == 25).all()
+    s.close()
+
+
+def test_c4_per_instance_plants_through_mpc_api(ref_mats):
+    """Config 4: distinct linearised plants per controller, N = 30, assembly on device + batched Cholesky."""
+    _, cfg = ref_mats
+    N, B = 30, 96
+    Ad, Bd = c4_plants(B, cfg, seed=2)
+    conf = dict(Ad=Ad, Bd=Bd, Cd=cfg["Cd"], K=cfg["K"], Q=cfg["Q"], R=cfg["R"], RD=cfg["RD"], horizon=N, per_instance=1)
+    mpc = sm.BatchedModelPredictiveControlAPI(conf, batch=B, **EPS)
+    assert (mpc.n_variables, mpc.n_constraints) == (30, 60) and mpc.solver.kernel_name == "admm_instance_kernel"
+    X, U, ref = c2_batch(B, seed=31)
+    mpc.set_state(X=X, U=U, ref=ref)
+    ok = mpc.controllerStep()
+    x, _ = mpc.solver.solution(); info = mpc.solver.info()
+    _, Uout = mpc.state()
+    fd, ubd = mpc.step_vectors()
+    nsolved = 0
+    for b in range(B):
+        mats = oracle.mpc_build(**{**cfg, "Ad": Ad[b], "Bd": Bd[b], "N": N})
+        if b % 16 == 0:
+            for name in ("H", "Gbar", "Fx", "Fu", "Fr"):
+                assert np.abs(mpc.matrix(name, b) - mats[name]).max() <= 1e-11 * np.abs(mats[name]).max(), name
+        f, ub = oracle.mpc_step_vectors(mats, X[b], U[b], ref[b])
+        assert np.abs(fd[b] - f).max() <= 1e-11 * np.abs(f).max() and np.abs(ubd[b] - ub).max() <= 1e-12 * np.abs(ub).max()
+        so = oracle.Solver(mats["H"], np.zeros(N), mats["Gbar"], mats["lb"], mats["W0"], **EPS)
+        so.update_lin_cost(f); so.update_upper_bound(ub)
+        r = so.solve()
+        assert info["status"][b] == r["status"] and info["iter"][b] == r["iter"], b
+        assert rel_err(x[b], r["x"]) < 1e-6
+        if r["status"] == 1:
+            nsolved += 1
+            assert abs(Uout[b] - (U[b] + r["x"][0])) < 1e-8
+        else:
+            assert Uout[b] == U[b]
+    assert ok == (nsolved == B) and nsolved >= B // 2
+    mpc.close()
