@@ -118,6 +118,9 @@ int smpc_solver_reset(smpc_solver *s);
  * i.e. each instance behaves like a freshly constructed solver -- the "independent cold QPs" workload
  * (BASELINE config 2).  Default off: warm start and rho persist across solves as in OSQP (cpp:52). */
 int smpc_solver_set_cold_solves(smpc_solver *s, int on);
+/* on != 0 (default): the small-QP kernel orders its work queue longest-expected-first with a cheap pre-pass
+ * (classify_small_kernel); results do not depend on it */
+int smpc_solver_set_scheduling(smpc_solver *s, int on);
 /* on != 0: bracket the ADMM kernel of every solve with CUDA events on the handle's stream;
  * smpc_solver_kernel_ms sums and counts them (used by bench.py for the roofline line) */
 int smpc_solver_enable_timing(smpc_solver *s, int on);

@@ -66,6 +66,7 @@ SIGNATURES = {
     "smpc_solver_cold_start": (_i, [_vp]),
     "smpc_solver_reset": (_i, [_vp]),
     "smpc_solver_set_cold_solves": (_i, [_vp, _i]),
+    "smpc_solver_set_scheduling": (_i, [_vp, _i]),
     "smpc_solver_enable_timing": (_i, [_vp, _i]),
     "smpc_solver_kernel_ms": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(_i), _i]),
     "smpc_solver_solve": (_i, [_vp]),

@@ -26,6 +26,7 @@ namespace {
 
 constexpr int NP = 16, MP = 32, KH = (NP + MP) / 2;   // padded sizes; 24 concatenated entries per half-warp
 constexpr unsigned kFull = 0xffffffffu;
+constexpr int kClasses = 5;   // difficulty classes of the scheduling pre-pass
 
 __device__ __forceinline__ double2 lds128(uint32_t addr) {
   double2 v;
@@ -196,8 +197,40 @@ __device__ __noinline__ CheckOut check_step(const double *sm, double *cbuf, doub
 
 }  // namespace
 
+// Scheduling pre-pass.  The expensive instances are the MARGINALLY constrained ones: with x_unc the minimiser of the
+// cost alone, key = max_r ((A̅ x_unc)_r - ū_r, l̄_r - (A̅ x_unc)_r) is slightly positive for them (measured on config 2:
+// sorting by key / ||bounds|| ascending puts 61 of the 64 instances that need >= 100 iterations among the first 207).
+// In plan coordinates A̅ x_unc = -W q̂ (S^-1 = V V'), i.e. one z-phase product.  Classes (processed in this order):
+// ratio in (0, .02], (.02, .05], (.05, .15], > .15 (saturated), <= 0 (unconstrained optimum feasible).
+// The order changes nothing but the schedule: every instance is solved exactly as before.
+__global__ void classify_small_kernel(SmallPackDev K, SharedPlanDev P, BatchDev Bt, int *counts, int *lists) {
+  const int lane = threadIdx.x & 31, b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= Bt.B) return;
+  const int n = P.n, m = P.m, i = lane & 15, r = lane;
+  const double qb = (i < n && Bt.q) ? P.c * (K.D[i] * Bt.q[(size_t)b * n + i]) : 0.0;
+  double qh = 0.0;
+#pragma unroll
+  for (int k = 0; k < NP; ++k) qh = fma(K.V[k * NP + i], __shfl_sync(kFull, qb, k), qh);
+  double zu = 0.0;
+#pragma unroll
+  for (int k = 0; k < NP; ++k) zu = fma(-K.WT[k * MP + r], __shfl_sync(kFull, qh, k), zu);
+  double key = -1e300, ref = 0.0;
+  if (r < m) {
+    const double lo = K.E[r] * (Bt.l ? Bt.l[(size_t)b * m + r] : P.l0[r]), hi = K.E[r] * (Bt.u ? Bt.u[(size_t)b * m + r] : P.u0[r]);
+    if (hi < kInfty * kMinScaling) { key = fmax(key, zu - hi); ref = fmax(ref, fabs(hi)); }
+    if (lo > -kInfty * kMinScaling) { key = fmax(key, lo - zu); ref = fmax(ref, fabs(lo)); }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { key = fmax(key, __shfl_xor_sync(kFull, key, o)); ref = fmax(ref, __shfl_xor_sync(kFull, ref, o)); }
+  if (lane == 0) {
+    const double ratio = key / fmax(ref, 1e-300);
+    const int cls = !(key > 0.0) ? 4 : (ratio <= 0.02 ? 0 : (ratio <= 0.05 ? 1 : (ratio <= 0.15 ? 2 : 3)));
+    lists[(size_t)cls * Bt.B + atomicAdd(counts + cls, 1)] = b;
+  }
+}
+
 __global__ void __launch_bounds__(128, 3)
-admm_shared_small_kernel(SmallPackDev K, SharedPlanDev P, BatchDev Bt, SettingsDev S, int *queue) {
+admm_shared_small_kernel(SmallPackDev K, SharedPlanDev P, BatchDev Bt, SettingsDev S, int *queue, const int *lists) {
   extern __shared__ __align__(16) double smem[];
   double *sV = smem + NP * NP * 2 + MP * NP;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -229,10 +262,24 @@ admm_shared_small_kernel(SmallPackDev K, SharedPlanDev P, BatchDev Bt, SettingsD
   __syncthreads();
 
   for (;;) {
+    // longest-expected-first: the queue walks the difficulty classes written by classify_small_kernel
     int b = 0;
-    if (lane == 0) b = atomicAdd(queue, 1);
+    if (lane == 0) {
+      int q = atomicAdd(queue, 1);
+      b = -1;
+      if (q < Bt.B) {
+        if (lists == nullptr) b = q;
+        else {
+#pragma unroll
+          for (int k = 0; k < kClasses; ++k) {
+            const int cnt = queue[1 + k];
+            if (b < 0) { if (q < cnt) b = lists[(size_t)k * Bt.B + q]; else q -= cnt; }
+          }
+        }
+      }
+    }
     b = __shfl_sync(kFull, b, 0);
-    if (b >= Bt.B) break;
+    if (b < 0) break;
 
     // ---- load the instance (osqp_update_lin_cost / osqp_update_bounds scaling)
     const bool warm = S.warm_start && !Bt.fresh;
@@ -378,16 +425,24 @@ bool small_kernel_supports(int n, int m) { return n >= 1 && n <= NP && m >= 0 &&
 
 size_t small_pack_doubles() { return (size_t)(NP + MP) * NP + NP * MP + 3 * NP * NP + MP * NP + 3 * NP + 2 * MP; }
 
+int small_queue_ints() { return 1 + kClasses; }
+
+// queue: [0] work counter, [1..kClasses] class sizes; lists: kClasses * B instance indices (nullptr = index order)
 cudaError_t launch_admm_shared_small(const SmallPackDev &K, const SharedPlanDev &P, const BatchDev &Bt,
-                                     const SettingsDev &S, int *queue, int num_sms, cudaStream_t stream) {
+                                     const SettingsDev &S, int *queue, int *lists, int num_sms, cudaStream_t stream) {
   const int wpc = 4;
   const size_t smem = (size_t)(kCtaMatDoubles + wpc * kWarpDoubles) * sizeof(double);
-  cudaError_t e = cudaMemsetAsync(queue, 0, sizeof(int), stream);
+  cudaError_t e = cudaMemsetAsync(queue, 0, sizeof(int) * (1 + kClasses), stream);
   if (e != cudaSuccess) return e;
+  if (lists) {
+    classify_small_kernel<<<(Bt.B + 7) / 8, 256, 0, stream>>>(K, P, Bt, queue + 1, lists);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
   int grid = (Bt.B + wpc - 1) / wpc;
   const int resident = num_sms * 3;   // __launch_bounds__(128, 3): three CTAs (12 warps) per SM
   if (grid > resident) grid = resident;
-  admm_shared_small_kernel<<<grid, wpc * 32, smem, stream>>>(K, P, Bt, S, queue);
+  admm_shared_small_kernel<<<grid, wpc * 32, smem, stream>>>(K, P, Bt, S, queue, lists);
   return cudaGetLastError();
 }
 

@@ -63,8 +63,9 @@ struct smpc_solver {
   smpc::InstanceDataDev dinst{};
   DeviceBuf packbuf;                                  // small-kernel operator pack + work queue
   smpc::SmallPackDev dpack{};
-  int *d_queue = nullptr;
+  int *d_queue = nullptr, *d_lists = nullptr;
   int num_sms = 148;
+  bool schedule = true;   // longest-expected-first pre-pass of the small kernel
   long long launches = 0;
   int kernel = 1;
   bool solved_once = false;
@@ -176,7 +177,8 @@ int upload_small_pack(smpc_solver *s) {
   size_t bytes = 0;
   for (size_t c : {M1T.size(), WT.size(), VT.size(), PVT.size(), Ab.size(), V.size(), lam.size(), D.size(), Dinv.size(), E.size(), Einv.size()})
     bytes += DeviceBuf::need(c * sizeof(double));
-  bytes += DeviceBuf::need(MP * sizeof(int)) + DeviceBuf::need(sizeof(int));
+  bytes += DeviceBuf::need(MP * sizeof(int)) + DeviceBuf::need(sizeof(int) * smpc::small_queue_ints()) +
+           DeviceBuf::need(sizeof(int) * (size_t)(smpc::small_queue_ints() - 1) * s->B);
   CK(s->packbuf.alloc(bytes));
   auto put = [&](const std::vector<double> &v, const double **dst) -> cudaError_t {
     double *d = s->packbuf.take<double>(v.size());
@@ -189,9 +191,10 @@ int upload_small_pack(smpc_solver *s) {
   int *dct = s->packbuf.take<int>(MP);
   CK(cudaMemcpy(dct, ct.data(), MP * sizeof(int), cudaMemcpyHostToDevice));
   k.ctype = dct;
-  s->d_queue = s->packbuf.take<int>(1);
-  if (!s->d_queue) return fail(SMPC_ERR_CUDA, "internal: pack buffer carve-out overflow");
-  CK(cudaMemset(s->d_queue, 0, sizeof(int)));
+  s->d_queue = s->packbuf.take<int>(smpc::small_queue_ints());
+  s->d_lists = s->packbuf.take<int>((size_t)(smpc::small_queue_ints() - 1) * s->B);
+  if (!s->d_lists) return fail(SMPC_ERR_CUDA, "internal: pack buffer carve-out overflow");
+  CK(cudaMemset(s->d_queue, 0, sizeof(int) * smpc::small_queue_ints()));
   int sms = 0;
   CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
   s->num_sms = sms > 0 ? sms : 148;
@@ -463,11 +466,11 @@ int smpc_solver_solve(smpc_solver *s) {
     CK(cudaEventRecord(ev0, s->stream));
   }
   cudaError_t e = s->regime == 1 ? smpc::launch_admm_instance(s->dinst, b, sd, s->stream)
-                  : s->kernel == 2 ? smpc::launch_admm_shared_small(s->dpack, s->dplan, b, sd, s->d_queue, s->num_sms, s->stream)
+                  : s->kernel == 2 ? smpc::launch_admm_shared_small(s->dpack, s->dplan, b, sd, s->d_queue, s->schedule ? s->d_lists : nullptr, s->num_sms, s->stream)
                                    : smpc::launch_admm_shared_generic(s->dplan, b, sd, s->stream);
   if (e != cudaSuccess) return cuda_fail(e, "ADMM kernel launch");
   if (s->timing) { CK(cudaEventRecord(ev1, s->stream)); s->events.emplace_back(ev0, ev1); }
-  s->launches++;
+  s->launches += (s->regime == 0 && s->kernel == 2 && s->schedule) ? 2 : 1;
   s->solved_once = true;
   return SMPC_OK;
 }
@@ -475,6 +478,11 @@ int smpc_solver_solve(smpc_solver *s) {
 int smpc_solver_set_cold_solves(smpc_solver *s, int on) {
   if (!s) return fail(SMPC_ERR_ARG, "null handle");
   s->cold_solves = on != 0;
+  return SMPC_OK;
+}
+int smpc_solver_set_scheduling(smpc_solver *s, int on) {
+  if (!s) return fail(SMPC_ERR_ARG, "null handle");
+  s->schedule = on != 0;
   return SMPC_OK;
 }
 int smpc_solver_enable_timing(smpc_solver *s, int on) {

@@ -17,8 +17,9 @@ cudaError_t launch_warm_start(const SharedPlanDev &P, int B, const double *x, co
 // admm_shared_small.cu : register-resident kernel for small QPs (n <= 16, m <= 32)
 bool small_kernel_supports(int n, int m);
 size_t small_pack_doubles();
+int small_queue_ints();
 cudaError_t launch_admm_shared_small(const SmallPackDev &K, const SharedPlanDev &P, const BatchDev &Bt,
-                                     const SettingsDev &S, int *queue, int num_sms, cudaStream_t stream);
+                                     const SettingsDev &S, int *queue, int *lists, int num_sms, cudaStream_t stream);
 
 // admm_instance.cu : per-instance regime (own P_i, A_i per QP; batched Cholesky in shared memory)
 cudaError_t launch_ruiz_instance(const InstanceDataDev &I, int iters, cudaStream_t stream);

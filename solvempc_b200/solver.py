@@ -119,6 +119,10 @@ class BatchedSolver:
         """Every solve behaves like a freshly constructed solver (x = z = y = 0, rho = settings.rho)."""
         L.check(L.lib().smpc_solver_set_cold_solves(self._h, int(on)))
 
+    def set_scheduling(self, on=True):
+        """Longest-expected-first ordering of the small kernel's work queue (default on; results identical)."""
+        L.check(L.lib().smpc_solver_set_scheduling(self._h, int(on)))
+
     def enable_timing(self, on=True):
         L.check(L.lib().smpc_solver_enable_timing(self._h, int(on)))
 

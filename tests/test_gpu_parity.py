@@ -133,6 +133,13 @@ def test_generic_and_small_kernels_agree_bitwise_on_status(ref_mats):
         s.close()
     assert np.array_equal(out[0][1]["iter"], out[1][1]["iter"])
     assert rel_err(out[0][0], out[1][0]) < 1e-9
+    # the longest-expected-first schedule of the small kernel changes the order of work only: bitwise same answers
+    s = sm.BatchedSolver(m["H"], m["Gbar"], m["lb"], m["W0"], batch=512, kernel=2, **EPS)
+    s.set_scheduling(False)
+    s.update_gradient(f); s.update_upper_bound(ub); s.solve()
+    x_off, y_off = s.solution()
+    assert np.array_equal(x_off, out[1][0]) and np.array_equal(s.info()["iter"], out[1][1]["iter"])
+    s.close()
 
 
 @pytest.mark.parametrize("n,m,B", [(3, 0, 8), (12, 20, 64), (16, 32, 64), (17, 33, 32), (40, 70, 32), (100, 200, 8)])
