@@ -61,7 +61,8 @@ typedef struct smpc_settings {
   int max_iter, check_termination, scaling;
   int adaptive_rho, adaptive_rho_interval;
   int warm_start, scaled_termination;
-  int kernel;               /* 0 = auto; 1 = generic warp kernel; 2 = register-resident small-QP kernel */
+  int kernel;               /* 0 = auto; 1 = generic warp kernel; 2 = register-resident small-QP kernel (n <= 16, m <= 32);
+                               4 = DMMA tile kernel (8/16 QPs per CTA, FP64 tensor pipe; auto choice for n > 16) */
 } smpc_settings;
 
 void smpc_default_settings(smpc_settings *s);   /* OSQP 0.6 defaults (eps 1e-3) */

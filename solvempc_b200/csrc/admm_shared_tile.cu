@@ -1,0 +1,719 @@
+// admm_shared_tile.cu -- shared-factor ADMM kernel for mid-size QPs (n > 16: horizons 30..100, the 12-state
+// quadrotor), the "(n x n) . (n x batch) contraction" of the north star, on the FP64 tensor pipe (DMMA).
+//
+// One CTA owns a TILE of TB = 8*NB QPs ("slots") and keeps every iterate of the tile in shared memory for the
+// whole solve; HBM is touched once per solve (q, l, u in; x, y, status out).  The shared operators of the plan
+// (plan.hpp: sigma*G, W = A̅V, ...) are streamed from L2 once per tile-iteration as pre-packed
+// mma.sync.m8n8k4.f64 A-fragments (512 contiguous bytes per warp load) and multiplied against the tile's iterate
+// PANELS (the 8 slots of a panel are the N dimension of the DMMA).  Per iteration (OSQP 0.6.x osqp_solve in
+// plan coordinates, reference call site src/ModelPredictiveControlAPI.cpp:102; same maths as admm_shared_generic.cu):
+//     T  = ([sigma*G | W'] [xi; w] - q̂) .* dinv            GEMM 1, K = n + m      dinv = 1/(1 + rho_b*lambda_i)
+//     xi'= alpha T + (1-alpha) xi                           (double-buffered panel)
+//     Z̃  = W T                                              GEMM 2, K = n
+//     z, y, w = rho_vec z - y                               epilogue of GEMM 2 (clip to [l̄, ū], dual update)
+// with two CTA barriers per iteration.  Slots are independent QPs: each has its own rho, iteration counter and
+// status; termination checks / rho adaptation (four more panel GEMMs: x̄ = V xi, P̄x, A̅'y, A̅x̄) run when a slot is due.
+// A slot whose QP finished is stored and REFILLED from a device-wide work queue at that check, so a tile never
+// idles on its slowest member (per-problem convergence masking = slot recycling).
+//
+// Panel layout in shared memory: [nb][row][8] doubles (8-slot blocks), so a DMMA B-fragment load (4 k-rows x 8 slots)
+// is 32 consecutive doubles and the C-fragment of a thread is a double2 of the same panel layout.
+#include <cstdint>
+
+#include "device_types.cuh"
+#include "kernels.cuh"
+
+namespace smpc {
+
+namespace {
+
+constexpr int kTileWarps = 8;
+constexpr int kTileThreads = kTileWarps * 32;
+constexpr int kRG = 4;          // row-blocks (8 operator rows each) a warp accumulates at once
+constexpr int kRing = 3;        // A-fragment prefetch distance in k-pairs (covers the L2 latency)
+
+enum NormId {
+  N_RP_S, N_Z_S, N_AX_S, N_RP_U, N_Z_U, N_AX_U,
+  N_RD_S, N_Q_S, N_ATY_S, N_PX_S, N_RD_U, N_Q_U, N_ATY_U, N_PX_U,
+  N_DY, N_ATD, N_DX, N_PD, N_COUNT
+};
+enum SumId { S_OBJ, S_LHS, S_QD, S_COUNT };
+
+__device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+               : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ double2 ldg_stream(const double2 *p) {
+  double2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ double rho_of(int ct, double rho) { return ct == 0 ? rho : (ct == 1 ? kRhoEqOverIneq * rho : kRhoMin); }
+
+// per-tile bookkeeping in shared memory
+template <int TB>
+struct TileCtl {
+  unsigned long long nmax[N_COUNT][TB];    // max-norms as IEEE bit patterns of non-negative doubles
+  double psum[S_COUNT][kTileWarps][TB];
+  double rho[TB], rinv[TB], rho_eq[TB], rinv_eq[TB];
+  double obj[TB], pri[TB], dua[TB];
+  int inst[TB];        // QP index of the slot, -1 = empty
+  int it0[TB];         // tile iteration at which the slot's QP started
+  int rho_up[TB];
+  int status[TB];
+  int flags[TB];       // scratch bit flags per slot (F_*)
+  int next_event;      // next tile iteration at which some slot is due for a check / adaptation / max_iter
+  int active;          // number of occupied slots
+  int refill_mask, work_flag;
+};
+enum SlotFlag { F_DUE_CHECK = 1, F_DUE_ADAPT = 2, F_AT_MAX = 4, F_PRIM_OK = 8, F_DUAL_OK = 16, F_NEED_PINF = 32,
+                F_NEED_DINF = 64, F_BADROW = 128, F_DONE = 256, F_NEED_ATD = 512, F_NEED_DINF2 = 1024, F_RHO_NEW = 2048,
+                F_BADBOUNDS = 4096, F_CADENCE = 8192 };
+
+// acc[r][nb] += Op[rows of rbs[r]] (k-pairs kp0 .. kp0+cnt) * panel   (panel rows = k, [nb][krows][8])
+template <int NB>
+__device__ __forceinline__ void gemm_seg(const double2 *__restrict__ opl, int kpt, const int (&rbs)[kRG], int kp0, int cnt,
+                                         const double *panel, int krows, int lane, double (&acc)[kRG][NB][2]) {
+  const double2 *ap[kRG];
+#pragma unroll
+  for (int r = 0; r < kRG; ++r) ap[r] = opl + ((size_t)rbs[r] * kpt + kp0) * 32;
+  const double *bp = panel + (lane & 3) * 8 + (lane >> 2);
+  double2 ring[kRing][kRG];
+#pragma unroll
+  for (int d = 0; d < kRing; ++d)
+    if (d < cnt) {
+#pragma unroll
+      for (int r = 0; r < kRG; ++r) ring[d][r] = ldg_stream(ap[r] + d * 32);
+    }
+  for (int kp = 0; kp < cnt; kp += kRing) {
+#pragma unroll
+    for (int d = 0; d < kRing; ++d) {
+      if (kp + d < cnt) {
+        double b[NB][2];
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) {
+          b[nb][0] = bp[(nb * krows + 8 * (kp + d)) * 8];
+          b[nb][1] = bp[(nb * krows + 8 * (kp + d) + 4) * 8];
+        }
+        double2 a[kRG];
+#pragma unroll
+        for (int r = 0; r < kRG; ++r) a[r] = ring[d][r];
+        if (kp + d + kRing < cnt) {
+#pragma unroll
+          for (int r = 0; r < kRG; ++r) ring[d][r] = ldg_stream(ap[r] + (kp + d + kRing) * 32);
+        }
+#pragma unroll
+        for (int r = 0; r < kRG; ++r)
+#pragma unroll
+          for (int nb = 0; nb < NB; ++nb) { dmma(acc[r][nb], a[r].x, b[nb][0]); dmma(acc[r][nb], a[r].y, b[nb][1]); }
+      }
+    }
+  }
+}
+
+// max over the 8 row-groups of a warp (lanes with equal lane&3 hold the same slot pair)
+__device__ __forceinline__ double rmax8(double v) {
+  v = fmax(v, __shfl_xor_sync(0xffffffffu, v, 4));
+  v = fmax(v, __shfl_xor_sync(0xffffffffu, v, 8));
+  return fmax(v, __shfl_xor_sync(0xffffffffu, v, 16));
+}
+__device__ __forceinline__ double rsum8(double v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  v += __shfl_xor_sync(0xffffffffu, v, 8);
+  return v + __shfl_xor_sync(0xffffffffu, v, 16);
+}
+
+}  // namespace
+
+enum PassId { P_XBAR, P_PX, P_ATY, P_AX, P_ATD, P_DX, P_PD, P_ADX, P_QH, P_COUNT };
+
+template <int NB>
+__global__ void __launch_bounds__(kTileThreads, 1)
+admm_shared_tile_kernel(TilePackDev K, SharedPlanDev P, BatchDev Bt, SettingsDev S, int *queue) {
+  constexpr int TB = 8 * NB;
+  extern __shared__ __align__(16) double smem[];
+  const int n = P.n, m = P.m, n8 = K.n8, m8 = K.m8;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, q2 = 2 * (lane & 3);
+  // panels
+  double *xi0 = smem, *xi1 = xi0 + n8 * TB, *Tp = xi1 + n8 * TB, *qh = Tp + n8 * TB, *dinv = qh + n8 * TB, *Sp = dinv + n8 * TB;
+  double *wp = Sp + n8 * TB, *zp = wp + m8 * TB, *yp = zp + m8 * TB, *lbp = yp + m8 * TB, *ubp = lbp + m8 * TB;
+  TileCtl<TB> &C = *reinterpret_cast<TileCtl<TB> *>(ubp + m8 * TB);
+  const int NRB = n8 >> 3, MRB = m8 >> 3;
+  const int nrb0 = (warp * NRB) / kTileWarps, nrb1 = ((warp + 1) * NRB) / kTileWarps;
+  const int mrb0 = (warp * MRB) / kTileWarps, mrb1 = ((warp + 1) * MRB) / kTileWarps;
+  const int kpN = n8 >> 3, kpM = m8 >> 3;
+  const double alpha = S.alpha, oma = 1.0 - S.alpha;
+  const int check_every = S.check_every, adapt_every = (S.adaptive_rho && S.rho_interval > 0) ? S.rho_interval : 0;
+
+  auto zero_acc = [&](double (&acc)[kRG][NB][2]) {
+#pragma unroll
+    for (int r = 0; r < kRG; ++r)
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb) acc[r][nb][0] = acc[r][nb][1] = 0.0;
+  };
+  auto pidx = [&](int rows, int nb, int row) { return (nb * rows + row) * 8 + q2; };   // this thread's double2 in a panel
+
+  // ---- init: empty tile
+  for (int e = tid; e < (6 * n8 + 5 * m8) * TB; e += kTileThreads) smem[e] = 0.0;
+  if (tid < TB) {
+    C.inst[tid] = -1; C.it0[tid] = 0; C.rho_up[tid] = 0; C.status[tid] = SMPC_UNSOLVED; C.flags[tid] = 0;
+    C.rho[tid] = 1.0; C.rinv[tid] = 1.0; C.rho_eq[tid] = 1.0; C.rinv_eq[tid] = 1.0;
+  }
+  if (tid == 0) { C.next_event = 0x7fffffff; C.active = 0; C.refill_mask = (1 << TB) - 1; C.work_flag = 0; }
+  __syncthreads();
+  for (int e = tid; e < m8 * TB; e += kTileThreads) { lbp[e] = -1.0; ubp[e] = 1.0; }
+  for (int e = tid; e < n8 * TB; e += kTileThreads) dinv[e] = 1.0;
+  __syncthreads();
+
+  int k = 0;       // tile iteration counter
+  int p = 0;       // current xi buffer
+  bool event = true, initial = true;
+
+  for (;;) {
+    if (event) {
+      // ================= event: termination check / rho adaptation / max_iter for the slots that are due, then
+      // store + refill of the slots that finished.  The first event (k = 0) only fills the tile.
+      const double c = P.c, cinv = P.cinv;
+      const bool unscale = !S.scaled_termination;
+      const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+      const bool warm = S.warm_start && !Bt.fresh;
+      double *xi = p ? xi1 : xi0;            // current xi
+      double *xio = p ? xi0 : xi1;           // previous xi
+      auto nrm = [&](int id, int s) { return __longlong_as_double((long long)C.nmax[id][s]); };
+      auto total = [&](int id, int s) { double a = 0.0; for (int w = 0; w < kTileWarps; ++w) a += C.psum[id][w][s]; return a; };
+      auto any_flags = [&]() { int a = 0; for (int s = 0; s < TB; ++s) a |= C.flags[s]; return a; };
+
+      for (int e = tid; e < N_COUNT * TB; e += kTileThreads) (&C.nmax[0][0])[e] = 0ull;
+      for (int e = tid; e < S_COUNT * kTileWarps * TB; e += kTileThreads) (&C.psum[0][0][0])[e] = 0.0;
+      if (tid < TB) {
+        int f = 0;
+        if (C.inst[tid] >= 0) {
+          const int li = k - C.it0[tid];
+          if (check_every > 0 && li % check_every == 0) f |= F_DUE_CHECK | F_CADENCE;
+          if (adapt_every > 0 && li % adapt_every == 0) f |= F_DUE_ADAPT;
+          if (li >= S.max_iter) f |= F_AT_MAX | F_DUE_CHECK;
+        }
+        C.flags[tid] = f;
+      }
+      __syncthreads();
+      int any = initial ? 0 : any_flags();
+      int done = 0;
+
+      for (int pass = 0; pass < P_COUNT; ++pass) {
+        // ---------- what runs before the GEMM of this pass (block-uniform control flow)
+        bool run = false;
+        if (pass <= P_AX) run = !initial;
+        else if (pass == P_ATD) {
+          if (!initial) {
+            __syncthreads();   // norms of the four update_info passes are complete
+            // per-slot: update_info results, convergence tests with the plain tolerances
+            if (tid < TB && C.flags[tid]) {
+              const int s = tid;
+              int f = C.flags[s];
+              const double pri = m == 0 ? 0.0 : (unscale ? nrm(N_RP_U, s) : nrm(N_RP_S, s));
+              const double dua = unscale ? cinv * nrm(N_RD_U, s) : nrm(N_RD_S, s);
+              C.pri[s] = pri; C.dua[s] = dua;
+              C.obj[s] = (unscale ? cinv : 1.0) * total(S_OBJ, s);
+              if (f & F_DUE_CHECK) {
+                const double nEz = unscale ? nrm(N_Z_U, s) : nrm(N_Z_S, s), nEAx = unscale ? nrm(N_AX_U, s) : nrm(N_AX_S, s);
+                const double nDq = unscale ? nrm(N_Q_U, s) : nrm(N_Q_S, s), nDAty = unscale ? nrm(N_ATY_U, s) : nrm(N_ATY_S, s);
+                const double nDPx = unscale ? nrm(N_PX_U, s) : nrm(N_PX_S, s);
+                if (m == 0 || pri < S.eps_abs + S.eps_rel * fmax(nEz, nEAx)) f |= F_PRIM_OK; else f |= F_NEED_PINF;
+                if (dua < S.eps_abs + S.eps_rel * (unscale ? cinv : 1.0) * fmax(fmax(nDq, nDAty), nDPx)) f |= F_DUAL_OK; else f |= F_NEED_DINF;
+              }
+              C.flags[s] = f;
+            }
+            __syncthreads();
+            any = any_flags();
+            // is_primal_infeasible: project delta_y (carried by the w panel) on the polar of the recession cone
+            if (any & F_NEED_PINF) {
+              double lh[NB][2];
+#pragma unroll
+              for (int nb = 0; nb < NB; ++nb) lh[nb][0] = lh[nb][1] = 0.0;
+              for (int rb = mrb0; rb < mrb1; ++rb) {
+                const int row = 8 * rb + g;
+                const double E = row < m ? __ldg(P.E + row) : 1.0;
+#pragma unroll
+                for (int nb = 0; nb < NB; ++nb) {
+                  const int pi = pidx(m8, nb, row);
+                  const double2 d = *reinterpret_cast<const double2 *>(wp + pi);
+                  const double2 lo = *reinterpret_cast<const double2 *>(lbp + pi), hi = *reinterpret_cast<const double2 *>(ubp + pi);
+                  double dd[2] = {d.x, d.y}, nd[2];
+                  const double lo2[2] = {lo.x, lo.y}, hi2[2] = {hi.x, hi.y};
+#pragma unroll
+                  for (int j = 0; j < 2; ++j) {
+                    const bool uinf = hi2[j] > kInfty * kMinScaling, linf = lo2[j] < -kInfty * kMinScaling;
+                    if (uinf) dd[j] = linf ? 0.0 : fmin(dd[j], 0.0); else if (linf) dd[j] = fmax(dd[j], 0.0);
+                    if (row >= m) dd[j] = 0.0;
+                    nd[j] = fabs(unscale ? E * dd[j] : dd[j]);
+                    const double dp = fmax(dd[j], 0.0), dm = fmin(dd[j], 0.0);
+                    if (dp != 0.0) lh[nb][j] += hi2[j] * dp;
+                    if (dm != 0.0) lh[nb][j] += lo2[j] * dm;
+                  }
+                  *reinterpret_cast<double2 *>(wp + pi) = make_double2(dd[0], dd[1]);
+                  const double v0 = rmax8(nd[0]), v1 = rmax8(nd[1]);
+                  if (g == 0) {
+                    atomicMax(&C.nmax[N_DY][nb * 8 + q2], (unsigned long long)__double_as_longlong(v0));
+                    atomicMax(&C.nmax[N_DY][nb * 8 + q2 + 1], (unsigned long long)__double_as_longlong(v1));
+                  }
+                }
+              }
+#pragma unroll
+              for (int nb = 0; nb < NB; ++nb) {
+                const double s0 = rsum8(lh[nb][0]), s1 = rsum8(lh[nb][1]);
+                if (g == 0) { C.psum[S_LHS][warp][nb * 8 + q2] = s0; C.psum[S_LHS][warp][nb * 8 + q2 + 1] = s1; }
+              }
+              __syncthreads();
+              if (tid < TB && (C.flags[tid] & F_NEED_PINF)) {
+                const double nd = nrm(N_DY, tid), lhs = total(S_LHS, tid);
+                if (nd > S.eps_prim_inf && lhs < -S.eps_prim_inf * nd) C.flags[tid] |= F_NEED_ATD;
+              }
+              __syncthreads();
+              any = any_flags();
+            }
+            run = (any & F_NEED_ATD) != 0;
+          }
+        } else if (pass == P_DX) {
+          if (any & F_NEED_DINF) {
+            for (int e = tid; e < n8 * TB; e += kTileThreads) Sp[e] = xi[e] - xio[e];     // delta_xi
+            __syncthreads();
+            run = true;
+          }
+        } else if (pass == P_PD) {
+          if (any & F_NEED_DINF) {
+            __syncthreads();
+            if (tid < TB && (C.flags[tid] & F_NEED_DINF)) {
+              const double nd = nrm(N_DX, tid), qd = total(S_QD, tid), cs = unscale ? c : 1.0;
+              if (nd > S.eps_dual_inf && qd < -cs * S.eps_dual_inf * nd) C.flags[tid] |= F_NEED_DINF2;
+            }
+            __syncthreads();
+            any = any_flags();
+          }
+          run = (any & F_NEED_DINF2) != 0;
+        } else if (pass == P_ADX) {
+          run = (any & F_NEED_DINF2) != 0;
+        } else {   // P_QH: decisions, store, refill, then q̂ for the (re)filled tile
+          __syncthreads();
+          if (!initial && tid < TB && C.flags[tid]) {
+            const int s = tid;
+            int f = C.flags[s];
+            int status = SMPC_UNSOLVED;
+            double obj = C.obj[s];
+            auto decide = [&](bool approx) {
+              const double mul = approx ? 10.0 : 1.0;
+              const double ea = mul * S.eps_abs, er = mul * S.eps_rel, epi = mul * S.eps_prim_inf, edi = mul * S.eps_dual_inf;
+              const double nEz = unscale ? nrm(N_Z_U, s) : nrm(N_Z_S, s), nEAx = unscale ? nrm(N_AX_U, s) : nrm(N_AX_S, s);
+              const double nDq = unscale ? nrm(N_Q_U, s) : nrm(N_Q_S, s), nDAty = unscale ? nrm(N_ATY_U, s) : nrm(N_ATY_S, s);
+              const double nDPx = unscale ? nrm(N_PX_U, s) : nrm(N_PX_S, s);
+              bool prim_ok = false, dual_ok = false, prim_inf = false, dual_inf = false;
+              if (m == 0 || C.pri[s] < ea + er * fmax(nEz, nEAx)) prim_ok = true;
+              else {
+                const double nd = nrm(N_DY, s), lhs = total(S_LHS, s);
+                if (nd > epi && lhs < -epi * nd) prim_inf = nrm(N_ATD, s) < epi * nd;
+              }
+              if (C.dua[s] < ea + er * (unscale ? cinv : 1.0) * fmax(fmax(nDq, nDAty), nDPx)) dual_ok = true;
+              else {
+                const double nd = nrm(N_DX, s), qd = total(S_QD, s), cs = unscale ? c : 1.0;
+                if (nd > edi && qd < -cs * edi * nd && nrm(N_PD, s) < cs * edi * nd) dual_inf = !(f & (approx ? (F_BADROW << 16) : F_BADROW));
+              }
+              if (prim_ok && dual_ok) status = approx ? SMPC_SOLVED_INACCURATE : SMPC_SOLVED;
+              else if (prim_inf) { status = approx ? SMPC_PRIMAL_INFEASIBLE_INACCURATE : SMPC_PRIMAL_INFEASIBLE; obj = kInfty; }
+              else if (dual_inf) { status = approx ? SMPC_DUAL_INFEASIBLE_INACCURATE : SMPC_DUAL_INFEASIBLE; obj = -kInfty; }
+            };
+            // order of admm_shared_generic.cu: cadence check, rho adaptation, then (at max_iter) the final plain + 10x checks
+            if (f & F_CADENCE) decide(false);
+            if ((f & F_DUE_ADAPT) && status == SMPC_UNSOLVED) {
+              // compute_rho_estimate / adapt_rho on the SCALED norms
+              const double rho = C.rho[s];
+              const double pr = nrm(N_RP_S, s) / (fmax(nrm(N_Z_S, s), nrm(N_AX_S, s)) + kDivTol);
+              const double dr = nrm(N_RD_S, s) / (fmax(fmax(nrm(N_Q_S, s), nrm(N_ATY_S, s)), nrm(N_PX_S, s)) + kDivTol);
+              const double rn = fmin(fmax(rho * sqrt(pr / (dr + kDivTol)), kRhoMin), kRhoMax);
+              if (rn > rho * S.rho_tol || rn < rho / S.rho_tol) {
+                C.rho[s] = rn; C.rinv[s] = 1.0 / rn; C.rho_eq[s] = kRhoEqOverIneq * rn; C.rinv_eq[s] = 1.0 / (kRhoEqOverIneq * rn);
+                C.rho_up[s]++; f |= F_RHO_NEW;
+              }
+            }
+            if ((f & F_AT_MAX) && status == SMPC_UNSOLVED) {
+              if (!(f & F_CADENCE)) decide(false);
+              if (status == SMPC_UNSOLVED) {
+                decide(true);
+                if (status == SMPC_UNSOLVED) status = SMPC_MAX_ITER_REACHED;
+              }
+            }
+            if (status != SMPC_UNSOLVED) { f |= F_DONE; C.status[s] = status; C.obj[s] = obj; }
+            C.flags[s] = f;
+          }
+          __syncthreads();
+          // ---- store_solution for the QPs that finished; new dinv where rho changed
+          int rho_new = 0;
+          if (!initial)
+            for (int s = 0; s < TB; ++s) { if (C.flags[s] & F_DONE) done |= 1 << s; if (C.flags[s] & F_RHO_NEW) rho_new |= 1 << s; }
+          if (done | rho_new) {
+            for (int e = tid; e < n8 * TB; e += kTileThreads) {
+              const int s8 = e & 7, rest = e >> 3, i = rest % n8, nb = rest / n8, s = nb * 8 + s8;
+              if (((rho_new & ~done) >> s) & 1) dinv[e] = 1.0 / (1.0 + C.rho[s] * (i < n ? __ldg(P.lam + i) : 0.0));
+              if (!((done >> s) & 1)) continue;
+              if (i < n) {
+                const int b = C.inst[s], st = C.status[s];
+                const bool has_sol = !(st == SMPC_PRIMAL_INFEASIBLE || st == SMPC_PRIMAL_INFEASIBLE_INACCURATE || st == SMPC_DUAL_INFEASIBLE || st == SMPC_DUAL_INFEASIBLE_INACCURATE);
+                if (Bt.x_out) Bt.x_out[(size_t)b * n + i] = has_sol ? __ldg(P.D + i) * Tp[e] : qnan;
+                Bt.xi[(size_t)b * n + i] = has_sol ? xi[e] : 0.0;
+              }
+              xi0[e] = 0.0; xi1[e] = 0.0; Tp[e] = 0.0; qh[e] = 0.0; dinv[e] = 1.0;   // an unfilled slot iterates on zeros
+            }
+          }
+          if (done) {
+            for (int e = tid; e < m8 * TB; e += kTileThreads) {
+              const int s8 = e & 7, rest = e >> 3, r = rest % m8, nb = rest / m8, s = nb * 8 + s8;
+              if (!((done >> s) & 1)) continue;
+              if (r < m) {
+                const int b = C.inst[s], st = C.status[s];
+                const bool has_sol = !(st == SMPC_PRIMAL_INFEASIBLE || st == SMPC_PRIMAL_INFEASIBLE_INACCURATE || st == SMPC_DUAL_INFEASIBLE || st == SMPC_DUAL_INFEASIBLE_INACCURATE);
+                if (Bt.y_out) Bt.y_out[(size_t)b * m + r] = has_sol ? cinv * (__ldg(P.E + r) * yp[e]) : qnan;
+                Bt.z[(size_t)b * m + r] = has_sol ? zp[e] : 0.0;
+                Bt.y[(size_t)b * m + r] = has_sol ? yp[e] : 0.0;
+              }
+              zp[e] = 0.0; yp[e] = 0.0; lbp[e] = -1.0; ubp[e] = 1.0;
+            }
+            if (tid < TB && ((done >> tid) & 1)) {
+              const int b = C.inst[tid];
+              Bt.rho[b] = C.rho[tid]; Bt.status[b] = C.status[tid]; Bt.iter[b] = k - C.it0[tid]; Bt.rho_updates[b] = C.rho_up[tid];
+              Bt.obj[b] = C.obj[tid]; Bt.pri_res[b] = C.pri[tid]; Bt.dua_res[b] = C.dua[tid];
+            }
+            if (tid == 0) C.refill_mask = done;
+          }
+          __syncthreads();
+          // ---- refill: pull new QPs from the queue into the slots of C.refill_mask.  QPs with invalid bounds (see
+          // admm_shared_generic.cu) are stored as UNSOLVED at once and their slot is refilled again.
+          const bool any_refill = C.refill_mask != 0;
+          while (any_refill) {
+            if (tid < TB && ((C.refill_mask >> tid) & 1)) {
+              const int b = atomicAdd(queue, 1);
+              const bool ok = b < Bt.B;
+              C.inst[tid] = ok ? b : -1;
+              C.it0[tid] = k; C.rho_up[tid] = 0; C.status[tid] = SMPC_UNSOLVED; C.flags[tid] = 0;
+              const double rho = ok ? (Bt.fresh ? fmin(fmax(S.rho0, kRhoMin), kRhoMax) : Bt.rho[b]) : 1.0;
+              C.rho[tid] = rho; C.rinv[tid] = 1.0 / rho; C.rho_eq[tid] = kRhoEqOverIneq * rho; C.rinv_eq[tid] = 1.0 / (kRhoEqOverIneq * rho);
+              C.obj[tid] = 0.0; C.pri[tid] = 0.0; C.dua[tid] = 0.0;
+            }
+            __syncthreads();
+            const int mask = C.refill_mask;
+            // slot-fast mapping (lane & 7 = slot): conflict-free panel accesses
+            for (int e = tid; e < n8 * TB; e += kTileThreads) {
+              const int s8 = e & 7, rest = e >> 3, i = rest % n8, nb = rest / n8, s = nb * 8 + s8;
+              if (!((mask >> s) & 1)) continue;
+              const int b = C.inst[s];
+              const double v = (b >= 0 && i < n && warm) ? Bt.xi[(size_t)b * n + i] : 0.0;
+              xi0[e] = v; xi1[e] = v;
+              dinv[e] = b >= 0 ? 1.0 / (1.0 + C.rho[s] * (i < n ? __ldg(P.lam + i) : 0.0)) : 1.0;
+            }
+            for (int e = tid; e < m8 * TB; e += kTileThreads) {
+              const int s8 = e & 7, rest = e >> 3, r = rest % m8, nb = rest / m8, s = nb * 8 + s8;
+              if (!((mask >> s) & 1)) continue;
+              const int b = C.inst[s];
+              double lo = -1.0, hi = 1.0, zz = 0.0, yy = 0.0;
+              if (b >= 0 && r < m) {
+                const double E = __ldg(P.E + r);
+                lo = E * (Bt.l ? Bt.l[(size_t)b * m + r] : __ldg(P.l0 + r));
+                hi = E * (Bt.u ? Bt.u[(size_t)b * m + r] : __ldg(P.u0 + r));
+                if (warm) { zz = Bt.z[(size_t)b * m + r]; yy = Bt.y[(size_t)b * m + r]; }
+                const int ct = (lo < -kInfty * kMinScaling && hi > kInfty * kMinScaling) ? -1 : ((hi - lo < kRhoTolRow) ? 1 : 0);
+                if (lo > hi || ct != (int)__ldg(P.ctype + r)) atomicOr(&C.flags[s], F_BADBOUNDS);
+              }
+              lbp[e] = lo; ubp[e] = hi; zp[e] = zz; yp[e] = yy;
+            }
+            __syncthreads();
+            int again = 0;
+            for (int s = 0; s < TB; ++s) {
+              if (!((mask >> s) & 1) || C.inst[s] < 0 || !(C.flags[s] & F_BADBOUNDS)) continue;
+              again |= 1 << s;
+              const int b = C.inst[s];
+              for (int i = tid; i < n; i += kTileThreads) { if (Bt.x_out) Bt.x_out[(size_t)b * n + i] = qnan; Bt.xi[(size_t)b * n + i] = 0.0; }
+              for (int r = tid; r < m; r += kTileThreads) {
+                if (Bt.y_out) Bt.y_out[(size_t)b * m + r] = qnan;
+                Bt.z[(size_t)b * m + r] = 0.0; Bt.y[(size_t)b * m + r] = 0.0;
+              }
+              if (tid == 0) {
+                Bt.rho[b] = C.rho[s]; Bt.status[b] = SMPC_UNSOLVED; Bt.iter[b] = 0; Bt.rho_updates[b] = 0;
+                Bt.obj[b] = 0.0; Bt.pri_res[b] = 0.0; Bt.dua_res[b] = 0.0;
+              }
+            }
+            __syncthreads();
+            if (!again) break;
+            if (tid == 0) C.refill_mask = again;
+            for (int e = tid; e < m8 * TB; e += kTileThreads) {
+              const int s = ((e >> 3) / m8) * 8 + (e & 7);
+              if ((again >> s) & 1) { lbp[e] = -1.0; ubp[e] = 1.0; zp[e] = 0.0; yp[e] = 0.0; }
+            }
+            __syncthreads();
+          }
+          if (any_refill) {
+            // q̄ = c D q (osqp_update_lin_cost) of every slot -> S ; q̂ = V' q̄ follows as this pass's GEMM
+            for (int e = tid; e < n8 * TB; e += kTileThreads) {
+              const int s8 = e & 7, rest = e >> 3, i = rest % n8, nb = rest / n8, s = nb * 8 + s8;
+              const int b = C.inst[s];
+              Sp[e] = (b >= 0 && i < n && Bt.q) ? c * (__ldg(P.D + i) * Bt.q[(size_t)b * n + i]) : 0.0;
+            }
+            __syncthreads();
+            run = true;
+          }
+        }
+        if (!run) continue;
+
+        // ---------- the GEMM of this pass: one loop for every operator / panel combination
+        const double2 *op; const double *panel; int kpt, rb0, rb1;
+        switch (pass) {
+          case P_XBAR: op = reinterpret_cast<const double2 *>(K.Vp);  kpt = kpN; panel = xi; rb0 = nrb0; rb1 = nrb1; break;
+          case P_PX:   op = reinterpret_cast<const double2 *>(K.PVp); kpt = kpN; panel = xi; rb0 = nrb0; rb1 = nrb1; break;
+          case P_ATY:  op = reinterpret_cast<const double2 *>(K.ATp); kpt = kpM; panel = yp; rb0 = nrb0; rb1 = nrb1; break;
+          case P_AX:   op = reinterpret_cast<const double2 *>(K.Wp);  kpt = kpN; panel = xi; rb0 = mrb0; rb1 = mrb1; break;
+          case P_ATD:  op = reinterpret_cast<const double2 *>(K.ATp); kpt = kpM; panel = wp; rb0 = nrb0; rb1 = nrb1; break;
+          case P_DX:   op = reinterpret_cast<const double2 *>(K.Vp);  kpt = kpN; panel = Sp; rb0 = nrb0; rb1 = nrb1; break;
+          case P_PD:   op = reinterpret_cast<const double2 *>(K.PVp); kpt = kpN; panel = Sp; rb0 = nrb0; rb1 = nrb1; break;
+          case P_ADX:  op = reinterpret_cast<const double2 *>(K.Wp);  kpt = kpN; panel = Sp; rb0 = mrb0; rb1 = mrb1; break;
+          default:     op = reinterpret_cast<const double2 *>(K.VTp); kpt = kpN; panel = Sp; rb0 = nrb0; rb1 = nrb1; break;
+        }
+        const int krows = kpt * 8;
+        const int nmax_base = pass == P_ATY ? N_RD_S : pass == P_AX ? N_RP_S : pass == P_ATD ? N_ATD : pass == P_DX ? N_DX : N_PD;
+        const int nmax_cnt = pass == P_ATY ? 8 : pass == P_AX ? 6 : (pass == P_ATD || pass == P_DX || pass == P_PD) ? 1 : 0;
+        const int sum_id = pass == P_ATY ? S_OBJ : pass == P_DX ? S_QD : -1;
+        for (int rb = rb0; rb < rb1; rb += kRG) {
+          int rbs[kRG];
+#pragma unroll
+          for (int r = 0; r < kRG; ++r) rbs[r] = min(rb + r, rb1 - 1);
+          double acc[kRG][NB][2];
+          zero_acc(acc);
+          gemm_seg<NB>(op + lane, kpt, rbs, 0, kpt, panel, krows, lane, acc);
+          double mx[NB][8][2], sm[NB][2];
+#pragma unroll
+          for (int nb = 0; nb < NB; ++nb) {
+            sm[nb][0] = sm[nb][1] = 0.0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) mx[nb][j][0] = mx[nb][j][1] = 0.0;
+          }
+#pragma unroll
+          for (int r = 0; r < kRG; ++r) {
+            if (rb + r >= rb1) continue;
+            const int row = 8 * (rb + r) + g;
+#pragma unroll
+            for (int nb = 0; nb < NB; ++nb) {
+              const double a0 = acc[r][nb][0], a1 = acc[r][nb][1];
+              if (pass == P_XBAR) *reinterpret_cast<double2 *>(Tp + pidx(n8, nb, row)) = make_double2(a0, a1);
+              else if (pass == P_PX) *reinterpret_cast<double2 *>(Sp + pidx(n8, nb, row)) = make_double2(a0, a1);
+              else if (pass == P_QH) *reinterpret_cast<double2 *>(qh + pidx(n8, nb, row)) = make_double2(a0, a1);
+              else if (pass == P_ATY) {
+                // dual residual P̄x + q̄ + A̅'y (the owner thread reads back its own x̄ / P̄x entries)
+                const double Di = row < n ? __ldg(P.D + row) : 1.0, Dinv = row < n ? __ldg(P.Dinv + row) : 1.0;
+                const int pi = pidx(n8, nb, row);
+                const double2 xb = *reinterpret_cast<const double2 *>(Tp + pi), px = *reinterpret_cast<const double2 *>(Sp + pi);
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                  const int b = C.inst[nb * 8 + q2 + j];
+                  const double qb = (b >= 0 && row < n && Bt.q) ? c * (Di * Bt.q[(size_t)b * n + row]) : 0.0;
+                  const double aty = j ? a1 : a0, pxj = j ? px.y : px.x, xbj = j ? xb.y : xb.x;
+                  const double rd = (qb + pxj) + aty;
+                  mx[nb][0][j] = fmax(mx[nb][0][j], fabs(rd)); mx[nb][1][j] = fmax(mx[nb][1][j], fabs(qb));
+                  mx[nb][2][j] = fmax(mx[nb][2][j], fabs(aty)); mx[nb][3][j] = fmax(mx[nb][3][j], fabs(pxj));
+                  mx[nb][4][j] = fmax(mx[nb][4][j], fabs(Dinv * rd)); mx[nb][5][j] = fmax(mx[nb][5][j], fabs(Dinv * qb));
+                  mx[nb][6][j] = fmax(mx[nb][6][j], fabs(Dinv * aty)); mx[nb][7][j] = fmax(mx[nb][7][j], fabs(Dinv * pxj));
+                  sm[nb][j] += 0.5 * xbj * pxj + qb * xbj;
+                }
+              } else if (pass == P_AX) {
+                const double Einv = row < m ? __ldg(P.Einv + row) : 1.0;
+                const double2 zz = *reinterpret_cast<const double2 *>(zp + pidx(m8, nb, row));
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                  const double Ax = j ? a1 : a0, zj = j ? zz.y : zz.x, rp = Ax - zj;
+                  mx[nb][0][j] = fmax(mx[nb][0][j], fabs(rp)); mx[nb][1][j] = fmax(mx[nb][1][j], fabs(zj)); mx[nb][2][j] = fmax(mx[nb][2][j], fabs(Ax));
+                  mx[nb][3][j] = fmax(mx[nb][3][j], fabs(Einv * rp)); mx[nb][4][j] = fmax(mx[nb][4][j], fabs(Einv * zj));
+                  mx[nb][5][j] = fmax(mx[nb][5][j], fabs(Einv * Ax));
+                }
+              } else if (pass == P_ATD || pass == P_PD) {
+                const double Dinv = (unscale && row < n) ? __ldg(P.Dinv + row) : 1.0;
+                mx[nb][0][0] = fmax(mx[nb][0][0], fabs(Dinv * a0)); mx[nb][0][1] = fmax(mx[nb][0][1], fabs(Dinv * a1));
+              } else if (pass == P_DX) {
+                const double Di = row < n ? __ldg(P.D + row) : 1.0;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                  const int b = C.inst[nb * 8 + q2 + j];
+                  const double qb = (b >= 0 && row < n && Bt.q) ? c * (Di * Bt.q[(size_t)b * n + row]) : 0.0;
+                  const double dx = j ? a1 : a0;
+                  mx[nb][0][j] = fmax(mx[nb][0][j], fabs(unscale ? Di * dx : dx));
+                  sm[nb][j] += qb * dx;
+                }
+              } else if (row < m) {   // P_ADX: A̅ dx against the finite bounds, plain and 10x tolerance
+                const double Einv = unscale ? __ldg(P.Einv + row) : 1.0;
+                const int pi = pidx(m8, nb, row);
+                const double2 lo = *reinterpret_cast<const double2 *>(lbp + pi), hi = *reinterpret_cast<const double2 *>(ubp + pi);
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                  const int s = nb * 8 + q2 + j;
+                  const double v = Einv * (j ? a1 : a0), nd = nrm(N_DX, s), lj = j ? lo.y : lo.x, hj = j ? hi.y : hi.x;
+                  const double e1 = S.eps_dual_inf * nd, e10 = 10.0 * e1;
+                  const bool fu = hj < kInfty * kMinScaling, fl = lj > -kInfty * kMinScaling;
+                  int bits = 0;
+                  if ((fu && v > e1) || (fl && v < -e1)) bits |= F_BADROW;
+                  if ((fu && v > e10) || (fl && v < -e10)) bits |= F_BADROW << 16;
+                  if (bits) atomicOr(&C.flags[s], bits);
+                }
+              }
+            }
+          }
+#pragma unroll
+          for (int nb = 0; nb < NB; ++nb) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (j < nmax_cnt) {
+                const double v0 = rmax8(mx[nb][j][0]), v1 = rmax8(mx[nb][j][1]);
+                if (g == 0) {
+                  atomicMax(&C.nmax[nmax_base + j][nb * 8 + q2], (unsigned long long)__double_as_longlong(v0));
+                  atomicMax(&C.nmax[nmax_base + j][nb * 8 + q2 + 1], (unsigned long long)__double_as_longlong(v1));
+                }
+              }
+            if (sum_id >= 0) {
+              const double s0 = rsum8(sm[nb][0]), s1 = rsum8(sm[nb][1]);
+              if (g == 0) { C.psum[sum_id][warp][nb * 8 + q2] += s0; C.psum[sum_id][warp][nb * 8 + q2 + 1] += s1; }
+            }
+          }
+        }
+      }
+
+      // ---- w = rho_vec z - y (the w panel carried delta_y); schedule the next event
+      __syncthreads();
+      for (int e = tid; e < m8 * TB; e += kTileThreads) {
+        const int s8 = e & 7, rest = e >> 3, r = rest % m8, nb = rest / m8, s = nb * 8 + s8;
+        const int ct = r < m ? (int)__ldg(P.ctype + r) : 0;
+        wp[e] = rho_of(ct, C.rho[s]) * zp[e] - yp[e];
+      }
+      if (tid == 0) {
+        int act = 0, ne = 0x7fffffff;
+        for (int s = 0; s < TB; ++s) {
+          if (C.inst[s] < 0) continue;
+          ++act;
+          const int li = k - C.it0[s];
+          int nx = S.max_iter;
+          if (check_every > 0) nx = min(nx, (li / check_every + 1) * check_every);
+          if (adapt_every > 0) nx = min(nx, (li / adapt_every + 1) * adapt_every);
+          ne = min(ne, C.it0[s] + nx);
+        }
+        C.active = act; C.next_event = ne; C.refill_mask = 0;
+      }
+      __syncthreads();
+      initial = false;
+      if (C.active == 0) break;
+    }
+
+    // ================= one ADMM iteration for the whole tile
+    ++k;
+    event = (k == C.next_event);
+    const double *xi = p ? xi1 : xi0;
+    double *xin = p ? xi0 : xi1;
+    const double2 *M1l = reinterpret_cast<const double2 *>(K.M1) + lane, *Wl = reinterpret_cast<const double2 *>(K.Wp) + lane;
+    // ---- GEMM 1: T = ([sigma G | W'] [xi; w] - q̂) .* dinv ; xi' = alpha T + (1 - alpha) xi
+    for (int rb = nrb0; rb < nrb1; rb += kRG) {
+      int rbs[kRG];
+#pragma unroll
+      for (int r = 0; r < kRG; ++r) rbs[r] = min(rb + r, nrb1 - 1);
+      double acc[kRG][NB][2];
+      zero_acc(acc);
+#pragma unroll 1
+      for (int seg = 0; seg < 2; ++seg)
+        gemm_seg<NB>(M1l, kpN + kpM, rbs, seg ? kpN : 0, seg ? kpM : kpN, seg ? wp : xi, seg ? m8 : n8, lane, acc);
+#pragma unroll
+      for (int r = 0; r < kRG; ++r)
+        if (rb + r < nrb1) {
+#pragma unroll
+          for (int nb = 0; nb < NB; ++nb) {
+            const int pi = pidx(n8, nb, 8 * (rb + r) + g);
+            const double2 qv = *reinterpret_cast<const double2 *>(qh + pi), dv = *reinterpret_cast<const double2 *>(dinv + pi);
+            const double2 xo = *reinterpret_cast<const double2 *>(xi + pi);
+            const double t0 = (acc[r][nb][0] - qv.x) * dv.x, t1 = (acc[r][nb][1] - qv.y) * dv.y;
+            *reinterpret_cast<double2 *>(Tp + pi) = make_double2(t0, t1);
+            *reinterpret_cast<double2 *>(xin + pi) = make_double2(alpha * t0 + oma * xo.x, alpha * t1 + oma * xo.y);
+          }
+        }
+    }
+    __syncthreads();
+    // ---- GEMM 2: z̃ = W T ; z, y updates (OSQP update_z / update_y) ; w = rho_vec z - y
+    for (int rb = mrb0; rb < mrb1; rb += kRG) {
+      int rbs[kRG];
+#pragma unroll
+      for (int r = 0; r < kRG; ++r) rbs[r] = min(rb + r, mrb1 - 1);
+      double acc[kRG][NB][2];
+      zero_acc(acc);
+      gemm_seg<NB>(Wl, kpN, rbs, 0, kpN, Tp, n8, lane, acc);
+#pragma unroll
+      for (int r = 0; r < kRG; ++r)
+        if (rb + r < mrb1) {
+          const int row = 8 * (rb + r) + g;
+          const int ct = row < m ? (int)__ldg(P.ctype + row) : 0;
+#pragma unroll
+          for (int nb = 0; nb < NB; ++nb) {
+            const int pi = pidx(m8, nb, row), s = nb * 8 + q2;
+            const double2 zo = *reinterpret_cast<const double2 *>(zp + pi), yo = *reinterpret_cast<const double2 *>(yp + pi);
+            const double2 lo = *reinterpret_cast<const double2 *>(lbp + pi), hi = *reinterpret_cast<const double2 *>(ubp + pi);
+            double rv0, rv1, ri0, ri1;
+            if (ct == 0) { rv0 = C.rho[s]; rv1 = C.rho[s + 1]; ri0 = C.rinv[s]; ri1 = C.rinv[s + 1]; }
+            else if (ct == 1) { rv0 = C.rho_eq[s]; rv1 = C.rho_eq[s + 1]; ri0 = C.rinv_eq[s]; ri1 = C.rinv_eq[s + 1]; }
+            else { rv0 = rv1 = kRhoMin; ri0 = ri1 = 1.0 / kRhoMin; }
+            const double zr0 = alpha * acc[r][nb][0] + oma * zo.x, zr1 = alpha * acc[r][nb][1] + oma * zo.y;
+            const double zn0 = fmin(fmax(zr0 + ri0 * yo.x, lo.x), hi.x), zn1 = fmin(fmax(zr1 + ri1 * yo.y, lo.y), hi.y);
+            const double d0 = rv0 * (zr0 - zn0), d1 = rv1 * (zr1 - zn1);
+            const double yn0 = yo.x + d0, yn1 = yo.y + d1;
+            *reinterpret_cast<double2 *>(zp + pi) = make_double2(zn0, zn1);
+            *reinterpret_cast<double2 *>(yp + pi) = make_double2(yn0, yn1);
+            // before an event the w panel carries delta_y (is_primal_infeasible); w is rebuilt after the event
+            *reinterpret_cast<double2 *>(wp + pi) = event ? make_double2(d0, d1) : make_double2(rv0 * zn0 - yn0, rv1 * zn1 - yn1);
+          }
+        }
+    }
+    __syncthreads();
+    p ^= 1;
+  }
+}
+
+bool tile_kernel_supports(int n, int m) { return tile_kernel_nb(n, m) > 0; }
+
+size_t tile_smem_bytes(int n, int m, int nb) {
+  const size_t n8 = (n + 7) & ~7, m8 = (m + 7) & ~7, TB = 8 * nb;
+  const size_t ctl = nb == 1 ? sizeof(TileCtl<8>) : sizeof(TileCtl<16>);
+  return (6 * n8 + 5 * m8) * TB * sizeof(double) + ctl;
+}
+
+int tile_kernel_nb(int n, int m) {
+  if (n < 1 || m < 0) return 0;
+  const size_t cap = 227 * 1024;
+  if (tile_smem_bytes(n, m, 2) <= cap) return 2;
+  if (tile_smem_bytes(n, m, 1) <= cap) return 1;
+  return 0;
+}
+
+cudaError_t launch_admm_shared_tile(const TilePackDev &K, const SharedPlanDev &P, const BatchDev &Bt, const SettingsDev &S,
+                                    int *queue, int nb, int num_sms, cudaStream_t stream) {
+  if (nb == 0) nb = tile_kernel_nb(P.n, P.m);
+  if (nb != 1 && nb != 2) return cudaErrorInvalidValue;
+  const size_t smem = tile_smem_bytes(P.n, P.m, nb);
+  if (smem > 227 * 1024) return cudaErrorInvalidValue;
+  cudaError_t e = cudaMemsetAsync(queue, 0, sizeof(int), stream);
+  if (e != cudaSuccess) return e;
+  const int TB = 8 * nb;
+  int grid = (Bt.B + TB - 1) / TB;
+  // one CTA per SM when the tile fills shared memory; small problems let several CTAs share an SM
+  int per_sm = (int)((227 * 1024) / (smem + 1024));
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 4) per_sm = 4;
+  if (grid > num_sms * per_sm) grid = num_sms * per_sm;
+  if (nb == 1) {
+    e = cudaFuncSetAttribute(admm_shared_tile_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    admm_shared_tile_kernel<1><<<grid, kTileThreads, smem, stream>>>(K, P, Bt, S, queue);
+  } else {
+    e = cudaFuncSetAttribute(admm_shared_tile_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    admm_shared_tile_kernel<2><<<grid, kTileThreads, smem, stream>>>(K, P, Bt, S, queue);
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace smpc

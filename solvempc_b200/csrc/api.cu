@@ -64,6 +64,9 @@ struct smpc_solver {
   DeviceBuf packbuf;                                  // small-kernel operator pack + work queue
   smpc::SmallPackDev dpack{};
   int *d_queue = nullptr, *d_lists = nullptr;
+  DeviceBuf tilebuf;                                  // tile-kernel operator packs (DMMA A fragments) + work queue
+  smpc::TilePackDev dtile{};
+  int tile_nb = 0;
   int num_sms = 148;
   bool schedule = true;   // longest-expected-first pre-pass of the small kernel
   long long launches = 0;
@@ -201,6 +204,53 @@ int upload_small_pack(smpc_solver *s) {
   return SMPC_OK;
 }
 
+// DMMA A-fragment packs for admm_shared_tile_kernel (layout: device_types.cuh TilePackDev)
+int upload_tile_pack(smpc_solver *s) {
+  const smpc::SharedPlan &p = s->plan;
+  const int n = p.n, m = p.m, n8 = (n + 7) & ~7, m8 = (m + 7) & ~7;
+  auto pack = [](int rows8, int K8, auto &&at) {
+    std::vector<double> out((size_t)rows8 * K8);
+    const int kpt = K8 / 8;
+    for (int rb = 0; rb < rows8 / 8; ++rb)
+      for (int kp = 0; kp < kpt; ++kp)
+        for (int lane = 0; lane < 32; ++lane)
+          for (int j = 0; j < 2; ++j)
+            out[(((size_t)rb * kpt + kp) * 32 + lane) * 2 + j] = at(8 * rb + lane / 4, 8 * kp + 4 * j + lane % 4);
+    return out;
+  };
+  auto M1 = pack(n8, n8 + m8, [&](int i, int k) -> double {
+    if (i >= n) return 0.0;
+    if (k < n8) return k < n ? p.SG[(size_t)i * n + k] : 0.0;
+    const int r = k - n8;
+    return r < m ? p.W[(size_t)r * n + i] : 0.0;
+  });
+  auto Wp = pack(m8, n8, [&](int r, int k) -> double { return (r < m && k < n) ? p.W[(size_t)r * n + k] : 0.0; });
+  auto VTp = pack(n8, n8, [&](int i, int k) -> double { return (i < n && k < n) ? p.V[(size_t)k * n + i] : 0.0; });
+  auto Vp = pack(n8, n8, [&](int i, int k) -> double { return (i < n && k < n) ? p.V[(size_t)i * n + k] : 0.0; });
+  auto PVp = pack(n8, n8, [&](int i, int k) -> double { return (i < n && k < n) ? p.PVT[(size_t)k * n + i] : 0.0; });
+  auto ATp = pack(n8, m8, [&](int i, int r) -> double { return (i < n && r < m) ? p.Abar[(size_t)r * n + i] : 0.0; });
+  size_t bytes = DeviceBuf::need(sizeof(int) * 4);
+  for (const std::vector<double> *v : {&M1, &Wp, &VTp, &Vp, &PVp, &ATp}) bytes += DeviceBuf::need((v->size() ? v->size() : 1) * sizeof(double));
+  CK(s->tilebuf.alloc(bytes));
+  auto put = [&](const std::vector<double> &v, const double **dst) -> cudaError_t {
+    double *d = s->tilebuf.take<double>(v.size() ? v.size() : 1);
+    *dst = d;
+    if (v.empty()) return cudaSuccess;
+    return cudaMemcpy(d, v.data(), v.size() * sizeof(double), cudaMemcpyHostToDevice);
+  };
+  smpc::TilePackDev &k = s->dtile;
+  k.n8 = n8; k.m8 = m8;
+  CK(put(M1, &k.M1)); CK(put(Wp, &k.Wp)); CK(put(VTp, &k.VTp)); CK(put(Vp, &k.Vp)); CK(put(PVp, &k.PVp)); CK(put(ATp, &k.ATp));
+  s->d_queue = s->tilebuf.take<int>(4);
+  if (!s->d_queue) return fail(SMPC_ERR_CUDA, "internal: tile buffer carve-out overflow");
+  CK(cudaMemset(s->d_queue, 0, sizeof(int) * 4));
+  int sms = 0;
+  CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
+  s->num_sms = sms > 0 ? sms : 148;
+  s->tile_nb = smpc::tile_kernel_nb(n, m);
+  return SMPC_OK;
+}
+
 int alloc_batch(smpc_solver *s) {
   const size_t n = s->n, m = s->m, B = s->B;
   size_t bytes = 0;
@@ -273,11 +323,16 @@ int create_shared_common(smpc_solver **out, int device, int n, int m, int batch,
   }
   if (rc == SMPC_OK) { cudaError_t e = cudaStreamSynchronize(s->stream); if (e != cudaSuccess) rc = cuda_fail(e, "setup sync"); }
   s->kernel = 1;
+  if (rc == SMPC_OK && settings->kernel != 0 && settings->kernel != 1 && settings->kernel != 2 && settings->kernel != 4)
+    rc = fail(SMPC_ERR_ARG, "settings.kernel must be 0 (auto), 1 (generic), 2 (small) or 4 (tile)");
   if (rc == SMPC_OK && (settings->kernel == 2 || (settings->kernel == 0 && smpc::small_kernel_supports(n, m)))) {
     if (!smpc::small_kernel_supports(n, m)) rc = fail(SMPC_ERR_ARG, "kernel 2 (register-resident) supports n <= 16, m <= 32 only");
     else { s->kernel = 2; rc = upload_small_pack(s); }
+  } else if (rc == SMPC_OK && (settings->kernel == 4 || (settings->kernel == 0 && smpc::tile_kernel_supports(n, m)))) {
+    if (!smpc::tile_kernel_supports(n, m)) rc = fail(SMPC_ERR_ARG, "kernel 4 (DMMA tile): the iterates of 8 QPs do not fit shared memory");
+    else { s->kernel = 4; rc = upload_tile_pack(s); }
   }
-  if (rc != SMPC_OK) { s->planbuf.release(); s->batchbuf.release(); s->packbuf.release(); delete s; return rc; }
+  if (rc != SMPC_OK) { s->planbuf.release(); s->batchbuf.release(); s->packbuf.release(); s->tilebuf.release(); delete s; return rc; }
   *out = s;
   return SMPC_OK;
 }
@@ -385,7 +440,7 @@ int smpc_solver_destroy(smpc_solver *s) {
   if (!s) return SMPC_OK;
   cudaSetDevice(s->device);
   cudaStreamSynchronize(s->stream);
-  s->planbuf.release(); s->batchbuf.release(); s->packbuf.release(); s->instbuf.release();
+  s->planbuf.release(); s->batchbuf.release(); s->packbuf.release(); s->instbuf.release(); s->tilebuf.release();
   delete s;
   return SMPC_OK;
 }
@@ -467,6 +522,7 @@ int smpc_solver_solve(smpc_solver *s) {
   }
   cudaError_t e = s->regime == 1 ? smpc::launch_admm_instance(s->dinst, b, sd, s->stream)
                   : s->kernel == 2 ? smpc::launch_admm_shared_small(s->dpack, s->dplan, b, sd, s->d_queue, s->schedule ? s->d_lists : nullptr, s->num_sms, s->stream)
+                  : s->kernel == 4 ? smpc::launch_admm_shared_tile(s->dtile, s->dplan, b, sd, s->d_queue, s->tile_nb, s->num_sms, s->stream)
                                    : smpc::launch_admm_shared_generic(s->dplan, b, sd, s->stream);
   if (e != cudaSuccess) return cuda_fail(e, "ADMM kernel launch");
   if (s->timing) { CK(cudaEventRecord(ev1, s->stream)); s->events.emplace_back(ev0, ev1); }
@@ -573,7 +629,8 @@ int smpc_solver_get_scaling(smpc_solver *s, double *D, double *E, double *c) {
 long long smpc_solver_launch_count(const smpc_solver *s) { return s ? s->launches : 0; }
 const char *smpc_solver_kernel_name(const smpc_solver *s) {
   if (!s) return "";
-  return s->regime == 1 ? "admm_instance_kernel" : s->kernel == 2 ? "admm_shared_small_kernel" : "admm_shared_generic_kernel";
+  return s->regime == 1 ? "admm_instance_kernel" : s->kernel == 2 ? "admm_shared_small_kernel"
+         : s->kernel == 4 ? "admm_shared_tile_kernel" : "admm_shared_generic_kernel";
 }
 
 /* host-only inspection of the shared plan (no device needed): used by the CPU tests of the host logic */

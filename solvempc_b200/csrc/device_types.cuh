@@ -42,6 +42,20 @@ struct SmallPackDev {
   const int *ctype;               // [32]
 };
 
+// DMMA A-fragment packs of the plan for the tile kernel (admm_shared_tile.cu).  An operator Op (rows x K, both
+// zero-padded to multiples of 8) is stored as [row-block][k-pair][lane][2]:
+//   pack[((rb*(K8/8) + kp)*32 + lane)*2 + j] = Op[8 rb + lane/4][8 kp + 4 j + lane%4]
+// i.e. one 16-byte load per lane feeds two mma.sync.m8n8k4.f64 A operands.
+struct TilePackDev {
+  int n8, m8;          // n, m rounded up to multiples of 8
+  const double *M1;    // [sigma*G | W']  n8 x (n8 + m8)
+  const double *Wp;    // W = A̅V          m8 x n8
+  const double *VTp;   // V'              n8 x n8   (q̂ = V' q̄)
+  const double *Vp;    // V               n8 x n8   (x̄ = V xi)
+  const double *PVp;   // P̄V              n8 x n8
+  const double *ATp;   // A̅'              n8 x m8
+};
+
 // per-instance regime: every QP has its own (scaled) P̄_i, A̅_i and scaling
 struct InstanceDataDev {
   int n, m, B;

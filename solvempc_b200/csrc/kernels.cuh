@@ -21,6 +21,13 @@ int small_queue_ints();
 cudaError_t launch_admm_shared_small(const SmallPackDev &K, const SharedPlanDev &P, const BatchDev &Bt,
                                      const SettingsDev &S, int *queue, int *lists, int num_sms, cudaStream_t stream);
 
+// admm_shared_tile.cu : DMMA tile kernel for mid-size QPs (8 or 16 QPs per CTA, iterates in shared memory)
+bool tile_kernel_supports(int n, int m);
+int tile_kernel_nb(int n, int m);                 // 8-slot blocks per tile that fit shared memory (0 = unsupported)
+size_t tile_smem_bytes(int n, int m, int nb);
+cudaError_t launch_admm_shared_tile(const TilePackDev &K, const SharedPlanDev &P, const BatchDev &Bt, const SettingsDev &S,
+                                    int *queue, int nb, int num_sms, cudaStream_t stream);
+
 // admm_instance.cu : per-instance regime (own P_i, A_i per QP; batched Cholesky in shared memory)
 cudaError_t launch_ruiz_instance(const InstanceDataDev &I, int iters, cudaStream_t stream);
 cudaError_t launch_admm_instance(const InstanceDataDev &I, const BatchDev &Bt, const SettingsDev &S, cudaStream_t stream);
