@@ -8,7 +8,7 @@
 // PANELS (the 8 slots of a panel are the N dimension of the DMMA).  Per iteration (OSQP 0.6.x osqp_solve in
 // plan coordinates, reference call site src/ModelPredictiveControlAPI.cpp:102; same maths as admm_shared_generic.cu):
 //     T  = ([sigma*G | W'] [xi; w] - q̂) .* dinv            GEMM 1, K = n + m      dinv = 1/(1 + rho_b*lambda_i)
-//     xi'= alpha T + (1-alpha) xi                           (double-buffered panel)
+//     xi'= alpha T + (1-alpha) xi                           (after the barrier, by the warp that owns the rows)
 //     Z̃  = W T                                              GEMM 2, K = n
 //     z, y, w = rho_vec z - y                               epilogue of GEMM 2 (clip to [l̄, ū], dual update)
 // with two CTA barriers per iteration.  Slots are independent QPs: each has its own rho, iteration counter and
@@ -40,7 +40,7 @@ enum NormId {
 enum SumId { S_OBJ, S_LHS, S_QD, S_COUNT };
 
 __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
                : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
 __device__ __forceinline__ double2 ldg_stream(const double2 *p) {
@@ -70,45 +70,63 @@ enum SlotFlag { F_DUE_CHECK = 1, F_DUE_ADAPT = 2, F_AT_MAX = 4, F_PRIM_OK = 8, F
                 F_NEED_DINF = 64, F_BADROW = 128, F_DONE = 256, F_NEED_ATD = 512, F_NEED_DINF2 = 1024, F_RHO_NEW = 2048,
                 F_BADBOUNDS = 4096, F_CADENCE = 8192 };
 
-// acc[r][nb] += Op[rows of rbs[r]] (k-pairs kp0 .. kp0+cnt) * panel   (panel rows = k, [nb][krows][8])
-template <int NB>
-__device__ __forceinline__ void gemm_seg(const double2 *__restrict__ opl, int kpt, const int (&rbs)[kRG], int kp0, int cnt,
-                                         const double *panel, int krows, int lane, double (&acc)[kRG][NB][2]) {
-  const double2 *ap[kRG];
+// acc[r][nb] += Op[row-blocks rb .. rb+NR) (k-pairs kp0 .. kp0+cnt) * panel.  opl = pack + lane; kpt = k-pairs per
+// operator row-block; bp = panel + (lane&3)*8 + (lane>>2) (+ 64*first k-pair); nbs = doubles between 8-slot blocks.
+// The A fragments run kRing k-pairs ahead of their use in a register ring (covers the L2 latency); the main loop is
+// branch-free (prefetches past the end are clamped to the last k-pair).
+template <int NB, int NR>
+__device__ __forceinline__ void gemm_run(const double2 *__restrict__ opl, int kpt, int rb, int kp0, int cnt,
+                                         const double *bp, int nbs, double (&acc)[kRG][NB][2]) {
+  const double2 *ap[NR];
 #pragma unroll
-  for (int r = 0; r < kRG; ++r) ap[r] = opl + ((size_t)rbs[r] * kpt + kp0) * 32;
-  const double *bp = panel + (lane & 3) * 8 + (lane >> 2);
-  double2 ring[kRing][kRG];
+  for (int r = 0; r < NR; ++r) ap[r] = opl + ((size_t)(rb + r) * kpt + kp0) * 32;
+  double2 ring[kRing][NR];
 #pragma unroll
-  for (int d = 0; d < kRing; ++d)
-    if (d < cnt) {
+  for (int d = 0; d < kRing; ++d) {
+    const int kk = min(d, cnt - 1) * 32;
 #pragma unroll
-      for (int r = 0; r < kRG; ++r) ring[d][r] = ldg_stream(ap[r] + d * 32);
-    }
-  for (int kp = 0; kp < cnt; kp += kRing) {
+    for (int r = 0; r < NR; ++r) ring[d][r] = ldg_stream(ap[r] + kk);
+  }
+  int kp = 0;
+  for (; kp + kRing <= cnt; kp += kRing) {
 #pragma unroll
     for (int d = 0; d < kRing; ++d) {
-      if (kp + d < cnt) {
-        double b[NB][2];
+      double b[NB][2];
 #pragma unroll
-        for (int nb = 0; nb < NB; ++nb) {
-          b[nb][0] = bp[(nb * krows + 8 * (kp + d)) * 8];
-          b[nb][1] = bp[(nb * krows + 8 * (kp + d) + 4) * 8];
-        }
-        double2 a[kRG];
+      for (int nb = 0; nb < NB; ++nb) { b[nb][0] = bp[nb * nbs + d * 64]; b[nb][1] = bp[nb * nbs + d * 64 + 32]; }
+      double2 a[NR];
 #pragma unroll
-        for (int r = 0; r < kRG; ++r) a[r] = ring[d][r];
-        if (kp + d + kRing < cnt) {
+      for (int r = 0; r < NR; ++r) a[r] = ring[d][r];
+      const int kk = min(kp + d + kRing, cnt - 1) * 32;
 #pragma unroll
-          for (int r = 0; r < kRG; ++r) ring[d][r] = ldg_stream(ap[r] + (kp + d + kRing) * 32);
-        }
+      for (int r = 0; r < NR; ++r) ring[d][r] = ldg_stream(ap[r] + kk);
 #pragma unroll
-        for (int r = 0; r < kRG; ++r)
+      for (int r = 0; r < NR; ++r)
 #pragma unroll
-          for (int nb = 0; nb < NB; ++nb) { dmma(acc[r][nb], a[r].x, b[nb][0]); dmma(acc[r][nb], a[r].y, b[nb][1]); }
+        for (int nb = 0; nb < NB; ++nb) { dmma(acc[r][nb], a[r].x, b[nb][0]); dmma(acc[r][nb], a[r].y, b[nb][1]); }
+    }
+    bp += kRing * 64;
+  }
+#pragma unroll
+  for (int d = 0; d < kRing - 1; ++d)
+    if (kp + d < cnt) {
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb) {
+        const double b0 = bp[nb * nbs + d * 64], b1 = bp[nb * nbs + d * 64 + 32];
+#pragma unroll
+        for (int r = 0; r < NR; ++r) { dmma(acc[r][nb], ring[d][r].x, b0); dmma(acc[r][nb], ring[d][r].y, b1); }
       }
     }
-  }
+}
+// nr (1..kRG) row-blocks starting at rb: dispatch to the compile-time variants (nr is warp-uniform)
+template <int NB>
+__device__ __forceinline__ void gemm_seg(const double2 *__restrict__ opl, int kpt, int rb, int nr, int kp0, int cnt,
+                                         const double *bp, int nbs, double (&acc)[kRG][NB][2]) {
+  if (cnt <= 0) return;
+  if (nr >= 4) gemm_run<NB, 4>(opl, kpt, rb, kp0, cnt, bp, nbs, acc);
+  else if (nr == 3) gemm_run<NB, 3>(opl, kpt, rb, kp0, cnt, bp, nbs, acc);
+  else if (nr == 2) gemm_run<NB, 2>(opl, kpt, rb, kp0, cnt, bp, nbs, acc);
+  else gemm_run<NB, 1>(opl, kpt, rb, kp0, cnt, bp, nbs, acc);
 }
 
 // max over the 8 row-groups of a warp (lanes with equal lane&3 hold the same slot pair)
@@ -136,8 +154,11 @@ admm_shared_tile_kernel(TilePackDev K, SharedPlanDev P, BatchDev Bt, SettingsDev
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, q2 = 2 * (lane & 3);
   // panels
-  double *xi0 = smem, *xi1 = xi0 + n8 * TB, *Tp = xi1 + n8 * TB, *qh = Tp + n8 * TB, *dinv = qh + n8 * TB, *Sp = dinv + n8 * TB;
-  double *wp = Sp + n8 * TB, *zp = wp + m8 * TB, *yp = zp + m8 * TB, *lbp = yp + m8 * TB, *ubp = lbp + m8 * TB;
+  // cv = [xi; w] as ONE panel of n8 + m8 rows per 8-slot block (the K dimension of GEMM 1)
+  const int cvr = n8 + m8;
+  double *cv = smem, *Tp = cv + cvr * TB, *qh = Tp + n8 * TB, *dinv = qh + n8 * TB, *Sp = dinv + n8 * TB, *Dp = Sp + n8 * TB;
+  double *zp = Dp + n8 * TB, *yp = zp + m8 * TB, *lbp = yp + m8 * TB, *ubp = lbp + m8 * TB;
+  const int bfrag = (lane & 3) * 8 + (lane >> 2);     // this lane's element of a B fragment
   TileCtl<TB> &C = *reinterpret_cast<TileCtl<TB> *>(ubp + m8 * TB);
   const int NRB = n8 >> 3, MRB = m8 >> 3;
   const int nrb0 = (warp * NRB) / kTileWarps, nrb1 = ((warp + 1) * NRB) / kTileWarps;
@@ -153,6 +174,8 @@ admm_shared_tile_kernel(TilePackDev K, SharedPlanDev P, BatchDev Bt, SettingsDev
       for (int nb = 0; nb < NB; ++nb) acc[r][nb][0] = acc[r][nb][1] = 0.0;
   };
   auto pidx = [&](int rows, int nb, int row) { return (nb * rows + row) * 8 + q2; };   // this thread's double2 in a panel
+  auto xi_at = [&](int e_n) { const int nb = e_n / (n8 * 8); return e_n + nb * m8 * 8; };            // n-panel index -> cv index (xi part)
+  auto w_at = [&](int e_m) { const int nb = e_m / (m8 * 8); return e_m + (nb + 1) * n8 * 8; };        // m-panel index -> cv index (w part)
 
   // ---- init: empty tile
   for (int e = tid; e < (6 * n8 + 5 * m8) * TB; e += kTileThreads) smem[e] = 0.0;
@@ -167,7 +190,6 @@ admm_shared_tile_kernel(TilePackDev K, SharedPlanDev P, BatchDev Bt, SettingsDev
   __syncthreads();
 
   int k = 0;       // tile iteration counter
-  int p = 0;       // current xi buffer
   bool event = true, initial = true;
 
   for (;;) {
@@ -178,8 +200,6 @@ admm_shared_tile_kernel(TilePackDev K, SharedPlanDev P, BatchDev Bt, SettingsDev
       const bool unscale = !S.scaled_termination;
       const double qnan = __longlong_as_double(0x7ff8000000000000LL);
       const bool warm = S.warm_start && !Bt.fresh;
-      double *xi = p ? xi1 : xi0;            // current xi
-      double *xio = p ? xi0 : xi1;           // previous xi
       auto nrm = [&](int id, int s) { return __longlong_as_double((long long)C.nmax[id][s]); };
       auto total = [&](int id, int s) { double a = 0.0; for (int w = 0; w < kTileWarps; ++w) a += C.psum[id][w][s]; return a; };
       auto any_flags = [&]() { int a = 0; for (int s = 0; s < TB; ++s) a |= C.flags[s]; return a; };
@@ -237,7 +257,7 @@ admm_shared_tile_kernel(TilePackDev K, SharedPlanDev P, BatchDev Bt, SettingsDev
 #pragma unroll
                 for (int nb = 0; nb < NB; ++nb) {
                   const int pi = pidx(m8, nb, row);
-                  const double2 d = *reinterpret_cast<const double2 *>(wp + pi);
+                  const double2 d = *reinterpret_cast<const double2 *>(cv + pidx(cvr, nb, n8 + row));
                   const double2 lo = *reinterpret_cast<const double2 *>(lbp + pi), hi = *reinterpret_cast<const double2 *>(ubp + pi);
                   double dd[2] = {d.x, d.y}, nd[2];
                   const double lo2[2] = {lo.x, lo.y}, hi2[2] = {hi.x, hi.y};
@@ -251,7 +271,7 @@ admm_shared_tile_kernel(TilePackDev K, SharedPlanDev P, BatchDev Bt, SettingsDev
                     if (dp != 0.0) lh[nb][j] += hi2[j] * dp;
                     if (dm != 0.0) lh[nb][j] += lo2[j] * dm;
                   }
-                  *reinterpret_cast<double2 *>(wp + pi) = make_double2(dd[0], dd[1]);
+                  *reinterpret_cast<double2 *>(cv + pidx(cvr, nb, n8 + row)) = make_double2(dd[0], dd[1]);
                   const double v0 = rmax8(nd[0]), v1 = rmax8(nd[1]);
                   if (g == 0) {
                     atomicMax(&C.nmax[N_DY][nb * 8 + q2], (unsigned long long)__double_as_longlong(v0));
@@ -275,11 +295,7 @@ admm_shared_tile_kernel(TilePackDev K, SharedPlanDev P, BatchDev Bt, SettingsDev
             run = (any & F_NEED_ATD) != 0;
           }
         } else if (pass == P_DX) {
-          if (any & F_NEED_DINF) {
-            for (int e = tid; e < n8 * TB; e += kTileThreads) Sp[e] = xi[e] - xio[e];     // delta_xi
-            __syncthreads();
-            run = true;
-          }
+          run = (any & F_NEED_DINF) != 0;     // delta_xi of the event iteration is in the Dp panel
         } else if (pass == P_PD) {
           if (any & F_NEED_DINF) {
             __syncthreads();
@@ -358,9 +374,9 @@ admm_shared_tile_kernel(TilePackDev K, SharedPlanDev P, BatchDev Bt, SettingsDev
                 const int b = C.inst[s], st = C.status[s];
                 const bool has_sol = !(st == SMPC_PRIMAL_INFEASIBLE || st == SMPC_PRIMAL_INFEASIBLE_INACCURATE || st == SMPC_DUAL_INFEASIBLE || st == SMPC_DUAL_INFEASIBLE_INACCURATE);
                 if (Bt.x_out) Bt.x_out[(size_t)b * n + i] = has_sol ? __ldg(P.D + i) * Tp[e] : qnan;
-                Bt.xi[(size_t)b * n + i] = has_sol ? xi[e] : 0.0;
+                Bt.xi[(size_t)b * n + i] = has_sol ? cv[xi_at(e)] : 0.0;
               }
-              xi0[e] = 0.0; xi1[e] = 0.0; Tp[e] = 0.0; qh[e] = 0.0; dinv[e] = 1.0;   // an unfilled slot iterates on zeros
+              cv[xi_at(e)] = 0.0; Dp[e] = 0.0; Tp[e] = 0.0; qh[e] = 0.0; dinv[e] = 1.0;   // an unfilled slot iterates on zeros
             }
           }
           if (done) {
@@ -405,7 +421,7 @@ admm_shared_tile_kernel(TilePackDev K, SharedPlanDev P, BatchDev Bt, SettingsDev
               if (!((mask >> s) & 1)) continue;
               const int b = C.inst[s];
               const double v = (b >= 0 && i < n && warm) ? Bt.xi[(size_t)b * n + i] : 0.0;
-              xi0[e] = v; xi1[e] = v;
+              cv[xi_at(e)] = v; Dp[e] = 0.0;
               dinv[e] = b >= 0 ? 1.0 / (1.0 + C.rho[s] * (i < n ? __ldg(P.lam + i) : 0.0)) : 1.0;
             }
             for (int e = tid; e < m8 * TB; e += kTileThreads) {
@@ -462,29 +478,25 @@ admm_shared_tile_kernel(TilePackDev K, SharedPlanDev P, BatchDev Bt, SettingsDev
         if (!run) continue;
 
         // ---------- the GEMM of this pass: one loop for every operator / panel combination
-        const double2 *op; const double *panel; int kpt, rb0, rb1;
+        const double2 *op; const double *panel; int kpt, rb0, rb1, krows;   // krows: panel rows per 8-slot block
         switch (pass) {
-          case P_XBAR: op = reinterpret_cast<const double2 *>(K.Vp);  kpt = kpN; panel = xi; rb0 = nrb0; rb1 = nrb1; break;
-          case P_PX:   op = reinterpret_cast<const double2 *>(K.PVp); kpt = kpN; panel = xi; rb0 = nrb0; rb1 = nrb1; break;
-          case P_ATY:  op = reinterpret_cast<const double2 *>(K.ATp); kpt = kpM; panel = yp; rb0 = nrb0; rb1 = nrb1; break;
-          case P_AX:   op = reinterpret_cast<const double2 *>(K.Wp);  kpt = kpN; panel = xi; rb0 = mrb0; rb1 = mrb1; break;
-          case P_ATD:  op = reinterpret_cast<const double2 *>(K.ATp); kpt = kpM; panel = wp; rb0 = nrb0; rb1 = nrb1; break;
-          case P_DX:   op = reinterpret_cast<const double2 *>(K.Vp);  kpt = kpN; panel = Sp; rb0 = nrb0; rb1 = nrb1; break;
-          case P_PD:   op = reinterpret_cast<const double2 *>(K.PVp); kpt = kpN; panel = Sp; rb0 = nrb0; rb1 = nrb1; break;
-          case P_ADX:  op = reinterpret_cast<const double2 *>(K.Wp);  kpt = kpN; panel = Sp; rb0 = mrb0; rb1 = mrb1; break;
-          default:     op = reinterpret_cast<const double2 *>(K.VTp); kpt = kpN; panel = Sp; rb0 = nrb0; rb1 = nrb1; break;
+          case P_XBAR: op = reinterpret_cast<const double2 *>(K.Vp);  kpt = kpN; panel = cv;          krows = cvr; rb0 = nrb0; rb1 = nrb1; break;
+          case P_PX:   op = reinterpret_cast<const double2 *>(K.PVp); kpt = kpN; panel = cv;          krows = cvr; rb0 = nrb0; rb1 = nrb1; break;
+          case P_ATY:  op = reinterpret_cast<const double2 *>(K.ATp); kpt = kpM; panel = yp;          krows = m8;  rb0 = nrb0; rb1 = nrb1; break;
+          case P_AX:   op = reinterpret_cast<const double2 *>(K.Wp);  kpt = kpN; panel = cv;          krows = cvr; rb0 = mrb0; rb1 = mrb1; break;
+          case P_ATD:  op = reinterpret_cast<const double2 *>(K.ATp); kpt = kpM; panel = cv + n8 * 8; krows = cvr; rb0 = nrb0; rb1 = nrb1; break;
+          case P_DX:   op = reinterpret_cast<const double2 *>(K.Vp);  kpt = kpN; panel = Dp;          krows = n8;  rb0 = nrb0; rb1 = nrb1; break;
+          case P_PD:   op = reinterpret_cast<const double2 *>(K.PVp); kpt = kpN; panel = Dp;          krows = n8;  rb0 = nrb0; rb1 = nrb1; break;
+          case P_ADX:  op = reinterpret_cast<const double2 *>(K.Wp);  kpt = kpN; panel = Dp;          krows = n8;  rb0 = mrb0; rb1 = mrb1; break;
+          default:     op = reinterpret_cast<const double2 *>(K.VTp); kpt = kpN; panel = Sp;          krows = n8;  rb0 = nrb0; rb1 = nrb1; break;
         }
-        const int krows = kpt * 8;
         const int nmax_base = pass == P_ATY ? N_RD_S : pass == P_AX ? N_RP_S : pass == P_ATD ? N_ATD : pass == P_DX ? N_DX : N_PD;
         const int nmax_cnt = pass == P_ATY ? 8 : pass == P_AX ? 6 : (pass == P_ATD || pass == P_DX || pass == P_PD) ? 1 : 0;
         const int sum_id = pass == P_ATY ? S_OBJ : pass == P_DX ? S_QD : -1;
         for (int rb = rb0; rb < rb1; rb += kRG) {
-          int rbs[kRG];
-#pragma unroll
-          for (int r = 0; r < kRG; ++r) rbs[r] = min(rb + r, rb1 - 1);
           double acc[kRG][NB][2];
           zero_acc(acc);
-          gemm_seg<NB>(op + lane, kpt, rbs, 0, kpt, panel, krows, lane, acc);
+          gemm_seg<NB>(op + lane, kpt, rb, min(kRG, rb1 - rb), 0, kpt, panel + bfrag, krows * 8, acc);
           double mx[NB][8][2], sm[NB][2];
 #pragma unroll
           for (int nb = 0; nb < NB; ++nb) {
@@ -584,7 +596,7 @@ admm_shared_tile_kernel(TilePackDev K, SharedPlanDev P, BatchDev Bt, SettingsDev
       for (int e = tid; e < m8 * TB; e += kTileThreads) {
         const int s8 = e & 7, rest = e >> 3, r = rest % m8, nb = rest / m8, s = nb * 8 + s8;
         const int ct = r < m ? (int)__ldg(P.ctype + r) : 0;
-        wp[e] = rho_of(ct, C.rho[s]) * zp[e] - yp[e];
+        cv[w_at(e)] = rho_of(ct, C.rho[s]) * zp[e] - yp[e];
       }
       if (tid == 0) {
         int act = 0, ne = 0x7fffffff;
@@ -607,19 +619,12 @@ admm_shared_tile_kernel(TilePackDev K, SharedPlanDev P, BatchDev Bt, SettingsDev
     // ================= one ADMM iteration for the whole tile
     ++k;
     event = (k == C.next_event);
-    const double *xi = p ? xi1 : xi0;
-    double *xin = p ? xi0 : xi1;
     const double2 *M1l = reinterpret_cast<const double2 *>(K.M1) + lane, *Wl = reinterpret_cast<const double2 *>(K.Wp) + lane;
-    // ---- GEMM 1: T = ([sigma G | W'] [xi; w] - q̂) .* dinv ; xi' = alpha T + (1 - alpha) xi
+    // ---- GEMM 1: T = ([sigma G | W'] [xi; w] - q̂) .* dinv
     for (int rb = nrb0; rb < nrb1; rb += kRG) {
-      int rbs[kRG];
-#pragma unroll
-      for (int r = 0; r < kRG; ++r) rbs[r] = min(rb + r, nrb1 - 1);
       double acc[kRG][NB][2];
       zero_acc(acc);
-#pragma unroll 1
-      for (int seg = 0; seg < 2; ++seg)
-        gemm_seg<NB>(M1l, kpN + kpM, rbs, seg ? kpN : 0, seg ? kpM : kpN, seg ? wp : xi, seg ? m8 : n8, lane, acc);
+      gemm_seg<NB>(M1l, kpN + kpM, rb, min(kRG, nrb1 - rb), 0, kpN + kpM, cv + bfrag, cvr * 8, acc);
 #pragma unroll
       for (int r = 0; r < kRG; ++r)
         if (rb + r < nrb1) {
@@ -627,22 +632,28 @@ admm_shared_tile_kernel(TilePackDev K, SharedPlanDev P, BatchDev Bt, SettingsDev
           for (int nb = 0; nb < NB; ++nb) {
             const int pi = pidx(n8, nb, 8 * (rb + r) + g);
             const double2 qv = *reinterpret_cast<const double2 *>(qh + pi), dv = *reinterpret_cast<const double2 *>(dinv + pi);
-            const double2 xo = *reinterpret_cast<const double2 *>(xi + pi);
-            const double t0 = (acc[r][nb][0] - qv.x) * dv.x, t1 = (acc[r][nb][1] - qv.y) * dv.y;
-            *reinterpret_cast<double2 *>(Tp + pi) = make_double2(t0, t1);
-            *reinterpret_cast<double2 *>(xin + pi) = make_double2(alpha * t0 + oma * xo.x, alpha * t1 + oma * xo.y);
+            *reinterpret_cast<double2 *>(Tp + pi) = make_double2((acc[r][nb][0] - qv.x) * dv.x, (acc[r][nb][1] - qv.y) * dv.y);
           }
         }
     }
     __syncthreads();
+    // ---- xi = alpha T + (1 - alpha) xi on the rows this warp produced (nobody reads xi in this phase);
+    //      the iteration before an event also keeps delta_xi (is_dual_infeasible)
+    for (int rb = nrb0; rb < nrb1; ++rb) {
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb) {
+        const int row = 8 * rb + g, pi = pidx(n8, nb, row), ci = pidx(cvr, nb, row);
+        const double2 t = *reinterpret_cast<const double2 *>(Tp + pi), xo = *reinterpret_cast<const double2 *>(cv + ci);
+        const double x0 = alpha * t.x + oma * xo.x, x1 = alpha * t.y + oma * xo.y;
+        *reinterpret_cast<double2 *>(cv + ci) = make_double2(x0, x1);
+        if (event) *reinterpret_cast<double2 *>(Dp + pi) = make_double2(x0 - xo.x, x1 - xo.y);
+      }
+    }
     // ---- GEMM 2: z̃ = W T ; z, y updates (OSQP update_z / update_y) ; w = rho_vec z - y
     for (int rb = mrb0; rb < mrb1; rb += kRG) {
-      int rbs[kRG];
-#pragma unroll
-      for (int r = 0; r < kRG; ++r) rbs[r] = min(rb + r, mrb1 - 1);
       double acc[kRG][NB][2];
       zero_acc(acc);
-      gemm_seg<NB>(Wl, kpN, rbs, 0, kpN, Tp, n8, lane, acc);
+      gemm_seg<NB>(Wl, kpN, rb, min(kRG, mrb1 - rb), 0, kpN, Tp + bfrag, n8 * 8, acc);
 #pragma unroll
       for (int r = 0; r < kRG; ++r)
         if (rb + r < mrb1) {
@@ -664,12 +675,11 @@ admm_shared_tile_kernel(TilePackDev K, SharedPlanDev P, BatchDev Bt, SettingsDev
             *reinterpret_cast<double2 *>(zp + pi) = make_double2(zn0, zn1);
             *reinterpret_cast<double2 *>(yp + pi) = make_double2(yn0, yn1);
             // before an event the w panel carries delta_y (is_primal_infeasible); w is rebuilt after the event
-            *reinterpret_cast<double2 *>(wp + pi) = event ? make_double2(d0, d1) : make_double2(rv0 * zn0 - yn0, rv1 * zn1 - yn1);
+            *reinterpret_cast<double2 *>(cv + pidx(cvr, nb, n8 + row)) = event ? make_double2(d0, d1) : make_double2(rv0 * zn0 - yn0, rv1 * zn1 - yn1);
           }
         }
     }
     __syncthreads();
-    p ^= 1;
   }
 }
 

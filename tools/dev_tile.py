@@ -88,3 +88,29 @@ if __name__ == "__main__":
     if what in ("all", "perf"):
         mpc_case(100, 16384, reps=2)
         shape_case(200, 400, 4096, 6, reps=1)
+    if what == "tileperf":
+        for N, B in ((100, 16384), (100, 65536), (30, 65536), (50, 65536)):
+            cfg = oracle.load_config(os.path.join(ROOT, "config", "MPC_API.json"))
+            mats = oracle.mpc_build(**{**cfg, "N": N})
+            X, U, ref = c2_batch(B, seed=3)
+            f, ub = oracle.mpc_batch_vectors(mats, X, U, ref)
+            s = sm.BatchedSolver(mats["H"], mats["Gbar"], mats["lb"], mats["W0"], batch=B, kernel=4, **EPS)
+            s.update_gradient(f); s.update_upper_bound(ub); s.set_cold_solves(True)
+            s.solve(); s.sync(); s.enable_timing(True); s.kernel_ms(reset=True)
+            for _ in range(2): s.solve()
+            s.sync(); ms, cnt = s.kernel_ms(); ms /= cnt
+            info = s.info(); it = info["iter"].astype(np.int64).sum(); n, m = N, 2 * N
+            print(f"tile N={N} B={B}: {ms:.3f} ms, {B / (ms * 1e-3):.3e} solves/s, iters mean {info['iter'].mean():.1f} max {info['iter'].max()}, "
+                  f"executed {it * 2.0 * (n * n + 2 * m * n) / (ms * 1e-3) / 1e12:.2f} TFLOP/s, solved {(info['status'] == 1).mean():.4f}", flush=True)
+            s.close()
+    if what == "ncu":
+        N, B = 100, 16384
+        cfg = oracle.load_config(os.path.join(ROOT, "config", "MPC_API.json"))
+        mats = oracle.mpc_build(**{**cfg, "N": N})
+        X, U, ref = c2_batch(B, seed=3)
+        f, ub = oracle.mpc_batch_vectors(mats, X, U, ref)
+        s = sm.BatchedSolver(mats["H"], mats["Gbar"], mats["lb"], mats["W0"], batch=B, kernel=4, **EPS)
+        s.update_gradient(f); s.update_upper_bound(ub); s.set_cold_solves(True)
+        s.solve(); s.sync()
+        print("ncu run done", s.info()["iter"].mean())
+        s.close()
