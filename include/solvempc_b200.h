@@ -201,6 +201,14 @@ int smpc_mpc_set_state(smpc_mpc *m, const double *X, const double *U, const doub
 int smpc_mpc_controller_step(smpc_mpc *m);
 /* synthetic plant for closed-loop runs (the reference's plant is hardware): X <- Ad X + Bd U */
 int smpc_mpc_plant_step(smpc_mpc *m);
+/* Closed-loop driver: the reference's main loop (src/solver.cpp:43-74: read state -> controllerStep -> write U) for the
+ * whole batch without leaving the device.  Each of the `steps` iterations sets the reference (ref_period >= 2: square wave
+ * +-ref_amplitude with that period in steps and a per-instance `phase` offset, host int[batch] or NULL = 0;
+ * ref_period == 0: keep the current reference), runs controllerStep (warm started, rho persistent, cpp:52) and the
+ * synthetic plant step X <- Ad X + Bd U.  use_graph != 0 captures one step into a CUDA graph and replays it.
+ * Outputs (may be NULL): solves that did not end SOLVED, and the total number of ADMM iterations.  Synchronises. */
+int smpc_mpc_closed_loop(smpc_mpc *m, int steps, double ref_amplitude, int ref_period, const int *phase, int use_graph,
+                         long long *not_solved, long long *iterations);
 int smpc_mpc_get_state(smpc_mpc *m, double *X, double *U, int loc);
 /* vectors handed to the solver in the last controllerStep: f:[batch][n], ub:[batch][2N] */
 int smpc_mpc_get_step_vectors(smpc_mpc *m, double *f, double *ub, int loc);

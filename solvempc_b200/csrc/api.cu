@@ -88,6 +88,8 @@ struct smpc_mpc {
   double *d_Ad = nullptr, *d_Bd = nullptr, *d_Cd = nullptr, *d_K = nullptr;
   smpc::MpcMatsDev mats{};
   double *d_X = nullptr, *d_U = nullptr, *d_ref = nullptr;
+  int *d_phase = nullptr, *d_step = nullptr;          // closed-loop driver: per-instance phase, device step counter
+  unsigned long long *d_stats = nullptr;              // [0] solves that did not reach SOLVED, [1] ADMM iterations
   smpc_solver *solver = nullptr;
   long long launches = 0;
 };
@@ -654,6 +656,7 @@ static int mpc_alloc(smpc_mpc *M, const smpc_mpc_config *cfg) {
   size_t bytes = 0;
   for (size_t c : {P * nx * nx, P * nx, nx, nx, P * N * N, P * 2 * N * N, P * N * nx, P * N, P * N * N, P * 2 * N * nx, P * 2 * N,
                    P * 2 * N, P * N * nx, P * N * N, P * N, B * nx, B, B}) bytes += DeviceBuf::need(c * sizeof(double));
+  bytes += DeviceBuf::need(B * sizeof(int)) + DeviceBuf::need(sizeof(int)) + DeviceBuf::need(2 * sizeof(unsigned long long));
   CK(M->buf.alloc(bytes));
   DeviceBuf &b = M->buf;
   M->d_Ad = b.take<double>(P * nx * nx); M->d_Bd = b.take<double>(P * nx); M->d_Cd = b.take<double>(nx); M->d_K = b.take<double>(nx);
@@ -662,7 +665,8 @@ static int mpc_alloc(smpc_mpc *M, const smpc_mpc_config *cfg) {
   t.Fr = b.take<double>(P * N * N); t.Sbar = b.take<double>(P * 2 * N * nx); t.Ku = b.take<double>(P * 2 * N); t.W0 = b.take<double>(P * 2 * N);
   t.Sx = b.take<double>(P * N * nx); t.Su = b.take<double>(P * N * N); t.CAB = b.take<double>(P * N);
   M->d_X = b.take<double>(B * nx); M->d_U = b.take<double>(B); M->d_ref = b.take<double>(B);
-  if (!M->d_ref) return fail(SMPC_ERR_CUDA, "internal: mpc buffer carve-out overflow");
+  M->d_phase = b.take<int>(B); M->d_step = b.take<int>(1); M->d_stats = b.take<unsigned long long>(2);
+  if (!M->d_stats) return fail(SMPC_ERR_CUDA, "internal: mpc buffer carve-out overflow");
   CK(cudaMemset(b.base, 0, b.size));
   CK(cudaMemcpy(M->d_Ad, cfg->Ad, P * nx * nx * sizeof(double), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(M->d_Bd, cfg->Bd, P * nx * sizeof(double), cudaMemcpyHostToDevice));
@@ -821,6 +825,71 @@ int smpc_mpc_plant_step(smpc_mpc *M) {
   CK(smpc::launch_mpc_plant_step(M->B, M->dims.nx, M->per_instance, M->d_Ad, M->d_Bd, M->d_X, M->d_U, M->stream));
   M->launches++;
   return SMPC_OK;
+}
+
+int smpc_mpc_closed_loop(smpc_mpc *M, int steps, double ref_amplitude, int ref_period, const int *phase, int use_graph,
+                         long long *not_solved, long long *iterations) {
+  if (!M) return fail(SMPC_ERR_ARG, "null handle");
+  if (steps < 0 || (ref_period != 0 && ref_period < 2)) return fail(SMPC_ERR_ARG, "need steps >= 0 and ref_period 0 (constant reference) or >= 2");
+  CK(cudaSetDevice(M->device));
+  smpc_solver *s = M->solver;
+  if (s->timing) return fail(SMPC_ERR_STATE, "disable kernel timing before a closed-loop run");
+  cudaStream_t st = M->stream;
+  cudaStream_t own = nullptr;
+  if (use_graph && st == nullptr) {   // the legacy default stream cannot be captured
+    CK(cudaStreamCreateWithFlags(&own, cudaStreamNonBlocking));
+    CK(cudaDeviceSynchronize());
+    st = own;
+    smpc_mpc_set_stream(M, st);
+  }
+  auto restore = [&]() { if (own) { cudaStreamSynchronize(own); smpc_mpc_set_stream(M, nullptr); cudaStreamDestroy(own); } };
+  auto body = [&]() -> int {
+    CK(cudaMemsetAsync(M->d_stats, 0, 2 * sizeof(unsigned long long), st));
+    CK(cudaMemsetAsync(M->d_step, 0, sizeof(int), st));
+    if (phase) CK(cudaMemcpyAsync(M->d_phase, phase, sizeof(int) * M->B, cudaMemcpyHostToDevice, st));
+    else CK(cudaMemsetAsync(M->d_phase, 0, sizeof(int) * M->B, st));
+    auto one_step = [&]() -> int {
+      if (ref_period) { CK(smpc::launch_mpc_square_ref(M->B, ref_amplitude, ref_period, M->d_phase, M->d_step, M->d_ref, st)); M->launches++; }
+      CK(smpc::launch_mpc_step_vectors(M->dims, M->B, M->per_instance, M->mats, M->d_X, M->d_U, M->d_ref, s->d_q, s->d_u, st));
+      M->launches++;
+      s->have_q = true; s->have_u = true;
+      if (int rc = smpc_solver_solve(s)) return rc;
+      CK(smpc::launch_mpc_advance(M->B, s->n, M->dims.nx, M->per_instance, M->d_Ad, M->d_Bd, s->d_x, s->d_status, s->d_iter, M->d_X,
+                                  M->d_U, M->d_stats, M->d_step, st));
+      M->launches++;
+      return SMPC_OK;
+    };
+    if (use_graph && steps > 1) {
+      // one controller step + plant step captured once, replayed `steps` times (launch-bound for small QPs)
+      cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
+      CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+      const long long l0 = M->launches, sl0 = s->launches;
+      int rc = one_step();
+      cudaError_t e = cudaStreamEndCapture(st, &graph);
+      if (rc != SMPC_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+      if (e != cudaSuccess) return cuda_fail(e, "cudaStreamEndCapture");
+      const long long per_step = M->launches - l0, s_per_step = s->launches - sl0;
+      e = cudaGraphInstantiate(&exec, graph, 0);
+      if (e != cudaSuccess) { cudaGraphDestroy(graph); return cuda_fail(e, "cudaGraphInstantiate"); }
+      for (int k = 0; k < steps && e == cudaSuccess; ++k) e = cudaGraphLaunch(exec, st);
+      M->launches += per_step * (steps - 1); s->launches += s_per_step * (steps - 1);
+      cudaError_t e2 = cudaStreamSynchronize(st);
+      cudaGraphExecDestroy(exec); cudaGraphDestroy(graph);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaGraphLaunch");
+      if (e2 != cudaSuccess) return cuda_fail(e2, "closed-loop sync");
+    } else {
+      for (int k = 0; k < steps; ++k) if (int rc = one_step()) return rc;
+    }
+    unsigned long long h[2] = {0, 0};
+    CK(cudaMemcpyAsync(h, M->d_stats, sizeof(h), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (not_solved) *not_solved = (long long)h[0];
+    if (iterations) *iterations = (long long)h[1];
+    return SMPC_OK;
+  };
+  int rc = body();
+  restore();
+  return rc;
 }
 
 int smpc_mpc_get_state(smpc_mpc *M, double *X, double *U, int loc) {

@@ -52,4 +52,11 @@ cudaError_t launch_mpc_apply_control(int B, int n, const double *x, const int *s
 cudaError_t launch_mpc_plant_step(int B, int nx, int per_instance, const double *Ad, const double *Bd,
                                   double *X, const double *U, cudaStream_t stream);
 
+// closed-loop driver pieces: square-wave reference generator; U += dU[0], plant step, statistics, step counter
+cudaError_t launch_mpc_square_ref(int B, double amplitude, int period, const int *phase, const int *step, double *ref,
+                                  cudaStream_t stream);
+cudaError_t launch_mpc_advance(int B, int n, int nx, int per_instance, const double *Ad, const double *Bd, const double *x,
+                               const int *status, const int *iter, double *X, double *U, unsigned long long *stats, int *step,
+                               cudaStream_t stream);
+
 }  // namespace smpc

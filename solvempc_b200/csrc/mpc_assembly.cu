@@ -118,6 +118,57 @@ __global__ void mpc_plant_step_kernel(int B, int nx, int per_instance, const dou
   for (int c = 0; c < nx; ++c) X[(size_t)b * nx + c] = xn[c];
 }
 
+// Closed-loop driver (the caller of the hot path, reference main loop src/solver.cpp:43-74, with the serial port
+// replaced by an on-device reference generator and a synthetic plant).
+// ref_b(step) = amplitude * (+1 | -1): square wave of `period` steps, per-instance phase.
+__global__ void mpc_square_ref_kernel(int B, double amplitude, int period, const int *__restrict__ phase,
+                                      const int *__restrict__ step, double *__restrict__ ref) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int t = (*step + (phase ? phase[b] : 0)) % period;
+  ref[b] = (2 * t < period) ? amplitude : -amplitude;
+}
+
+// U += dU*[0] (cpp:105, only when SOLVED as cpp:102 returns early otherwise), X <- Ad X + Bd U, statistics, step += 1
+__global__ void mpc_advance_kernel(int B, int n, int nx, int per_instance, const double *__restrict__ Ad,
+                                   const double *__restrict__ Bd, const double *__restrict__ x,
+                                   const int *__restrict__ status, const int *__restrict__ iter, double *__restrict__ X,
+                                   double *__restrict__ U, unsigned long long *stats, int *step) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  int bad = 0, it = 0;
+  if (b < B) {
+    const bool ok = status[b] == SMPC_SOLVED;
+    bad = !ok; it = iter[b];
+    double u = U[b];
+    if (ok) u += x[(size_t)b * n];
+    U[b] = u;
+    const double *A = Ad + (per_instance ? (size_t)b * nx * nx : 0), *Bv = Bd + (per_instance ? (size_t)b * nx : 0);
+    double xo[kMaxNx], xn[kMaxNx];
+    for (int c = 0; c < nx; ++c) xo[c] = X[(size_t)b * nx + c];
+    for (int r = 0; r < nx; ++r) { double s = 0; for (int c = 0; c < nx; ++c) s += A[r * nx + c] * xo[c]; xn[r] = s + Bv[r] * u; }
+    for (int c = 0; c < nx; ++c) X[(size_t)b * nx + c] = xn[c];
+  }
+  for (int o = 16; o > 0; o >>= 1) { bad += __shfl_xor_sync(0xffffffffu, bad, o); it += __shfl_xor_sync(0xffffffffu, it, o); }
+  if ((threadIdx.x & 31) == 0) {
+    if (bad) atomicAdd(stats, (unsigned long long)bad);
+    atomicAdd(stats + 1, (unsigned long long)it);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(step, 1);
+}
+
+cudaError_t launch_mpc_square_ref(int B, double amplitude, int period, const int *phase, const int *step, double *ref,
+                                  cudaStream_t stream) {
+  mpc_square_ref_kernel<<<(B + 255) / 256, 256, 0, stream>>>(B, amplitude, period, phase, step, ref);
+  return cudaGetLastError();
+}
+cudaError_t launch_mpc_advance(int B, int n, int nx, int per_instance, const double *Ad, const double *Bd, const double *x,
+                               const int *status, const int *iter, double *X, double *U, unsigned long long *stats, int *step,
+                               cudaStream_t stream) {
+  if (nx > kMaxNx) return cudaErrorInvalidValue;
+  mpc_advance_kernel<<<(B + 127) / 128, 128, 0, stream>>>(B, n, nx, per_instance, Ad, Bd, x, status, iter, X, U, stats, step);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_mpc_assemble(const MpcDims &d, int plants, const double *Ad, const double *Bd, const double *Cd,
                                 const double *K, const MpcMatsDev &out, cudaStream_t stream) {
   if (d.nx > kMaxNx || d.nx < 1 || d.N < 1) return cudaErrorInvalidValue;

@@ -278,6 +278,17 @@ class BatchedModelPredictiveControlAPI:
     def plant_step(self):
         L.check(L.lib().smpc_mpc_plant_step(self._h))
 
+    def closed_loop(self, steps, ref_amplitude=0.0, ref_period=0, phase=None, use_graph=True):
+        """The reference's main loop (src/solver.cpp:43-74) for the whole batch on the device: `steps` times
+        [square-wave reference ->] controllerStep -> synthetic plant step.  Returns (not_solved, iterations)."""
+        ph = None if phase is None else np.ascontiguousarray(phase, dtype=np.int32)
+        if ph is not None and ph.size != self.batch:
+            raise ValueError("phase: expected one int per instance")
+        bad, it = C.c_longlong(), C.c_longlong()
+        L.check(L.lib().smpc_mpc_closed_loop(self._h, int(steps), float(ref_amplitude), int(ref_period),
+                                             None if ph is None else ph.ctypes.data, int(use_graph), C.byref(bad), C.byref(it)))
+        return bad.value, it.value
+
     def state(self):
         X, U = np.empty((self.batch, self.N_S)), np.empty(self.batch)
         L.check(L.lib().smpc_mpc_get_state(self._h, X.ctypes.data, U.ctypes.data, L.HOST))

@@ -1,0 +1,71 @@
+"""Closed-loop driver (BASELINE config 5): the reference's main loop (src/solver.cpp:43-74) for a batch,
+on the device -- square-wave reference, warm-started controllerStep, synthetic plant step -- against the same loop
+run with one CPU oracle solver per instance."""
+import numpy as np
+import pytest
+
+import oracle
+import solvempc_b200 as sm
+from problems import c2_batch
+
+pytestmark = pytest.mark.gpu
+EPS = dict(eps_abs=1e-5, eps_rel=1e-5)
+
+
+def oracle_loop(cfg, mats, X, U, steps, amp, period, phase):
+    B, n = X.shape[0], mats["N"]
+    solvers = [oracle.Solver(mats["H"], np.zeros(n), mats["Gbar"], mats["lb"], mats["W0"], **EPS) for _ in range(B)]
+    X, U = X.copy(), U.copy()
+    iters = 0
+    for k in range(steps):
+        for b in range(B):
+            ref = amp if 2 * ((k + phase[b]) % period) < period else -amp
+            f, ub = oracle.mpc_step_vectors(mats, X[b], U[b], ref)
+            solvers[b].update_lin_cost(f); solvers[b].update_upper_bound(ub)
+            r = solvers[b].solve()
+            assert r["status"] == 1
+            iters += r["iter"]
+            U[b] += r["x"][0]
+            X[b] = cfg["Ad"] @ X[b] + cfg["Bd"] * U[b]
+    return X, U, iters
+
+
+@pytest.mark.parametrize("N,kernel,B,steps", [(15, 2, 24, 40), (15, 4, 24, 40), (100, 4, 20, 12), (100, 1, 6, 6)])
+def test_closed_loop_driver_matches_oracle_loop(ref_mats, N, kernel, B, steps):
+    _, cfg = ref_mats
+    mats = oracle.mpc_build(**{**cfg, "N": N})
+    conf = dict(Ad=cfg["Ad"], Bd=cfg["Bd"], Cd=cfg["Cd"], K=cfg["K"], Q=cfg["Q"], R=cfg["R"], RD=cfg["RD"], horizon=N)
+    X0, U0, _ = c2_batch(B, seed=31)
+    X0 *= 0.2; U0 *= 0.1
+    rng = np.random.default_rng(5)
+    amp, period = 0.1, 10
+    phase = rng.integers(0, period, B).astype(np.int32)
+    Xo, Uo, it_o = oracle_loop(cfg, mats, X0, U0, steps, amp, period, phase)
+    res = []
+    for use_graph in (False, True):
+        mpc = sm.BatchedModelPredictiveControlAPI(conf, batch=B, kernel=kernel, **EPS)
+        mpc.set_state(X=X0, U=U0, ref=np.zeros(B))
+        bad, it = mpc.closed_loop(steps, ref_amplitude=amp, ref_period=period, phase=phase, use_graph=use_graph)
+        X, U = mpc.state()
+        assert bad == 0
+        assert np.abs(U - Uo).max() < 1e-6 * max(1.0, np.abs(Uo).max())
+        assert np.abs(X - Xo).max() < 1e-6 * max(1.0, np.abs(Xo).max())
+        assert abs(it - it_o) <= 0.02 * it_o          # the tile kernel may stop a borderline instance one check apart
+        if kernel != 4:
+            assert it == it_o
+        res.append((X, U, it))
+        mpc.close()
+    # the CUDA-graph replay is the same sequence of launches: bitwise the same trajectory
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1]) and res[0][2] == res[1][2]
+
+
+def test_closed_loop_argument_checks(ref_mats, repo_root):
+    import os
+    mpc = sm.BatchedModelPredictiveControlAPI(os.path.join(repo_root, "config", "MPC_API.json"), batch=4, **EPS)
+    with pytest.raises(sm.SolveMpcError):
+        mpc.closed_loop(5, ref_amplitude=0.1, ref_period=1)
+    with pytest.raises(ValueError):
+        mpc.closed_loop(5, ref_amplitude=0.1, ref_period=4, phase=np.zeros(3, np.int32))
+    bad, it = mpc.closed_loop(0)
+    assert (bad, it) == (0, 0)
+    mpc.close()

@@ -48,7 +48,10 @@ def cfg_path(repo_root):
     return os.path.join(repo_root, "config", "MPC_API.json")
 
 
-@pytest.mark.parametrize("kernel", [1, 2])
+KERNEL_NAMES = {1: "admm_shared_generic_kernel", 2: "admm_shared_small_kernel", 4: "admm_shared_tile_kernel"}
+
+
+@pytest.mark.parametrize("kernel", [1, 2, 4])
 def test_c1_reference_cases_through_mpc_api(cfg_path, golden, ref_mats, kernel):
     """Config 1: shipped plant + horizon, the four known-answer states, one controller each (B=1) and batched."""
     m, _ = ref_mats
@@ -87,7 +90,7 @@ def test_c1_reference_cases_through_mpc_api(cfg_path, golden, ref_mats, kernel):
         assert set(np.nonzero(active_set(m["Gbar"], x[j], y[j], ub[j]))[0]) == set(c["active"])
 
 
-@pytest.mark.parametrize("kernel", [1, 2])
+@pytest.mark.parametrize("kernel", [1, 2, 4])
 def test_c2_batch_4096_matches_oracle(ref_mats, kernel):
     """Config 2: 4096 random x0 / references sharing P and A, cold solves."""
     m, _ = ref_mats
@@ -96,7 +99,7 @@ def test_c2_batch_4096_matches_oracle(ref_mats, kernel):
     f, ub = oracle.mpc_batch_vectors(m, X, U, ref)
     ora = oracle.solve_batch(m["H"], m["Gbar"], m["lb"], m["W0"], f, ub, nthreads=os.cpu_count() or 1, **EPS)
     s = sm.BatchedSolver(m["H"], m["Gbar"], m["lb"], m["W0"], batch=B, kernel=kernel, **EPS)
-    assert s.kernel_name == ("admm_shared_small_kernel" if kernel == 2 else "admm_shared_generic_kernel")
+    assert s.kernel_name == KERNEL_NAMES[kernel]
     s.update_gradient(f)
     s.update_upper_bound(ub)
     s.solve()
@@ -126,13 +129,13 @@ def test_generic_and_small_kernels_agree_bitwise_on_status(ref_mats):
     X, U, ref = c2_batch(512, seed=5)
     f, ub = oracle.mpc_batch_vectors(m, X, U, ref)
     out = []
-    for kernel in (1, 2):
+    for kernel in (1, 2, 4):
         s = sm.BatchedSolver(m["H"], m["Gbar"], m["lb"], m["W0"], batch=512, kernel=kernel, **EPS)
         s.update_gradient(f); s.update_upper_bound(ub); s.solve()
         out.append((s.solution()[0], s.info()))
         s.close()
-    assert np.array_equal(out[0][1]["iter"], out[1][1]["iter"])
-    assert rel_err(out[0][0], out[1][0]) < 1e-9
+    assert np.array_equal(out[0][1]["iter"], out[1][1]["iter"]) and np.array_equal(out[0][1]["iter"], out[2][1]["iter"])
+    assert rel_err(out[0][0], out[1][0]) < 1e-9 and rel_err(out[0][0], out[2][0]) < 1e-9
     # the longest-expected-first schedule of the small kernel changes the order of work only: bitwise same answers
     s = sm.BatchedSolver(m["H"], m["Gbar"], m["lb"], m["W0"], batch=512, kernel=2, **EPS)
     s.set_scheduling(False)
@@ -142,9 +145,13 @@ def test_generic_and_small_kernels_agree_bitwise_on_status(ref_mats):
     s.close()
 
 
-@pytest.mark.parametrize("n,m,B", [(3, 0, 8), (12, 20, 64), (16, 32, 64), (17, 33, 32), (40, 70, 32), (100, 200, 8)])
-def test_random_qps_generic_shapes(n, m, B):
-    """Two-sided bounds, equality rows and a free row; every instance gets its own q, l, u."""
+@pytest.mark.parametrize("kernel", [1, 4])
+@pytest.mark.parametrize("n,m,B", [(3, 0, 8), (12, 20, 64), (16, 32, 64), (17, 33, 32), (40, 70, 37), (100, 200, 8)])
+def test_random_qps_generic_shapes(n, m, B, kernel):
+    """Two-sided bounds, equality rows and a free row; every instance gets its own q, l, u.  The tile kernel (4)
+    sums its dot products in DMMA order, so an instance sitting on a termination threshold may stop one check
+    (25 iterations) away from the oracle: iteration counts must agree on >= 90 % of the instances and the
+    solutions within the north-star tolerance everywhere."""
     P, q0, A, l0, u0 = random_qp(n, max(m, 1), seed=n * 7 + m)
     if m == 0:
         A, l0, u0 = np.zeros((0, n)), np.zeros(0), np.zeros(0)
@@ -163,22 +170,27 @@ def test_random_qps_generic_shapes(n, m, B):
             so.update_bounds(l[b], u[b])
         r = so.solve()
         xs.append(r["x"]); ys.append(r["y"]); st.append(r["status"]); it.append(r["iter"])
-    s = sm.BatchedSolver(P, A, l0, u0, batch=B, **EPS)
+    s = sm.BatchedSolver(P, A, l0, u0, batch=B, kernel=kernel, **EPS)
+    assert s.kernel_name == KERNEL_NAMES[kernel]
     s.update_gradient(q)
     if m:
         s.update_bounds(l, u)
     s.solve()
     x, y = s.solution()
     info = s.info()
-    assert np.array_equal(info["status"], np.array(st)) and np.array_equal(info["iter"], np.array(it))
-    assert rel_err(x, np.array(xs)) < TIGHT
+    assert np.array_equal(info["status"], np.array(st))
+    same = info["iter"] == np.array(it)
+    if kernel == 1:
+        assert same.all()
+    assert same.mean() >= 0.9 and rel_err(x, np.array(xs)) < REL
+    assert rel_err(x[same], np.array(xs)[same]) < TIGHT
     if m:
-        assert rel_err(y, np.array(ys)) < 1e-5
+        assert rel_err(y[same], np.array(ys)[same]) < 1e-5
     assert (np.array(st) == 1).sum() >= 1          # (the shifted bounds make some instances infeasible: NaN parity above)
     s.close()
 
 
-@pytest.mark.parametrize("kernel", [1, 2])
+@pytest.mark.parametrize("kernel", [1, 2, 4])
 @pytest.mark.parametrize("opts", [dict(adaptive_rho=0), dict(scaling=0), dict(scaled_termination=1),
                                   dict(adaptive_rho_interval=50), dict(check_termination=10, adaptive_rho_interval=30),
                                   dict(max_iter=30), dict(alpha=1.0, rho=1.0, eps_abs=1e-3, eps_rel=1e-3)])
@@ -197,7 +209,7 @@ def test_settings_follow_the_oracle(ref_mats, kernel, opts):
     s.close()
 
 
-@pytest.mark.parametrize("kernel", [1, 2])
+@pytest.mark.parametrize("kernel", [1, 2, 4])
 def test_infeasible_unbounded_and_bad_bounds(kernel):
     P = np.eye(2); A = np.array([[1.0, 0.0], [1.0, 0.0]])
     l = np.array([[1.0, -np.inf], [-2.0, -np.inf], [0.5, -np.inf]]); u = np.array([[np.inf, -1.0], [np.inf, 3.0], [np.inf, 0.25]])
@@ -231,7 +243,7 @@ def test_infeasible_unbounded_and_bad_bounds(kernel):
     s.close()
 
 
-@pytest.mark.parametrize("kernel", [1, 2])
+@pytest.mark.parametrize("kernel", [1, 2, 4])
 def test_closed_loop_warm_start_matches_reference_run(cfg_path, golden, ref_mats, kernel):
     """40 warm-started controllerStep + plant steps: the golden trajectory came from the reference's own class."""
     m, cfg = ref_mats
@@ -330,13 +342,16 @@ def test_full_size_properties_and_sharding(ref_mats):
     s.close(); s2.close()
 
 
-def test_horizon_100_config5_shape(ref_mats, repo_root):
-    """Config 5 shape (N = 100 -> n = 100, m = 200) through the MPC API on the generic kernel."""
+@pytest.mark.parametrize("kernel,B", [(1, 16), (4, 16), (4, 300)])
+def test_horizon_100_config5_shape(ref_mats, repo_root, kernel, B):
+    """Config 5 shape (N = 100 -> n = 100, m = 200) through the MPC API on the generic and the DMMA tile kernel
+    (B = 300 > one wave of 16-slot tiles per SM exercises the slot recycling)."""
     _, cfg = ref_mats
-    N, B = 100, 16
+    N = 100
     mats = oracle.mpc_build(**{**cfg, "N": N})
     conf = dict(Ad=cfg["Ad"], Bd=cfg["Bd"], Cd=cfg["Cd"], K=cfg["K"], Q=cfg["Q"], R=cfg["R"], RD=cfg["RD"], horizon=N)
-    mpc = sm.BatchedModelPredictiveControlAPI(conf, batch=B, **EPS)
+    mpc = sm.BatchedModelPredictiveControlAPI(conf, batch=B, kernel=kernel, **EPS)
+    assert mpc.solver.kernel_name == KERNEL_NAMES[kernel]
     for name in ("H", "Gbar", "Fx", "Fu", "Fr", "Sbar"):
         assert np.abs(mpc.matrix(name) - mats[name]).max() <= 1e-11 * np.abs(mats[name]).max(), name
     X, U, ref = c2_batch(B, seed=9)
@@ -345,7 +360,7 @@ def test_horizon_100_config5_shape(ref_mats, repo_root):
     f, ub = oracle.mpc_batch_vectors(mats, X, U, ref)
     fd, ubd = mpc.step_vectors()
     assert np.abs(fd - f).max() < 1e-11 * np.abs(f).max() and np.abs(ubd - ub).max() < 1e-11 * np.abs(ub).max()
-    ora = oracle.solve_batch(mats["H"], mats["Gbar"], mats["lb"], mats["W0"], f, ub, nthreads=4, **EPS)
+    ora = oracle.solve_batch(mats["H"], mats["Gbar"], mats["lb"], mats["W0"], f, ub, nthreads=os.cpu_count() or 1, **EPS)
     x, _ = mpc.solver.solution(); info = mpc.solver.info()
     assert ok == bool((ora["status"] == 1).all())
     assert np.array_equal(info["status"], ora["status"]) and np.array_equal(info["iter"], ora["iter"])

@@ -103,6 +103,25 @@ if __name__ == "__main__":
             print(f"tile N={N} B={B}: {ms:.3f} ms, {B / (ms * 1e-3):.3e} solves/s, iters mean {info['iter'].mean():.1f} max {info['iter'].max()}, "
                   f"executed {it * 2.0 * (n * n + 2 * m * n) / (ms * 1e-3) / 1e12:.2f} TFLOP/s, solved {(info['status'] == 1).mean():.4f}", flush=True)
             s.close()
+    if what == "c5":
+        import time
+        N, B, steps = 100, int(sys.argv[2]) if len(sys.argv) > 2 else 65536, int(sys.argv[3]) if len(sys.argv) > 3 else 200
+        cfg = oracle.load_config(os.path.join(ROOT, "config", "MPC_API.json"))
+        conf = dict(Ad=cfg["Ad"], Bd=cfg["Bd"], Cd=cfg["Cd"], K=cfg["K"], Q=cfg["Q"], R=cfg["R"], RD=cfg["RD"], horizon=N)
+        X0, U0, _ = c2_batch(B, seed=31); X0 *= 0.2; U0 *= 0.1
+        phase = np.random.default_rng(5).integers(0, 200, B).astype(np.int32)
+        for kernel in (4,):
+            mpc = sm.BatchedModelPredictiveControlAPI(conf, batch=B, kernel=kernel, **EPS)
+            mpc.set_state(X=X0, U=U0, ref=np.zeros(B))
+            mpc.closed_loop(3, 0.1, 200, phase)     # warm-up
+            mpc.set_state(X=X0, U=U0, ref=np.zeros(B)); mpc.solver.reset()
+            t0 = time.perf_counter()
+            bad, it = mpc.closed_loop(steps, 0.1, 200, phase)
+            dt = time.perf_counter() - t0
+            n, m = N, 2 * N
+            print(f"c5 closed loop N={N} B={B} steps={steps} kernel={mpc.solver.kernel_name}: {dt:.3f} s, {B * steps / dt:.3e} solves/s, "
+                  f"not solved {bad}, mean iters {it / (B * steps):.2f}, executed {it * 2.0 * (n * n + 2 * m * n) / dt / 1e12:.2f} TFLOP/s", flush=True)
+            mpc.close()
     if what == "ncu":
         N, B = 100, 16384
         cfg = oracle.load_config(os.path.join(ROOT, "config", "MPC_API.json"))
