@@ -214,6 +214,45 @@ int smpc_mpc_get_state(smpc_mpc *m, double *X, double *U, int loc);
 int smpc_mpc_get_step_vectors(smpc_mpc *m, double *f, double *ub, int loc);
 long long smpc_mpc_launch_count(const smpc_mpc *m);
 
+/* ------------------------------------------------- multi-input MPC layer (BASELINE config 3) */
+/* The reference class is single-input (N_C = N_O = 1, include/ModelPredictiveControlAPI.h:31-32).  For
+ * multi-input plants (the 12-state / 4-input quadrotor of BASELINE config 3) this layer
+ * builds the condensed QP the same way the reference does (setTransformations / setH / setFVars,
+ * src/ModelPredictiveControlAPI.cpp:180-263,303-307: eliminate the states through powers of Ad, dense
+ * Hessian 2(Su' Qbar Su + Rbar), gradient linear in the measured state and the reference) with
+ *   decision  z = [u_0; ...; u_{N-1}]  (n = N*nu),   x_{k+1} = Ad x_k + Bd u_k,
+ *   cost      sum_{k=1..N} (x_k - xr)' Q (x_k - xr) + sum_{k<N} u_k' R u_k      (Q, R diagonal),
+ *   rows      [I; -I] z <= [umax; -umin] with l = -DBL_MAX: the two-sided input box written as 2n one-sided
+ *             rows, as the reference writes its PWM limit (cpp:42,335)  ->  m = 2*N*nu.
+ * Every controller shares the plant (shared-factor regime); per controller: x0 and xr (nx each). */
+typedef struct smpc_mimo smpc_mimo;
+typedef struct smpc_mimo_config {
+  int horizon, nx, nu;
+  const double *Ad;     /* nx*nx row-major */
+  const double *Bd;     /* nx*nu row-major */
+  const double *Q;      /* nx: diagonal state weight */
+  const double *R;      /* nu: diagonal input weight */
+  const double *umin;   /* nu */
+  const double *umax;   /* nu */
+} smpc_mimo_config;
+/* assembles Su, H, Fx, Fr ON THE DEVICE, then sets up the batched shared-factor solver */
+int smpc_mimo_create(smpc_mimo **out, int device, const smpc_mimo_config *cfg, int batch, const smpc_settings *settings);
+/* JSON keys: "horizon", "Ad", "Bd", "Q" (nx diagonal), "R" (nu diagonal), "umin", "umax" */
+int smpc_mimo_create_from_json(smpc_mimo **out, int device, const char *json_path, int batch, const smpc_settings *settings);
+int smpc_mimo_destroy(smpc_mimo *m);
+int smpc_mimo_set_stream(smpc_mimo *m, void *cuda_stream);
+int smpc_mimo_dims(const smpc_mimo *m, int *horizon, int *nx, int *nu, int *n, int *mrows, int *batch);
+smpc_solver *smpc_mimo_solver(smpc_mimo *m);
+/* "H" (n*n) "A" (m*n) "ub" (m) "Fx" (n*nx) "Fr" (n*nx) "Su" (N*nx x n) "Sx" (N*nx x nx), row-major */
+int smpc_mimo_get_matrix(smpc_mimo *m, const char *name, double *out, int capacity);
+/* measured states x0:[batch][nx] and state references xr:[batch][nx] (held over the horizon); NULL keeps the value */
+int smpc_mimo_set_state(smpc_mimo *m, const double *x0, const double *xr, int loc);
+/* one controller step for every instance: q = Fx x0 + Fr xr -> updateGradient -> solve; asynchronous */
+int smpc_mimo_controller_step(smpc_mimo *m);
+/* the first move u_0 of every instance, u0:[batch][nu] (NaN where the solve did not end SOLVED) */
+int smpc_mimo_get_control(smpc_mimo *m, double *u0, int loc);
+long long smpc_mimo_launch_count(const smpc_mimo *m);
+
 #ifdef __cplusplus
 }
 #endif

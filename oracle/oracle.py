@@ -250,3 +250,51 @@ def kkt_report(P, q, A, l, u, x, y):
     yp, ym = np.maximum(y, 0), np.minimum(y, 0)
     comp = max(np.abs(yp * (u - Ax)).max(), np.abs(np.where(np.isfinite(lo), ym * (Ax - np.where(l > -1e300, l, 0)), 0)).max())
     return dict(stationarity=stat, infeasibility=feas, complementarity=comp)
+
+
+# --------------------------------------------------------------------------- multi-input condensed MPC (config 3)
+def load_mimo_config(path):
+    """config/quadrotor.json: horizon, Ad, Bd, Q (diagonal), R (diagonal), umin, umax."""
+    with open(path) as f:
+        cfg = json.load(f)
+    return dict(Ad=np.array(cfg["Ad"], dtype=np.float64), Bd=np.array(cfg["Bd"], dtype=np.float64),
+                Q=np.array(cfg["Q"], dtype=np.float64).reshape(-1), R=np.array(cfg["R"], dtype=np.float64).reshape(-1),
+                umin=np.array(cfg["umin"], dtype=np.float64).reshape(-1), umax=np.array(cfg["umax"], dtype=np.float64).reshape(-1),
+                N=int(cfg["horizon"]))
+
+
+def mimo_build(Ad, Bd, Q, R, umin, umax, N, **_):
+    """Condensed QP of the multi-input MPC layer, built the way the reference builds its own
+    (setTransformations cpp:180-208: states eliminated through powers of Ad; setH cpp:247-263:
+    H = 2(Su'Qbar Su + Rbar); setFVars cpp:303-307: gradient maps; two-sided limit as 2n one-sided
+    rows with l = -DBL_MAX, cpp:42,335), with nu inputs and full-state tracking (include/solvempc_b200.h).
+    Plain numpy with explicit Su / Sx -- deliberately a different evaluation order than the device kernel."""
+    Ad, Bd = _c(Ad), _c(Bd)
+    nx, nu = Bd.shape
+    n = N * nu
+    Sx = np.zeros((N * nx, nx))
+    Su = np.zeros((N * nx, n))
+    Ak = np.eye(nx)
+    AB = []
+    for k in range(N):
+        AB.append(Ak @ Bd)          # Ad^k Bd
+        Ak = Ak @ Ad
+        Sx[k * nx:(k + 1) * nx] = Ak   # x_{k+1} row block = Ad^(k+1)
+    for k in range(1, N + 1):
+        for j in range(k):
+            Su[(k - 1) * nx:k * nx, j * nu:(j + 1) * nu] = AB[k - 1 - j]
+    Qbar = np.tile(np.asarray(Q, dtype=np.float64), N)
+    Rbar = np.tile(np.asarray(R, dtype=np.float64), N)
+    SQ = Su.T * Qbar[None, :]
+    H = 2.0 * (SQ @ Su + np.diag(Rbar))
+    Fx = 2.0 * (SQ @ Sx)
+    Fr = -2.0 * (SQ @ np.tile(np.eye(nx), (N, 1)))
+    A = np.vstack([np.eye(n), -np.eye(n)])
+    ub = np.concatenate([np.tile(umax, N), -np.tile(umin, N)])
+    lb = np.full(2 * n, lib().orc_mpc_lower_bound())
+    return dict(H=H, A=A, ub=ub, lb=lb, Fx=Fx, Fr=Fr, Su=Su, Sx=Sx, N=N, nx=nx, nu=nu)
+
+
+def mimo_batch_vectors(mats, x0, xr):
+    """q = Fx x0 + Fr xr for a batch."""
+    return np.atleast_2d(x0) @ mats["Fx"].T + np.atleast_2d(xr) @ mats["Fr"].T

@@ -45,6 +45,13 @@ class MpcConfig(C.Structure):
     ]
 
 
+class MimoConfig(C.Structure):
+    _fields_ = [
+        ("horizon", C.c_int), ("nx", C.c_int), ("nu", C.c_int),
+        ("Ad", C.c_void_p), ("Bd", C.c_void_p), ("Q", C.c_void_p), ("R", C.c_void_p), ("umin", C.c_void_p), ("umax", C.c_void_p),
+    ]
+
+
 # every symbol include/solvempc_b200.h declares (tests/test_cabi.py checks the header against this list)
 _vp, _i, _dp = C.c_void_p, C.c_int, C.c_void_p
 SIGNATURES = {
@@ -93,6 +100,17 @@ SIGNATURES = {
     "smpc_mpc_get_state": (_i, [_vp, _dp, _dp, _i]),
     "smpc_mpc_get_step_vectors": (_i, [_vp, _dp, _dp, _i]),
     "smpc_mpc_launch_count": (C.c_longlong, [_vp]),
+    "smpc_mimo_create": (_i, [C.POINTER(_vp), _i, C.POINTER(MimoConfig), _i, C.POINTER(Settings)]),
+    "smpc_mimo_create_from_json": (_i, [C.POINTER(_vp), _i, C.c_char_p, _i, C.POINTER(Settings)]),
+    "smpc_mimo_destroy": (_i, [_vp]),
+    "smpc_mimo_set_stream": (_i, [_vp, _vp]),
+    "smpc_mimo_dims": (_i, [_vp] + [C.POINTER(_i)] * 6),
+    "smpc_mimo_solver": (_vp, [_vp]),
+    "smpc_mimo_get_matrix": (_i, [_vp, C.c_char_p, _dp, _i]),
+    "smpc_mimo_set_state": (_i, [_vp, _dp, _dp, _i]),
+    "smpc_mimo_controller_step": (_i, [_vp]),
+    "smpc_mimo_get_control": (_i, [_vp, _dp, _i]),
+    "smpc_mimo_launch_count": (C.c_longlong, [_vp]),
 }
 
 _lib = None

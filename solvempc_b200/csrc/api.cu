@@ -12,10 +12,11 @@
 
 #include "../../include/solvempc_b200.h"
 #include "json_min.hpp"
+#include "handles.hpp"
 #include "kernels.cuh"
 #include "plan.hpp"
 
-namespace {
+namespace smpc {
 
 thread_local std::string g_err;
 
@@ -24,59 +25,29 @@ int cuda_fail(cudaError_t e, const char *what) {
   g_err = std::string(what) + ": " + cudaGetErrorString(e);
   return SMPC_ERR_CUDA;
 }
-#define CK(call)                                         \
-  do {                                                   \
-    cudaError_t e__ = (call);                            \
-    if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
-  } while (0)
 
-struct DeviceBuf {   // one cudaMalloc carved into aligned pieces
-  char *base = nullptr;
-  size_t size = 0, used = 0;
-  cudaError_t alloc(size_t bytes) { size = bytes; used = 0; return cudaMalloc((void **)&base, bytes ? bytes : 256); }
-  template <typename T> T *take(size_t count) {
-    size_t off = (used + 255) & ~size_t(255);
-    used = off + count * sizeof(T);
-    return used <= size ? reinterpret_cast<T *>(base + off) : nullptr;
+}  // namespace smpc
+
+namespace smpc {
+int select_device(int device) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    g_err = "no CUDA device available (this library has no CPU fallback)";
+    if (e != cudaSuccess) { g_err += std::string(": ") + cudaGetErrorString(e); cudaGetLastError(); }
+    return SMPC_ERR_CUDA;
   }
-  static size_t need(size_t bytes) { return ((bytes + 255) & ~size_t(255)) + 256; }
-  void release() { if (base) cudaFree(base); base = nullptr; }
-};
+  if (device < 0 || device >= count) return fail(SMPC_ERR_ARG, "device index out of range");
+  CK(cudaSetDevice(device));
+  return SMPC_OK;
+}
+}  // namespace smpc
 
-}  // namespace
-
-struct smpc_solver {
-  int device = 0, n = 0, m = 0, B = 0;
-  int regime = 0;  // 0 shared-factor, 1 per-instance
-  smpc_settings st{};
-  cudaStream_t stream = nullptr;
-  smpc::SharedPlan plan;
-  DeviceBuf planbuf, batchbuf;
-  smpc::SharedPlanDev dplan{};
-  double *d_q = nullptr, *d_l = nullptr, *d_u = nullptr;
-  bool have_q = false, have_l = false, have_u = false;
-  double *d_xi = nullptr, *d_z = nullptr, *d_y = nullptr, *d_rho = nullptr;
-  double *d_x = nullptr, *d_yout = nullptr, *d_obj = nullptr, *d_pri = nullptr, *d_dua = nullptr;
-  int *d_status = nullptr, *d_iter = nullptr, *d_rhoup = nullptr;
-  double *d_stage_x = nullptr, *d_stage_y = nullptr;  // warm-start staging
-  DeviceBuf instbuf;                                  // per-instance regime: P̄, A̅, D, E, c
-  smpc::InstanceDataDev dinst{};
-  DeviceBuf packbuf;                                  // small-kernel operator pack + work queue
-  smpc::SmallPackDev dpack{};
-  int *d_queue = nullptr, *d_lists = nullptr;
-  DeviceBuf tilebuf;                                  // tile-kernel operator packs (DMMA A fragments) + work queue
-  smpc::TilePackDev dtile{};
-  int tile_nb = 0;
-  int num_sms = 148;
-  bool schedule = true;   // longest-expected-first pre-pass of the small kernel
-  long long launches = 0;
-  int kernel = 1;
-  bool solved_once = false;
-  bool cold_solves = false, timing = false;
-  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;   // pending kernel timings
-  double timed_ms = 0.0;
-  int timed_launches = 0;
-};
+using smpc::cuda_fail;
+using smpc::DeviceBuf;
+using smpc::fail;
+using smpc::g_err;
+using smpc::select_device;
 
 struct smpc_mpc {
   int device = 0, B = 0, plants = 1;
@@ -110,19 +81,6 @@ int check_settings(const smpc_settings &s) {
   if (s.eps_abs < 0 || s.eps_rel < 0 || (s.eps_abs == 0 && s.eps_rel == 0)) return fail(SMPC_ERR_ARG, "eps_abs/eps_rel must be >= 0 and not both 0");
   if (s.max_iter <= 0 || s.check_termination < 0 || s.scaling < 0 || s.adaptive_rho_interval < 0) return fail(SMPC_ERR_ARG, "max_iter > 0; check_termination, scaling, adaptive_rho_interval >= 0");
   if (s.adaptive_rho && !(s.adaptive_rho_tolerance >= 1.0)) return fail(SMPC_ERR_ARG, "adaptive_rho_tolerance must be >= 1");
-  return SMPC_OK;
-}
-
-int select_device(int device) {
-  int count = 0;
-  cudaError_t e = cudaGetDeviceCount(&count);
-  if (e != cudaSuccess || count == 0) {
-    g_err = "no CUDA device available (this library has no CPU fallback)";
-    if (e != cudaSuccess) { g_err += std::string(": ") + cudaGetErrorString(e); cudaGetLastError(); }
-    return SMPC_ERR_CUDA;
-  }
-  if (device < 0 || device >= count) return fail(SMPC_ERR_ARG, "device index out of range");
-  CK(cudaSetDevice(device));
   return SMPC_OK;
 }
 

@@ -59,4 +59,14 @@ cudaError_t launch_mpc_advance(int B, int n, int nx, int per_instance, const dou
                                const int *status, const int *iter, double *X, double *U, unsigned long long *stats, int *step,
                                cudaStream_t stream);
 
+// mimo_assembly.cu : multi-input condensed MPC (BASELINE config 3)
+struct MimoDims { int N, nx, nu; };
+struct MimoMatsDev { double *H, *A, *ub, *Fx, *Fr, *Su, *Sx; };   // row-major; shapes in include/solvempc_b200.h
+cudaError_t launch_mimo_assemble(const MimoDims &d, const double *Ad, const double *Bd, const double *Q, const double *R,
+                                 const double *umin, const double *umax, double *AB, double *AP, const MimoMatsDev &out,
+                                 cudaStream_t stream);
+cudaError_t launch_mimo_step_vectors(const MimoDims &d, int B, const double *Fx, const double *Fr, const double *X0,
+                                     const double *Xr, double *q, cudaStream_t stream);
+cudaError_t launch_mimo_first_move(int B, int n, int nu, const double *x, const int *status, double *u0, cudaStream_t stream);
+
 }  // namespace smpc

@@ -1,0 +1,164 @@
+// mimo_assembly.cu -- on-device condensed-QP assembly and per-step gradient of the multi-input MPC layer
+// (BASELINE config 3: 12-state / 4-input quadrotor, horizon 50 -> n = 200, m = 400).
+//
+// Same construction as the reference builders (src/ModelPredictiveControlAPI.cpp: setTransformations cpp:180-208
+// eliminates the states through powers of Ad; setH cpp:247-263 forms 2(Su' Qbar Su + Rbar); setFVars cpp:303-307
+// forms the gradient maps), generalised from N_C = N_O = 1 (h:31-32) to nu inputs and full-state tracking:
+//   x_k = Ad^k x0 + sum_{j<k} Ad^(k-1-j) Bd u_j                      (k = 1..N)
+//   Sx  = [Ad; Ad^2; ...; Ad^N]            (N*nx x nx)      Su(k,j) = Ad^(k-1-j) Bd for j < k, else 0   (N*nx x N*nu)
+//   H   = 2 (Su' Qbar Su + Rbar)           Fx = 2 Su' Qbar Sx           Fr = -2 Su' Qbar [I; ...; I]
+//   A   = [I; -I]   ub = [umax x N; -umin x N]   lb = -DBL_MAX         (two one-sided row sets, cpp:42,335)
+// and per controller  q = Fx x0 + Fr xr.
+#include <cfloat>
+
+#include "kernels.cuh"
+
+namespace smpc {
+
+namespace {
+constexpr int kMimoMaxNx = 16;
+}
+
+// AB[k] = Ad^k Bd (k < N), AP[k] = Ad^(k+1) (k < N): one CTA, sequential in k (tiny)
+__global__ void __launch_bounds__(256) mimo_powers_kernel(MimoDims d, const double *__restrict__ Ad, const double *__restrict__ Bd,
+                                                          double *__restrict__ AB, double *__restrict__ AP) {
+  const int N = d.N, nx = d.nx, nu = d.nu, tid = threadIdx.x, nt = blockDim.x;
+  __shared__ double A[kMimoMaxNx * kMimoMaxNx], Ak[kMimoMaxNx * kMimoMaxNx], An[kMimoMaxNx * kMimoMaxNx];
+  for (int e = tid; e < nx * nx; e += nt) { A[e] = Ad[e]; Ak[e] = (e / nx == e % nx) ? 1.0 : 0.0; }
+  __syncthreads();
+  for (int k = 0; k < N; ++k) {
+    for (int e = tid; e < nx * nu; e += nt) {   // AB[k] = Ak Bd, Ak = Ad^k
+      const int r = e / nu, c = e % nu;
+      double s = 0.0;
+      for (int j = 0; j < nx; ++j) s += Ak[r * nx + j] * Bd[j * nu + c];
+      AB[(size_t)k * nx * nu + e] = s;
+    }
+    for (int e = tid; e < nx * nx; e += nt) {
+      const int r = e / nx, c = e % nx;
+      double s = 0.0;
+      for (int j = 0; j < nx; ++j) s += Ak[r * nx + j] * A[j * nx + c];
+      An[e] = s;
+    }
+    __syncthreads();
+    for (int e = tid; e < nx * nx; e += nt) { Ak[e] = An[e]; AP[(size_t)k * nx * nx + e] = An[e]; }
+    __syncthreads();
+  }
+}
+
+// one thread per entry of H (n x n), Fx (n x nx), Fr (n x nx), A (m x n), ub (m), Su (N nx x n), Sx (N nx x nx)
+__global__ void __launch_bounds__(256) mimo_assemble_kernel(MimoDims d, const double *__restrict__ AB, const double *__restrict__ AP,
+                                                            const double *__restrict__ Q, const double *__restrict__ R,
+                                                            const double *__restrict__ umin, const double *__restrict__ umax,
+                                                            MimoMatsDev o) {
+  const int N = d.N, nx = d.nx, nu = d.nu, n = N * nu, m = 2 * n;
+  const size_t nH = (size_t)n * n, nF = (size_t)n * nx, nA = (size_t)m * n, nSu = (size_t)N * nx * n, nSx = (size_t)N * nx * nx;
+  const size_t total = nH + 2 * nF + nA + m + nSu + nSx;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    size_t t = e;
+    if (t < nH) {
+      // H[(a,p),(b,q)] = 2 sum_{k > max(a,b)} sum_s Q_s AB[k-1-a][s,p] AB[k-1-b][s,q] + 2 R_p [a==b, p==q]
+      const int i = (int)(t / n), j = (int)(t % n), a = i / nu, p = i % nu, b = j / nu, q = j % nu;
+      const int k0 = (a > b ? a : b) + 1;
+      double s = 0.0;
+      for (int k = k0; k <= N; ++k) {
+        const double *Ma = AB + (size_t)(k - 1 - a) * nx * nu, *Mb = AB + (size_t)(k - 1 - b) * nx * nu;
+        double r = 0.0;
+        for (int c = 0; c < nx; ++c) r += Q[c] * (Ma[c * nu + p] * Mb[c * nu + q]);
+        s += r;
+      }
+      o.H[t] = 2.0 * (s + (i == j ? R[p] : 0.0));
+      continue;
+    }
+    t -= nH;
+    if (t < nF) {
+      // Fx[(a,p), c2] = 2 sum_{k > a} sum_s Q_s AB[k-1-a][s,p] (Ad^k)[s,c2]
+      const int i = (int)(t / nx), c2 = (int)(t % nx), a = i / nu, p = i % nu;
+      double s = 0.0;
+      for (int k = a + 1; k <= N; ++k) {
+        const double *Ma = AB + (size_t)(k - 1 - a) * nx * nu, *Pk = AP + (size_t)(k - 1) * nx * nx;
+        double r = 0.0;
+        for (int c = 0; c < nx; ++c) r += Q[c] * (Ma[c * nu + p] * Pk[c * nx + c2]);
+        s += r;
+      }
+      o.Fx[t] = 2.0 * s;
+      continue;
+    }
+    t -= nF;
+    if (t < nF) {
+      // Fr[(a,p), c2] = -2 Q_c2 sum_{k > a} AB[k-1-a][c2,p]
+      const int i = (int)(t / nx), c2 = (int)(t % nx), a = i / nu, p = i % nu;
+      double s = 0.0;
+      for (int k = a + 1; k <= N; ++k) s += AB[(size_t)(k - 1 - a) * nx * nu + c2 * nu + p];
+      o.Fr[t] = -2.0 * (Q[c2] * s);
+      continue;
+    }
+    t -= nF;
+    if (t < nA) {
+      const int r = (int)(t / n), j = (int)(t % n);
+      o.A[t] = r < n ? (r == j ? 1.0 : 0.0) : (r - n == j ? -1.0 : 0.0);
+      continue;
+    }
+    t -= nA;
+    if (t < (size_t)m) {
+      const int r = (int)t;
+      o.ub[t] = r < n ? umax[r % nu] : -umin[(r - n) % nu];
+      continue;
+    }
+    t -= m;
+    if (t < nSu) {
+      const int row = (int)(t / n), j = (int)(t % n), k = row / nx + 1, c = row % nx, b = j / nu, q = j % nu;   // x_k, k = 1..N
+      o.Su[t] = b < k ? AB[(size_t)(k - 1 - b) * nx * nu + c * nu + q] : 0.0;
+      continue;
+    }
+    t -= nSu;
+    o.Sx[t] = AP[t];   // Sx block k-1 = Ad^k
+  }
+}
+
+// q = Fx x0 + Fr xr : one warp per controller, lanes over the n rows (Fx, Fr stay in L1/L2)
+__global__ void __launch_bounds__(256) mimo_step_vectors_kernel(MimoDims d, int B, const double *__restrict__ Fx,
+                                                                const double *__restrict__ Fr, const double *__restrict__ X0,
+                                                                const double *__restrict__ Xr, double *__restrict__ q) {
+  const int lane = threadIdx.x & 31, b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const int nx = d.nx, n = d.N * d.nu;
+  double x0[kMimoMaxNx], xr[kMimoMaxNx];
+  for (int c = 0; c < nx; ++c) { x0[c] = X0[(size_t)b * nx + c]; xr[c] = Xr[(size_t)b * nx + c]; }
+  for (int i = lane; i < n; i += 32) {
+    double s = 0.0, r = 0.0;
+    for (int c = 0; c < nx; ++c) { s += Fx[(size_t)i * nx + c] * x0[c]; r += Fr[(size_t)i * nx + c] * xr[c]; }
+    q[(size_t)b * n + i] = s + r;
+  }
+}
+
+// u0[b][:] = z_b[0:nu] when the solve ended SOLVED, else NaN
+__global__ void mimo_first_move_kernel(int B, int n, int nu, const double *__restrict__ x, const int *__restrict__ status,
+                                       double *__restrict__ u0) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= B * nu) return;
+  const int b = e / nu, c = e % nu;
+  u0[e] = status[b] == SMPC_SOLVED ? x[(size_t)b * n + c] : __longlong_as_double(0x7ff8000000000000LL);
+}
+
+cudaError_t launch_mimo_assemble(const MimoDims &d, const double *Ad, const double *Bd, const double *Q, const double *R,
+                                 const double *umin, const double *umax, double *AB, double *AP, const MimoMatsDev &out,
+                                 cudaStream_t stream) {
+  if (d.nx < 1 || d.nx > kMimoMaxNx || d.nu < 1 || d.N < 1) return cudaErrorInvalidValue;
+  mimo_powers_kernel<<<1, 256, 0, stream>>>(d, Ad, Bd, AB, AP);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  mimo_assemble_kernel<<<148 * 4, 256, 0, stream>>>(d, AB, AP, Q, R, umin, umax, out);
+  return cudaGetLastError();
+}
+cudaError_t launch_mimo_step_vectors(const MimoDims &d, int B, const double *Fx, const double *Fr, const double *X0,
+                                     const double *Xr, double *q, cudaStream_t stream) {
+  const int wpc = 8;
+  mimo_step_vectors_kernel<<<(B + wpc - 1) / wpc, wpc * 32, 0, stream>>>(d, B, Fx, Fr, X0, Xr, q);
+  return cudaGetLastError();
+}
+cudaError_t launch_mimo_first_move(int B, int n, int nu, const double *x, const int *status, double *u0, cudaStream_t stream) {
+  mimo_first_move_kernel<<<(B * nu + 255) / 256, 256, 0, stream>>>(B, n, nu, x, status, u0);
+  return cudaGetLastError();
+}
+
+}  // namespace smpc

@@ -306,3 +306,74 @@ class BatchedModelPredictiveControlAPI:
     @property
     def launches(self):
         return L.lib().smpc_mpc_launch_count(self._h)
+
+
+class BatchedMimoMPC:
+    """A batch of multi-input condensed MPC controllers sharing one plant (BASELINE config 3: the 12-state /
+    4-input quadrotor).  Same construction as the reference builders (cpp:180-263,303-307) generalised to nu
+    inputs; see include/solvempc_b200.h (smpc_mimo_*)."""
+
+    def __init__(self, config, batch=1, device=0, settings=None, **kw):
+        self.settings = settings if settings is not None else L.default_settings(**kw)
+        h = C.c_void_p()
+        if isinstance(config, (str, bytes)):
+            path = config if isinstance(config, bytes) else config.encode()
+            L.check(L.lib().smpc_mimo_create_from_json(C.byref(h), device, path, batch, C.byref(self.settings)))
+        else:
+            cfg = L.MimoConfig()
+            Ad = np.ascontiguousarray(config["Ad"], dtype=np.float64)
+            Bd = np.ascontiguousarray(config["Bd"], dtype=np.float64).reshape(Ad.shape[0], -1)
+            self._keep = [Ad, Bd] + [np.ascontiguousarray(config[k], dtype=np.float64).reshape(-1) for k in ("Q", "R", "umin", "umax")]
+            cfg.horizon, cfg.nx, cfg.nu = int(config.get("horizon", config.get("N"))), Ad.shape[0], Bd.shape[1]
+            cfg.Ad, cfg.Bd, cfg.Q, cfg.R, cfg.umin, cfg.umax = [a.ctypes.data for a in self._keep]
+            L.check(L.lib().smpc_mimo_create(C.byref(h), device, C.byref(cfg), batch, C.byref(self.settings)))
+        self._h = h
+        d = [C.c_int() for _ in range(6)]
+        L.check(L.lib().smpc_mimo_dims(self._h, *[C.byref(v) for v in d]))
+        self.horizon, self.nx, self.nu, self.n_variables, self.n_constraints, self.batch = [v.value for v in d]
+        self.solver = BatchedSolver(None, None, _handle=L.lib().smpc_mimo_solver(self._h), settings=self.settings)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            L.lib().smpc_mimo_destroy(self._h)
+        self._h = None
+
+    __del__ = close
+
+    def set_stream(self, cuda_stream):
+        L.check(L.lib().smpc_mimo_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def matrix(self, name):
+        N, nx, n, m = self.horizon, self.nx, self.n_variables, self.n_constraints
+        shape = {"H": (n, n), "A": (m, n), "ub": (m,), "Fx": (n, nx), "Fr": (n, nx), "Su": (N * nx, n), "Sx": (N * nx, nx)}[name]
+        out = np.empty(shape)
+        L.check(L.lib().smpc_mimo_get_matrix(self._h, name.encode(), out.ctypes.data, out.size))
+        return out
+
+    def set_state(self, x0=None, xr=None):
+        p0, l0, _k0 = _loc_ptr(x0, self.batch * self.nx, "x0")
+        p1, l1, _k1 = _loc_ptr(xr, self.batch * self.nx, "xr")
+        locs = {l for a, l in ((x0, l0), (xr, l1)) if a is not None}
+        if len(locs) > 1:
+            raise ValueError("x0 and xr must live in the same place")
+        L.check(L.lib().smpc_mimo_set_state(self._h, p0, p1, locs.pop() if locs else L.HOST))
+
+    def controllerStep(self):
+        L.check(L.lib().smpc_mimo_controller_step(self._h))
+        return self.solver.count_solved() == self.batch
+
+    def controller_step_async(self):
+        L.check(L.lib().smpc_mimo_controller_step(self._h))
+
+    def control(self):
+        u0 = np.empty((self.batch, self.nu))
+        L.check(L.lib().smpc_mimo_get_control(self._h, u0.ctypes.data, L.HOST))
+        return u0
+
+    def control_into(self, u0):
+        p, loc, _k = _loc_ptr(u0, self.batch * self.nu, "u0")
+        L.check(L.lib().smpc_mimo_get_control(self._h, p, loc))
+
+    @property
+    def launches(self):
+        return L.lib().smpc_mimo_launch_count(self._h)

@@ -55,3 +55,13 @@ def c4_plants(B, cfg, seed=0):
         out_B[k] = -(Ai - np.eye(nx))[:, 0]
         k += 1
     return out_A, out_B
+
+
+def c3_batch(B, seed=0):
+    """Config 3 inputs: x0 ~ U(-0.5, 0.5) on the positions, 0 elsewhere; reference = hover at z in U(0, 1)."""
+    rng = np.random.default_rng(seed)
+    x0 = np.zeros((B, 12))
+    x0[:, :3] = rng.uniform(-0.5, 0.5, (B, 3))
+    xr = np.zeros((B, 12))
+    xr[:, 2] = rng.uniform(0.0, 1.0, B)
+    return x0, xr
