@@ -61,8 +61,10 @@ typedef struct smpc_settings {
   int max_iter, check_termination, scaling;
   int adaptive_rho, adaptive_rho_interval;
   int warm_start, scaled_termination;
-  int kernel;               /* 0 = auto; 1 = generic warp kernel; 2 = register-resident small-QP kernel (n <= 16, m <= 32);
-                               4 = DMMA tile kernel (8/16 QPs per CTA, FP64 tensor pipe; auto choice for n > 16) */
+  int kernel;               /* 0 = auto; 1 = generic warp kernel; 2 = register-resident small-QP kernel (n <= 16, m <= 32; auto choice there);
+                               4 = DMMA tile kernel (8/16 QPs per CTA, FP64 tensor pipe; auto choice for n > 16);
+                               5 = DMMA variant of the small-QP kernel (8 QPs per 4-warp CTA; higher throughput ceiling at very
+                                   large batches, longer single-iteration latency than 2) */
 } smpc_settings;
 
 void smpc_default_settings(smpc_settings *s);   /* OSQP 0.6 defaults (eps 1e-3) */

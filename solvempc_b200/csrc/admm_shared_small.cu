@@ -16,6 +16,7 @@
 // Termination checks / rho adaptation (every check_termination / adaptive_rho_interval iterations) are an
 // out-of-line routine that reads its operators from shared memory.
 #include <cstdint>
+#include <cstdio>
 
 #include "device_types.cuh"
 #include "kernels.cuh"
@@ -421,24 +422,403 @@ admm_shared_small_kernel(SmallPackDev K, SharedPlanDev P, BatchDev Bt, SettingsD
   }
 }
 
+// =====================================================================================================================
+// DMMA variant of the small-QP kernel: one CTA of four warps owns a TILE of 8 QPs ("slots").
+//
+// The one-warp-per-QP kernel above is bound by shared-memory wavefronts: every lane needs all 40 inputs of its two
+// dot products per iteration, one broadcast wavefront per double (ncu: 58 wavefronts per QP-iteration, 75 % of the
+// SM's LSU pipe at saturation).  Here the 8 slots are the N dimension of mma.sync.m8n8k4.f64, whose B operand is
+// DISTRIBUTED over the lanes (one double each), so [xi; w] is read once per warp as 32 distinct doubles:
+//   GEMM 1  T  = [sigma G | W'] (16 x 48) . [xi; w] (48 x 8)      warp w: row-block w & 1, K-half w >> 1, 6 DMMA,
+//                                                                 partial sums through shared memory (2 KB)
+//   t = (half 0 + half 1) .* dinv   (the - q̂ term is the initial accumulator of half 0)  computed by every warp
+//                                                                 straight in B-fragment layout: no T panel
+//   GEMM 2  Z̃  = W (32 x 16) . T (16 x 8)                          warp w: row-block w, 4 DMMA; z, y, w in registers
+// with two CTA barriers and ~12 shared-memory wavefronts per QP-iteration.  The A fragments (10 doubles per lane)
+// and the element-wise state of the thread's C-fragment entries stay in registers between events.
+// Events (termination check / rho adaptation / max_iter, every check_termination iterations of a slot): each warp
+// runs check_step -- the SAME routine as the one-warp-per-QP kernel -- for its two slots (warp, warp + 4), stores
+// the QPs that finished and refills their slots from the work queue (per-problem convergence masking).
+namespace {
+
+constexpr int kSlots = 8;
+// shared memory of one CTA (doubles): operator block of check_step | per-warp cbuf[16] + sbuf[32] | panels [row][8]
+constexpr int kMmaWarpDoubles = NP + MP;
+constexpr int oS = 0;                        // [xi (16 rows); w (32 rows)]
+constexpr int oP0 = oS + (NP + MP) * 8;      // GEMM 1 partial sums, K-half 0 / 1
+constexpr int oP1 = oP0 + NP * 8;
+constexpr int oDx = oP1 + NP * 8;            // delta_xi of the event iteration
+constexpr int oQh = oDx + NP * 8;            // q̂ = V' q̄
+constexpr int oQb = oQh + NP * 8;            // q̄ = c D q
+constexpr int oDv = oQb + NP * 8;            // 1 / (1 + rho lambda)
+constexpr int oZ = oDv + NP * 8;
+constexpr int oY = oZ + MP * 8;
+constexpr int oLb = oY + MP * 8;
+constexpr int oUb = oLb + MP * 8;
+constexpr int kMmaPanelDoubles = oUb + MP * 8;
+
+struct MmaCtl {
+  double rho[kSlots];
+  int inst[kSlots];      // QP index of the slot, -1 = empty
+  int it0[kSlots];       // tile iteration at which the slot's QP started
+  int rho_up[kSlots];
+  int next_event, active;
+};
+
+__device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+      : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+
+// next QP of the work queue (index order, or longest-expected-first through the class lists); -1 when it is empty
+__device__ __forceinline__ int pop_instance(int *queue, const int *lists, int B) {
+  int q = atomicAdd(queue, 1);
+  if (q >= B) return -1;
+  if (lists == nullptr) return q;
+#pragma unroll
+  for (int k = 0; k < kClasses; ++k) {
+    const int cnt = queue[1 + k];
+    if (q < cnt) return lists[(size_t)k * B + q];
+    q -= cnt;
+  }
+  return -1;
+}
+
+}  // namespace
+
+namespace {
+template <int OFF> __device__ __forceinline__ double lds64o(uint32_t addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(addr), "n"(OFF) : "memory");
+  return v;
+}
+template <int OFF> __device__ __forceinline__ double2 lds128o(uint32_t addr) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(v.x), "=d"(v.y) : "r"(addr), "n"(OFF) : "memory");
+  return v;
+}
+template <int OFF> __device__ __forceinline__ void sts64o(uint32_t addr, double v) {
+  asm volatile("st.shared.f64 [%0+%1], %2;" ::"r"(addr), "n"(OFF), "d"(v) : "memory");
+}
+template <int OFF> __device__ __forceinline__ void sts128o(uint32_t addr, double a, double b) {
+  asm volatile("st.shared.v2.f64 [%0+%1], {%2, %3};" ::"r"(addr), "n"(OFF), "d"(a), "d"(b) : "memory");
+}
+}  // namespace
+
+__global__ void __launch_bounds__(128, 4)
+admm_shared_small_mma_kernel(SmallPackDev K, SharedPlanDev P, BatchDev Bt, SettingsDev S, int *queue, const int *lists) {
+  extern __shared__ __align__(16) double smem[];
+  double *sV = smem + NP * NP * 2 + MP * NP;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double *cbuf = smem + kCtaMatDoubles + warp * kMmaWarpDoubles, *sbuf = cbuf + NP;
+  double *pan = smem + kCtaMatDoubles + 4 * kMmaWarpDoubles;
+  MmaCtl &C = *reinterpret_cast<MmaCtl *>(pan + kMmaPanelDoubles);
+  const int h = lane >> 4, i = lane & 15, r = lane;          // check_step roles (one slot per pass)
+  const int g = lane >> 2, q2 = 2 * (lane & 3);               // DMMA roles: C fragment = rows 8 rb + g, slots q2, q2 + 1
+  const int bfrag = (lane & 3) * 8 + g;                       // B fragment element: k-row lane & 3, slot g
+  const int n = P.n, m = P.m;
+
+  for (int e = tid; e < NP * NP; e += blockDim.x) {
+    smem[e] = K.VT[e]; smem[NP * NP + e] = K.PVT[e]; sV[e] = K.V[e];
+  }
+  for (int e = tid; e < MP * NP; e += blockDim.x) {
+    smem[2 * NP * NP + e] = K.Ab[e];
+    const int rr = e / NP, kk = e % NP;
+    smem[3 * NP * NP + MP * NP + kk * MP + rr] = K.Ab[e];   // AbT[k][r]
+  }
+  for (int e = tid; e < kMmaPanelDoubles; e += blockDim.x) pan[e] = 0.0;
+  if (tid < kSlots) { C.inst[tid] = -1; C.it0[tid] = 0; C.rho_up[tid] = 0; C.rho[tid] = 1.0; }
+  if (tid == 0) { C.next_event = 0; C.active = 0; }
+
+  const double alpha = S.alpha, oma = 1.0 - S.alpha;
+  const int check_every = S.check_every > 0 ? S.check_every : 0, adapt_every = (S.adaptive_rho && S.rho_interval > 0) ? S.rho_interval : 0;
+  const bool warm = S.warm_start && !Bt.fresh;
+
+  // GEMM 1 unit of this warp = row-block warp & 1, k-steps 6 (warp >> 1) .. +5 of [sigma G | W'] (K = 48); GEMM 2 unit =
+  // row-block warp of W (K = 16).  The A fragments (a1, a2) are (re)loaded after every event so that they are not live
+  // across the event code.
+  const int rb1 = warp & 1, kh = warp >> 1;
+  double a1[6], a2[4];
+  const int ct_c = K.ctype[8 * warp + g];                     // row class of this thread's C-fragment row
+
+  // loop-invariant shared-memory addresses (32-bit shared window, byte offsets as immediates)
+  const uint32_t sPan = (uint32_t)__cvta_generic_to_shared(pan);
+  const uint32_t aB = sPan + 8 * bfrag;                                      // B-fragment element of a panel row group
+  const uint32_t aB1 = aB + 8 * 192 * kh;                                    // GEMM 1 B fragments of this K-half: + 256 j
+  const uint32_t aPartSt = sPan + 8 * ((kh ? oP1 : oP0) + (8 * rb1 + g) * 8 + q2);
+  const uint32_t aXi = aB + 8 * 32 * warp;                                   // this warp updates xi rows 4 warp .. 4 warp + 3
+  const uint32_t aC = sPan + 8 * ((8 * warp + g) * 8 + q2);                  // C-fragment offset inside an m-panel
+  const bool sel1 = warp & 1, sel2 = warp & 2;
+
+  // element-wise state in registers between events
+  double r_nq[2], r_dv[4], r_xi = 0.0, r_omxi = 0.0, r_y[2], r_lo[2], r_hi[2], r_rv[2], r_ri[2], r_base[2];
+  int k = 0, next_event = 0;
+  __syncthreads();
+
+#ifdef SMPC_PROFILE
+  long long pf_ev = 0, pf_it = 0, pf_t0 = clock64(), pf_chk = 0; int pf_nev = 0;
+#endif
+  for (;;) {
+    if (k == next_event) {
+#ifdef SMPC_PROFILE
+      { const long long tt = clock64(); pf_it += tt - pf_t0; pf_t0 = tt; }
+#endif
+      // ================= event: every warp handles the slots warp and warp + 4
+      // (per-lane plan constants are loaded here, not kept in registers across the main loop)
+      const double lam_i = __ldg(K.lam + i), c = P.c, cinv = P.cinv;
+      const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+      LaneConst LC;
+      LC.D = __ldg(K.D + i); LC.Dinv = __ldg(K.Dinv + i); LC.E = __ldg(K.E + r); LC.Einv = __ldg(K.Einv + r); LC.ct = __ldg(K.ctype + r);
+      for (int s = warp; s < kSlots; s += 4) {
+        int b = C.inst[s];
+        double rho = C.rho[s];
+        bool refill = b < 0 && k == 0;            // the first event only fills the tile
+        if (b >= 0) {
+          const int li = k - C.it0[s];
+          const bool do_check = check_every && li % check_every == 0, do_adapt = adapt_every && li % adapt_every == 0;
+          const bool at_max = li >= S.max_iter;
+          if (do_check || do_adapt || at_max) {
+            // this slot's column of the panels in the one-warp-per-QP register layout of check_step
+            const double qb_i = pan[oQb + i * 8 + s], dxi_i = pan[oDx + i * 8 + s], xi_i = pan[oS + i * 8 + s];
+            const double z_r = pan[oZ + r * 8 + s], y_r = pan[oY + r * 8 + s], dy_r = pan[oS + (NP + r) * 8 + s];
+            const double lb_r = pan[oLb + r * 8 + s], ub_r = pan[oUb + r * 8 + s];
+            if (h == 0) cbuf[i] = xi_i;
+            __syncwarp();
+            int status = SMPC_UNSOLVED;
+            CheckOut co;
+            co.obj = 0.0; co.pri_res = 0.0; co.dua_res = 0.0; co.xbar = 0.0;
+            if (do_check || do_adapt) {
+#ifdef SMPC_PROFILE
+              const long long tc = clock64();
+#endif
+              co = check_step(smem, cbuf, sbuf, S, n, m, c, cinv, LC, rho, qb_i, z_r, y_r, dy_r, dxi_i, lb_r, ub_r, do_check, false, do_adapt);
+              status = co.status;
+#ifdef SMPC_PROFILE
+              pf_chk += clock64() - tc;
+#endif
+              if (status == SMPC_UNSOLVED && co.rho_changed) {
+                rho = co.rho;
+                if (lane == 0) { C.rho[s] = rho; C.rho_up[s]++; }
+                if (h == 0) pan[oDv + i * 8 + s] = 1.0 / (1.0 + rho * lam_i);
+              }
+            }
+            if (at_max && status == SMPC_UNSOLVED) {
+              if (!do_check) {
+                co = check_step(smem, cbuf, sbuf, S, n, m, c, cinv, LC, rho, qb_i, z_r, y_r, dy_r, dxi_i, lb_r, ub_r, true, false, false);
+                status = co.status;
+              }
+              if (status == SMPC_UNSOLVED) {
+                const CheckOut ca = check_step(smem, cbuf, sbuf, S, n, m, c, cinv, LC, rho, qb_i, z_r, y_r, dy_r, dxi_i, lb_r, ub_r, true, true, false);
+                status = ca.status == SMPC_UNSOLVED ? SMPC_MAX_ITER_REACHED : ca.status;
+                if (ca.status != SMPC_UNSOLVED) co.obj = ca.obj;
+              }
+            }
+            __syncwarp();
+            if (status != SMPC_UNSOLVED) {
+              // ---- store_solution
+              const bool has_sol = !(status == SMPC_PRIMAL_INFEASIBLE || status == SMPC_PRIMAL_INFEASIBLE_INACCURATE ||
+                                     status == SMPC_DUAL_INFEASIBLE || status == SMPC_DUAL_INFEASIBLE_INACCURATE);
+              if (h == 0 && i < n) {
+                if (Bt.x_out) Bt.x_out[(size_t)b * n + i] = has_sol ? LC.D * co.xbar : qnan;
+                Bt.xi[(size_t)b * n + i] = has_sol ? xi_i : 0.0;
+              }
+              if (r < m) {
+                if (Bt.y_out) Bt.y_out[(size_t)b * m + r] = has_sol ? cinv * (LC.E * y_r) : qnan;
+                Bt.z[(size_t)b * m + r] = has_sol ? z_r : 0.0;
+                Bt.y[(size_t)b * m + r] = has_sol ? y_r : 0.0;
+              }
+              if (lane == 0) {
+                Bt.rho[b] = rho;
+                Bt.status[b] = status; Bt.iter[b] = li; Bt.rho_updates[b] = C.rho_up[s];
+                Bt.obj[b] = co.obj; Bt.pri_res[b] = co.pri_res; Bt.dua_res[b] = co.dua_res;
+              }
+              refill = true;
+            }
+          }
+        }
+        if (refill) {
+          // ---- next QP of the queue into slot s (osqp_update_lin_cost / osqp_update_bounds scaling); QPs with invalid
+          //      bounds (see admm_shared_generic.cu) are stored as UNSOLVED at once and the slot is filled again
+          for (;;) {
+            b = 0;
+            if (lane == 0) b = pop_instance(queue, lists, Bt.B);
+            b = __shfl_sync(kFull, b, 0);
+            double qb_i = 0.0, xi_i = 0.0, lb_r = -1.0, ub_r = 1.0, z_r = 0.0, y_r = 0.0, nqh = 0.0;
+            rho = 1.0;
+            if (b >= 0) {
+              qb_i = (i < n && Bt.q) ? c * (LC.D * Bt.q[(size_t)b * n + i]) : 0.0;
+              if (i < n && warm) xi_i = Bt.xi[(size_t)b * n + i];
+              if (r < m) {
+                lb_r = LC.E * (Bt.l ? Bt.l[(size_t)b * m + r] : P.l0[r]);
+                ub_r = LC.E * (Bt.u ? Bt.u[(size_t)b * m + r] : P.u0[r]);
+                if (warm) { z_r = Bt.z[(size_t)b * m + r]; y_r = Bt.y[(size_t)b * m + r]; }
+              }
+              rho = Bt.fresh ? fmin(fmax(S.rho0, kRhoMin), kRhoMax) : Bt.rho[b];
+              const int ct_now = (lb_r < -kInfty * kMinScaling && ub_r > kInfty * kMinScaling) ? -1 : ((ub_r - lb_r < kRhoTolRow) ? 1 : 0);
+              if (__any_sync(kFull, r < m && (lb_r > ub_r || ct_now != LC.ct))) {
+                if (h == 0 && i < n) { if (Bt.x_out) Bt.x_out[(size_t)b * n + i] = qnan; Bt.xi[(size_t)b * n + i] = 0.0; }
+                if (r < m) { if (Bt.y_out) Bt.y_out[(size_t)b * m + r] = qnan; Bt.z[(size_t)b * m + r] = 0.0; Bt.y[(size_t)b * m + r] = 0.0; }
+                if (lane == 0) {
+                  Bt.rho[b] = rho; Bt.status[b] = SMPC_UNSOLVED; Bt.iter[b] = 0; Bt.rho_updates[b] = 0;
+                  Bt.obj[b] = 0.0; Bt.pri_res[b] = 0.0; Bt.dua_res[b] = 0.0;
+                }
+                continue;
+              }
+              // q̂ = V' q̄
+              if (h == 0) sbuf[i] = qb_i;
+              __syncwarp();
+              double a = 0.0;
+#pragma unroll
+              for (int kk = 0; kk < NP / 2; ++kk) a = fma(sV[(8 * h + kk) * NP + i], sbuf[8 * h + kk], a);
+              a += __shfl_xor_sync(kFull, a, 16);
+              nqh = a;
+              __syncwarp();
+            }
+            if (h == 0) {
+              pan[oS + i * 8 + s] = xi_i; pan[oQb + i * 8 + s] = qb_i; pan[oQh + i * 8 + s] = nqh; pan[oDx + i * 8 + s] = 0.0;
+              pan[oDv + i * 8 + s] = b >= 0 ? 1.0 / (1.0 + rho * lam_i) : 1.0;
+            }
+            pan[oZ + r * 8 + s] = z_r; pan[oY + r * 8 + s] = y_r; pan[oLb + r * 8 + s] = lb_r; pan[oUb + r * 8 + s] = ub_r;
+            if (lane == 0) { C.inst[s] = b; C.it0[s] = k; C.rho_up[s] = 0; C.rho[s] = rho; }
+            break;
+          }
+        }
+        // ---- w = rho_vec z - y (the w panel carried delta_y during the event iteration)
+        __syncwarp();
+        pan[oS + (NP + r) * 8 + s] = rho_row(LC.ct, rho) * pan[oZ + r * 8 + s] - pan[oY + r * 8 + s];
+      }
+      __syncthreads();
+      if (tid == 0) {
+        int act = 0, ne = 0x7fffffff;
+        for (int s = 0; s < kSlots; ++s) {
+          if (C.inst[s] < 0) continue;
+          ++act;
+          const int li = k - C.it0[s];
+          int nx = S.max_iter;
+          if (check_every) nx = min(nx, (li / check_every + 1) * check_every);
+          if (adapt_every) nx = min(nx, (li / adapt_every + 1) * adapt_every);
+          ne = min(ne, C.it0[s] + nx);
+        }
+        C.active = act; C.next_event = ne;
+      }
+      __syncthreads();
+#ifdef SMPC_PROFILE
+      { const long long tt = clock64(); pf_ev += tt - pf_t0; pf_t0 = tt; ++pf_nev; }
+      if (C.active == 0 && blockIdx.x == 0 && tid == 0) printf("mma profile: %d events %lld cycles (check_step %lld), %d iterations %lld cycles\n", pf_nev, pf_ev, pf_chk, k, pf_it);
+#endif
+      if (C.active == 0) break;
+      next_event = C.next_event;
+      // ---- reload this thread's registers from the panels; operator fragments from L1 / L2 (M1T, WT are k-major:
+      //      fragment element (row 8 rb + g, k = 4 ks + (lane & 3)))
+#pragma unroll
+      for (int j = 0; j < 6; ++j) a1[j] = __ldg(K.M1T + (4 * (6 * kh + j) + (lane & 3)) * NP + 8 * rb1 + g);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) a2[j] = __ldg(K.WT + (4 * j + (lane & 3)) * MP + 8 * warp + g);
+      r_dv[0] = lds64o<8 * oDv>(aB); r_dv[1] = lds64o<8 * (oDv + 32)>(aB); r_dv[2] = lds64o<8 * (oDv + 64)>(aB); r_dv[3] = lds64o<8 * (oDv + 96)>(aB);
+      r_xi = lds64o<8 * oS>(aXi); r_omxi = oma * r_xi;
+      {
+        const double2 qv = *reinterpret_cast<const double2 *>(pan + oQh + (8 * rb1 + g) * 8 + q2);
+        r_nq[0] = kh ? 0.0 : -qv.x; r_nq[1] = kh ? 0.0 : -qv.y;
+        const double2 zz = lds128o<8 * oZ>(aC), yy = lds128o<8 * oY>(aC), lo = lds128o<8 * oLb>(aC), hi = lds128o<8 * oUb>(aC);
+        const double r_z[2] = {zz.x, zz.y};
+        r_y[0] = yy.x; r_y[1] = yy.y; r_lo[0] = lo.x; r_lo[1] = lo.y; r_hi[0] = hi.x; r_hi[1] = hi.y;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          r_rv[j] = rho_row(ct_c, C.rho[q2 + j]); r_ri[j] = 1.0 / r_rv[j];
+          r_base[j] = fma(r_ri[j], r_y[j], oma * r_z[j]);
+        }
+      }
+    }
+
+    // ================= one ADMM iteration of the tile (same arithmetic per QP as admm_shared_small_kernel)
+    ++k;
+    const bool event = k == next_event;
+    // ---- GEMM 1 partial sums
+    {
+      const double b0 = lds64o<0>(aB1), b1 = lds64o<256>(aB1), b2 = lds64o<512>(aB1);
+      const double b3 = lds64o<768>(aB1), b4 = lds64o<1024>(aB1), b5 = lds64o<1280>(aB1);
+      double c0[2] = {r_nq[0], r_nq[1]}, c1[2] = {0.0, 0.0};
+      dmma(c0, a1[0], b0); dmma(c1, a1[1], b1); dmma(c0, a1[2], b2);
+      dmma(c1, a1[3], b3); dmma(c0, a1[4], b4); dmma(c1, a1[5], b5);
+      sts128o<0>(aPartSt, c0[0] + c1[0], c0[1] + c1[1]);
+    }
+    __syncthreads();
+    // ---- t in B-fragment layout, x update by the warp that owns the rows
+    double t[4];
+    t[0] = (lds64o<8 * oP0>(aB) + lds64o<8 * oP1>(aB)) * r_dv[0];
+    t[1] = (lds64o<8 * (oP0 + 32)>(aB) + lds64o<8 * (oP1 + 32)>(aB)) * r_dv[1];
+    t[2] = (lds64o<8 * (oP0 + 64)>(aB) + lds64o<8 * (oP1 + 64)>(aB)) * r_dv[2];
+    t[3] = (lds64o<8 * (oP0 + 96)>(aB) + lds64o<8 * (oP1 + 96)>(aB)) * r_dv[3];
+    // ---- GEMM 2 and the z, y, w updates (OSQP update_z / update_y re-associated as in the one-warp kernel)
+    {
+      double c0[2] = {0.0, 0.0}, c1[2] = {0.0, 0.0};
+      dmma(c0, a2[0], t[0]); dmma(c1, a2[1], t[1]); dmma(c0, a2[2], t[2]); dmma(c1, a2[3], t[3]);
+      {
+        const double ta = sel1 ? t[1] : t[0], tb = sel1 ? t[3] : t[2], tw = sel2 ? tb : ta;
+        const double xn = fma(alpha, tw, r_omxi);
+        sts64o<8 * oS>(aXi, xn);
+        if (event) sts64o<8 * oDx>(aXi, xn - r_xi);
+        r_xi = xn; r_omxi = oma * xn;
+      }
+      double wv[2], r_z[2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const double v = fma(alpha, c0[j] + c1[j], r_base[j]);
+        const double zn = v < r_lo[j] ? r_lo[j] : (v > r_hi[j] ? r_hi[j] : v);
+        const double yn = r_rv[j] * (v - zn);
+        wv[j] = event ? yn - r_y[j] : r_rv[j] * fma(2.0, zn, -v);   // before an event the w panel carries delta_y
+        r_y[j] = yn; r_z[j] = zn;
+        r_base[j] = fma(r_ri[j], yn, oma * zn);
+      }
+      sts128o<8 * (oS + NP * 8)>(aC, wv[0], wv[1]);
+      if (event) { sts128o<8 * oZ>(aC, r_z[0], r_z[1]); sts128o<8 * oY>(aC, r_y[0], r_y[1]); }
+    }
+    __syncthreads();
+  }
+}
+
 bool small_kernel_supports(int n, int m) { return n >= 1 && n <= NP && m >= 0 && m <= MP; }
 
 size_t small_pack_doubles() { return (size_t)(NP + MP) * NP + NP * MP + 3 * NP * NP + MP * NP + 3 * NP + 2 * MP; }
 
 int small_queue_ints() { return 1 + kClasses; }
 
+// scheduling pre-pass: zeroes the queue ([0] work counter, [1..kClasses] class sizes) and fills the class lists
+static cudaError_t launch_classify_small(const SmallPackDev &K, const SharedPlanDev &P, const BatchDev &Bt, int *queue, int *lists,
+                                         cudaStream_t stream) {
+  cudaError_t e = cudaMemsetAsync(queue, 0, sizeof(int) * (1 + kClasses), stream);
+  if (e != cudaSuccess) return e;
+  classify_small_kernel<<<(Bt.B + 7) / 8, 256, 0, stream>>>(K, P, Bt, queue + 1, lists);
+  return cudaGetLastError();
+}
+
+// DMMA variant: 8 QPs per CTA of four warps, up to four CTAs per SM
+cudaError_t launch_admm_shared_small_mma(const SmallPackDev &K, const SharedPlanDev &P, const BatchDev &Bt,
+                                         const SettingsDev &S, int *queue, int *lists, int num_sms, cudaStream_t stream) {
+  const size_t smem = (size_t)(kCtaMatDoubles + 4 * kMmaWarpDoubles + kMmaPanelDoubles) * sizeof(double) + sizeof(MmaCtl);
+  cudaError_t e = lists ? launch_classify_small(K, P, Bt, queue, lists, stream)
+                        : cudaMemsetAsync(queue, 0, sizeof(int) * (1 + kClasses), stream);
+  if (e != cudaSuccess) return e;
+  int grid = (Bt.B + kSlots - 1) / kSlots;
+  if (grid > num_sms * 4) grid = num_sms * 4;
+  static bool attr_set = false;
+  if (!attr_set) {
+    e = cudaFuncSetAttribute(admm_shared_small_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  admm_shared_small_mma_kernel<<<grid, 128, smem, stream>>>(K, P, Bt, S, queue, lists);
+  return cudaGetLastError();
+}
+
 // queue: [0] work counter, [1..kClasses] class sizes; lists: kClasses * B instance indices (nullptr = index order)
 cudaError_t launch_admm_shared_small(const SmallPackDev &K, const SharedPlanDev &P, const BatchDev &Bt,
                                      const SettingsDev &S, int *queue, int *lists, int num_sms, cudaStream_t stream) {
   const int wpc = 4;
   const size_t smem = (size_t)(kCtaMatDoubles + wpc * kWarpDoubles) * sizeof(double);
-  cudaError_t e = cudaMemsetAsync(queue, 0, sizeof(int) * (1 + kClasses), stream);
+  cudaError_t e = lists ? launch_classify_small(K, P, Bt, queue, lists, stream)
+                        : cudaMemsetAsync(queue, 0, sizeof(int) * (1 + kClasses), stream);
   if (e != cudaSuccess) return e;
-  if (lists) {
-    classify_small_kernel<<<(Bt.B + 7) / 8, 256, 0, stream>>>(K, P, Bt, queue + 1, lists);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-  }
   int grid = (Bt.B + wpc - 1) / wpc;
   const int resident = num_sms * 3;   // __launch_bounds__(128, 3): three CTAs (12 warps) per SM
   if (grid > resident) grid = resident;

@@ -283,11 +283,11 @@ int create_shared_common(smpc_solver **out, int device, int n, int m, int batch,
   }
   if (rc == SMPC_OK) { cudaError_t e = cudaStreamSynchronize(s->stream); if (e != cudaSuccess) rc = cuda_fail(e, "setup sync"); }
   s->kernel = 1;
-  if (rc == SMPC_OK && settings->kernel != 0 && settings->kernel != 1 && settings->kernel != 2 && settings->kernel != 4)
-    rc = fail(SMPC_ERR_ARG, "settings.kernel must be 0 (auto), 1 (generic), 2 (small) or 4 (tile)");
-  if (rc == SMPC_OK && (settings->kernel == 2 || (settings->kernel == 0 && smpc::small_kernel_supports(n, m)))) {
-    if (!smpc::small_kernel_supports(n, m)) rc = fail(SMPC_ERR_ARG, "kernel 2 (register-resident) supports n <= 16, m <= 32 only");
-    else { s->kernel = 2; rc = upload_small_pack(s); }
+  if (rc == SMPC_OK && settings->kernel != 0 && settings->kernel != 1 && settings->kernel != 2 && settings->kernel != 4 && settings->kernel != 5)
+    rc = fail(SMPC_ERR_ARG, "settings.kernel must be 0 (auto), 1 (generic), 2 (small), 4 (tile) or 5 (small, DMMA)");
+  if (rc == SMPC_OK && (settings->kernel == 2 || settings->kernel == 5 || (settings->kernel == 0 && smpc::small_kernel_supports(n, m)))) {
+    if (!smpc::small_kernel_supports(n, m)) rc = fail(SMPC_ERR_ARG, "kernels 2 and 5 (small QPs) support n <= 16, m <= 32 only");
+    else { s->kernel = settings->kernel == 5 ? 5 : 2; rc = upload_small_pack(s); }
   } else if (rc == SMPC_OK && (settings->kernel == 4 || (settings->kernel == 0 && smpc::tile_kernel_supports(n, m)))) {
     if (!smpc::tile_kernel_supports(n, m)) rc = fail(SMPC_ERR_ARG, "kernel 4 (DMMA tile): the iterates of 8 QPs do not fit shared memory");
     else { s->kernel = 4; rc = upload_tile_pack(s); }
@@ -482,11 +482,12 @@ int smpc_solver_solve(smpc_solver *s) {
   }
   cudaError_t e = s->regime == 1 ? smpc::launch_admm_instance(s->dinst, b, sd, s->stream)
                   : s->kernel == 2 ? smpc::launch_admm_shared_small(s->dpack, s->dplan, b, sd, s->d_queue, s->schedule ? s->d_lists : nullptr, s->num_sms, s->stream)
+                  : s->kernel == 5 ? smpc::launch_admm_shared_small_mma(s->dpack, s->dplan, b, sd, s->d_queue, s->schedule ? s->d_lists : nullptr, s->num_sms, s->stream)
                   : s->kernel == 4 ? smpc::launch_admm_shared_tile(s->dtile, s->dplan, b, sd, s->d_queue, s->tile_nb, s->num_sms, s->stream)
                                    : smpc::launch_admm_shared_generic(s->dplan, b, sd, s->stream);
   if (e != cudaSuccess) return cuda_fail(e, "ADMM kernel launch");
   if (s->timing) { CK(cudaEventRecord(ev1, s->stream)); s->events.emplace_back(ev0, ev1); }
-  s->launches += (s->regime == 0 && s->kernel == 2 && s->schedule) ? 2 : 1;
+  s->launches += (s->regime == 0 && (s->kernel == 2 || s->kernel == 5) && s->schedule) ? 2 : 1;
   s->solved_once = true;
   return SMPC_OK;
 }
@@ -590,7 +591,7 @@ long long smpc_solver_launch_count(const smpc_solver *s) { return s ? s->launche
 const char *smpc_solver_kernel_name(const smpc_solver *s) {
   if (!s) return "";
   return s->regime == 1 ? "admm_instance_kernel" : s->kernel == 2 ? "admm_shared_small_kernel"
-         : s->kernel == 4 ? "admm_shared_tile_kernel" : "admm_shared_generic_kernel";
+         : s->kernel == 4 ? "admm_shared_tile_kernel" : s->kernel == 5 ? "admm_shared_small_mma_kernel" : "admm_shared_generic_kernel";
 }
 
 /* host-only inspection of the shared plan (no device needed): used by the CPU tests of the host logic */

@@ -21,6 +21,10 @@ int small_queue_ints();
 cudaError_t launch_admm_shared_small(const SmallPackDev &K, const SharedPlanDev &P, const BatchDev &Bt,
                                      const SettingsDev &S, int *queue, int *lists, int num_sms, cudaStream_t stream);
 
+// DMMA variant of the small-QP kernel: 8 QPs per CTA of four warps (same packs, same queue / lists)
+cudaError_t launch_admm_shared_small_mma(const SmallPackDev &K, const SharedPlanDev &P, const BatchDev &Bt,
+                                         const SettingsDev &S, int *queue, int *lists, int num_sms, cudaStream_t stream);
+
 // admm_shared_tile.cu : DMMA tile kernel for mid-size QPs (8 or 16 QPs per CTA, iterates in shared memory)
 bool tile_kernel_supports(int n, int m);
 int tile_kernel_nb(int n, int m);                 // 8-slot blocks per tile that fit shared memory (0 = unsupported)

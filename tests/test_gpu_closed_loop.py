@@ -30,7 +30,7 @@ def oracle_loop(cfg, mats, X, U, steps, amp, period, phase):
     return X, U, iters
 
 
-@pytest.mark.parametrize("N,kernel,B,steps", [(15, 2, 24, 40), (15, 4, 24, 40), (100, 4, 20, 12), (100, 1, 6, 6)])
+@pytest.mark.parametrize("N,kernel,B,steps", [(15, 2, 24, 40), (15, 4, 24, 40), (15, 5, 24, 40), (100, 4, 20, 12), (100, 1, 6, 6)])
 def test_closed_loop_driver_matches_oracle_loop(ref_mats, N, kernel, B, steps):
     _, cfg = ref_mats
     mats = oracle.mpc_build(**{**cfg, "N": N})

@@ -48,10 +48,11 @@ def cfg_path(repo_root):
     return os.path.join(repo_root, "config", "MPC_API.json")
 
 
-KERNEL_NAMES = {1: "admm_shared_generic_kernel", 2: "admm_shared_small_kernel", 4: "admm_shared_tile_kernel"}
+KERNEL_NAMES = {1: "admm_shared_generic_kernel", 2: "admm_shared_small_kernel", 4: "admm_shared_tile_kernel",
+                5: "admm_shared_small_mma_kernel"}
 
 
-@pytest.mark.parametrize("kernel", [1, 2, 4])
+@pytest.mark.parametrize("kernel", [1, 2, 4, 5])
 def test_c1_reference_cases_through_mpc_api(cfg_path, golden, ref_mats, kernel):
     """Config 1: shipped plant + horizon, the four known-answer states, one controller each (B=1) and batched."""
     m, _ = ref_mats
@@ -90,7 +91,7 @@ def test_c1_reference_cases_through_mpc_api(cfg_path, golden, ref_mats, kernel):
         assert set(np.nonzero(active_set(m["Gbar"], x[j], y[j], ub[j]))[0]) == set(c["active"])
 
 
-@pytest.mark.parametrize("kernel", [1, 2, 4])
+@pytest.mark.parametrize("kernel", [1, 2, 4, 5])
 def test_c2_batch_4096_matches_oracle(ref_mats, kernel):
     """Config 2: 4096 random x0 / references sharing P and A, cold solves."""
     m, _ = ref_mats
@@ -145,9 +146,20 @@ def test_generic_and_small_kernels_agree_bitwise_on_status(ref_mats):
     s.close()
 
 
+@pytest.mark.parametrize("kernel", [2, 5])
+@pytest.mark.parametrize("n,m,B", [(3, 0, 8), (12, 20, 64), (16, 32, 64), (9, 14, 19)])
+def test_random_qps_small_kernels(n, m, B, kernel):
+    """The two small-QP kernels (one warp per QP; DMMA tile of 8 QPs) on every shape class they accept."""
+    _random_qps(n, m, B, kernel)
+
+
 @pytest.mark.parametrize("kernel", [1, 4])
 @pytest.mark.parametrize("n,m,B", [(3, 0, 8), (12, 20, 64), (16, 32, 64), (17, 33, 32), (40, 70, 37), (100, 200, 8)])
 def test_random_qps_generic_shapes(n, m, B, kernel):
+    _random_qps(n, m, B, kernel)
+
+
+def _random_qps(n, m, B, kernel):
     """Two-sided bounds, equality rows and a free row; every instance gets its own q, l, u.  The tile kernel (4)
     sums its dot products in DMMA order, so an instance sitting on a termination threshold may stop one check
     (25 iterations) away from the oracle: iteration counts must agree on >= 90 % of the instances and the
@@ -190,7 +202,7 @@ def test_random_qps_generic_shapes(n, m, B, kernel):
     s.close()
 
 
-@pytest.mark.parametrize("kernel", [1, 2, 4])
+@pytest.mark.parametrize("kernel", [1, 2, 4, 5])
 @pytest.mark.parametrize("opts", [dict(adaptive_rho=0), dict(scaling=0), dict(scaled_termination=1),
                                   dict(adaptive_rho_interval=50), dict(check_termination=10, adaptive_rho_interval=30),
                                   dict(max_iter=30), dict(alpha=1.0, rho=1.0, eps_abs=1e-3, eps_rel=1e-3)])
@@ -209,7 +221,7 @@ def test_settings_follow_the_oracle(ref_mats, kernel, opts):
     s.close()
 
 
-@pytest.mark.parametrize("kernel", [1, 2, 4])
+@pytest.mark.parametrize("kernel", [1, 2, 4, 5])
 def test_infeasible_unbounded_and_bad_bounds(kernel):
     P = np.eye(2); A = np.array([[1.0, 0.0], [1.0, 0.0]])
     l = np.array([[1.0, -np.inf], [-2.0, -np.inf], [0.5, -np.inf]]); u = np.array([[np.inf, -1.0], [np.inf, 3.0], [np.inf, 0.25]])
@@ -243,7 +255,7 @@ def test_infeasible_unbounded_and_bad_bounds(kernel):
     s.close()
 
 
-@pytest.mark.parametrize("kernel", [1, 2, 4])
+@pytest.mark.parametrize("kernel", [1, 2, 4, 5])
 def test_closed_loop_warm_start_matches_reference_run(cfg_path, golden, ref_mats, kernel):
     """40 warm-started controllerStep + plant steps: the golden trajectory came from the reference's own class."""
     m, cfg = ref_mats
