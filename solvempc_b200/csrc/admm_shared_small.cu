@@ -50,6 +50,15 @@ __device__ __forceinline__ double wsum(double v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
   return v;
 }
+// queue layout: [0] work counter, [1..kClasses] class sizes, [1 + kClasses] warps / CTAs that finished
+__device__ __forceinline__ void release_queue(int *queue, int participants) {
+  __threadfence();
+  if (atomicAdd(queue + 1 + kClasses, 1) == participants - 1) {
+#pragma unroll
+    for (int k = 0; k <= 1 + kClasses; ++k) queue[k] = 0;
+    __threadfence();
+  }
+}
 __device__ __forceinline__ double rho_row(int ct, double rho) {
   return ct == 0 ? rho : (ct == 1 ? kRhoEqOverIneq * rho : kRhoMin);
 }
@@ -418,8 +427,11 @@ admm_shared_small_kernel(SmallPackDev K, SharedPlanDev P, BatchDev Bt, SettingsD
       Bt.rho[b] = rho;
       Bt.status[b] = status; Bt.iter[b] = iter; Bt.rho_updates[b] = rho_updates;
       Bt.obj[b] = co.obj; Bt.pri_res[b] = co.pri_res; Bt.dua_res[b] = co.dua_res;
+      if (Bt.u_apply && status == SMPC_SOLVED) Bt.u_apply[b] += LC.D * co.xbar;   // U += dU*[0] (cpp:105), lane 0 holds x[0]
     }
   }
+  // the last warp of the grid to leave re-arms the queue for the next launch (no memset node per solve)
+  if (lane == 0) release_queue(queue, gridDim.x * (blockDim.x >> 5));
 }
 
 // =====================================================================================================================
@@ -631,6 +643,7 @@ admm_shared_small_mma_kernel(SmallPackDev K, SharedPlanDev P, BatchDev Bt, Setti
                 Bt.rho[b] = rho;
                 Bt.status[b] = status; Bt.iter[b] = li; Bt.rho_updates[b] = C.rho_up[s];
                 Bt.obj[b] = co.obj; Bt.pri_res[b] = co.pri_res; Bt.dua_res[b] = co.dua_res;
+                if (Bt.u_apply && status == SMPC_SOLVED) Bt.u_apply[b] += LC.D * co.xbar;   // U += dU*[0] (cpp:105)
               }
               refill = true;
             }
@@ -775,19 +788,19 @@ admm_shared_small_mma_kernel(SmallPackDev K, SharedPlanDev P, BatchDev Bt, Setti
     }
     __syncthreads();
   }
+  if (tid == 0) release_queue(queue, gridDim.x);
 }
 
 bool small_kernel_supports(int n, int m) { return n >= 1 && n <= NP && m >= 0 && m <= MP; }
 
 size_t small_pack_doubles() { return (size_t)(NP + MP) * NP + NP * MP + 3 * NP * NP + MP * NP + 3 * NP + 2 * MP; }
 
-int small_queue_ints() { return 1 + kClasses; }
+int small_queue_ints() { return 2 + kClasses; }
 
-// scheduling pre-pass: zeroes the queue ([0] work counter, [1..kClasses] class sizes) and fills the class lists
+// scheduling pre-pass: fills the class lists and sizes (the queue is zero on entry: cleared at upload and re-armed by
+// the last warp of every solve, see release_queue)
 static cudaError_t launch_classify_small(const SmallPackDev &K, const SharedPlanDev &P, const BatchDev &Bt, int *queue, int *lists,
                                          cudaStream_t stream) {
-  cudaError_t e = cudaMemsetAsync(queue, 0, sizeof(int) * (1 + kClasses), stream);
-  if (e != cudaSuccess) return e;
   classify_small_kernel<<<(Bt.B + 7) / 8, 256, 0, stream>>>(K, P, Bt, queue + 1, lists);
   return cudaGetLastError();
 }
@@ -796,8 +809,7 @@ static cudaError_t launch_classify_small(const SmallPackDev &K, const SharedPlan
 cudaError_t launch_admm_shared_small_mma(const SmallPackDev &K, const SharedPlanDev &P, const BatchDev &Bt,
                                          const SettingsDev &S, int *queue, int *lists, int num_sms, cudaStream_t stream) {
   const size_t smem = (size_t)(kCtaMatDoubles + 4 * kMmaWarpDoubles + kMmaPanelDoubles) * sizeof(double) + sizeof(MmaCtl);
-  cudaError_t e = lists ? launch_classify_small(K, P, Bt, queue, lists, stream)
-                        : cudaMemsetAsync(queue, 0, sizeof(int) * (1 + kClasses), stream);
+  cudaError_t e = lists ? launch_classify_small(K, P, Bt, queue, lists, stream) : cudaSuccess;
   if (e != cudaSuccess) return e;
   int grid = (Bt.B + kSlots - 1) / kSlots;
   if (grid > num_sms * 4) grid = num_sms * 4;
@@ -816,8 +828,7 @@ cudaError_t launch_admm_shared_small(const SmallPackDev &K, const SharedPlanDev 
                                      const SettingsDev &S, int *queue, int *lists, int num_sms, cudaStream_t stream) {
   const int wpc = 4;
   const size_t smem = (size_t)(kCtaMatDoubles + wpc * kWarpDoubles) * sizeof(double);
-  cudaError_t e = lists ? launch_classify_small(K, P, Bt, queue, lists, stream)
-                        : cudaMemsetAsync(queue, 0, sizeof(int) * (1 + kClasses), stream);
+  cudaError_t e = lists ? launch_classify_small(K, P, Bt, queue, lists, stream) : cudaSuccess;
   if (e != cudaSuccess) return e;
   int grid = (Bt.B + wpc - 1) / wpc;
   const int resident = num_sms * 3;   // __launch_bounds__(128, 3): three CTAs (12 warps) per SM

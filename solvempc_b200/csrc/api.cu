@@ -474,6 +474,7 @@ int smpc_solver_solve(smpc_solver *s) {
   b.x_out = s->d_x; b.y_out = s->d_yout; b.status = s->d_status; b.iter = s->d_iter; b.rho_updates = s->d_rhoup;
   b.obj = s->d_obj; b.pri_res = s->d_pri; b.dua_res = s->d_dua;
   b.fresh = s->cold_solves ? 1 : 0;
+  b.u_apply = (s->regime == 0 && (s->kernel == 2 || s->kernel == 5)) ? s->u_apply : nullptr;
   smpc::SettingsDev sd = to_dev(s->st);
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   if (s->timing) {
@@ -757,10 +758,14 @@ int smpc_mpc_set_state(smpc_mpc *M, const double *X, const double *U, const doub
   if (!M) return fail(SMPC_ERR_ARG, "null handle");
   if (loc != SMPC_HOST && loc != SMPC_DEVICE) return fail(SMPC_ERR_ARG, "loc must be SMPC_HOST or SMPC_DEVICE");
   CK(cudaSetDevice(M->device));
-  cudaMemcpyKind k = loc == SMPC_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
-  if (X) CK(cudaMemcpyAsync(M->d_X, X, sizeof(double) * M->B * M->dims.nx, k, M->stream));
-  if (U) CK(cudaMemcpyAsync(M->d_U, U, sizeof(double) * M->B, k, M->stream));
-  if (ref) CK(cudaMemcpyAsync(M->d_ref, ref, sizeof(double) * M->B, k, M->stream));
+  if (loc == SMPC_DEVICE) {   // one gather kernel instead of up to three copy nodes
+    CK(smpc::launch_mpc_copy_state(M->B, M->dims.nx, X, U, ref, M->d_X, M->d_U, M->d_ref, M->stream));
+    M->launches++;
+    return SMPC_OK;
+  }
+  if (X) CK(cudaMemcpyAsync(M->d_X, X, sizeof(double) * M->B * M->dims.nx, cudaMemcpyHostToDevice, M->stream));
+  if (U) CK(cudaMemcpyAsync(M->d_U, U, sizeof(double) * M->B, cudaMemcpyHostToDevice, M->stream));
+  if (ref) CK(cudaMemcpyAsync(M->d_ref, ref, sizeof(double) * M->B, cudaMemcpyHostToDevice, M->stream));
   return SMPC_OK;
 }
 
@@ -772,9 +777,16 @@ int smpc_mpc_controller_step(smpc_mpc *M) {
   CK(smpc::launch_mpc_step_vectors(M->dims, M->B, M->per_instance, M->mats, M->d_X, M->d_U, M->d_ref, s->d_q, s->d_u, M->stream));
   M->launches++;
   s->have_q = true; s->have_u = true;
-  if (int rc = smpc_solver_solve(s)) return rc;                                            // cpp:102
-  CK(smpc::launch_mpc_apply_control(M->B, s->n, s->d_x, s->d_status, M->d_U, M->stream));  // cpp:105
-  M->launches++;
+  // cpp:102 solve, cpp:105 U += dU*[0]: inside the small-QP kernels' store_solution, a separate kernel otherwise
+  const bool fused = s->regime == 0 && (s->kernel == 2 || s->kernel == 5);
+  s->u_apply = fused ? M->d_U : nullptr;
+  const int rc = smpc_solver_solve(s);
+  s->u_apply = nullptr;
+  if (rc) return rc;
+  if (!fused) {
+    CK(smpc::launch_mpc_apply_control(M->B, s->n, s->d_x, s->d_status, M->d_U, M->stream));
+    M->launches++;
+  }
   return SMPC_OK;
 }
 

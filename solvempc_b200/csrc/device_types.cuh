@@ -77,6 +77,8 @@ struct BatchDev {
   double *x_out, *y_out;                 // [B][n], [B][m] unscaled solution
   int *status, *iter, *rho_updates;      // [B]
   double *obj, *pri_res, *dua_res;       // [B]
+  double *u_apply;      // [B] or NULL: MPC layer's U, incremented by x[0] of every instance that ends SOLVED (cpp:105);
+                        // honoured by the small-QP kernels only (the API launches mpc_apply_control_kernel otherwise)
 };
 
 }  // namespace smpc

@@ -50,6 +50,9 @@ cudaError_t launch_mpc_assemble(const MpcDims &d, int plants, const double *Ad, 
 cudaError_t launch_mpc_step_vectors(const MpcDims &d, int B, int per_instance, const MpcMatsDev &mats,
                                     const double *X, const double *U, const double *ref, double *f,
                                     double *ub, cudaStream_t stream);
+// set_state from device buffers: X, U, ref (any may be NULL) -> the controller's own copies, one launch
+cudaError_t launch_mpc_copy_state(int B, int nx, const double *X, const double *U, const double *ref, double *dX, double *dU,
+                                  double *dref, cudaStream_t stream);
 // U += dU[0]
 cudaError_t launch_mpc_apply_control(int B, int n, const double *x, const int *status, double *U, cudaStream_t stream);
 // X <- Ad X + Bd U

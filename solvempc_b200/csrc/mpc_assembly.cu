@@ -156,6 +156,24 @@ __global__ void mpc_advance_kernel(int B, int n, int nx, int per_instance, const
   if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(step, 1);
 }
 
+__global__ void mpc_copy_state_kernel(int B, int nx, const double *__restrict__ X, const double *__restrict__ U,
+                                      const double *__restrict__ ref, double *__restrict__ dX, double *__restrict__ dU,
+                                      double *__restrict__ dref) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (X && e < B * nx) dX[e] = X[e];
+  if (e < B) {
+    if (U) dU[e] = U[e];
+    if (ref) dref[e] = ref[e];
+  }
+}
+cudaError_t launch_mpc_copy_state(int B, int nx, const double *X, const double *U, const double *ref, double *dX, double *dU,
+                                  double *dref, cudaStream_t stream) {
+  if (!X && !U && !ref) return cudaSuccess;
+  const int count = X ? B * nx : B;
+  mpc_copy_state_kernel<<<(count + 255) / 256, 256, 0, stream>>>(B, nx, X, U, ref, dX, dU, dref);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_mpc_square_ref(int B, double amplitude, int period, const int *phase, const int *step, double *ref,
                                   cudaStream_t stream) {
   mpc_square_ref_kernel<<<(B + 255) / 256, 256, 0, stream>>>(B, amplitude, period, phase, step, ref);
