@@ -19,6 +19,7 @@
 // Panel layout in shared memory: [nb][row][8] doubles (8-slot blocks), so a DMMA B-fragment load (4 k-rows x 8 slots)
 // is 32 consecutive doubles and the C-fragment of a thread is a double2 of the same panel layout.
 #include <cstdint>
+#include <cstdio>
 
 #include "device_types.cuh"
 #include "kernels.cuh"
@@ -100,22 +101,33 @@ __device__ __forceinline__ void gemm_run(const double2 *__restrict__ opl, int kp
       const int kk = min(kp + d + kRing, cnt - 1) * 32;
 #pragma unroll
       for (int r = 0; r < NR; ++r) ring[d][r] = ldg_stream(ap[r] + kk);
+      // the two k-steps of a pair hit the same accumulator: issue every chain's first step, then every chain's second,
+      // so that dependent DMMAs are NR * NB issues apart (dependent latency 26 cycles, issue 16)
 #pragma unroll
       for (int r = 0; r < NR; ++r)
 #pragma unroll
-        for (int nb = 0; nb < NB; ++nb) { dmma(acc[r][nb], a[r].x, b[nb][0]); dmma(acc[r][nb], a[r].y, b[nb][1]); }
+        for (int nb = 0; nb < NB; ++nb) dmma(acc[r][nb], a[r].x, b[nb][0]);
+#pragma unroll
+      for (int r = 0; r < NR; ++r)
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) dmma(acc[r][nb], a[r].y, b[nb][1]);
     }
     bp += kRing * 64;
   }
 #pragma unroll
   for (int d = 0; d < kRing - 1; ++d)
     if (kp + d < cnt) {
+      double b0[NB], b1[NB];
 #pragma unroll
-      for (int nb = 0; nb < NB; ++nb) {
-        const double b0 = bp[nb * nbs + d * 64], b1 = bp[nb * nbs + d * 64 + 32];
+      for (int nb = 0; nb < NB; ++nb) { b0[nb] = bp[nb * nbs + d * 64]; b1[nb] = bp[nb * nbs + d * 64 + 32]; }
 #pragma unroll
-        for (int r = 0; r < NR; ++r) { dmma(acc[r][nb], ring[d][r].x, b0); dmma(acc[r][nb], ring[d][r].y, b1); }
-      }
+      for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+        for (int r = 0; r < NR; ++r) dmma(acc[r][nb], ring[d][r].x, b0[nb]);
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+        for (int r = 0; r < NR; ++r) dmma(acc[r][nb], ring[d][r].y, b1[nb]);
     }
 }
 // nr (1..kRG) row-blocks starting at rb: dispatch to the compile-time variants (nr is warp-uniform)
@@ -192,7 +204,16 @@ admm_shared_tile_kernel(TilePackDev K, SharedPlanDev P, BatchDev Bt, SettingsDev
   int k = 0;       // tile iteration counter
   bool event = true, initial = true;
 
+#ifdef SMPC_TILE_PROFILE
+  long long pf_pass[P_COUNT + 3] = {0}, pf_pre[P_COUNT] = {0}, pf_it = 0, pf_t0 = clock64(), pf_c = 0; int pf_nev = 0;
+#define PFM(arr, i) { const long long tt = clock64(); arr[i] += tt - pf_c; pf_c = tt; }
+#else
+#define PFM(arr, i)
+#endif
   for (;;) {
+#ifdef SMPC_TILE_PROFILE
+    if (event) { const long long tt = clock64(); pf_it += tt - pf_t0; pf_c = tt; }
+#endif
     if (event) {
       // ================= event: termination check / rho adaptation / max_iter for the slots that are due, then
       // store + refill of the slots that finished.  The first event (k = 0) only fills the tile.
@@ -220,6 +241,7 @@ admm_shared_tile_kernel(TilePackDev K, SharedPlanDev P, BatchDev Bt, SettingsDev
       int any = initial ? 0 : any_flags();
       int done = 0;
 
+      PFM(pf_pass, P_COUNT)
       for (int pass = 0; pass < P_COUNT; ++pass) {
         // ---------- what runs before the GEMM of this pass (block-uniform control flow)
         bool run = false;
@@ -475,6 +497,7 @@ admm_shared_tile_kernel(TilePackDev K, SharedPlanDev P, BatchDev Bt, SettingsDev
             run = true;
           }
         }
+        PFM(pf_pre, pass)
         if (!run) continue;
 
         // ---------- the GEMM of this pass: one loop for every operator / panel combination
@@ -589,8 +612,10 @@ admm_shared_tile_kernel(TilePackDev K, SharedPlanDev P, BatchDev Bt, SettingsDev
             }
           }
         }
+        PFM(pf_pass, pass)
       }
 
+      PFM(pf_pass, P_COUNT + 1)
       // ---- w = rho_vec z - y (the w panel carried delta_y); schedule the next event
       __syncthreads();
       for (int e = tid; e < m8 * TB; e += kTileThreads) {
@@ -613,6 +638,14 @@ admm_shared_tile_kernel(TilePackDev K, SharedPlanDev P, BatchDev Bt, SettingsDev
       }
       __syncthreads();
       initial = false;
+#ifdef SMPC_TILE_PROFILE
+      PFM(pf_pass, P_COUNT + 2)
+      pf_t0 = clock64(); ++pf_nev;
+      if (C.active == 0 && blockIdx.x == 0 && tid == 0) {
+        printf("tile profile: %d events, %d iterations %lld cycles\n  zero/flags %lld  w-rebuild/schedule %lld (gemm-tail %lld)\n", pf_nev, k, pf_it, pf_pass[P_COUNT], pf_pass[P_COUNT + 2], pf_pass[P_COUNT + 1]);
+        for (int p = 0; p < P_COUNT; ++p) printf("  pass %d: pre %lld gemm+epilogue %lld\n", p, pf_pre[p], pf_pass[p]);
+      }
+#endif
       if (C.active == 0) break;
     }
 
