@@ -1,19 +1,23 @@
 #!/usr/bin/env python
 """bench.py -- QP solves/s (eps_abs = eps_rel = 1e-5) of the batched MPC hot path on B200.
 
-A "step" is one pass of the hot path over one batch: BASELINE.json config 2 -- the reference plant and
-horizon (config/MPC_API.json, n = 15, m = 30), 4096 independent controllers per GPU with random x0 / U /
-references sharing P and A, each solved cold (as 4096 freshly constructed reference controllers would on their
-first controllerStep).  Weak scaling: every rank owns its own 4096 instances, no data-path collective.
+A "step" is one pass of the hot path over one batch of synthetic input.  The default workload is BASELINE.json
+config 2 (the configuration the metric is quoted on that fits one GPU): the reference plant and horizon
+(config/MPC_API.json, n = 15, m = 30), 4096 independent controllers per GPU with random x0 / U / references
+sharing P and A, each solved cold.  `--config c3 | c4 | c5` runs the other BASELINE configurations with the same
+JSON contract (c3: 12-state quadrotor N = 50, 131072 controllers per GPU = the 1M batch over 8 GPUs; c4: 65536
+per-instance plants N = 30; c5: warm-started closed loop of 65536 controllers, N = 100).  Weak scaling: every rank
+owns its own instances, no data-path collective; NCCL carries only the barrier and the max-over-ranks.
 
-  value        device-resident: X, U, ref already in HBM; per step set_state (D2D) + controllerStep
-  e2e          same call with HOST (pinned) X, U, ref in and U, status out inside the timed region
-  roofline     the ADMM kernel against the FP64 pipe (it keeps all iterates on chip, so HBM is touched once
-               per solve; the HBM-equivalent of a one-launch-per-iteration design is reported beside it)
+  value        device-resident: inputs already in HBM; per step set_state (device) + controllerStep
+  e2e          the same public call with HOST (pinned) inputs in and the control / status out inside the timed region
+  roofline     the ADMM kernel against the FP64 pipe (DFMA / DMMA, one shared peak on B200; measured in this run);
+               it keeps all iterates on chip, so HBM is touched once per solve -- the HBM-equivalent of a
+               one-launch-per-iteration design (24 (n + 2m) B per problem-iteration) is reported beside it
   cpu_baseline the CPU oracle (oracle/, an OSQP-equivalent restatement; osqp-eigen itself is not installable
                here) on the host cores, one solver per core, bounded sample
 
-`--impl reference` times that CPU path alone with the same metric/config (rank 0 only).
+`--impl reference` times that CPU path alone with the same metric / config (rank 0 only).
 """
 import argparse
 import json
@@ -29,13 +33,8 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 EPS = 1e-5
-N_VAR, N_CON = 15, 30
 METRIC = "QP solves/sec (eps 1e-5)"
-
-
-def workload(batch, seed):
-    from problems import c2_batch
-    return c2_batch(batch, seed=seed)
+CPU_NOTE = "one OSQP-equivalent solver per core (oracle/osqp_port.c; osqp-eigen is not installable offline)"
 
 
 def load_peaks():
@@ -81,43 +80,283 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons)}
 
 
-def cpu_solves_per_s(batch, seed, min_seconds, threads):
-    """The CPU oracle on the same QPs, one solver per core; returns (solves/s, solves done, seconds)."""
-    import oracle
-    cfg = oracle.load_config(os.path.join(ROOT, "config", "MPC_API.json"))
-    m = oracle.mpc_build(**cfg)
-    X, U, ref = workload(batch, seed)
-    f, ub = oracle.mpc_batch_vectors(m, X, U, ref)
-    st = oracle.default_settings(eps_abs=EPS, eps_rel=EPS)
-    done, secs = 0, 0.0
+# ------------------------------------------------------------------------------------------------ workloads
+class Workload:
+    """One BASELINE configuration: builds the controllers of this rank, steps them, and knows its flop / byte counts."""
+    key = name = ""
+    default_batch = 0
+    l2_note = "inputs larger than L2 (no flush needed)"
+    flush_l2 = False
+
+    def __init__(self, batch, rank):
+        self.B, self.rank = batch, rank
+
+    # -- CPU side (oracle): returns (solves, seconds) for `count` QPs of this workload on `threads` cores
+    def cpu_solve(self, count, threads):
+        raise NotImplementedError
+
+
+class C2(Workload):
+    key, default_batch, flush_l2 = "c2", 4096, True
+    l2_note = "flushed with a 256 MB write between timed steps"
+    N = 15
+
+    def describe(self):
+        return f"config2: reference plant N=15 (n=15, m=30), {self.B} random x0/U/ref per GPU sharing P and A, cold solves"
+
+    def _inputs(self, count, seed):
+        from problems import c2_batch
+        return c2_batch(count, seed=seed)
+
+    def _conf(self):
+        return os.path.join(ROOT, "config", "MPC_API.json")
+
+    def setup(self, sm, torch, device, kernel):
+        X, U, ref = self._inputs(self.B, 1000 * self.rank)
+        self.host = [np.ascontiguousarray(a) for a in (X, U, ref)]
+        self.mpc = sm.BatchedModelPredictiveControlAPI(self._conf(), batch=self.B, device=device, eps_abs=EPS, eps_rel=EPS, kernel=kernel)
+        self.mpc.solver.set_cold_solves(True)
+        self.dev = [torch.from_numpy(a).cuda() for a in self.host]
+        self.pin = [torch.from_numpy(a).pin_memory() for a in self.host]
+        self.out_u = torch.empty(self.B, dtype=torch.float64).pin_memory()
+        self.out_st = torch.empty(self.B, dtype=torch.int32).pin_memory()
+        self.n, self.m = self.mpc.n_variables, self.mpc.n_constraints
+        self.solver = self.mpc.solver
+        self.h2d = int(sum(a.nbytes for a in self.host))
+        self.d2h = int(self.B * 8 + self.B * 4)
+
+    def step_device(self):
+        self.mpc.set_state(X=self.dev[0], U=self.dev[1], ref=self.dev[2])
+        self.mpc.controller_step_async()
+
+    def step_e2e(self):
+        self.mpc.set_state(X=self.pin[0], U=self.pin[1], ref=self.pin[2])   # H2D from pinned memory
+        self.mpc.controller_step_async()
+        self.mpc.control_into(self.out_u)                                   # D2H of the result (synchronises)
+        self.solver.status_into(self.out_st)
+
+    def nnz_A(self):
+        return int(np.count_nonzero(self.mpc.matrix("Gbar")))
+
+    def launches(self):
+        return self.mpc.launches
+
+    def close(self):
+        self.mpc.close()
+
+    def cpu_solve(self, count, threads):
+        import oracle
+        cfg = oracle.load_config(self._conf())
+        m = oracle.mpc_build(**{**cfg, "N": self.N})
+        X, U, ref = self._inputs(count, 0)
+        f, ub = oracle.mpc_batch_vectors(m, X, U, ref)
+        out = oracle.solve_batch(m["H"], m["Gbar"], m["lb"], m["W0"], f, ub, settings=oracle.default_settings(eps_abs=EPS, eps_rel=EPS), nthreads=threads)
+        return count, out["seconds"], threads
+
+
+class C3(Workload):
+    key, default_batch = "c3", 131072
+
+    def describe(self):
+        return (f"config3: 12-state / 4-input quadrotor, N=50, condensed n=200, m=400 (input box as +/- rows), {self.B} random "
+                "x0 / hover references per GPU (= the 1M batch over 8 GPUs) sharing P and A, cold solves")
+
+    def _conf(self):
+        return os.path.join(ROOT, "config", "quadrotor.json")
+
+    def setup(self, sm, torch, device, kernel):
+        from problems import c3_batch
+        x0, xr = c3_batch(self.B, seed=1000 * self.rank)
+        self.host = [np.ascontiguousarray(x0), np.ascontiguousarray(xr)]
+        self.mpc = sm.BatchedMimoMPC(self._conf(), batch=self.B, device=device, eps_abs=EPS, eps_rel=EPS, kernel=kernel)
+        self.mpc.solver.set_cold_solves(True)
+        self.dev = [torch.from_numpy(a).cuda() for a in self.host]
+        self.pin = [torch.from_numpy(a).pin_memory() for a in self.host]
+        self.out_u = torch.empty(self.B * self.mpc.nu, dtype=torch.float64).pin_memory()
+        self.out_st = torch.empty(self.B, dtype=torch.int32).pin_memory()
+        self.n, self.m = self.mpc.n_variables, self.mpc.n_constraints
+        self.solver = self.mpc.solver
+        self.h2d = int(sum(a.nbytes for a in self.host))
+        self.d2h = int(self.out_u.numel() * 8 + self.B * 4)
+
+    def step_device(self):
+        self.mpc.set_state(x0=self.dev[0], xr=self.dev[1])
+        self.mpc.controller_step_async()
+
+    def step_e2e(self):
+        self.mpc.set_state(x0=self.pin[0], xr=self.pin[1])
+        self.mpc.controller_step_async()
+        self.mpc.control_into(self.out_u)
+        self.solver.status_into(self.out_st)
+
+    def nnz_A(self):
+        return 2 * self.n
+
+    def launches(self):
+        return self.mpc.launches
+
+    def close(self):
+        self.mpc.close()
+
+    def cpu_solve(self, count, threads):
+        import oracle
+        from problems import c3_batch
+        m = oracle.mimo_build(**oracle.load_mimo_config(self._conf()))
+        x0, xr = c3_batch(count, seed=0)
+        q = oracle.mimo_batch_vectors(m, x0, xr)
+        out = oracle.solve_batch(m["H"], m["A"], m["lb"], m["ub"], q, np.tile(m["ub"], (count, 1)),
+                                 settings=oracle.default_settings(eps_abs=EPS, eps_rel=EPS), nthreads=threads)
+        return count, out["seconds"], threads
+
+
+class C4(C2):
+    key, default_batch, flush_l2 = "c4", 65536, False
+    l2_note = "inputs larger than L2 (no flush needed)"
+    N = 30
+
+    def describe(self):
+        return (f"config4: per-instance linearised plants (distinct P, A per problem; reference dimensions), N=30 (n=30, m=60), "
+                f"{self.B} controllers per GPU, on-device assembly + batched Cholesky path, cold solves")
+
+    def setup(self, sm, torch, device, kernel):
+        import oracle
+        from problems import c4_plants
+        cfg = oracle.load_config(self._conf())
+        Ad, Bd = c4_plants(self.B, cfg, seed=2 + 1000 * self.rank)
+        conf = dict(Ad=Ad, Bd=Bd, Cd=cfg["Cd"], K=cfg["K"], Q=cfg["Q"], R=cfg["R"], RD=cfg["RD"], horizon=self.N, per_instance=1)
+        X, U, ref = self._inputs(self.B, 31 + 1000 * self.rank)
+        self.host = [np.ascontiguousarray(a) for a in (X, U, ref)]
+        self.mpc = sm.BatchedModelPredictiveControlAPI(conf, batch=self.B, device=device, eps_abs=EPS, eps_rel=EPS)
+        self.mpc.solver.set_cold_solves(True)
+        self.dev = [torch.from_numpy(a).cuda() for a in self.host]
+        self.pin = [torch.from_numpy(a).pin_memory() for a in self.host]
+        self.out_u = torch.empty(self.B, dtype=torch.float64).pin_memory()
+        self.out_st = torch.empty(self.B, dtype=torch.int32).pin_memory()
+        self.n, self.m = self.mpc.n_variables, self.mpc.n_constraints
+        self.solver = self.mpc.solver
+        self.h2d = int(sum(a.nbytes for a in self.host))
+        self.d2h = int(self.B * 8 + self.B * 4)
+
+    def nnz_A(self):
+        return self.N * (self.N + 1)
+
+    def cpu_solve(self, count, threads):
+        import oracle
+        from problems import c4_plants
+        cfg = oracle.load_config(self._conf())
+        Ad, Bd = c4_plants(count, cfg, seed=2)
+        X, U, ref = self._inputs(count, 31)
+        st = oracle.default_settings(eps_abs=EPS, eps_rel=EPS)
+        t0 = time.perf_counter()   # ONE core: setup (assembly, scaling, factor) + solve per instance, as a per-plant controller pays it
+        for b in range(count):
+            mats = oracle.mpc_build(**{**cfg, "Ad": Ad[b], "Bd": Bd[b], "N": self.N})
+            f, ub = oracle.mpc_step_vectors(mats, X[b], U[b], ref[b])
+            so = oracle.Solver(mats["H"], np.zeros(self.N), mats["Gbar"], mats["lb"], mats["W0"], settings=st)
+            so.update_lin_cost(f); so.update_upper_bound(ub)
+            so.solve()
+        return count, time.perf_counter() - t0, 1
+
+
+class C5(C2):
+    key, default_batch, flush_l2 = "c5", 65536, False
+    l2_note = "per-step working set (q, u, iterates, solution of 65536 x (100 + 200)) larger than L2 (no flush possible inside the closed loop)"
+    N = 100
+    AMP, PERIOD = 0.1, 200
+
+    def describe(self):
+        return (f"config5: closed-loop warm-started MPC, reference plant N=100 (n=100, m=200), {self.B} controllers per GPU, "
+                "square-wave references (amplitude 0.1, period 200 steps, random phase), synthetic plant step on device; "
+                "one step = one controllerStep of every controller + plant step")
+
+    def setup(self, sm, torch, device, kernel):
+        import oracle
+        cfg = oracle.load_config(self._conf())
+        conf = dict(Ad=cfg["Ad"], Bd=cfg["Bd"], Cd=cfg["Cd"], K=cfg["K"], Q=cfg["Q"], R=cfg["R"], RD=cfg["RD"], horizon=self.N)
+        X, U, _ = self._inputs(self.B, 31 + 1000 * self.rank)
+        self.host = [np.ascontiguousarray(X * 0.2), np.ascontiguousarray(U * 0.1), np.zeros(self.B)]
+        self.phase = np.random.default_rng(5 + self.rank).integers(0, self.PERIOD, self.B).astype(np.int32)
+        self.mpc = sm.BatchedModelPredictiveControlAPI(conf, batch=self.B, device=device, eps_abs=EPS, eps_rel=EPS, kernel=kernel)
+        self.mpc.set_state(X=self.host[0], U=self.host[1], ref=self.host[2])
+        self.n, self.m = self.mpc.n_variables, self.mpc.n_constraints
+        self.solver = self.mpc.solver
+        self.pin = [torch.from_numpy(a).pin_memory() for a in self.host]
+        self.out_u = torch.empty(self.B, dtype=torch.float64).pin_memory()
+        self.out_st = torch.empty(self.B, dtype=torch.int32).pin_memory()
+        self.h2d = int(self.B * 4 * 8)            # e2e: the measured state X goes in every step (the plant is outside)
+        self.d2h = int(self.B * 8 + self.B * 4)   # the control U and the status come back
+
+    def closed_loop(self, steps, graph):
+        """`steps` closed-loop steps on the device; returns (not_solved, iterations)."""
+        return self.mpc.closed_loop(steps, self.AMP, self.PERIOD, self.phase, use_graph=graph)
+
+    def step_e2e(self):
+        # hardware-in-the-loop shape of the reference's main loop (solver.cpp:43-74): state in, controllerStep, control out
+        self.mpc.set_state(X=self.pin[0])
+        self.mpc.controller_step_async()
+        self.mpc.control_into(self.out_u)
+        self.solver.status_into(self.out_st)
+
+    def nnz_A(self):
+        return self.N * (self.N + 1)
+
+    def cpu_solve(self, count, threads):
+        import oracle
+        cfg = oracle.load_config(self._conf())
+        m = oracle.mpc_build(**{**cfg, "N": self.N})
+        X, U, ref = self._inputs(count, 31)
+        X, U = X * 0.2, U * 0.1
+        st = oracle.default_settings(eps_abs=EPS, eps_rel=EPS)
+        solvers = [oracle.Solver(m["H"], np.zeros(self.N), m["Gbar"], m["lb"], m["W0"], settings=st) for _ in range(count)]
+        steps, secs = 5, 0.0
+        for k in range(steps + 1):           # step 0 is the cold solve (not counted), then warm-started steps
+            t0 = time.perf_counter()
+            for b, so in enumerate(solvers):
+                f, ub = oracle.mpc_step_vectors(m, X[b], U[b], self.AMP)
+                so.update_lin_cost(f); so.update_upper_bound(ub)
+                r = so.solve()
+                U[b] += r["x"][0]
+                X[b] = cfg["Ad"] @ X[b] + cfg["Bd"] * U[b]
+            if k:
+                secs += time.perf_counter() - t0
+        return count * steps, secs, 1
+
+
+WORKLOADS = {w.key: w for w in (C2, C3, C4, C5)}
+
+
+def cpu_solves_per_s(wl, min_seconds, threads, first=None):
+    """The CPU oracle on this workload's QPs; bounded sample.  Returns (solves/s, solves, seconds, cores used):
+    c2 / c3 run one solver per core on all host threads; c4 / c5 (per-instance setup, closed loop) drive the scalar
+    port from one core."""
+    count = first or {"c2": 4096, "c3": 8 * threads, "c4": 256, "c5": 16}[wl.key]
+    done, secs, cores = 0, 0.0, 1
     while done == 0 or secs < min_seconds:
-        out = oracle.solve_batch(m["H"], m["Gbar"], m["lb"], m["W0"], f, ub, settings=st, nthreads=threads)
-        assert (out["status"] == 1).all()
-        done += batch
-        secs += out["seconds"]
-    return done / secs, done, secs
+        c, s, cores = wl.cpu_solve(count, threads)
+        done += c
+        secs += s
+    return done / secs, done, secs, cores
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
+    wl = WORKLOADS[args.config](args.batch or WORKLOADS[args.config].default_batch, 0)
     threads = os.cpu_count() or 1
-    per_step = []
+    per_step, solves = [], 0
     for i in range(args.warmup + args.steps):
-        v, done, secs = cpu_solves_per_s(args.batch, 0, 0.0, threads)   # one pass over the batch per step
+        c, s, cores = wl.cpu_solve({"c2": wl.B, "c3": 4 * threads, "c4": 128, "c5": 8}[wl.key], threads)   # one bounded sample per step
         if i >= args.warmup:
-            per_step.append(secs)
+            per_step.append(s)
+            solves = c
     ms = 1e3 * float(np.mean(per_step))
-    value = args.batch / (ms / 1e3)
+    value = solves / (ms / 1e3)
+    sample = f"{args.steps} samples of {solves} solves of this workload, {CPU_NOTE}"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "config2: reference plant N=15 (n=15, m=30), 4096 random x0/U/ref sharing P and A, cold solves",
-                   "batch": args.batch, "eps_abs": EPS, "eps_rel": EPS},
-        "cpu_baseline": {"value": value, "unit": "solves/s", "cores": threads, "kind": "port",
-                         "sample": f"{args.steps} passes over the same {args.batch}-QP batch, one OSQP-equivalent solver per core "
-                                   "(oracle/osqp_port.c; osqp-eigen is not installable offline)"},
+        "config": {"workload": wl.describe(), "eps_abs": EPS, "eps_rel": EPS, "solves_per_step": solves},
+        "cpu_baseline": {"value": value, "unit": "solves/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -134,15 +373,13 @@ def run_ours(args, rank, local_rank, world):
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    B = args.batch
-    X, U, ref = workload(B, seed=1000 * rank)
-    mpc = sm.BatchedModelPredictiveControlAPI(os.path.join(ROOT, "config", "MPC_API.json"), batch=B, device=local_rank,
-                                              eps_abs=EPS, eps_rel=EPS, kernel=args.kernel)
+    wl = WORKLOADS[args.config](args.batch or WORKLOADS[args.config].default_batch, rank)
+    B = wl.B
+    wl.setup(sm, torch, local_rank, args.kernel)
     stream = torch.cuda.current_stream()
-    mpc.set_stream(stream.cuda_stream)
-    mpc.solver.set_cold_solves(True)
-    dX, dU, dref = [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (X, U, ref)]
-    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")   # 256 MB > 126 MB L2
+    wl.mpc.set_stream(stream.cuda_stream)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda") if wl.flush_l2 else None   # 256 MB > 126 MB L2
+    closed_loop = wl.key == "c5"
 
     def barrier():
         torch.cuda.synchronize()
@@ -150,35 +387,53 @@ def run_ours(args, rank, local_rank, world):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_device():
-        mpc.set_state(X=dX, U=dU, ref=dref)
-        mpc.controller_step_async()
-
     sampler = ClockSampler(local_rank)
     # ---- device-resident value
-    for _ in range(args.warmup):
-        step_device()
-    torch.cuda.synchronize()
-    assert mpc.solver.count_solved() == B, "warm-up solve did not reach SOLVED on every instance"
-    iters = mpc.solver.info()["iter"].astype(np.int64)
-    mpc.solver.enable_timing(True)
-    mpc.solver.kernel_ms(reset=True)
-    launches0 = mpc.launches
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
-    sampler.start()
-    wall0 = time.perf_counter()
-    for e0, e1 in evs:
-        flush.zero_()                     # evict the inputs from L2 between timed steps
+    if closed_loop:
+        bad, _ = wl.closed_loop(max(args.warmup, 3), graph=True)
+        assert bad == 0, "warm-up closed-loop steps did not reach SOLVED on every instance"
+        wl.solver.enable_timing(True)
+        wl.solver.kernel_ms(reset=True)
+        launches0 = wl.launches()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        sampler.start()
+        wall0 = time.perf_counter()
         e0.record(stream)
-        step_device()
+        bad, total_iters = wl.closed_loop(args.steps, graph=False)   # (kernel timing events cannot be captured into a graph)
         e1.record(stream)
-    barrier()
-    wall_ms = 1e3 * (time.perf_counter() - wall0)
-    step_ms = np.array([e0.elapsed_time(e1) for e0, e1 in evs])
-    launches = (mpc.launches - launches0)
-    kern_ms, kern_n = mpc.solver.kernel_ms(reset=True)
-    mpc.solver.enable_timing(False)
+        barrier()
+        wall_ms = 1e3 * (time.perf_counter() - wall0)
+        assert bad == 0
+        step_ms = np.array([e0.elapsed_time(e1) / args.steps])
+        prob_iters = total_iters / args.steps                          # per step
+        iters_mean, iters_max = total_iters / (args.steps * B), None
+    else:
+        for _ in range(args.warmup):
+            wl.step_device()
+        torch.cuda.synchronize()
+        assert wl.solver.count_solved() == B, "warm-up solve did not reach SOLVED on every instance"
+        iters = wl.solver.info()["iter"].astype(np.int64)
+        wl.solver.enable_timing(True)
+        wl.solver.kernel_ms(reset=True)
+        launches0 = wl.launches()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        barrier()
+        sampler.start()
+        wall0 = time.perf_counter()
+        for e0, e1 in evs:
+            if flush is not None:
+                flush.zero_()                 # evict the inputs from L2 between timed steps
+            e0.record(stream)
+            wl.step_device()
+            e1.record(stream)
+        barrier()
+        wall_ms = 1e3 * (time.perf_counter() - wall0)
+        step_ms = np.array([a.elapsed_time(b) for a, b in evs])
+        prob_iters, iters_mean, iters_max = int(iters.sum()), float(iters.mean()), int(iters.max())
+    launches = wl.launches() - launches0
+    kern_ms, kern_n = wl.solver.kernel_ms(reset=True)
+    wl.solver.enable_timing(False)
     ms_per_step = float(step_ms.mean())
     if world > 1:
         t = torch.tensor([ms_per_step], device="cuda", dtype=torch.float64)
@@ -187,31 +442,21 @@ def run_ours(args, rank, local_rank, world):
     value = world * B / (ms_per_step / 1e3)
 
     # ---- end to end through the public call with host buffers
-    hX, hU, href = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in (X, U, ref)]
-    hUout = torch.empty(B, dtype=torch.float64).pin_memory()
-    hstat = torch.empty(B, dtype=torch.int32).pin_memory()
-
-    def step_e2e():
-        mpc.set_state(X=hX, U=hU, ref=href)          # H2D from pinned memory
-        mpc.controller_step_async()
-        mpc.control_into(hUout)                       # D2H of the result (synchronises)
-        mpc.solver.status_into(hstat)
-
     for _ in range(max(3, args.warmup)):
-        step_e2e()
-    e2e_steps = args.steps
+        wl.step_e2e()
     barrier()
     t_e2e = []
-    for _ in range(e2e_steps):
-        flush.zero_()
+    for _ in range(args.steps):
+        if flush is not None:
+            flush.zero_()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        step_e2e()
+        wl.step_e2e()
         torch.cuda.synchronize()
         t_e2e.append(time.perf_counter() - t0)
     barrier()
     clocks = sampler.stop()
-    assert (hstat.numpy() == 1).all()
+    assert (wl.out_st.numpy() == 1).all()
     e2e_ms = 1e3 * float(np.mean(t_e2e))
     if world > 1:
         t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
@@ -230,43 +475,42 @@ def run_ours(args, rank, local_rank, world):
             e0.record(); torch.matmul(a, b); e1.record(); torch.cuda.synchronize()
             best = min(best, e0.elapsed_time(e1))
         fp64_peak = 2 * 4096 ** 3 / (best * 1e-3) / 1e12
-        n, m = N_VAR, N_CON
-        prob_iters = int(iters.sum())
-        nnzA = int(np.count_nonzero(mpc.matrix("Gbar")))
+        n, m = wl.n, wl.m
+        nnzA = wl.nnz_A()
         flops_per_launch = prob_iters * (2.0 * n * n + 4.0 * nnzA)       # 2 n^2 (KKT contraction) + 4 nnz(A) (A x, A'y)
         executed_per_launch = prob_iters * 2.0 * (n * n + 2 * m * n)     # what the plan-coordinate iteration executes (dense W = A̅V)
         bytes_per_launch = prob_iters * 24.0 * (n + 2 * m)               # what one launch per iteration would stream
         kms = kern_ms / max(kern_n, 1)
         achieved = flops_per_launch / (kms * 1e-3) / 1e12
         cpu_threads = os.cpu_count() or 1
-        cpu_v, cpu_done, cpu_secs = cpu_solves_per_s(B, 0, args.cpu_seconds, cpu_threads)
+        cpu_v, cpu_done, cpu_secs, cpu_cores = cpu_solves_per_s(wl, args.cpu_seconds, cpu_threads)
         line = {
             "metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": "config2: reference plant N=15 (n=15, m=30), 4096 random x0/U/ref per GPU sharing P and A, cold solves",
-                       "batch_per_gpu": B, "eps_abs": EPS, "eps_rel": EPS, "adaptive_rho_interval": 25,
-                       "l2": "flushed with a 256 MB write between timed steps", "kernel": mpc.solver.kernel_name,
-                       "iters_mean": float(iters.mean()), "iters_max": int(iters.max()), "wall_ms_timed_region": wall_ms},
+            "config": {"workload": wl.describe(), "batch_per_gpu": B, "eps_abs": EPS, "eps_rel": EPS, "adaptive_rho_interval": 25,
+                       "l2": wl.l2_note, "kernel": wl.solver.kernel_name, "iters_mean": iters_mean, "iters_max": iters_max,
+                       "wall_ms_timed_region": wall_ms},
             "e2e": {"value": e2e_value, "unit": "solves/s", "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": int(B * (4 + 1 + 1) * 8), "d2h_bytes_per_step": int(B * 8 + B * 4)},
+                    "h2d_bytes_per_step": wl.h2d, "d2h_bytes_per_step": wl.d2h},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
-                         "traffic": None, "kernel": mpc.solver.kernel_name, "kernel_ms": kms, "kernel_share_of_step": kms / float(step_ms.mean()),
+                         "traffic": None, "kernel": wl.solver.kernel_name, "kernel_ms": kms, "kernel_share_of_step": kms / float(step_ms.mean()),
                          "flops_per_launch": flops_per_launch, "executed_flops_per_launch": executed_per_launch,
+                         "executed_frac": executed_per_launch / (kms * 1e-3) / 1e12 / fp64_peak,
                          "algorithmic_flops_per_instance_iteration": 2.0 * n * n + 4.0 * nnzA,
-                         "peak_source": "FP64 pipe: cuBLAS DGEMM 4096^3 measured in this run (MEASURED_PEAKS.json has no fp64 entry)",
+                         "peak_source": "FP64 pipe (DFMA and DMMA share one peak on B200): cuBLAS DGEMM 4096^3 measured in this run "
+                                        "(MEASURED_PEAKS.json has no fp64 entry)",
                          "hbm_equivalent": {"achieved": bytes_per_launch / (kms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                             "frac": bytes_per_launch / (kms * 1e-3) / 1e9 / peaks["hbm_gbs"], "peak_source": peak_src,
                                             "note": "24(n+2m) B per problem-iteration that a one-launch-per-iteration kernel would stream; "
                                                     "this kernel keeps the iterates on chip and reads/writes HBM once per solve"}},
-            "cpu_baseline": {"value": cpu_v, "unit": "solves/s", "cores": cpu_threads, "kind": "port",
-                             "sample": f"{cpu_done} cold solves of the same config-2 QPs in {cpu_secs:.1f} s, one OSQP-equivalent solver per core "
-                                       "(oracle/osqp_port.c; osqp-eigen is not installable offline)"},
+            "cpu_baseline": {"value": cpu_v, "unit": "solves/s", "cores": cpu_cores, "kind": "port",
+                             "sample": f"{cpu_done} solves of this workload's QPs in {cpu_secs:.1f} s, {CPU_NOTE}"},
         }
         print(json.dumps(line), flush=True)
-    mpc.close()
+    wl.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -274,13 +518,16 @@ def run_ours(args, rank, local_rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=4096)
+    ap.add_argument("--config", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="instances per GPU (0 = the configuration's own size)")
     ap.add_argument("--kernel", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     args = ap.parse_args()
+    if args.steps is None:
+        args.steps = {"c2": 50, "c3": 10, "c4": 10, "c5": 50}[args.config]
     args.warmup = max(args.warmup, 3)
     rank, local_rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     if args.impl == "reference":

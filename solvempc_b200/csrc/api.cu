@@ -804,7 +804,7 @@ int smpc_mpc_closed_loop(smpc_mpc *M, int steps, double ref_amplitude, int ref_p
   if (steps < 0 || (ref_period != 0 && ref_period < 2)) return fail(SMPC_ERR_ARG, "need steps >= 0 and ref_period 0 (constant reference) or >= 2");
   CK(cudaSetDevice(M->device));
   smpc_solver *s = M->solver;
-  if (s->timing) return fail(SMPC_ERR_STATE, "disable kernel timing before a closed-loop run");
+  if (s->timing && use_graph) return fail(SMPC_ERR_STATE, "kernel timing events cannot be captured: disable timing or run without the graph");
   cudaStream_t st = M->stream;
   cudaStream_t own = nullptr;
   if (use_graph && st == nullptr) {   // the legacy default stream cannot be captured
