@@ -6,7 +6,8 @@ thin Python host mirror used by the tests and bench.py.  There is no CPU fallbac
 from ._lib import (DEVICE, HOST, LIB_PATH, SOLVED, SOLVED_INACCURATE, MAX_ITER_REACHED, PRIMAL_INFEASIBLE,
                    DUAL_INFEASIBLE, UNSOLVED, PRIMAL_INFEASIBLE_INACCURATE, DUAL_INFEASIBLE_INACCURATE,
                    Settings, SolveMpcError, default_settings, lib)
+from .sharding import gather_results, shard_arrays, shard_bounds
 from .solver import BatchedMimoMPC, BatchedModelPredictiveControlAPI, BatchedSolver, shared_plan_inspect
 
 __all__ = ["BatchedMimoMPC", "BatchedModelPredictiveControlAPI", "BatchedSolver", "shared_plan_inspect", "default_settings",
-           "Settings", "SolveMpcError", "lib", "HOST", "DEVICE", "LIB_PATH"]
+           "Settings", "SolveMpcError", "lib", "HOST", "DEVICE", "LIB_PATH", "shard_bounds", "shard_arrays", "gather_results"]
