@@ -9,6 +9,8 @@
 // Restates OSQP 0.6.x -- the arithmetic the reference reaches through solver.initSolver() /
 // solver.solve() (src/ModelPredictiveControlAPI.cpp:64,102).  Shared-memory rows are padded to an odd number of
 // doubles so that "lane = row" and "lane = column" sweeps are both bank-conflict free.
+#include <cstdio>
+
 #include "device_types.cuh"
 #include "kernels.cuh"
 
@@ -19,10 +21,14 @@ namespace {
 constexpr unsigned kFull = 0xffffffffu;
 constexpr double kMaxScaling = 1e4;
 
+// exact max over the warp of NON-NEGATIVE doubles (every use below reduces absolute values): compare the IEEE bit
+// patterns as two 32-bit halves with REDUX instead of five 64-bit shuffle + compare steps
 __device__ __forceinline__ double wmax(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(kFull, v, o));
-  return v;
+  const unsigned hi = (unsigned)__double2hiint(v);
+  const unsigned mh = __reduce_max_sync(kFull, hi);
+  const unsigned lo = hi == mh ? (unsigned)__double2loint(v) : 0u;
+  const unsigned ml = __reduce_max_sync(kFull, lo);
+  return __hiloint2double((int)mh, (int)ml);
 }
 __device__ __forceinline__ double wsum(double v) {
 #pragma unroll
@@ -410,6 +416,393 @@ __global__ void __launch_bounds__(256) admm_instance_kernel(InstanceDataDev I, B
   }
 }
 
+// --------------------------------------------------------------------------------------- solve, n <= 32, m <= 64
+// Register-operator variant of admm_instance_kernel (same algorithm, same order of the OSQP steps): the rows of A̅ that a
+// lane multiplies in z̃ = A̅ x̃ (rows lane and lane + 32) and its row of M^-1 live in REGISTERS, A̅' is kept row-major in
+// shared memory (row i = column i of A̅) so that A̅'w is a row sweep too, and every dot product reads its operands with
+// 16-byte shared-memory loads into four independent accumulators.  Per iteration and lane: 160 DFMA, 96 LDS.128
+// (v1: 150 DFMA behind 300 dependent LDS.64 in two accumulators).  Rows of A̅' are padded to ldT = 14 (mod 16) doubles:
+// 16-byte row sweeps by 8 consecutive lanes then hit 8 different 16-byte bank groups.
+constexpr int kRegN = 32, kRegM = 64;
+__host__ __device__ __forceinline__ int reg_ldT(int m) { int l = (m + 1) & ~1; while ((l & 15) != 14) l += 2; return l; }
+__host__ __device__ __forceinline__ size_t instance_reg_warp_doubles(int n, int m) {
+  return (size_t)n * reg_ldT(m) + (size_t)n * reg_ldT(n) + 8 * (size_t)kRegN + 10 * (size_t)kRegM;
+}
+// sum_{k < len} row[k] * vec[k], len even, both 16-byte aligned
+__device__ __forceinline__ double dot_s128(const double *row, const double *vec, int len) {
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  int k = 0;
+#pragma unroll 4
+  for (; k + 4 <= len; k += 4) {
+    const double2 r0 = *reinterpret_cast<const double2 *>(row + k), v0 = *reinterpret_cast<const double2 *>(vec + k);
+    const double2 r1 = *reinterpret_cast<const double2 *>(row + k + 2), v1 = *reinterpret_cast<const double2 *>(vec + k + 2);
+    a0 = fma(r0.x, v0.x, a0); a1 = fma(r0.y, v0.y, a1); a2 = fma(r1.x, v1.x, a2); a3 = fma(r1.y, v1.y, a3);
+  }
+  if (k < len) {
+    const double2 r0 = *reinterpret_cast<const double2 *>(row + k), v0 = *reinterpret_cast<const double2 *>(vec + k);
+    a0 = fma(r0.x, v0.x, a0); a1 = fma(r0.y, v0.y, a1);
+  }
+  return (a0 + a1) + (a2 + a3);
+}
+// sum_{k < 32} reg[k] * vec[k] with the row in registers (zero padded) and vec (zero padded to 32) broadcast from shared memory
+__device__ __forceinline__ double dot_reg32(const double (&reg)[kRegN], const double *vec) {
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+  for (int k = 0; k < kRegN; k += 4) {
+    const double2 v0 = *reinterpret_cast<const double2 *>(vec + k), v1 = *reinterpret_cast<const double2 *>(vec + k + 2);
+    a0 = fma(reg[k], v0.x, a0); a1 = fma(reg[k + 1], v0.y, a1); a2 = fma(reg[k + 2], v1.x, a2); a3 = fma(reg[k + 3], v1.y, a3);
+  }
+  return (a0 + a1) + (a2 + a3);
+}
+
+__global__ void __launch_bounds__(256, 1) admm_instance_reg_kernel(InstanceDataDev I, BatchDev Bt, SettingsDev S, int warps_per_cta) {
+  extern __shared__ __align__(16) double smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.x * warps_per_cta + warp;
+  if (b >= Bt.B) return;
+  const int n = I.n, m = I.m, ldT = reg_ldT(m), ldM = reg_ldT(n), mv = (m + 1) & ~1;
+  double *base = smem + (size_t)warp * ((instance_reg_warp_doubles(n, m) + 1) & ~(size_t)1);
+  // vectors first (strides kRegN / kRegM, zero padded, 16-byte aligned), then A̅' and the two n x n scratch matrices
+  double *x = base, *dx = x + kRegN, *qb = dx + kRegN, *xt = qb + kRegN, *sPx = xt + kRegN, *sAty = sPx + kRegN, *Dv = sAty + kRegN, *Dinv = Dv + kRegN;
+  double *z = Dinv + kRegN, *y = z + kRegM, *lb = y + kRegM, *ub = lb + kRegM, *w = ub + kRegM, *zt = w + kRegM, *dy = zt + kRegM, *rv = dy + kRegM, *Ev = rv + kRegM, *Einv = Ev + kRegM;
+  double *At = Einv + kRegM, *Sc = At + n * ldT;
+  const double *gP = I.P + (size_t)b * n * n, *gA = I.A + (size_t)b * m * n;
+  const int li = lane < n ? lane : n - 1;          // lanes >= n sweep a valid row and drop the result
+#ifdef SMPC_PROFILE
+  long long pf[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pc = clock64();
+#define PFI(i) { const long long tt = clock64(); pf[i] += tt - pc; pc = tt; }
+#else
+#define PFI(i)
+#endif
+  for (int e = lane; e < 8 * kRegN + 10 * kRegM; e += 32) base[e] = 0.0;
+  for (int e = lane; e < n * ldT; e += 32) At[e] = 0.0;
+  __syncwarp();
+  const double alpha = S.alpha, c = I.c[b], cinv = 1.0 / c;
+  const bool unscale = !S.scaled_termination;
+  const bool warm = S.warm_start && !Bt.fresh;
+
+  // ---- load the instance: A̅' into shared memory, rows lane and lane + 32 of A̅ into registers
+  for (int row = 0; row < m; ++row)                 // coalesced row reads, transposed (conflict-free) shared-memory writes
+    for (int col = lane; col < n; col += 32) At[col * ldT + row] = gA[row * n + col];
+  __syncwarp();
+  double ar0[kRegN], ar1[kRegN], mi[kRegN];
+#pragma unroll
+  for (int k = 0; k < kRegN; ++k) {
+    ar0[k] = (k < n && lane < m) ? At[k * ldT + lane] : 0.0;
+    ar1[k] = (k < n && lane + 32 < m) ? At[k * ldT + lane + 32] : 0.0;
+    mi[k] = 0.0;
+  }
+  for (int i = lane; i < n; i += 32) {
+    const double d = I.D[(size_t)b * n + i];
+    Dv[i] = d; Dinv[i] = 1.0 / d;
+    qb[i] = Bt.q ? c * (d * Bt.q[(size_t)b * n + i]) : 0.0;
+    x[i] = warm ? Bt.xi[(size_t)b * n + i] : 0.0;
+    dx[i] = 0.0;
+  }
+  double rho = Bt.fresh ? fmin(fmax(S.rho0, kRhoMin), kRhoMax) : Bt.rho[b];
+  int bad_rows = 0;
+  for (int r = lane; r < m; r += 32) {
+    const double e = I.E[(size_t)b * m + r];
+    Ev[r] = e; Einv[r] = 1.0 / e;
+    lb[r] = e * (Bt.l ? Bt.l[(size_t)b * m + r] : I.l0[r]);
+    ub[r] = e * (Bt.u ? Bt.u[(size_t)b * m + r] : I.u0[r]);
+    z[r] = warm ? Bt.z[(size_t)b * m + r] : 0.0;
+    y[r] = warm ? Bt.y[(size_t)b * m + r] : 0.0;
+    dy[r] = 0.0;
+    bad_rows |= lb[r] > ub[r];
+  }
+  const bool bad_bounds = __any_sync(kFull, bad_rows);
+  int rho_updates = 0;
+  __syncwarp();
+
+  // rho_vec from the instance's own (scaled) bounds: OSQP set_rho_vec / update_rho_vec
+  auto set_rho_vec = [&]() {
+    for (int r = lane; r < m; r += 32) {
+      const bool fr = lb[r] < -kInfty * kMinScaling && ub[r] > kInfty * kMinScaling;
+      rv[r] = fr ? kRhoMin : ((ub[r] - lb[r] < kRhoTolRow) ? kRhoEqOverIneq * rho : rho);
+    }
+    __syncwarp();
+  };
+
+  // M = P̄ + sigma I + A̅' diag(rho_vec) A̅ (lower triangle, in Sc) ;  M = L L' in place ;  then lane c solves
+  // L L' v = e_c with v in its registers: v is row c of M^-1, exactly the operand of x̃ = M^-1 rhs.  No explicit L^-1,
+  // no M^-1 in shared memory.  Returns false if M is not positive definite.
+  auto refactor = [&]() -> bool {
+    PFI(2)
+    const int tri = n * (n + 1) / 2;
+    for (int e = lane; e < tri; e += 32) {
+      int i = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
+      while ((i + 1) * (i + 2) / 2 <= e) ++i;
+      while (i * (i + 1) / 2 > e) --i;
+      const int j = e - i * (i + 1) / 2;
+      double s0 = gP[i * n + j] + (i == j ? S.sigma : 0.0), s1 = 0.0;
+      const double *ai = At + i * ldT, *aj = At + j * ldT;
+      for (int r = 0; r < mv; r += 2) {      // same summation order as admm_instance_kernel (pad column and rv pad are 0)
+        const double2 rr = *reinterpret_cast<const double2 *>(rv + r), a = *reinterpret_cast<const double2 *>(ai + r), c2 = *reinterpret_cast<const double2 *>(aj + r);
+        s0 = fma(rr.x * a.x, c2.x, s0);
+        s1 = fma(rr.y * a.y, c2.y, s1);
+      }
+      Sc[i * ldM + j] = s0 + s1;
+    }
+    __syncwarp();
+    PFI(3)
+    // left-looking Cholesky, lower triangle of Sc in place; zt[j] = 1 / L_jj
+    int ok = 1;
+    for (int j = 0; j < n; ++j) {
+      if (lane >= j && lane < n) {
+        const double *ri = Sc + lane * ldM, *rj = Sc + j * ldM;
+        double s0 = ri[j], s1 = 0.0;
+        int k = 0;
+        for (; k + 2 <= j; k += 2) {
+          const double2 a = *reinterpret_cast<const double2 *>(ri + k), c2 = *reinterpret_cast<const double2 *>(rj + k);
+          s0 = fma(-a.x, c2.x, s0); s1 = fma(-a.y, c2.y, s1);
+        }
+        if (k < j) s0 = fma(-ri[k], rj[k], s0);
+        xt[lane] = s0 + s1;    // column j before scaling (xt is free here)
+      }
+      __syncwarp();
+      const double d = xt[j];
+      if (!(d > 0.0)) { ok = 0; break; }
+      const double sd = sqrt(d);
+      if (lane >= j && lane < n) Sc[lane * ldM + j] = lane == j ? sd : xt[lane] / sd;
+      if (lane == 0) zt[j] = 1.0 / sd;
+      __syncwarp();
+    }
+    if (!ok) return false;
+    PFI(4)
+    // forward substitution L v = e_lane (v in mi[]), then backward L' x = v in place; L is read with warp-uniform addresses
+#pragma unroll
+    for (int i = 0; i < kRegN; ++i) {
+      if (i < n) {
+        double s0 = i == lane ? 1.0 : 0.0, s1 = 0.0;
+#pragma unroll
+        for (int k = 0; k + 1 < i; k += 2) {
+          const double2 l = *reinterpret_cast<const double2 *>(Sc + i * ldM + k);
+          s0 = fma(-l.x, mi[k], s0); s1 = fma(-l.y, mi[k + 1], s1);
+        }
+        if (i & 1) s0 = fma(-Sc[i * ldM + i - 1], mi[i - 1], s0);
+        mi[i] = (s0 + s1) * zt[i];
+      } else {
+        mi[i] = 0.0;
+      }
+    }
+#pragma unroll
+    for (int i = kRegN - 1; i >= 0; --i) {
+      if (i < n) {
+        double s0 = mi[i], s1 = 0.0;
+#pragma unroll
+        for (int k = i + 1; k < kRegN; ++k) {
+          if (k < n) {
+            if (k & 1) s1 = fma(-Sc[k * ldM + i], mi[k], s1); else s0 = fma(-Sc[k * ldM + i], mi[k], s0);
+          }
+        }
+        mi[i] = (s0 + s1) * zt[i];
+      }
+    }
+    if (lane >= n) {
+#pragma unroll
+      for (int k = 0; k < kRegN; ++k) mi[k] = 0.0;
+    }
+    __syncwarp();
+    PFI(5)
+    return true;
+  };
+
+  int status = SMPC_UNSOLVED, iter = 0;
+  bool can_check = false;
+  Info F = {};
+
+  auto update_info = [&]() {
+    for (int i = lane; i < n; i += 32) {
+      double s = 0.0;
+      for (int k = 0; k < n; ++k) s = fma(gP[k * n + i], x[k], s);   // P̄ x: P̄ is stored full symmetric, column sweep = coalesced
+      sPx[i] = s;
+      sAty[i] = dot_s128(At + i * ldT, y, mv);
+    }
+    if (lane < m) w[lane] = dot_reg32(ar0, x);
+    if (lane + 32 < m) w[lane + 32] = dot_reg32(ar1, x);
+    __syncwarp();
+    double a_rp = 0, a_z = 0, a_Ax = 0, u_rp = 0, u_z = 0, u_Ax = 0;
+    for (int r = lane; r < m; r += 32) {
+      const double rp = w[r] - z[r], ei = Einv[r];
+      a_rp = fmax(a_rp, fabs(rp)); a_z = fmax(a_z, fabs(z[r])); a_Ax = fmax(a_Ax, fabs(w[r]));
+      u_rp = fmax(u_rp, fabs(ei * rp)); u_z = fmax(u_z, fabs(ei * z[r])); u_Ax = fmax(u_Ax, fabs(ei * w[r]));
+    }
+    double a_rd = 0, a_q = 0, a_Aty = 0, a_Px = 0, u_rd = 0, u_q = 0, u_Aty = 0, u_Px = 0, ob = 0;
+    for (int i = lane; i < n; i += 32) {
+      const double rd = (qb[i] + sPx[i]) + sAty[i], di = Dinv[i];
+      a_rd = fmax(a_rd, fabs(rd)); a_q = fmax(a_q, fabs(qb[i])); a_Aty = fmax(a_Aty, fabs(sAty[i])); a_Px = fmax(a_Px, fabs(sPx[i]));
+      u_rd = fmax(u_rd, fabs(di * rd)); u_q = fmax(u_q, fabs(di * qb[i])); u_Aty = fmax(u_Aty, fabs(di * sAty[i])); u_Px = fmax(u_Px, fabs(di * sPx[i]));
+      ob += 0.5 * x[i] * sPx[i] + qb[i] * x[i];
+    }
+    F.s_rp = wmax(a_rp); F.s_z = wmax(a_z); F.s_Ax = wmax(a_Ax);
+    F.s_rd = wmax(a_rd); F.s_q = wmax(a_q); F.s_Aty = wmax(a_Aty); F.s_Px = wmax(a_Px);
+    if (unscale) {
+      F.pri_res = wmax(u_rp); F.nEz = wmax(u_z); F.nEAx = wmax(u_Ax);
+      F.dua_res = cinv * wmax(u_rd); F.nDq = wmax(u_q); F.nDAty = wmax(u_Aty); F.nDPx = wmax(u_Px);
+      F.obj = cinv * wsum(ob);
+    } else {
+      F.pri_res = F.s_rp; F.nEz = F.s_z; F.nEAx = F.s_Ax;
+      F.dua_res = F.s_rd; F.nDq = F.s_q; F.nDAty = F.s_Aty; F.nDPx = F.s_Px;
+      F.obj = wsum(ob);
+    }
+    if (m == 0) F.pri_res = 0.0;
+  };
+
+  auto primal_infeasible = [&](double eps) -> bool {
+    double nd = 0.0;
+    for (int r = lane; r < m; r += 32) {
+      double d = dy[r];
+      const bool uinf = ub[r] > kInfty * kMinScaling, linf = lb[r] < -kInfty * kMinScaling;
+      if (uinf) d = linf ? 0.0 : fmin(d, 0.0); else if (linf) d = fmax(d, 0.0);
+      dy[r] = d;
+      nd = fmax(nd, fabs(unscale ? Ev[r] * d : d));
+    }
+    nd = wmax(nd);
+    __syncwarp();
+    if (!(nd > eps)) return false;
+    double lhs = 0.0;
+    for (int r = lane; r < m; r += 32) {
+      const double dp = fmax(dy[r], 0.0), dm = fmin(dy[r], 0.0);
+      if (dp != 0.0) lhs += ub[r] * dp;
+      if (dm != 0.0) lhs += lb[r] * dm;
+    }
+    lhs = wsum(lhs);
+    if (!(lhs < -eps * nd)) return false;
+    double na = 0.0;
+    for (int i = lane; i < n; i += 32) {
+      const double v = dot_s128(At + i * ldT, dy, mv);
+      na = fmax(na, fabs(unscale ? Dinv[i] * v : v));
+    }
+    return wmax(na) < eps * nd;
+  };
+
+  auto dual_infeasible = [&](double eps) -> bool {
+    double nd = 0.0, qd = 0.0;
+    for (int i = lane; i < n; i += 32) {
+      nd = fmax(nd, fabs(unscale ? Dv[i] * dx[i] : dx[i]));
+      qd += qb[i] * dx[i];
+    }
+    nd = wmax(nd); qd = wsum(qd);
+    const double cs = unscale ? c : 1.0;
+    if (!(nd > eps)) return false;
+    if (!(qd < -cs * eps * nd)) return false;
+    double np = 0.0;
+    for (int i = lane; i < n; i += 32) {
+      double s = 0.0;
+      for (int k = 0; k < n; ++k) s = fma(gP[k * n + i], dx[k], s);
+      np = fmax(np, fabs(unscale ? Dinv[i] * s : s));
+    }
+    if (!(wmax(np) < cs * eps * nd)) return false;
+    int bad = 0;
+    for (int r = lane; r < m; r += 32) {
+      double v = r == lane ? dot_reg32(ar0, dx) : dot_reg32(ar1, dx);
+      if (unscale) v *= Einv[r];
+      if (((ub[r] < kInfty * kMinScaling) && (v > eps * nd)) || ((lb[r] > -kInfty * kMinScaling) && (v < -eps * nd))) bad = 1;
+    }
+    return !__any_sync(kFull, bad);
+  };
+
+  auto check_termination = [&](bool approx) -> bool {
+    double ea = S.eps_abs, er = S.eps_rel, epi = S.eps_prim_inf, edi = S.eps_dual_inf;
+    if (approx) { ea *= 10; er *= 10; epi *= 10; edi *= 10; }
+    bool prim_ok = false, dual_ok = false, prim_inf = false, dual_inf = false;
+    if (m == 0) prim_ok = true;
+    else if (F.pri_res < ea + er * fmax(F.nEz, F.nEAx)) prim_ok = true;
+    else prim_inf = primal_infeasible(epi);
+    if (F.dua_res < ea + er * (unscale ? cinv : 1.0) * fmax(fmax(F.nDq, F.nDAty), F.nDPx)) dual_ok = true;
+    else dual_inf = dual_infeasible(edi);
+    if (prim_ok && dual_ok) { status = approx ? SMPC_SOLVED_INACCURATE : SMPC_SOLVED; return true; }
+    if (prim_inf) { status = approx ? SMPC_PRIMAL_INFEASIBLE_INACCURATE : SMPC_PRIMAL_INFEASIBLE; F.obj = kInfty; return true; }
+    if (dual_inf) { status = approx ? SMPC_DUAL_INFEASIBLE_INACCURATE : SMPC_DUAL_INFEASIBLE; F.obj = -kInfty; return true; }
+    return false;
+  };
+
+  PFI(0)
+  bool factor_ok = true, need_factor = true;   // (re)factor at the top of the iteration that first needs it: one call site
+  for (iter = 1; iter <= S.max_iter && !bad_bounds && factor_ok; ++iter) {
+    if (need_factor) {
+      set_rho_vec();
+      factor_ok = refactor();
+      need_factor = false;
+      if (!factor_ok) break;
+    }
+    for (int r = lane; r < m; r += 32) w[r] = rv[r] * z[r] - y[r];
+    __syncwarp();
+    {
+      const double aw = dot_s128(At + li * ldT, w, mv);
+      if (lane < n) sAty[lane] = (S.sigma * x[lane] - qb[lane]) + aw;                                     // rhs
+    }
+    __syncwarp();
+    {
+      const double xv = dot_reg32(mi, sAty);                                                              // x̃ = M^-1 rhs
+      if (lane < n) xt[lane] = xv;
+    }
+    __syncwarp();
+    for (int r = lane; r < m; r += 32) {
+      const double ztl = r == lane ? dot_reg32(ar0, xt) : dot_reg32(ar1, xt);
+      const double rr = rv[r], rinv = 1.0 / rr;
+      const double zr = alpha * ztl + (1.0 - alpha) * z[r];
+      const double zn = fmin(fmax(zr + rinv * y[r], lb[r]), ub[r]);
+      const double d = rr * (zr - zn);
+      z[r] = zn; y[r] += d; dy[r] = d;
+    }
+    for (int i = lane; i < n; i += 32) {
+      const double xn = alpha * xt[i] + (1.0 - alpha) * x[i];
+      dx[i] = xn - x[i];
+      x[i] = xn;
+    }
+    __syncwarp();
+    PFI(1)
+    can_check = S.check_every && (iter % S.check_every == 0);
+    if (can_check) {
+      update_info();
+      if (check_termination(false)) break;
+    }
+    if (S.adaptive_rho && S.rho_interval && (iter % S.rho_interval == 0)) {
+      if (!can_check) update_info();
+      const double pr = F.s_rp / (fmax(F.s_z, F.s_Ax) + kDivTol);
+      const double dr = F.s_rd / (fmax(fmax(F.s_q, F.s_Aty), F.s_Px) + kDivTol);
+      const double rn = fmin(fmax(rho * sqrt(pr / (dr + kDivTol)), kRhoMin), kRhoMax);
+      if (rn > rho * S.rho_tol || rn < rho / S.rho_tol) {
+        rho = rn; ++rho_updates;
+        need_factor = true;
+      }
+    }
+    __syncwarp();
+    PFI(6)
+  }
+  if (iter > S.max_iter) iter = S.max_iter;
+  if (bad_bounds || !factor_ok) iter = 0;
+  else {
+    if (!can_check) { update_info(); check_termination(false); }
+    if (status == SMPC_UNSOLVED) { if (!check_termination(true)) status = SMPC_MAX_ITER_REACHED; }
+  }
+
+  const bool has_sol = !bad_bounds && factor_ok && !(status == SMPC_PRIMAL_INFEASIBLE || status == SMPC_PRIMAL_INFEASIBLE_INACCURATE ||
+                                                     status == SMPC_DUAL_INFEASIBLE || status == SMPC_DUAL_INFEASIBLE_INACCURATE);
+  const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+  __syncwarp();
+  for (int i = lane; i < n; i += 32) {
+    if (Bt.x_out) Bt.x_out[(size_t)b * n + i] = has_sol ? Dv[i] * x[i] : qnan;
+    Bt.xi[(size_t)b * n + i] = has_sol ? x[i] : 0.0;
+  }
+  for (int r = lane; r < m; r += 32) {
+    if (Bt.y_out) Bt.y_out[(size_t)b * m + r] = has_sol ? cinv * (Ev[r] * y[r]) : qnan;
+    Bt.z[(size_t)b * m + r] = has_sol ? z[r] : 0.0;
+    Bt.y[(size_t)b * m + r] = has_sol ? y[r] : 0.0;
+  }
+#ifdef SMPC_PROFILE
+  PFI(7)
+  if (b == 0 && lane == 0) printf("instance profile (cycles): load %lld, iterations %lld, pre-assembly %lld, M assembly %lld, cholesky %lld, tri solves %lld, checks %lld, tail %lld; iters %d rho updates %d\n", pf[0], pf[1], pf[2], pf[3], pf[4], pf[5], pf[6], pf[7], iter, rho_updates);
+#endif
+  if (lane == 0) {
+    Bt.rho[b] = rho;
+    Bt.status[b] = status; Bt.iter[b] = iter; Bt.rho_updates[b] = rho_updates;
+    Bt.obj[b] = F.obj; Bt.pri_res[b] = F.pri_res; Bt.dua_res[b] = F.dua_res;
+  }
+}
+
 // osqp_warm_start in the per-instance regime: x̄ = D^-1 x, z = A̅ x̄, ȳ = c E^-1 y
 __global__ void warm_start_instance_kernel(InstanceDataDev I, const double *x, const double *y, double *xs, double *z, double *ys) {
   const int lane = threadIdx.x & 31, b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -428,7 +821,7 @@ __global__ void warm_start_instance_kernel(InstanceDataDev I, const double *x, c
 
 static int pick_wpc(size_t per_warp_bytes) {
   int wpc = 8;
-  while (wpc > 1 && wpc * per_warp_bytes > 200 * 1024) --wpc;
+  while (wpc > 1 && wpc * per_warp_bytes > 224 * 1024) --wpc;
   return wpc;
 }
 
@@ -451,6 +844,19 @@ cudaError_t launch_ruiz_instance(const InstanceDataDev &I, int iters, cudaStream
 }
 
 cudaError_t launch_admm_instance(const InstanceDataDev &I, const BatchDev &Bt, const SettingsDev &S, cudaStream_t stream) {
+  if (I.n <= kRegN && I.m <= kRegM && I.m >= 1) {   // register-operator variant
+    const size_t per = ((instance_reg_warp_doubles(I.n, I.m) + 1) & ~(size_t)1) * sizeof(double);
+    const int wpc = pick_wpc(per);
+    const size_t smem = wpc * per;
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(admm_instance_reg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (e != cudaSuccess) return e;
+      attr_set = true;
+    }
+    admm_instance_reg_kernel<<<(Bt.B + wpc - 1) / wpc, wpc * 32, smem, stream>>>(I, Bt, S, wpc);
+    return cudaGetLastError();
+  }
   const size_t per = instance_warp_doubles(I.n, I.m) * sizeof(double);
   const int wpc = pick_wpc(per);
   const size_t smem = wpc * per;
