@@ -147,6 +147,9 @@ int smpc_solver_get_scaling(smpc_solver *s, double *D, double *E, double *c);
 /* kernels launched by this handle since creation (bench.py gpu_launches) */
 long long smpc_solver_launch_count(const smpc_solver *s);
 const char *smpc_solver_kernel_name(const smpc_solver *s);
+/* m / 2 when the constraint rows come as pairs [G; -G] (the reference's two-sided limit, cpp:335) AND the handle's
+ * kernel exploits it (tile kernel: iteration GEMMs on the top half only, identical iterates); 0 otherwise */
+int smpc_solver_row_pairs(const smpc_solver *s);
 
 /* Host-only inspection of the shared-factor plan built at create time (Ruiz scaling D, E, c as
  * OSQP scale_data computes them; the pencil decomposition V, lambda; the operators the kernels

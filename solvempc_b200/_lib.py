@@ -84,6 +84,7 @@ SIGNATURES = {
     "smpc_solver_get_scaling": (_i, [_vp, _dp, _dp, C.POINTER(C.c_double)]),
     "smpc_solver_launch_count": (C.c_longlong, [_vp]),
     "smpc_solver_kernel_name": (C.c_char_p, [_vp]),
+    "smpc_solver_row_pairs": (_i, [_vp]),
     "smpc_shared_plan_inspect": (_i, [_i, _i, _dp, _dp, _dp, _dp, _dp, C.POINTER(Settings), _dp, _dp, C.POINTER(C.c_double),
                                       _dp, _dp, _dp, _dp, _dp, _dp, _vp]),
     "smpc_mpc_create": (_i, [C.POINTER(_vp), _i, C.POINTER(MpcConfig), _i, C.POINTER(Settings)]),

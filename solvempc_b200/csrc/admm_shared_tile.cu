@@ -157,7 +157,7 @@ __device__ __forceinline__ double rsum8(double v) {
 
 enum PassId { P_XBAR, P_PX, P_ATY, P_AX, P_ATD, P_DX, P_PD, P_ADX, P_QH, P_COUNT };
 
-template <int NB>
+template <int NB, bool PAIRED>
 __global__ void __launch_bounds__(kTileThreads, 1)
 admm_shared_tile_kernel(TilePackDev K, SharedPlanDev P, BatchDev Bt, SettingsDev S, int *queue) {
   constexpr int TB = 8 * NB;
@@ -176,6 +176,10 @@ admm_shared_tile_kernel(TilePackDev K, SharedPlanDev P, BatchDev Bt, SettingsDev
   const int nrb0 = (warp * NRB) / kTileWarps, nrb1 = ((warp + 1) * NRB) / kTileWarps;
   const int mrb0 = (warp * MRB) / kTileWarps, mrb1 = ((warp + 1) * MRB) / kTileWarps;
   const int kpN = n8 >> 3, kpM = m8 >> 3;
+  // PAIRED: rows r and r + mp of W are negatives of each other; the iteration GEMMs use the top half only and the first
+  // mp rows of the w part of the cv panel carry wd = w_top - w_bot between events (events see the full panels)
+  const int mp = PAIRED ? K.mp : 0, kpMp = PAIRED ? (K.mp8 >> 3) : 0, MRBp = kpMp;
+  const int prb0 = (warp * MRBp) / kTileWarps, prb1 = ((warp + 1) * MRBp) / kTileWarps;
   const double alpha = S.alpha, oma = 1.0 - S.alpha;
   const int check_every = S.check_every, adapt_every = (S.adaptive_rho && S.rho_interval > 0) ? S.rho_interval : 0;
 
@@ -618,10 +622,22 @@ admm_shared_tile_kernel(TilePackDev K, SharedPlanDev P, BatchDev Bt, SettingsDev
       PFM(pf_pass, P_COUNT + 1)
       // ---- w = rho_vec z - y (the w panel carried delta_y); schedule the next event
       __syncthreads();
-      for (int e = tid; e < m8 * TB; e += kTileThreads) {
-        const int s8 = e & 7, rest = e >> 3, r = rest % m8, nb = rest / m8, s = nb * 8 + s8;
-        const int ct = r < m ? (int)__ldg(P.ctype + r) : 0;
-        cv[w_at(e)] = rho_of(ct, C.rho[s]) * zp[e] - yp[e];
+      if (PAIRED) {
+        const int mp8 = kpMp * 8;
+        for (int e = tid; e < mp8 * TB; e += kTileThreads) {
+          const int s8 = e & 7, rest = e >> 3, r = rest % mp8, nb = rest / mp8, s = nb * 8 + s8;
+          if (r >= mp) continue;
+          const int e1 = (nb * m8 + r) * 8 + s8, e2 = e1 + mp * 8;
+          const double w1 = rho_of((int)__ldg(P.ctype + r), C.rho[s]) * zp[e1] - yp[e1];
+          const double w2 = rho_of((int)__ldg(P.ctype + r + mp), C.rho[s]) * zp[e2] - yp[e2];
+          cv[w_at(e1)] = w1 - w2;
+        }
+      } else {
+        for (int e = tid; e < m8 * TB; e += kTileThreads) {
+          const int s8 = e & 7, rest = e >> 3, r = rest % m8, nb = rest / m8, s = nb * 8 + s8;
+          const int ct = r < m ? (int)__ldg(P.ctype + r) : 0;
+          cv[w_at(e)] = rho_of(ct, C.rho[s]) * zp[e] - yp[e];
+        }
       }
       if (tid == 0) {
         int act = 0, ne = 0x7fffffff;
@@ -652,12 +668,14 @@ admm_shared_tile_kernel(TilePackDev K, SharedPlanDev P, BatchDev Bt, SettingsDev
     // ================= one ADMM iteration for the whole tile
     ++k;
     event = (k == C.next_event);
-    const double2 *M1l = reinterpret_cast<const double2 *>(K.M1) + lane, *Wl = reinterpret_cast<const double2 *>(K.Wp) + lane;
+    const double2 *M1l = reinterpret_cast<const double2 *>(PAIRED ? K.M1p : K.M1) + lane;
+    const double2 *Wl = reinterpret_cast<const double2 *>(PAIRED ? K.Wtop : K.Wp) + lane;
+    const int kp1 = kpN + (PAIRED ? kpMp : kpM);      // k-pairs of GEMM 1
     // ---- GEMM 1: T = ([sigma G | W'] [xi; w] - q̂) .* dinv
     for (int rb = nrb0; rb < nrb1; rb += kRG) {
       double acc[kRG][NB][2];
       zero_acc(acc);
-      gemm_seg<NB>(M1l, kpN + kpM, rb, min(kRG, nrb1 - rb), 0, kpN + kpM, cv + bfrag, cvr * 8, acc);
+      gemm_seg<NB>(M1l, kp1, rb, min(kRG, nrb1 - rb), 0, kp1, cv + bfrag, cvr * 8, acc);
 #pragma unroll
       for (int r = 0; r < kRG; ++r)
         if (rb + r < nrb1) {
@@ -683,6 +701,50 @@ admm_shared_tile_kernel(TilePackDev K, SharedPlanDev P, BatchDev Bt, SettingsDev
       }
     }
     // ---- GEMM 2: z̃ = W T ; z, y updates (OSQP update_z / update_y) ; w = rho_vec z - y
+    if (PAIRED) {
+      // top half only: row p gives z̃_p, row p + mp gets -z̃_p; the panel row p of the w part carries w_p - w_{p+mp}
+      for (int rb = prb0; rb < prb1; rb += kRG) {
+        double acc[kRG][NB][2];
+        zero_acc(acc);
+        gemm_seg<NB>(Wl, kpN, rb, min(kRG, prb1 - rb), 0, kpN, Tp + bfrag, n8 * 8, acc);
+#pragma unroll
+        for (int r = 0; r < kRG; ++r)
+          if (rb + r < prb1) {
+            const int row = 8 * (rb + r) + g;
+            if (row < mp) {
+              const int ct1 = (int)__ldg(P.ctype + row), ct2 = (int)__ldg(P.ctype + row + mp);
+#pragma unroll
+              for (int nb = 0; nb < NB; ++nb) {
+                const int s = nb * 8 + q2;
+                double wsum2[2] = {0.0, 0.0};
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                  const int rr = row + half * mp, ct = half ? ct2 : ct1, pi = pidx(m8, nb, rr);
+                  const double sg = half ? -1.0 : 1.0;
+                  const double2 zo = *reinterpret_cast<const double2 *>(zp + pi), yo = *reinterpret_cast<const double2 *>(yp + pi);
+                  const double2 lo = *reinterpret_cast<const double2 *>(lbp + pi), hi = *reinterpret_cast<const double2 *>(ubp + pi);
+                  double rv0, rv1, ri0, ri1;
+                  if (ct == 0) { rv0 = C.rho[s]; rv1 = C.rho[s + 1]; ri0 = C.rinv[s]; ri1 = C.rinv[s + 1]; }
+                  else if (ct == 1) { rv0 = C.rho_eq[s]; rv1 = C.rho_eq[s + 1]; ri0 = C.rinv_eq[s]; ri1 = C.rinv_eq[s + 1]; }
+                  else { rv0 = rv1 = kRhoMin; ri0 = ri1 = 1.0 / kRhoMin; }
+                  const double zr0 = alpha * (sg * acc[r][nb][0]) + oma * zo.x, zr1 = alpha * (sg * acc[r][nb][1]) + oma * zo.y;
+                  const double zn0 = fmin(fmax(zr0 + ri0 * yo.x, lo.x), hi.x), zn1 = fmin(fmax(zr1 + ri1 * yo.y, lo.y), hi.y);
+                  const double d0 = rv0 * (zr0 - zn0), d1 = rv1 * (zr1 - zn1);
+                  const double yn0 = yo.x + d0, yn1 = yo.y + d1;
+                  *reinterpret_cast<double2 *>(zp + pi) = make_double2(zn0, zn1);
+                  *reinterpret_cast<double2 *>(yp + pi) = make_double2(yn0, yn1);
+                  // before an event the w panel carries delta_y of EVERY row (is_primal_infeasible); rebuilt after the event
+                  if (event) *reinterpret_cast<double2 *>(cv + pidx(cvr, nb, n8 + rr)) = make_double2(d0, d1);
+                  wsum2[0] += sg * (rv0 * zn0 - yn0); wsum2[1] += sg * (rv1 * zn1 - yn1);
+                }
+                if (!event) *reinterpret_cast<double2 *>(cv + pidx(cvr, nb, n8 + row)) = make_double2(wsum2[0], wsum2[1]);
+              }
+            }
+          }
+      }
+      __syncthreads();
+      continue;
+    }
     for (int rb = mrb0; rb < mrb1; rb += kRG) {
       double acc[kRG][NB][2];
       zero_acc(acc);
@@ -747,16 +809,15 @@ cudaError_t launch_admm_shared_tile(const TilePackDev &K, const SharedPlanDev &P
   if (per_sm < 1) per_sm = 1;
   if (per_sm > 4) per_sm = 4;
   if (grid > num_sms * per_sm) grid = num_sms * per_sm;
-  if (nb == 1) {
-    e = cudaFuncSetAttribute(admm_shared_tile_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    admm_shared_tile_kernel<1><<<grid, kTileThreads, smem, stream>>>(K, P, Bt, S, queue);
-  } else {
-    e = cudaFuncSetAttribute(admm_shared_tile_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    admm_shared_tile_kernel<2><<<grid, kTileThreads, smem, stream>>>(K, P, Bt, S, queue);
-  }
-  return cudaGetLastError();
+  auto go = [&](auto kernel) -> cudaError_t {
+    cudaError_t e2 = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e2 != cudaSuccess) return e2;
+    kernel<<<grid, kTileThreads, smem, stream>>>(K, P, Bt, S, queue);
+    return cudaGetLastError();
+  };
+  const bool paired = K.mp > 0;
+  if (nb == 1) return paired ? go(admm_shared_tile_kernel<1, true>) : go(admm_shared_tile_kernel<1, false>);
+  return paired ? go(admm_shared_tile_kernel<2, true>) : go(admm_shared_tile_kernel<2, false>);
 }
 
 }  // namespace smpc

@@ -189,8 +189,20 @@ int upload_tile_pack(smpc_solver *s) {
   auto Vp = pack(n8, n8, [&](int i, int k) -> double { return (i < n && k < n) ? p.V[(size_t)i * n + k] : 0.0; });
   auto PVp = pack(n8, n8, [&](int i, int k) -> double { return (i < n && k < n) ? p.PVT[(size_t)k * n + i] : 0.0; });
   auto ATp = pack(n8, m8, [&](int i, int r) -> double { return (i < n && r < m) ? p.Abar[(size_t)r * n + i] : 0.0; });
+  // paired rows [G; -G] (plan.pairs = m / 2): iteration operators on the top half only
+  const int mp = p.pairs, mp8 = (mp + 7) & ~7;
+  std::vector<double> M1p, Wtop;
+  if (mp > 0) {
+    M1p = pack(n8, n8 + mp8, [&](int i, int k) -> double {
+      if (i >= n) return 0.0;
+      if (k < n8) return k < n ? p.SG[(size_t)i * n + k] : 0.0;
+      const int r = k - n8;
+      return r < mp ? p.W[(size_t)r * n + i] : 0.0;
+    });
+    Wtop = pack(mp8, n8, [&](int r, int k) -> double { return (r < mp && k < n) ? p.W[(size_t)r * n + k] : 0.0; });
+  }
   size_t bytes = DeviceBuf::need(sizeof(int) * 4);
-  for (const std::vector<double> *v : {&M1, &Wp, &VTp, &Vp, &PVp, &ATp}) bytes += DeviceBuf::need((v->size() ? v->size() : 1) * sizeof(double));
+  for (const std::vector<double> *v : {&M1, &Wp, &VTp, &Vp, &PVp, &ATp, &M1p, &Wtop}) bytes += DeviceBuf::need((v->size() ? v->size() : 1) * sizeof(double));
   CK(s->tilebuf.alloc(bytes));
   auto put = [&](const std::vector<double> &v, const double **dst) -> cudaError_t {
     double *d = s->tilebuf.take<double>(v.size() ? v.size() : 1);
@@ -201,6 +213,8 @@ int upload_tile_pack(smpc_solver *s) {
   smpc::TilePackDev &k = s->dtile;
   k.n8 = n8; k.m8 = m8;
   CK(put(M1, &k.M1)); CK(put(Wp, &k.Wp)); CK(put(VTp, &k.VTp)); CK(put(Vp, &k.Vp)); CK(put(PVp, &k.PVp)); CK(put(ATp, &k.ATp));
+  k.mp = mp; k.mp8 = mp8;
+  CK(put(M1p, &k.M1p)); CK(put(Wtop, &k.Wtop));
   s->d_queue = s->tilebuf.take<int>(4);
   if (!s->d_queue) return fail(SMPC_ERR_CUDA, "internal: tile buffer carve-out overflow");
   CK(cudaMemset(s->d_queue, 0, sizeof(int) * 4));
@@ -589,6 +603,7 @@ int smpc_solver_get_scaling(smpc_solver *s, double *D, double *E, double *c) {
 }
 
 long long smpc_solver_launch_count(const smpc_solver *s) { return s ? s->launches : 0; }
+int smpc_solver_row_pairs(const smpc_solver *s) { return (s && s->regime == 0 && s->kernel == 4) ? s->dtile.mp : 0; }
 const char *smpc_solver_kernel_name(const smpc_solver *s) {
   if (!s) return "";
   return s->regime == 1 ? "admm_instance_kernel" : s->kernel == 2 ? "admm_shared_small_kernel"

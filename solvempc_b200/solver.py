@@ -186,6 +186,11 @@ class BatchedSolver:
     def kernel_name(self):
         return L.lib().smpc_solver_kernel_name(self._h).decode()
 
+    @property
+    def row_pairs(self):
+        """m / 2 when the rows come as [G; -G] pairs and the kernel runs its iteration GEMMs on the top half only."""
+        return L.lib().smpc_solver_row_pairs(self._h)
+
 
 def shared_plan_inspect(P, A, l0=None, u0=None, settings=None, q0=None, **kw):
     """Host-only view of the shared-factor plan (no device needed)."""

@@ -21,5 +21,5 @@ for B in [int(a) for a in sys.argv[1:]] or [8192]:
     info = mpc.solver.info(); it = info["iter"].astype(np.int64)
     n, m = mpc.n_variables, mpc.n_constraints
     print(f"c3 B={B} {mpc.solver.kernel_name}: {ms:.2f} ms, {B / (ms * 1e-3):.3e} solves/s, iters mean {it.mean():.1f} max {it.max()}, "
-          f"solved {(info['status'] == 1).mean():.4f}, executed {it.sum() * 2.0 * (n * n + 2 * m * n) / (ms * 1e-3) / 1e12:.2f} TFLOP/s", flush=True)
+          f"solved {(info['status'] == 1).mean():.4f}, executed {it.sum() * 2.0 * (n * n + 2 * (m // 2) * n) / (ms * 1e-3) / 1e12:.2f} TFLOP/s", flush=True)
     mpc.close()

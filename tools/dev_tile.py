@@ -71,7 +71,7 @@ def mpc_case(N, B, reps=1, big=False):
     it = g[2]["iter"].astype(np.int64).sum()
     n, m = N, 2 * N
     for nm, r in (("tile", t), ("generic", g)):
-        fl = it * 2.0 * (n * n + 2 * m * n)
+        fl = it * 2.0 * (n * n + 2 * (m // 2) * n)
         print(f"   {nm}: {B / (r[3] * 1e-3):.3e} solves/s, {it / (r[3] * 1e-3):.3e} inst-iter/s, executed {fl / (r[3] * 1e-3) / 1e12:.2f} TFLOP/s", flush=True)
 
 if __name__ == "__main__":
@@ -101,7 +101,7 @@ if __name__ == "__main__":
             s.sync(); ms, cnt = s.kernel_ms(); ms /= cnt
             info = s.info(); it = info["iter"].astype(np.int64).sum(); n, m = N, 2 * N
             print(f"tile N={N} B={B}: {ms:.3f} ms, {B / (ms * 1e-3):.3e} solves/s, iters mean {info['iter'].mean():.1f} max {info['iter'].max()}, "
-                  f"executed {it * 2.0 * (n * n + 2 * m * n) / (ms * 1e-3) / 1e12:.2f} TFLOP/s, solved {(info['status'] == 1).mean():.4f}", flush=True)
+                  f"executed {it * 2.0 * (n * n + 2 * (m // 2) * n) / (ms * 1e-3) / 1e12:.2f} TFLOP/s, solved {(info['status'] == 1).mean():.4f}", flush=True)
             s.close()
     if what == "c5":
         import time
@@ -120,7 +120,7 @@ if __name__ == "__main__":
             dt = time.perf_counter() - t0
             n, m = N, 2 * N
             print(f"c5 closed loop N={N} B={B} steps={steps} kernel={mpc.solver.kernel_name}: {dt:.3f} s, {B * steps / dt:.3e} solves/s, "
-                  f"not solved {bad}, mean iters {it / (B * steps):.2f}, executed {it * 2.0 * (n * n + 2 * m * n) / dt / 1e12:.2f} TFLOP/s", flush=True)
+                  f"not solved {bad}, mean iters {it / (B * steps):.2f}, executed {it * 2.0 * (n * n + 2 * (m // 2) * n) / dt / 1e12:.2f} TFLOP/s", flush=True)
             mpc.close()
     if what == "ncu":
         N, B = 100, 16384
