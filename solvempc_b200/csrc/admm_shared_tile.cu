@@ -36,7 +36,7 @@ constexpr int kRing = 3;        // A-fragment prefetch distance in k-pairs (cove
 enum NormId {
   N_RP_S, N_Z_S, N_AX_S, N_RP_U, N_Z_U, N_AX_U,
   N_RD_S, N_Q_S, N_ATY_S, N_PX_S, N_RD_U, N_Q_U, N_ATY_U, N_PX_U,
-  N_DY, N_ATD, N_DX, N_PD, N_COUNT
+  N_DY, N_ATD, N_DX, N_PD, N_DXI, N_COUNT
 };
 enum SumId { S_OBJ, S_LHS, S_QD, S_COUNT };
 
@@ -321,7 +321,27 @@ admm_shared_tile_kernel(TilePackDev K, SharedPlanDev P, BatchDev Bt, SettingsDev
             run = (any & F_NEED_ATD) != 0;
           }
         } else if (pass == P_DX) {
-          run = (any & F_NEED_DINF) != 0;     // delta_xi of the event iteration is in the Dp panel
+          // delta_xi of the event iteration is in the Dp panel.  Exact screen before the delta_x = V delta_xi GEMM:
+          // ||D delta_x||_inf <= ||D V||_inf ||delta_xi||_inf, so a slot whose bound is below eps_dual_inf cannot pass
+          // is_dual_infeasible's first test (at either tolerance) and needs none of the three dual-infeasibility passes
+          if (any & F_NEED_DINF) {
+            for (int rb = nrb0; rb < nrb1; ++rb) {
+#pragma unroll
+              for (int nb = 0; nb < NB; ++nb) {
+                const double2 d = *reinterpret_cast<const double2 *>(Dp + pidx(n8, nb, 8 * rb + g));
+                const double v0 = rmax8(fabs(d.x)), v1 = rmax8(fabs(d.y));
+                if (g == 0) {
+                  atomicMax(&C.nmax[N_DXI][nb * 8 + q2], (unsigned long long)__double_as_longlong(v0));
+                  atomicMax(&C.nmax[N_DXI][nb * 8 + q2 + 1], (unsigned long long)__double_as_longlong(v1));
+                }
+              }
+            }
+            __syncthreads();
+            if (tid < TB && (C.flags[tid] & F_NEED_DINF) && 1.000001 * P.dx_bound * nrm(N_DXI, tid) <= S.eps_dual_inf) C.flags[tid] &= ~F_NEED_DINF;
+            __syncthreads();
+            any = any_flags();
+          }
+          run = (any & F_NEED_DINF) != 0;
         } else if (pass == P_PD) {
           if (any & F_NEED_DINF) {
             __syncthreads();
@@ -392,8 +412,10 @@ admm_shared_tile_kernel(TilePackDev K, SharedPlanDev P, BatchDev Bt, SettingsDev
           if (!initial)
             for (int s = 0; s < TB; ++s) { if (C.flags[s] & F_DONE) done |= 1 << s; if (C.flags[s] & F_RHO_NEW) rho_new |= 1 << s; }
           if (done | rho_new) {
-            for (int e = tid; e < n8 * TB; e += kTileThreads) {
-              const int s8 = e & 7, rest = e >> 3, i = rest % n8, nb = rest / n8, s = nb * 8 + s8;
+            for (int nb = 0, s8 = tid & 7; nb < NB; ++nb)
+_Pragma("unroll 4")
+            for (int i = tid >> 3; i < n8; i += kTileThreads / 8) {
+              const int e = (nb * n8 + i) * 8 + s8, s = nb * 8 + s8;
               if (((rho_new & ~done) >> s) & 1) dinv[e] = 1.0 / (1.0 + C.rho[s] * (i < n ? __ldg(P.lam + i) : 0.0));
               if (!((done >> s) & 1)) continue;
               if (i < n) {
@@ -406,8 +428,10 @@ admm_shared_tile_kernel(TilePackDev K, SharedPlanDev P, BatchDev Bt, SettingsDev
             }
           }
           if (done) {
-            for (int e = tid; e < m8 * TB; e += kTileThreads) {
-              const int s8 = e & 7, rest = e >> 3, r = rest % m8, nb = rest / m8, s = nb * 8 + s8;
+            for (int nb = 0, s8 = tid & 7; nb < NB; ++nb)
+_Pragma("unroll 4")
+            for (int r = tid >> 3; r < m8; r += kTileThreads / 8) {
+              const int e = (nb * m8 + r) * 8 + s8, s = nb * 8 + s8;
               if (!((done >> s) & 1)) continue;
               if (r < m) {
                 const int b = C.inst[s], st = C.status[s];
@@ -442,16 +466,20 @@ admm_shared_tile_kernel(TilePackDev K, SharedPlanDev P, BatchDev Bt, SettingsDev
             __syncthreads();
             const int mask = C.refill_mask;
             // slot-fast mapping (lane & 7 = slot): conflict-free panel accesses
-            for (int e = tid; e < n8 * TB; e += kTileThreads) {
-              const int s8 = e & 7, rest = e >> 3, i = rest % n8, nb = rest / n8, s = nb * 8 + s8;
+            for (int nb = 0, s8 = tid & 7; nb < NB; ++nb)
+_Pragma("unroll 4")
+            for (int i = tid >> 3; i < n8; i += kTileThreads / 8) {
+              const int e = (nb * n8 + i) * 8 + s8, s = nb * 8 + s8;
               if (!((mask >> s) & 1)) continue;
               const int b = C.inst[s];
               const double v = (b >= 0 && i < n && warm) ? Bt.xi[(size_t)b * n + i] : 0.0;
               cv[xi_at(e)] = v; Dp[e] = 0.0;
               dinv[e] = b >= 0 ? 1.0 / (1.0 + C.rho[s] * (i < n ? __ldg(P.lam + i) : 0.0)) : 1.0;
             }
-            for (int e = tid; e < m8 * TB; e += kTileThreads) {
-              const int s8 = e & 7, rest = e >> 3, r = rest % m8, nb = rest / m8, s = nb * 8 + s8;
+            for (int nb = 0, s8 = tid & 7; nb < NB; ++nb)
+_Pragma("unroll 4")
+            for (int r = tid >> 3; r < m8; r += kTileThreads / 8) {
+              const int e = (nb * m8 + r) * 8 + s8, s = nb * 8 + s8;
               if (!((mask >> s) & 1)) continue;
               const int b = C.inst[s];
               double lo = -1.0, hi = 1.0, zz = 0.0, yy = 0.0;
@@ -484,16 +512,20 @@ admm_shared_tile_kernel(TilePackDev K, SharedPlanDev P, BatchDev Bt, SettingsDev
             __syncthreads();
             if (!again) break;
             if (tid == 0) C.refill_mask = again;
-            for (int e = tid; e < m8 * TB; e += kTileThreads) {
-              const int s = ((e >> 3) / m8) * 8 + (e & 7);
+            for (int nb = 0, s8 = tid & 7; nb < NB; ++nb)
+_Pragma("unroll 4")
+            for (int r = tid >> 3; r < m8; r += kTileThreads / 8) {
+              const int e = (nb * m8 + r) * 8 + s8, s = nb * 8 + s8;
               if ((again >> s) & 1) { lbp[e] = -1.0; ubp[e] = 1.0; zp[e] = 0.0; yp[e] = 0.0; }
             }
             __syncthreads();
           }
           if (any_refill) {
             // q̄ = c D q (osqp_update_lin_cost) of every slot -> S ; q̂ = V' q̄ follows as this pass's GEMM
-            for (int e = tid; e < n8 * TB; e += kTileThreads) {
-              const int s8 = e & 7, rest = e >> 3, i = rest % n8, nb = rest / n8, s = nb * 8 + s8;
+            for (int nb = 0, s8 = tid & 7; nb < NB; ++nb)
+_Pragma("unroll 4")
+            for (int i = tid >> 3; i < n8; i += kTileThreads / 8) {
+              const int e = (nb * n8 + i) * 8 + s8, s = nb * 8 + s8;
               const int b = C.inst[s];
               Sp[e] = (b >= 0 && i < n && Bt.q) ? c * (__ldg(P.D + i) * Bt.q[(size_t)b * n + i]) : 0.0;
             }
@@ -622,35 +654,40 @@ admm_shared_tile_kernel(TilePackDev K, SharedPlanDev P, BatchDev Bt, SettingsDev
       PFM(pf_pass, P_COUNT + 1)
       // ---- w = rho_vec z - y (the w panel carried delta_y); schedule the next event
       __syncthreads();
-      if (PAIRED) {
-        const int mp8 = kpMp * 8;
-        for (int e = tid; e < mp8 * TB; e += kTileThreads) {
-          const int s8 = e & 7, rest = e >> 3, r = rest % mp8, nb = rest / mp8, s = nb * 8 + s8;
-          if (r >= mp) continue;
-          const int e1 = (nb * m8 + r) * 8 + s8, e2 = e1 + mp * 8;
-          const double w1 = rho_of((int)__ldg(P.ctype + r), C.rho[s]) * zp[e1] - yp[e1];
-          const double w2 = rho_of((int)__ldg(P.ctype + r + mp), C.rho[s]) * zp[e2] - yp[e2];
-          cv[w_at(e1)] = w1 - w2;
-        }
-      } else {
-        for (int e = tid; e < m8 * TB; e += kTileThreads) {
-          const int s8 = e & 7, rest = e >> 3, r = rest % m8, nb = rest / m8, s = nb * 8 + s8;
-          const int ct = r < m ? (int)__ldg(P.ctype + r) : 0;
-          cv[w_at(e)] = rho_of(ct, C.rho[s]) * zp[e] - yp[e];
+      {
+        const int s8 = tid & 7;                      // thread -> slot inside an 8-slot block, rows tid / 8 + 32 j (no divisions)
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) {
+          const double rho_s = C.rho[nb * 8 + s8];
+          if (PAIRED) {
+            for (int r = tid >> 3; r < mp; r += kTileThreads / 8) {
+              const int e1 = (nb * m8 + r) * 8 + s8, e2 = e1 + mp * 8;
+              const double w1 = rho_of((int)__ldg(P.ctype + r), rho_s) * zp[e1] - yp[e1];
+              const double w2 = rho_of((int)__ldg(P.ctype + r + mp), rho_s) * zp[e2] - yp[e2];
+              cv[(nb * cvr + n8 + r) * 8 + s8] = w1 - w2;
+            }
+          } else {
+            for (int r = tid >> 3; r < m8; r += kTileThreads / 8) {
+              const int e = (nb * m8 + r) * 8 + s8;
+              const int ct = r < m ? (int)__ldg(P.ctype + r) : 0;
+              cv[(nb * cvr + n8 + r) * 8 + s8] = rho_of(ct, rho_s) * zp[e] - yp[e];
+            }
+          }
         }
       }
-      if (tid == 0) {
+      if (tid < 32) {   // one lane per slot, combined with warp reductions
         int act = 0, ne = 0x7fffffff;
-        for (int s = 0; s < TB; ++s) {
-          if (C.inst[s] < 0) continue;
-          ++act;
-          const int li = k - C.it0[s];
+        if (tid < TB && C.inst[tid] >= 0) {
+          act = 1;
+          const int li = k - C.it0[tid];
           int nx = S.max_iter;
           if (check_every > 0) nx = min(nx, (li / check_every + 1) * check_every);
           if (adapt_every > 0) nx = min(nx, (li / adapt_every + 1) * adapt_every);
-          ne = min(ne, C.it0[s] + nx);
+          ne = C.it0[tid] + nx;
         }
-        C.active = act; C.next_event = ne; C.refill_mask = 0;
+        act = __reduce_add_sync(0xffffffffu, act);
+        ne = __reduce_min_sync(0xffffffffu, ne);
+        if (tid == 0) { C.active = act; C.next_event = ne; C.refill_mask = 0; }
       }
       __syncthreads();
       initial = false;

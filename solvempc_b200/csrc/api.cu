@@ -99,6 +99,12 @@ int upload_plan(smpc_solver *s) {
   };
   smpc::SharedPlanDev &d = s->dplan;
   d.n = p.n; d.m = p.m; d.c = p.c; d.cinv = p.cinv;
+  d.dx_bound = 0.0;
+  for (size_t i = 0; i < n; ++i) {
+    double rs = 0.0;
+    for (size_t j = 0; j < n; ++j) rs += std::fabs(p.V[i * n + j]);
+    d.dx_bound = std::max(d.dx_bound, (s->st.scaled_termination ? 1.0 : p.D[i]) * rs);
+  }
   CK(put(p.SG, n * n, &d.SG)); CK(put(p.W, m * n, &d.W)); CK(put(p.WT, n * m, &d.WT));
   CK(put(p.V, n * n, &d.V)); CK(put(p.VT, n * n, &d.VT)); CK(put(p.PVT, n * n, &d.PVT));
   CK(put(p.VinvT, n * n, &d.VinvT)); CK(put(p.Abar, m * n, &d.Abar));

@@ -27,6 +27,7 @@ struct SharedPlanDev {
   const double *lam, *D, *Dinv, *E, *Einv;
   const double *l0, *u0;        // UNSCALED setup bounds (used when the batch has none of its own)
   const signed char *ctype;     // m
+  double dx_bound;              // ||diag(D) V||_inf (||V||_inf with scaled_termination): ||delta_x||_inf <= dx_bound ||delta_xi||_inf
 };
 
 // zero-padded, k-major packs of the plan for the register-resident small-QP kernel (n<=16, m<=32)
