@@ -726,6 +726,8 @@ __global__ void __launch_bounds__(256, 1) admm_instance_reg_kernel(InstanceDataD
       factor_ok = refactor();
       need_factor = false;
       if (!factor_ok) break;
+      for (int r = lane; r < m; r += 32) zt[r] = 1.0 / rv[r];   // 1 / rho_vec for the z update (zt was refactor scratch)
+      __syncwarp();
     }
     for (int r = lane; r < m; r += 32) w[r] = rv[r] * z[r] - y[r];
     __syncwarp();
@@ -741,7 +743,7 @@ __global__ void __launch_bounds__(256, 1) admm_instance_reg_kernel(InstanceDataD
     __syncwarp();
     for (int r = lane; r < m; r += 32) {
       const double ztl = r == lane ? dot_reg32(ar0, xt) : dot_reg32(ar1, xt);
-      const double rr = rv[r], rinv = 1.0 / rr;
+      const double rr = rv[r], rinv = zt[r];
       const double zr = alpha * ztl + (1.0 - alpha) * z[r];
       const double zn = fmin(fmax(zr + rinv * y[r], lb[r]), ub[r]);
       const double d = rr * (zr - zn);
