@@ -18,6 +18,7 @@
 #include <cstdint>
 #include <cstdio>
 
+#include "classify.cuh"
 #include "device_types.cuh"
 #include "kernels.cuh"
 
@@ -27,7 +28,7 @@ namespace {
 
 constexpr int NP = 16, MP = 32, KH = (NP + MP) / 2;   // padded sizes; 24 concatenated entries per half-warp
 constexpr unsigned kFull = 0xffffffffu;
-constexpr int kClasses = 5;   // difficulty classes of the scheduling pre-pass
+constexpr int kClasses = kSchedClasses;   // difficulty classes of the scheduling pre-pass (classify.cuh)
 
 __device__ __forceinline__ double2 lds128(uint32_t addr) {
   double2 v;
@@ -207,36 +208,15 @@ __device__ __noinline__ CheckOut check_step(const double *sm, double *cbuf, doub
 
 }  // namespace
 
-// Scheduling pre-pass.  The expensive instances are the MARGINALLY constrained ones: with x_unc the minimiser of the
-// cost alone, key = max_r ((A̅ x_unc)_r - ū_r, l̄_r - (A̅ x_unc)_r) is slightly positive for them (measured on config 2:
-// sorting by key / ||bounds|| ascending puts 61 of the 64 instances that need >= 100 iterations among the first 207).
-// In plan coordinates A̅ x_unc = -W q̂ (S^-1 = V V'), i.e. one z-phase product.  Classes (processed in this order):
-// ratio in (0, .02], (.02, .05], (.05, .15], > .15 (saturated), <= 0 (unconstrained optimum feasible).
-// The order changes nothing but the schedule: every instance is solved exactly as before.
+// Scheduling pre-pass (classify.cuh) as a stand-alone kernel: one warp per instance.
 __global__ void classify_small_kernel(SmallPackDev K, SharedPlanDev P, BatchDev Bt, int *counts, int *lists) {
   const int lane = threadIdx.x & 31, b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (b >= Bt.B) return;
   const int n = P.n, m = P.m, i = lane & 15, r = lane;
-  const double qb = (i < n && Bt.q) ? P.c * (K.D[i] * Bt.q[(size_t)b * n + i]) : 0.0;
-  double qh = 0.0;
-#pragma unroll
-  for (int k = 0; k < NP; ++k) qh = fma(K.V[k * NP + i], __shfl_sync(kFull, qb, k), qh);
-  double zu = 0.0;
-#pragma unroll
-  for (int k = 0; k < NP; ++k) zu = fma(-K.WT[k * MP + r], __shfl_sync(kFull, qh, k), zu);
-  double key = -1e300, ref = 0.0;
-  if (r < m) {
-    const double lo = K.E[r] * (Bt.l ? Bt.l[(size_t)b * m + r] : P.l0[r]), hi = K.E[r] * (Bt.u ? Bt.u[(size_t)b * m + r] : P.u0[r]);
-    if (hi < kInfty * kMinScaling) { key = fmax(key, zu - hi); ref = fmax(ref, fabs(hi)); }
-    if (lo > -kInfty * kMinScaling) { key = fmax(key, lo - zu); ref = fmax(ref, fabs(lo)); }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) { key = fmax(key, __shfl_xor_sync(kFull, key, o)); ref = fmax(ref, __shfl_xor_sync(kFull, ref, o)); }
-  if (lane == 0) {
-    const double ratio = key / fmax(ref, 1e-300);
-    const int cls = !(key > 0.0) ? 4 : (ratio <= 0.02 ? 0 : (ratio <= 0.05 ? 1 : (ratio <= 0.15 ? 2 : 3)));
-    lists[(size_t)cls * Bt.B + atomicAdd(counts + cls, 1)] = b;
-  }
+  const double q_i = (i < n && Bt.q) ? Bt.q[(size_t)b * n + i] : 0.0;
+  double lo = 0.0, hi = 0.0;
+  if (r < m) { lo = Bt.l ? Bt.l[(size_t)b * m + r] : P.l0[r]; hi = Bt.u ? Bt.u[(size_t)b * m + r] : P.u0[r]; }
+  classify_instance(K, P, Bt.B, b, lane, q_i, lo, hi, counts, lists);
 }
 
 __global__ void __launch_bounds__(128, 3)
@@ -807,9 +787,9 @@ static cudaError_t launch_classify_small(const SmallPackDev &K, const SharedPlan
 
 // DMMA variant: 8 QPs per CTA of four warps, up to four CTAs per SM
 cudaError_t launch_admm_shared_small_mma(const SmallPackDev &K, const SharedPlanDev &P, const BatchDev &Bt,
-                                         const SettingsDev &S, int *queue, int *lists, int num_sms, cudaStream_t stream) {
+                                         const SettingsDev &S, int *queue, int *lists, bool classified, int num_sms, cudaStream_t stream) {
   const size_t smem = (size_t)(kCtaMatDoubles + 4 * kMmaWarpDoubles + kMmaPanelDoubles) * sizeof(double) + sizeof(MmaCtl);
-  cudaError_t e = lists ? launch_classify_small(K, P, Bt, queue, lists, stream) : cudaSuccess;
+  cudaError_t e = (lists && !classified) ? launch_classify_small(K, P, Bt, queue, lists, stream) : cudaSuccess;
   if (e != cudaSuccess) return e;
   int grid = (Bt.B + kSlots - 1) / kSlots;
   if (grid > num_sms * 4) grid = num_sms * 4;
@@ -825,10 +805,10 @@ cudaError_t launch_admm_shared_small_mma(const SmallPackDev &K, const SharedPlan
 
 // queue: [0] work counter, [1..kClasses] class sizes; lists: kClasses * B instance indices (nullptr = index order)
 cudaError_t launch_admm_shared_small(const SmallPackDev &K, const SharedPlanDev &P, const BatchDev &Bt,
-                                     const SettingsDev &S, int *queue, int *lists, int num_sms, cudaStream_t stream) {
+                                     const SettingsDev &S, int *queue, int *lists, bool classified, int num_sms, cudaStream_t stream) {
   const int wpc = 4;
   const size_t smem = (size_t)(kCtaMatDoubles + wpc * kWarpDoubles) * sizeof(double);
-  cudaError_t e = lists ? launch_classify_small(K, P, Bt, queue, lists, stream) : cudaSuccess;
+  cudaError_t e = (lists && !classified) ? launch_classify_small(K, P, Bt, queue, lists, stream) : cudaSuccess;
   if (e != cudaSuccess) return e;
   int grid = (Bt.B + wpc - 1) / wpc;
   const int resident = num_sms * 3;   // __launch_bounds__(128, 3): three CTAs (12 warps) per SM

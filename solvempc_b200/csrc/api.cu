@@ -502,13 +502,14 @@ int smpc_solver_solve(smpc_solver *s) {
     CK(cudaEventRecord(ev0, s->stream));
   }
   cudaError_t e = s->regime == 1 ? smpc::launch_admm_instance(s->dinst, b, sd, s->stream)
-                  : s->kernel == 2 ? smpc::launch_admm_shared_small(s->dpack, s->dplan, b, sd, s->d_queue, s->schedule ? s->d_lists : nullptr, s->num_sms, s->stream)
-                  : s->kernel == 5 ? smpc::launch_admm_shared_small_mma(s->dpack, s->dplan, b, sd, s->d_queue, s->schedule ? s->d_lists : nullptr, s->num_sms, s->stream)
+                  : s->kernel == 2 ? smpc::launch_admm_shared_small(s->dpack, s->dplan, b, sd, s->d_queue, s->schedule ? s->d_lists : nullptr, s->classified, s->num_sms, s->stream)
+                  : s->kernel == 5 ? smpc::launch_admm_shared_small_mma(s->dpack, s->dplan, b, sd, s->d_queue, s->schedule ? s->d_lists : nullptr, s->classified, s->num_sms, s->stream)
                   : s->kernel == 4 ? smpc::launch_admm_shared_tile(s->dtile, s->dplan, b, sd, s->d_queue, s->tile_nb, s->num_sms, s->stream)
                                    : smpc::launch_admm_shared_generic(s->dplan, b, sd, s->stream);
   if (e != cudaSuccess) return cuda_fail(e, "ADMM kernel launch");
   if (s->timing) { CK(cudaEventRecord(ev1, s->stream)); s->events.emplace_back(ev0, ev1); }
-  s->launches += (s->regime == 0 && (s->kernel == 2 || s->kernel == 5) && s->schedule) ? 2 : 1;
+  s->launches += (s->regime == 0 && (s->kernel == 2 || s->kernel == 5) && s->schedule && !s->classified) ? 2 : 1;
+  s->classified = false;
   s->solved_once = true;
   return SMPC_OK;
 }
@@ -794,8 +795,16 @@ int smpc_mpc_controller_step(smpc_mpc *M) {
   if (!M) return fail(SMPC_ERR_ARG, "null handle");
   CK(cudaSetDevice(M->device));
   smpc_solver *s = M->solver;
-  // setF (cpp:90), W0 + Sbar X + Ku U (cpp:99) written straight into the solver's q / u (updateGradient, updateUpperBound)
-  CK(smpc::launch_mpc_step_vectors(M->dims, M->B, M->per_instance, M->mats, M->d_X, M->d_U, M->d_ref, s->d_q, s->d_u, M->stream));
+  // setF (cpp:90), W0 + Sbar X + Ku U (cpp:99) written straight into the solver's q / u (updateGradient, updateUpperBound);
+  // for the small-QP kernels the same launch also fills their longest-expected-first scheduling lists
+  const bool small = s->regime == 0 && (s->kernel == 2 || s->kernel == 5);
+  if (small && s->schedule && !M->per_instance && !s->have_l && M->dims.N <= 16) {
+    CK(smpc::launch_mpc_step_classify(M->dims, M->B, M->mats, M->d_X, M->d_U, M->d_ref, s->d_q, s->d_u, s->dpack, s->dplan,
+                                      s->d_queue + 1, s->d_lists, M->stream));
+    s->classified = true;
+  } else {
+    CK(smpc::launch_mpc_step_vectors(M->dims, M->B, M->per_instance, M->mats, M->d_X, M->d_U, M->d_ref, s->d_q, s->d_u, M->stream));
+  }
   M->launches++;
   s->have_q = true; s->have_u = true;
   // cpp:102 solve, cpp:105 U += dU*[0]: inside the small-QP kernels' store_solution, a separate kernel otherwise

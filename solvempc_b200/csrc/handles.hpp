@@ -65,6 +65,7 @@ struct smpc_solver {
   bool schedule = true;   // longest-expected-first pre-pass of the small kernel
   long long launches = 0;
   int kernel = 1;
+  bool classified = false;     // the scheduling lists of the next solve were filled by the MPC layer's fused step-vector kernel
   double *u_apply = nullptr;   // MPC layer: U to increment inside the small-QP kernels' store (cpp:105), else NULL
   bool solved_once = false;
   bool cold_solves = false, timing = false;

@@ -18,12 +18,14 @@ cudaError_t launch_warm_start(const SharedPlanDev &P, int B, const double *x, co
 bool small_kernel_supports(int n, int m);
 size_t small_pack_doubles();
 int small_queue_ints();
+// lists != nullptr: longest-expected-first order; classified: the class lists were already filled for this solve (fused
+// into the MPC layer's step-vector kernel), so the stand-alone pre-pass is skipped
 cudaError_t launch_admm_shared_small(const SmallPackDev &K, const SharedPlanDev &P, const BatchDev &Bt,
-                                     const SettingsDev &S, int *queue, int *lists, int num_sms, cudaStream_t stream);
+                                     const SettingsDev &S, int *queue, int *lists, bool classified, int num_sms, cudaStream_t stream);
 
 // DMMA variant of the small-QP kernel: 8 QPs per CTA of four warps (same packs, same queue / lists)
 cudaError_t launch_admm_shared_small_mma(const SmallPackDev &K, const SharedPlanDev &P, const BatchDev &Bt,
-                                         const SettingsDev &S, int *queue, int *lists, int num_sms, cudaStream_t stream);
+                                         const SettingsDev &S, int *queue, int *lists, bool classified, int num_sms, cudaStream_t stream);
 
 // admm_shared_tile.cu : DMMA tile kernel for mid-size QPs (8 or 16 QPs per CTA, iterates in shared memory)
 bool tile_kernel_supports(int n, int m);
@@ -53,6 +55,11 @@ cudaError_t launch_mpc_step_vectors(const MpcDims &d, int B, int per_instance, c
 // set_state from device buffers: X, U, ref (any may be NULL) -> the controller's own copies, one launch
 cudaError_t launch_mpc_copy_state(int B, int nx, const double *X, const double *U, const double *ref, double *dX, double *dU,
                                   double *dref, cudaStream_t stream);
+// step vectors of a shared plant with N <= 16 AND the small-QP kernels' scheduling pre-pass in one launch (classify.cuh):
+// counts = queue + 1, lists as launch_admm_shared_small takes them; lower bounds are the plan's (P.l0)
+cudaError_t launch_mpc_step_classify(const MpcDims &d, int B, const MpcMatsDev &mats, const double *X, const double *U,
+                                     const double *ref, double *f, double *ub, const SmallPackDev &K, const SharedPlanDev &P,
+                                     int *counts, int *lists, cudaStream_t stream);
 // U += dU[0]
 cudaError_t launch_mpc_apply_control(int B, int n, const double *x, const int *status, double *U, cudaStream_t stream);
 // X <- Ad X + Bd U

@@ -8,6 +8,7 @@
 // linearised plants (one CTA each, BASELINE config 4).
 // Reference quirks kept: S carries K in its first n_state_rows rows only;
 // Su strictly-upper = 0; Fu uses diag(LL' Rbar') = R.
+#include "classify.cuh"
 #include "kernels.cuh"
 
 namespace smpc {
@@ -97,6 +98,39 @@ __global__ void mpc_step_vectors_kernel(MpcDims d, int B, int per_instance, MpcM
     for (int c = 0; c < nx; ++c) s += Sbar[i * nx + c] * x[c];
     ub[(size_t)b * 2 * N + i] = (W0[i] + s) + Ku[i] * u;
   }
+}
+
+// The same for a shared plant with N <= 16 (n = N <= 16, m = 2N <= 32: lane = row), fused with the scheduling pre-pass of
+// the small-QP kernels: the warp that produced f and ub classifies its instance at once.
+__global__ void mpc_step_classify_kernel(MpcDims d, int B, MpcMatsDev mt, const double *__restrict__ X,
+                                         const double *__restrict__ U, const double *__restrict__ ref,
+                                         double *__restrict__ f, double *__restrict__ ub, SmallPackDev K, SharedPlanDev P,
+                                         int *counts, int *lists) {
+  const int lane = threadIdx.x & 31, b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const int N = d.N, nx = d.nx;
+  const double *x = X + (size_t)b * nx;
+  const double u = U[b], r = ref[b];
+  double f_i = 0.0, ub_r = 0.0;
+  if (lane < N) {
+    const int i = lane;
+    double s = 0;
+    for (int c = 0; c < nx; ++c) s += mt.Fx[i * nx + c] * x[c];
+    s += mt.Fu[i] * u;
+    double rr = 0;
+    for (int j = i; j < N; ++j) rr += mt.Fr[(size_t)i * N + j] * r;   // Fr(i,j) = 0 for j < i
+    f_i = s + rr;
+    f[(size_t)b * N + i] = f_i;
+  }
+  if (lane < 2 * N) {
+    const int i = lane;
+    double s = 0;
+    for (int c = 0; c < nx; ++c) s += mt.Sbar[i * nx + c] * x[c];
+    ub_r = (mt.W0[i] + s) + mt.Ku[i] * u;
+    ub[(size_t)b * 2 * N + i] = ub_r;
+  }
+  const double q_i = __shfl_sync(0xffffffffu, f_i, lane & 15);     // classify_instance wants entry lane & 15 on every lane
+  classify_instance(K, P, B, b, lane, q_i, lane < 2 * N ? P.l0[lane] : 0.0, ub_r, counts, lists);
 }
 
 // cpp:105: U += dU*[0] -- the reference returns before this line unless the status is SOLVED (cpp:102)
@@ -197,6 +231,14 @@ cudaError_t launch_mpc_step_vectors(const MpcDims &d, int B, int per_instance, c
                                     const double *U, const double *ref, double *f, double *ub, cudaStream_t stream) {
   const int wpc = 8;
   mpc_step_vectors_kernel<<<(B + wpc - 1) / wpc, wpc * 32, 0, stream>>>(d, B, per_instance, mats, X, U, ref, f, ub);
+  return cudaGetLastError();
+}
+cudaError_t launch_mpc_step_classify(const MpcDims &d, int B, const MpcMatsDev &mats, const double *X, const double *U,
+                                     const double *ref, double *f, double *ub, const SmallPackDev &K, const SharedPlanDev &P,
+                                     int *counts, int *lists, cudaStream_t stream) {
+  if (d.N > 16 || P.n != d.N || P.m != 2 * d.N) return cudaErrorInvalidValue;
+  const int wpc = 8;
+  mpc_step_classify_kernel<<<(B + wpc - 1) / wpc, wpc * 32, 0, stream>>>(d, B, mats, X, U, ref, f, ub, K, P, counts, lists);
   return cudaGetLastError();
 }
 cudaError_t launch_mpc_apply_control(int B, int n, const double *x, const int *status, double *U, cudaStream_t stream) {
