@@ -132,8 +132,7 @@ class C2(Workload):
     def step_e2e(self):
         self.mpc.set_state(X=self.pin[0], U=self.pin[1], ref=self.pin[2])   # H2D from pinned memory
         self.mpc.controller_step_async()
-        self.mpc.control_into(self.out_u)                                   # D2H of the result (synchronises)
-        self.solver.status_into(self.out_st)
+        self.mpc.results_into(self.out_u, self.out_st)                      # D2H of the control and the status (one sync)
 
     def nnz_A(self):
         return int(np.count_nonzero(self.mpc.matrix("Gbar")))
@@ -293,8 +292,7 @@ class C5(C2):
         # hardware-in-the-loop shape of the reference's main loop (solver.cpp:43-74): state in, controllerStep, control out
         self.mpc.set_state(X=self.pin[0])
         self.mpc.controller_step_async()
-        self.mpc.control_into(self.out_u)
-        self.solver.status_into(self.out_st)
+        self.mpc.results_into(self.out_u, self.out_st)
 
     def nnz_A(self):
         return self.N * (self.N + 1)

@@ -215,6 +215,9 @@ int smpc_mpc_plant_step(smpc_mpc *m);
 int smpc_mpc_closed_loop(smpc_mpc *m, int steps, double ref_amplitude, int ref_period, const int *phase, int use_graph,
                          long long *not_solved, long long *iterations);
 int smpc_mpc_get_state(smpc_mpc *m, double *X, double *U, int loc);
+/* what the reference's main loop reads after controllerStep (src/solver.cpp:55-60: the flag and U) in ONE transfer + one
+ * synchronisation: U:[batch] and the per-instance OSQP status:[batch] (either may be NULL) */
+int smpc_mpc_get_control_status(smpc_mpc *m, double *U, int *status, int loc);
 /* vectors handed to the solver in the last controllerStep: f:[batch][n], ub:[batch][2N] */
 int smpc_mpc_get_step_vectors(smpc_mpc *m, double *f, double *ub, int loc);
 long long smpc_mpc_launch_count(const smpc_mpc *m);

@@ -99,6 +99,7 @@ SIGNATURES = {
     "smpc_mpc_plant_step": (_i, [_vp]),
     "smpc_mpc_closed_loop": (_i, [_vp, _i, C.c_double, _i, _vp, _i, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
     "smpc_mpc_get_state": (_i, [_vp, _dp, _dp, _i]),
+    "smpc_mpc_get_control_status": (_i, [_vp, _dp, _vp, _i]),
     "smpc_mpc_get_step_vectors": (_i, [_vp, _dp, _dp, _i]),
     "smpc_mpc_launch_count": (C.c_longlong, [_vp]),
     "smpc_mimo_create": (_i, [C.POINTER(_vp), _i, C.POINTER(MimoConfig), _i, C.POINTER(Settings)]),

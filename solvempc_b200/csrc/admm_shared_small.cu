@@ -407,7 +407,7 @@ admm_shared_small_kernel(SmallPackDev K, SharedPlanDev P, BatchDev Bt, SettingsD
       Bt.rho[b] = rho;
       Bt.status[b] = status; Bt.iter[b] = iter; Bt.rho_updates[b] = rho_updates;
       Bt.obj[b] = co.obj; Bt.pri_res[b] = co.pri_res; Bt.dua_res[b] = co.dua_res;
-      if (Bt.u_apply && status == SMPC_SOLVED) Bt.u_apply[b] += LC.D * co.xbar;   // U += dU*[0] (cpp:105), lane 0 holds x[0]
+      if (Bt.u_apply && status == SMPC_SOLVED) Bt.u_apply[b] = __dadd_rn(Bt.u_apply[b], __dmul_rn(LC.D, co.xbar));   // U += dU*[0] (cpp:105): x[0] rounded first, no FMA
     }
   }
   // the last warp of the grid to leave re-arms the queue for the next launch (no memset node per solve)
@@ -623,7 +623,7 @@ admm_shared_small_mma_kernel(SmallPackDev K, SharedPlanDev P, BatchDev Bt, Setti
                 Bt.rho[b] = rho;
                 Bt.status[b] = status; Bt.iter[b] = li; Bt.rho_updates[b] = C.rho_up[s];
                 Bt.obj[b] = co.obj; Bt.pri_res[b] = co.pri_res; Bt.dua_res[b] = co.dua_res;
-                if (Bt.u_apply && status == SMPC_SOLVED) Bt.u_apply[b] += LC.D * co.xbar;   // U += dU*[0] (cpp:105)
+                if (Bt.u_apply && status == SMPC_SOLVED) Bt.u_apply[b] = __dadd_rn(Bt.u_apply[b], __dmul_rn(LC.D, co.xbar));   // U += dU*[0] (cpp:105)
               }
               refill = true;
             }

@@ -903,6 +903,18 @@ int smpc_mpc_get_state(smpc_mpc *M, double *X, double *U, int loc) {
   return SMPC_OK;
 }
 
+int smpc_mpc_get_control_status(smpc_mpc *M, double *U, int *status, int loc) {
+  if (!M) return fail(SMPC_ERR_ARG, "null handle");
+  if (loc != SMPC_HOST && loc != SMPC_DEVICE) return fail(SMPC_ERR_ARG, "loc must be SMPC_HOST or SMPC_DEVICE");
+  if (status && !M->solver->solved_once) return fail(SMPC_ERR_STATE, "status requested before the first controllerStep");
+  CK(cudaSetDevice(M->device));
+  cudaMemcpyKind k = loc == SMPC_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+  if (U) CK(cudaMemcpyAsync(U, M->d_U, sizeof(double) * M->B, k, M->stream));
+  if (status) CK(cudaMemcpyAsync(status, M->solver->d_status, sizeof(int) * M->B, k, M->stream));
+  if (loc == SMPC_HOST) CK(cudaStreamSynchronize(M->stream));
+  return SMPC_OK;
+}
+
 int smpc_mpc_get_step_vectors(smpc_mpc *M, double *f, double *ub, int loc) {
   if (!M) return fail(SMPC_ERR_ARG, "null handle");
   CK(cudaSetDevice(M->device));

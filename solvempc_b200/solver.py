@@ -303,6 +303,17 @@ class BatchedModelPredictiveControlAPI:
         p, loc, _k = _loc_ptr(U, self.batch, "U")
         L.check(L.lib().smpc_mpc_get_state(self._h, None, p, loc))
 
+    def results_into(self, U, status):
+        """U (float64) and the per-instance status (int32) of the last controllerStep in one transfer + one sync."""
+        pu, l1, _k1 = _loc_ptr(U, self.batch, "U")
+        if hasattr(status, "data_ptr"):
+            ps, l2 = status.data_ptr(), (L.DEVICE if status.is_cuda else L.HOST)
+        else:
+            ps, l2 = status.ctypes.data, L.HOST
+        if l1 != l2:
+            raise ValueError("U and status must live in the same place")
+        L.check(L.lib().smpc_mpc_get_control_status(self._h, pu, ps, l1))
+
     def step_vectors(self):
         f, ub = np.empty((self.batch, self.n_variables)), np.empty((self.batch, self.n_constraints))
         L.check(L.lib().smpc_mpc_get_step_vectors(self._h, f.ctypes.data, ub.ctypes.data, L.HOST))

@@ -378,3 +378,19 @@ def test_horizon_100_config5_shape(ref_mats, repo_root, kernel, B):
     assert np.array_equal(info["status"], ora["status"]) and np.array_equal(info["iter"], ora["iter"])
     assert rel_err(x, ora["x"]) < 1e-6
     mpc.close()
+
+
+def test_control_and_status_in_one_transfer(cfg_path):
+    """smpc_mpc_get_control_status = what the reference's main loop reads after controllerStep (solver.cpp:55-60)."""
+    B = 33
+    X, U, ref = c2_batch(B, seed=9)
+    mpc = sm.BatchedModelPredictiveControlAPI(cfg_path, batch=B, **EPS)
+    mpc.set_state(X=X, U=U, ref=ref)
+    mpc.controller_step_async()
+    Uo, st = np.empty(B), np.empty(B, np.int32)
+    mpc.results_into(Uo, st)
+    _, U2 = mpc.state()
+    assert np.array_equal(Uo, U2) and np.array_equal(st, mpc.solver.info()["status"]) and (st == 1).all()
+    x, _ = mpc.solver.solution()
+    assert np.array_equal(Uo, U + x[:, 0])
+    mpc.close()
