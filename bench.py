@@ -37,6 +37,19 @@ METRIC = "QP solves/sec (eps 1e-5)"
 CPU_NOTE = "one OSQP-equivalent solver per core (oracle/osqp_port.c; osqp-eigen is not installable offline)"
 
 
+def load_traffic(key, batch):
+    """dram bytes (read + write) per launch of this configuration's ADMM kernel from the committed ncu capture
+    (profiles/traffic.json, written by tools/make_traffic.py); None when there is no capture at this batch size."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None, None
+    with open(p) as f:
+        t = json.load(f).get(key)
+    if not t or t.get("batch_per_gpu") != batch:
+        return None, None
+    return t["dram_bytes_read"] + t["dram_bytes_write"], t["source"]
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -483,6 +496,7 @@ def run_ours(args, rank, local_rank, world):
         achieved = flops_per_launch / (kms * 1e-3) / 1e12
         cpu_threads = os.cpu_count() or 1
         cpu_v, cpu_done, cpu_secs, cpu_cores = cpu_solves_per_s(wl, args.cpu_seconds, cpu_threads)
+        traffic, traffic_src = load_traffic(wl.key, B)
         line = {
             "metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -496,7 +510,8 @@ def run_ours(args, rank, local_rank, world):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
-                         "traffic": None, "kernel": wl.solver.kernel_name, "kernel_ms": kms, "kernel_share_of_step": kms / float(step_ms.mean()),
+                         "traffic": traffic, "traffic_unit": "bytes of DRAM read + written per launch", "traffic_source": traffic_src,
+                         "kernel": wl.solver.kernel_name, "kernel_ms": kms, "kernel_share_of_step": kms / float(step_ms.mean()),
                          "flops_per_launch": flops_per_launch, "executed_flops_per_launch": executed_per_launch,
                          "executed_frac": executed_per_launch / (kms * 1e-3) / 1e12 / fp64_peak,
                          "algorithmic_flops_per_instance_iteration": 2.0 * n * n + 4.0 * nnzA,
