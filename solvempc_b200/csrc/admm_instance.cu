@@ -455,7 +455,10 @@ __device__ __forceinline__ double dot_reg32(const double (&reg)[kRegN], const do
   return (a0 + a1) + (a2 + a3);
 }
 
-__global__ void __launch_bounds__(256, 1) admm_instance_reg_kernel(InstanceDataDev I, BatchDev Bt, SettingsDev S, int warps_per_cta) {
+// prepare != 0 (create time): no solve; stores S0, T (M(rho) = S0 + rho T for the setup bounds' row classes) and the rows of
+// M(rho0)^-1, so that a solve starts without a factorisation (OSQP factors at osqp_setup, not in osqp_solve) and a rho update
+// re-forms M with n(n+1)/2 FMAs instead of n(n+1)/2 length-m dot products.
+__global__ void __launch_bounds__(256, 1) admm_instance_reg_kernel(InstanceDataDev I, BatchDev Bt, SettingsDev S, int warps_per_cta, int prepare) {
   extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int b = blockIdx.x * warps_per_cta + warp;
@@ -479,7 +482,7 @@ __global__ void __launch_bounds__(256, 1) admm_instance_reg_kernel(InstanceDataD
   __syncwarp();
   const double alpha = S.alpha, c = I.c[b], cinv = 1.0 / c;
   const bool unscale = !S.scaled_termination;
-  const bool warm = S.warm_start && !Bt.fresh;
+  const bool warm = S.warm_start && !Bt.fresh && !prepare;
 
   // ---- load the instance: A̅' into shared memory, rows lane and lane + 32 of A̅ into registers
   for (int row = 0; row < m; ++row)                 // coalesced row reads, transposed (conflict-free) shared-memory writes
@@ -499,7 +502,7 @@ __global__ void __launch_bounds__(256, 1) admm_instance_reg_kernel(InstanceDataD
     x[i] = warm ? Bt.xi[(size_t)b * n + i] : 0.0;
     dx[i] = 0.0;
   }
-  double rho = Bt.fresh ? fmin(fmax(S.rho0, kRhoMin), kRhoMax) : Bt.rho[b];
+  double rho = (Bt.fresh || prepare) ? fmin(fmax(S.rho0, kRhoMin), kRhoMax) : Bt.rho[b];
   int bad_rows = 0;
   for (int r = lane; r < m; r += 32) {
     const double e = I.E[(size_t)b * m + r];
@@ -516,11 +519,17 @@ __global__ void __launch_bounds__(256, 1) admm_instance_reg_kernel(InstanceDataD
   __syncwarp();
 
   // rho_vec from the instance's own (scaled) bounds: OSQP set_rho_vec / update_rho_vec
+  // row class: -1 free, 0 inequality, 1 equality (OSQP constr_type)
+  auto row_class = [&](double lo, double hi) { return (lo < -kInfty * kMinScaling && hi > kInfty * kMinScaling) ? -1 : ((hi - lo < kRhoTolRow) ? 1 : 0); };
+  bool split_ok = I.S0 != nullptr;   // the prepared S0 / T / Minv0 hold for the row classes of the SETUP bounds only
   auto set_rho_vec = [&]() {
+    int differs = 0;
     for (int r = lane; r < m; r += 32) {
-      const bool fr = lb[r] < -kInfty * kMinScaling && ub[r] > kInfty * kMinScaling;
-      rv[r] = fr ? kRhoMin : ((ub[r] - lb[r] < kRhoTolRow) ? kRhoEqOverIneq * rho : rho);
+      const int ct = row_class(lb[r], ub[r]);
+      rv[r] = ct < 0 ? kRhoMin : (ct == 1 ? kRhoEqOverIneq * rho : rho);
+      differs |= ct != row_class(Ev[r] * I.l0[r], Ev[r] * I.u0[r]);
     }
+    if (__any_sync(kFull, differs)) split_ok = false;
     __syncwarp();
   };
 
@@ -535,8 +544,24 @@ __global__ void __launch_bounds__(256, 1) admm_instance_reg_kernel(InstanceDataD
       while ((i + 1) * (i + 2) / 2 <= e) ++i;
       while (i * (i + 1) / 2 > e) --i;
       const int j = e - i * (i + 1) / 2;
-      double s0 = gP[i * n + j] + (i == j ? S.sigma : 0.0), s1 = 0.0;
+      if (split_ok && !prepare) {
+        Sc[i * ldM + j] = fma(rho, I.T[(size_t)b * tri + e], I.S0[(size_t)b * tri + e]);   // M(rho) = S0 + rho T
+        continue;
+      }
       const double *ai = At + i * ldT, *aj = At + j * ldT;
+      if (prepare) {
+        // S0 = P̄ + sigma I + rho_min A̅_f'A̅_f (free rows), T = A̅' diag(kappa) A̅ (kappa = 1 inequality, 1e3 equality)
+        double s0 = gP[i * n + j] + (i == j ? S.sigma : 0.0), t0 = 0.0;
+        for (int r = 0; r < m; ++r) {
+          const int ct = row_class(lb[r], ub[r]);
+          const double aa = ai[r] * aj[r];
+          if (ct < 0) s0 = fma(kRhoMin, aa, s0); else t0 = fma(ct == 1 ? kRhoEqOverIneq : 1.0, aa, t0);
+        }
+        I.S0[(size_t)b * tri + e] = s0; I.T[(size_t)b * tri + e] = t0;
+        Sc[i * ldM + j] = fma(rho, t0, s0);
+        continue;
+      }
+      double s0 = gP[i * n + j] + (i == j ? S.sigma : 0.0), s1 = 0.0;
       for (int r = 0; r < mv; r += 2) {      // same summation order as admm_instance_kernel (pad column and rv pad are 0)
         const double2 rr = *reinterpret_cast<const double2 *>(rv + r), a = *reinterpret_cast<const double2 *>(ai + r), c2 = *reinterpret_cast<const double2 *>(aj + r);
         s0 = fma(rr.x * a.x, c2.x, s0);
@@ -723,8 +748,22 @@ __global__ void __launch_bounds__(256, 1) admm_instance_reg_kernel(InstanceDataD
   for (iter = 1; iter <= S.max_iter && !bad_bounds && factor_ok; ++iter) {
     if (need_factor) {
       set_rho_vec();
-      factor_ok = refactor();
+      if (split_ok && !prepare && rho == I.rho_prepared) {
+        // the factorisation of osqp_setup: rows of M(rho0)^-1 prepared at create time
+#pragma unroll
+        for (int k = 0; k < kRegN; ++k) mi[k] = lane < n ? I.Minv0[((size_t)b * kRegN + k) * n + lane] : 0.0;   // [B][32][n]: coalesced over the lanes
+        factor_ok = true;
+      } else {
+        factor_ok = refactor();
+      }
       need_factor = false;
+      if (prepare) {
+        if (factor_ok && lane < n) {
+#pragma unroll
+          for (int k = 0; k < kRegN; ++k) I.Minv0[((size_t)b * kRegN + k) * n + lane] = mi[k];
+        }
+        return;
+      }
       if (!factor_ok) break;
       for (int r = lane; r < m; r += 32) zt[r] = 1.0 / rv[r];   // 1 / rho_vec for the z update (zt was refactor scratch)
       __syncwarp();
@@ -845,8 +884,11 @@ cudaError_t launch_ruiz_instance(const InstanceDataDev &I, int iters, cudaStream
   return cudaGetLastError();
 }
 
-cudaError_t launch_admm_instance(const InstanceDataDev &I, const BatchDev &Bt, const SettingsDev &S, cudaStream_t stream) {
-  if (I.n <= kRegN && I.m <= kRegM && I.m >= 1) {   // register-operator variant
+bool instance_reg_supports(int n, int m) { return n >= 1 && n <= kRegN && m >= 1 && m <= kRegM; }
+
+cudaError_t launch_admm_instance(const InstanceDataDev &I, const BatchDev &Bt, const SettingsDev &S, cudaStream_t stream, int prepare) {
+  if (prepare && !(instance_reg_supports(I.n, I.m) && I.S0)) return cudaSuccess;   // nothing to prepare for the generic kernel
+  if (instance_reg_supports(I.n, I.m)) {   // register-operator variant
     const size_t per = ((instance_reg_warp_doubles(I.n, I.m) + 1) & ~(size_t)1) * sizeof(double);
     const int wpc = pick_wpc(per);
     const size_t smem = wpc * per;
@@ -856,7 +898,7 @@ cudaError_t launch_admm_instance(const InstanceDataDev &I, const BatchDev &Bt, c
       if (e != cudaSuccess) return e;
       attr_set = true;
     }
-    admm_instance_reg_kernel<<<(Bt.B + wpc - 1) / wpc, wpc * 32, smem, stream>>>(I, Bt, S, wpc);
+    admm_instance_reg_kernel<<<(Bt.B + wpc - 1) / wpc, wpc * 32, smem, stream>>>(I, Bt, S, wpc, prepare);
     return cudaGetLastError();
   }
   const size_t per = instance_warp_doubles(I.n, I.m) * sizeof(double);

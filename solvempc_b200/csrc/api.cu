@@ -387,6 +387,9 @@ int smpc_solver_create_batched(smpc_solver **out, int device, int n, int m, int 
     const size_t N = n, M = m, B = batch;
     size_t bytes = 0;
     for (size_t c : {B * N * N, B * M * N, B * N, B * M, B, M, M}) bytes += DeviceBuf::need(c * sizeof(double));
+    const bool prep = smpc::instance_reg_supports(n, m);
+    const size_t tri = N * (N + 1) / 2;
+    if (prep) for (size_t c : {B * tri, B * tri, B * N * 32}) bytes += DeviceBuf::need(c * sizeof(double));
     CK(s->instbuf.alloc(bytes));
     smpc::InstanceDataDev &d = s->dinst;
     d.n = n; d.m = m; d.B = batch;
@@ -394,6 +397,12 @@ int smpc_solver_create_batched(smpc_solver **out, int device, int n, int m, int 
     d.D = s->instbuf.take<double>(B * N); d.E = s->instbuf.take<double>(B * M ? B * M : 1); d.c = s->instbuf.take<double>(B);
     double *dl0 = s->instbuf.take<double>(M ? M : 1), *du0 = s->instbuf.take<double>(M ? M : 1);
     if (!du0) return fail(SMPC_ERR_CUDA, "internal: instance buffer carve-out overflow");
+    d.S0 = d.T = d.Minv0 = nullptr; d.rho_prepared = 0.0;
+    if (prep) {
+      d.S0 = s->instbuf.take<double>(B * tri); d.T = s->instbuf.take<double>(B * tri); d.Minv0 = s->instbuf.take<double>(B * N * 32);
+      if (!d.Minv0) return fail(SMPC_ERR_CUDA, "internal: instance buffer carve-out overflow");
+      d.rho_prepared = std::min(std::max(s->st.rho, smpc::kRhoMin), smpc::kRhoMax);
+    }
     std::vector<double> hl(M), hu(M);
     for (size_t i = 0; i < M; ++i) { hl[i] = l0 ? l0[i] : -INFINITY; hu[i] = u0 ? u0[i] : INFINITY; }
     if (M) { CK(cudaMemcpy(dl0, hl.data(), M * sizeof(double), cudaMemcpyHostToDevice)); CK(cudaMemcpy(du0, hu.data(), M * sizeof(double), cudaMemcpyHostToDevice)); }
@@ -407,6 +416,12 @@ int smpc_solver_create_batched(smpc_solver **out, int device, int n, int m, int 
     }
     if (int rc = alloc_batch(s)) return rc;
     if (int rc = reset_state(s, true)) return rc;
+    if (prep) {   // what osqp_setup does once per solver: the factorisation for rho0 (and the rho-independent parts of M)
+      smpc::BatchDev pb{};
+      pb.B = batch;
+      CK(smpc::launch_admm_instance(d, pb, to_dev(s->st), nullptr, 1));
+      s->launches++;
+    }
     CK(cudaDeviceSynchronize());
     return SMPC_OK;
   };

@@ -70,6 +70,10 @@ struct InstanceDataDev {
   double *A;            // [B][m][n]  A̅
   double *D, *E, *c;    // [B][n], [B][m], [B]
   const double *l0, *u0;   // shared UNSCALED setup bounds (m)
+  // prepared at create time by the register-operator kernel (NULL when it does not apply): M(rho) = S0 + rho T for the
+  // row classes of the setup bounds, packed lower triangles [B][n(n+1)/2], and the rows of M(rho_prepared)^-1, k-major [B][32][n]
+  double *S0, *T, *Minv0;
+  double rho_prepared;
 };
 
 // per-instance data and state, [B][len] contiguous
