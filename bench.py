@@ -37,6 +37,17 @@ METRIC = "QP solves/sec (eps 1e-5)"
 CPU_NOTE = "one OSQP-equivalent solver per core (oracle/osqp_port.c; osqp-eigen is not installable offline)"
 
 
+def load_plant(path):
+    """The reference's MPC_API.json (keys as read at src/ModelPredictiveControlAPI.cpp:16,19,113-116,138-140) as numpy arrays.
+    The product arm parses the config itself: nothing of oracle/ is imported outside the cpu_baseline / reference legs."""
+    with open(path) as f:
+        cfg = json.load(f)
+    sc = lambda k: float(np.array(cfg[k]).reshape(-1)[0])
+    return dict(Ad=np.array(cfg["Ad"], dtype=np.float64), Bd=np.array(cfg["Bd"], dtype=np.float64).reshape(-1),
+                Cd=np.array(cfg["Cd"], dtype=np.float64).reshape(-1), K=np.array(cfg["K"], dtype=np.float64).reshape(-1),
+                Q=sc("Q"), R=sc("R"), RD=sc("RD"))
+
+
 def load_traffic(key, batch):
     """dram bytes (read + write) per launch of this configuration's ADMM kernel from the committed ncu capture
     (profiles/traffic.json, written by tools/make_traffic.py); None when there is no capture at this batch size."""
@@ -231,9 +242,8 @@ class C4(C2):
                 f"{self.B} controllers per GPU, on-device assembly + batched Cholesky path, cold solves")
 
     def setup(self, sm, torch, device, kernel):
-        import oracle
         from problems import c4_plants
-        cfg = oracle.load_config(self._conf())
+        cfg = load_plant(self._conf())
         Ad, Bd = c4_plants(self.B, cfg, seed=2 + 1000 * self.rank)
         conf = dict(Ad=Ad, Bd=Bd, Cd=cfg["Cd"], K=cfg["K"], Q=cfg["Q"], R=cfg["R"], RD=cfg["RD"], horizon=self.N, per_instance=1)
         X, U, ref = self._inputs(self.B, 31 + 1000 * self.rank)
@@ -281,8 +291,7 @@ class C5(C2):
                 "one step = one controllerStep of every controller + plant step")
 
     def setup(self, sm, torch, device, kernel):
-        import oracle
-        cfg = oracle.load_config(self._conf())
+        cfg = load_plant(self._conf())
         conf = dict(Ad=cfg["Ad"], Bd=cfg["Bd"], Cd=cfg["Cd"], K=cfg["K"], Q=cfg["Q"], R=cfg["R"], RD=cfg["RD"], horizon=self.N)
         X, U, _ = self._inputs(self.B, 31 + 1000 * self.rank)
         self.host = [np.ascontiguousarray(X * 0.2), np.ascontiguousarray(U * 0.1), np.zeros(self.B)]

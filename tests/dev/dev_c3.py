@@ -1,7 +1,7 @@
 """Development driver (GPU): config 3 (quadrotor N=50, n=200, m=400) throughput of the shared-factor kernels."""
 import os, sys
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import solvempc_b200 as sm
 from problems import c3_batch

@@ -2,7 +2,7 @@
 Replicates ONE config-2 instance B times (identical iteration counts, no tail) and times the ADMM kernel."""
 import os, sys
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import oracle
 import solvempc_b200 as sm

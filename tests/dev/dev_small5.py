@@ -1,7 +1,7 @@
 """Development driver (GPU): kernel 5 (register-operator DMMA tile) against kernel 2 (one warp per QP) on config 2."""
 import os, sys
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import oracle
 import solvempc_b200 as sm

@@ -1,7 +1,7 @@
 """Development driver (GPU): tile kernel (kernel=4) against the generic kernel (kernel=1) and timing of both."""
 import os, sys, time
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import oracle
 import solvempc_b200 as sm
