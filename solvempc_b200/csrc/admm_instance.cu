@@ -425,8 +425,8 @@ __global__ void __launch_bounds__(256) admm_instance_kernel(InstanceDataDev I, B
 // 16-byte row sweeps by 8 consecutive lanes then hit 8 different 16-byte bank groups.
 constexpr int kRegN = 32, kRegM = 64;
 __host__ __device__ __forceinline__ int reg_ldT(int m) { int l = (m + 1) & ~1; while ((l & 15) != 14) l += 2; return l; }
-__host__ __device__ __forceinline__ size_t instance_reg_warp_doubles(int n, int m) {
-  return (size_t)n * reg_ldT(m) + (size_t)n * reg_ldT(n) + 8 * (size_t)kRegN + 10 * (size_t)kRegM;
+__host__ __device__ __forceinline__ size_t instance_reg_warp_doubles(int n, int m, bool paired) {
+  return (size_t)n * reg_ldT(paired ? m / 2 : m) + (size_t)n * reg_ldT(n) + 8 * (size_t)kRegN + 11 * (size_t)kRegM;
 }
 // sum_{k < len} row[k] * vec[k], len even, both 16-byte aligned
 __device__ __forceinline__ double dot_s128(const double *row, const double *vec, int len) {
@@ -458,17 +458,23 @@ __device__ __forceinline__ double dot_reg32(const double (&reg)[kRegN], const do
 // prepare != 0 (create time): no solve; stores S0, T (M(rho) = S0 + rho T for the setup bounds' row classes) and the rows of
 // M(rho0)^-1, so that a solve starts without a factorisation (OSQP factors at osqp_setup, not in osqp_solve) and a rho update
 // re-forms M with n(n+1)/2 FMAs instead of n(n+1)/2 length-m dot products.
+// PAIRED: every instance's rows come as [G; -G] (the reference's two-sided limit, cpp:335; checked on the scaled data at
+// create time): only G (mp = m / 2 rows) is kept -- G' in shared memory, one row of G per lane in registers --
+// A̅'v = G'(v_top - v_bot) and (A̅ v)_bot = -(A̅ v)_top: 90 instead of 160 DFMA per lane-iteration, half the operator footprint.
+template <bool PAIRED>
 __global__ void __launch_bounds__(256, 1) admm_instance_reg_kernel(InstanceDataDev I, BatchDev Bt, SettingsDev S, int warps_per_cta, int prepare) {
   extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int b = blockIdx.x * warps_per_cta + warp;
   if (b >= Bt.B) return;
-  const int n = I.n, m = I.m, ldT = reg_ldT(m), ldM = reg_ldT(n), mv = (m + 1) & ~1;
-  double *base = smem + (size_t)warp * ((instance_reg_warp_doubles(n, m) + 1) & ~(size_t)1);
+  const int n = I.n, m = I.m, mp = PAIRED ? m / 2 : m;                  // rows of the operator kept on chip
+  const int ldT = reg_ldT(mp), ldM = reg_ldT(n), mv = (mp + 1) & ~1;
+  double *base = smem + (size_t)warp * ((instance_reg_warp_doubles(n, m, PAIRED) + 1) & ~(size_t)1);
   // vectors first (strides kRegN / kRegM, zero padded, 16-byte aligned), then A̅' and the two n x n scratch matrices
   double *x = base, *dx = x + kRegN, *qb = dx + kRegN, *xt = qb + kRegN, *sPx = xt + kRegN, *sAty = sPx + kRegN, *Dv = sAty + kRegN, *Dinv = Dv + kRegN;
   double *z = Dinv + kRegN, *y = z + kRegM, *lb = y + kRegM, *ub = lb + kRegM, *w = ub + kRegM, *zt = w + kRegM, *dy = zt + kRegM, *rv = dy + kRegM, *Ev = rv + kRegM, *Einv = Ev + kRegM;
-  double *At = Einv + kRegM, *Sc = At + n * ldT;
+  double *vd = Einv + kRegM;                       // PAIRED scratch: v_top - v_bot (mp entries) / top half of A̅ v
+  double *At = vd + kRegM, *Sc = At + n * ldT;
   const double *gP = I.P + (size_t)b * n * n, *gA = I.A + (size_t)b * m * n;
   const int li = lane < n ? lane : n - 1;          // lanes >= n sweep a valid row and drop the result
 #ifdef SMPC_PROFILE
@@ -477,24 +483,45 @@ __global__ void __launch_bounds__(256, 1) admm_instance_reg_kernel(InstanceDataD
 #else
 #define PFI(i)
 #endif
-  for (int e = lane; e < 8 * kRegN + 10 * kRegM; e += 32) base[e] = 0.0;
+  for (int e = lane; e < 8 * kRegN + 11 * kRegM; e += 32) base[e] = 0.0;
   for (int e = lane; e < n * ldT; e += 32) At[e] = 0.0;
   __syncwarp();
   const double alpha = S.alpha, c = I.c[b], cinv = 1.0 / c;
   const bool unscale = !S.scaled_termination;
   const bool warm = S.warm_start && !Bt.fresh && !prepare;
 
-  // ---- load the instance: A̅' into shared memory, rows lane and lane + 32 of A̅ into registers
-  for (int row = 0; row < m; ++row)                 // coalesced row reads, transposed (conflict-free) shared-memory writes
+  // ---- load the instance: A̅' (PAIRED: G') into shared memory, rows lane (and lane + 32) of it into registers
+  for (int row = 0; row < mp; ++row)                // coalesced row reads, transposed (conflict-free) shared-memory writes
     for (int col = lane; col < n; col += 32) At[col * ldT + row] = gA[row * n + col];
   __syncwarp();
-  double ar0[kRegN], ar1[kRegN], mi[kRegN];
+  double ar0[kRegN], ar1[PAIRED ? 1 : kRegN], mi[kRegN];
 #pragma unroll
   for (int k = 0; k < kRegN; ++k) {
-    ar0[k] = (k < n && lane < m) ? At[k * ldT + lane] : 0.0;
-    ar1[k] = (k < n && lane + 32 < m) ? At[k * ldT + lane + 32] : 0.0;
+    ar0[k] = (k < n && lane < mp) ? At[k * ldT + lane] : 0.0;
+    if constexpr (!PAIRED) ar1[k] = (k < n && lane + 32 < mp) ? At[k * ldT + lane + 32] : 0.0;
     mi[k] = 0.0;
   }
+  // (A̅' v)_li for an m-vector v in shared memory (valid on lanes < n)
+  auto AT_dot = [&](const double *v) -> double {
+    if (PAIRED) {
+      __syncwarp();
+      if (lane < mp) vd[lane] = v[lane] - v[lane + mp];
+      __syncwarp();
+      return dot_s128(At + li * ldT, vd, mv);
+    }
+    return dot_s128(At + li * ldT, v, mv);
+  };
+  // out[r] = (A̅ v)_r for every row r < m, v an n-vector in shared memory (zero padded to 32)
+  auto A_rows = [&](const double *v, double *out) {
+    if (PAIRED) {
+      const double top = dot_reg32(ar0, v);
+      if (lane < mp) { out[lane] = top; out[lane + mp] = -top; }
+    } else if constexpr (!PAIRED) {
+      if (lane < m) out[lane] = dot_reg32(ar0, v);
+      if (lane + 32 < m) out[lane + 32] = dot_reg32(ar1, v);
+    }
+    __syncwarp();
+  };
   for (int i = lane; i < n; i += 32) {
     const double d = I.D[(size_t)b * n + i];
     Dv[i] = d; Dinv[i] = 1.0 / d;
@@ -554,7 +581,8 @@ __global__ void __launch_bounds__(256, 1) admm_instance_reg_kernel(InstanceDataD
         double s0 = gP[i * n + j] + (i == j ? S.sigma : 0.0), t0 = 0.0;
         for (int r = 0; r < m; ++r) {
           const int ct = row_class(lb[r], ub[r]);
-          const double aa = ai[r] * aj[r];
+          const int rt = r < mp ? r : r - mp;          // PAIRED: row r + mp is -row r, the products coincide
+          const double aa = ai[rt] * aj[rt];
           if (ct < 0) s0 = fma(kRhoMin, aa, s0); else t0 = fma(ct == 1 ? kRhoEqOverIneq : 1.0, aa, t0);
         }
         I.S0[(size_t)b * tri + e] = s0; I.T[(size_t)b * tri + e] = t0;
@@ -562,10 +590,14 @@ __global__ void __launch_bounds__(256, 1) admm_instance_reg_kernel(InstanceDataD
         continue;
       }
       double s0 = gP[i * n + j] + (i == j ? S.sigma : 0.0), s1 = 0.0;
-      for (int r = 0; r < mv; r += 2) {      // same summation order as admm_instance_kernel (pad column and rv pad are 0)
-        const double2 rr = *reinterpret_cast<const double2 *>(rv + r), a = *reinterpret_cast<const double2 *>(ai + r), c2 = *reinterpret_cast<const double2 *>(aj + r);
-        s0 = fma(rr.x * a.x, c2.x, s0);
-        s1 = fma(rr.y * a.y, c2.y, s1);
+      if (PAIRED) {
+        for (int r = 0; r < mp; ++r) s0 = fma((rv[r] + rv[r + mp]) * ai[r], aj[r], s0);
+      } else {
+        for (int r = 0; r < mv; r += 2) {      // same summation order as admm_instance_kernel (pad column and rv pad are 0)
+          const double2 rr = *reinterpret_cast<const double2 *>(rv + r), a = *reinterpret_cast<const double2 *>(ai + r), c2 = *reinterpret_cast<const double2 *>(aj + r);
+          s0 = fma(rr.x * a.x, c2.x, s0);
+          s1 = fma(rr.y * a.y, c2.y, s1);
+        }
       }
       Sc[i * ldM + j] = s0 + s1;
     }
@@ -642,11 +674,12 @@ __global__ void __launch_bounds__(256, 1) admm_instance_reg_kernel(InstanceDataD
       double s = 0.0;
       for (int k = 0; k < n; ++k) s = fma(gP[k * n + i], x[k], s);   // P̄ x: P̄ is stored full symmetric, column sweep = coalesced
       sPx[i] = s;
-      sAty[i] = dot_s128(At + i * ldT, y, mv);
     }
-    if (lane < m) w[lane] = dot_reg32(ar0, x);
-    if (lane + 32 < m) w[lane + 32] = dot_reg32(ar1, x);
-    __syncwarp();
+    {
+      const double aty = AT_dot(y);
+      if (lane < n) sAty[lane] = aty;
+    }
+    A_rows(x, w);
     double a_rp = 0, a_z = 0, a_Ax = 0, u_rp = 0, u_z = 0, u_Ax = 0;
     for (int r = lane; r < m; r += 32) {
       const double rp = w[r] - z[r], ei = Einv[r];
@@ -695,9 +728,9 @@ __global__ void __launch_bounds__(256, 1) admm_instance_reg_kernel(InstanceDataD
     lhs = wsum(lhs);
     if (!(lhs < -eps * nd)) return false;
     double na = 0.0;
-    for (int i = lane; i < n; i += 32) {
-      const double v = dot_s128(At + i * ldT, dy, mv);
-      na = fmax(na, fabs(unscale ? Dinv[i] * v : v));
+    {
+      const double v = AT_dot(dy);
+      if (lane < n) na = fabs(unscale ? Dinv[lane] * v : v);
     }
     return wmax(na) < eps * nd;
   };
@@ -720,8 +753,9 @@ __global__ void __launch_bounds__(256, 1) admm_instance_reg_kernel(InstanceDataD
     }
     if (!(wmax(np) < cs * eps * nd)) return false;
     int bad = 0;
+    A_rows(dx, w);
     for (int r = lane; r < m; r += 32) {
-      double v = r == lane ? dot_reg32(ar0, dx) : dot_reg32(ar1, dx);
+      double v = w[r];
       if (unscale) v *= Einv[r];
       if (((ub[r] < kInfty * kMinScaling) && (v > eps * nd)) || ((lb[r] > -kInfty * kMinScaling) && (v < -eps * nd))) bad = 1;
     }
@@ -771,7 +805,7 @@ __global__ void __launch_bounds__(256, 1) admm_instance_reg_kernel(InstanceDataD
     for (int r = lane; r < m; r += 32) w[r] = rv[r] * z[r] - y[r];
     __syncwarp();
     {
-      const double aw = dot_s128(At + li * ldT, w, mv);
+      const double aw = AT_dot(w);
       if (lane < n) sAty[lane] = (S.sigma * x[lane] - qb[lane]) + aw;                                     // rhs
     }
     __syncwarp();
@@ -780,8 +814,9 @@ __global__ void __launch_bounds__(256, 1) admm_instance_reg_kernel(InstanceDataD
       if (lane < n) xt[lane] = xv;
     }
     __syncwarp();
+    A_rows(xt, w);                                                                                        // z̃ = A̅ x̃ (w is free after the rhs)
     for (int r = lane; r < m; r += 32) {
-      const double ztl = r == lane ? dot_reg32(ar0, xt) : dot_reg32(ar1, xt);
+      const double ztl = w[r];
       const double rr = rv[r], rinv = zt[r];
       const double zr = alpha * ztl + (1.0 - alpha) * z[r];
       const double zn = fmin(fmax(zr + rinv * y[r], lb[r]), ub[r]);
@@ -884,21 +919,41 @@ cudaError_t launch_ruiz_instance(const InstanceDataDev &I, int iters, cudaStream
   return cudaGetLastError();
 }
 
+// flag[0] &= "rows r and r + m/2 of every (scaled) A̅_i are exact negatives of each other"
+__global__ void instance_pairs_kernel(InstanceDataDev I, int *flag) {
+  const int mp = I.m / 2;
+  const size_t total = (size_t)I.B * mp * I.n;
+  int ok = 1;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const size_t bq = e / ((size_t)mp * I.n), rem = e % ((size_t)mp * I.n);
+    const double *A = I.A + bq * I.m * I.n;
+    ok &= A[rem + (size_t)mp * I.n] == -A[rem];
+  }
+  if (!__all_sync(0xffffffffu, ok) && (threadIdx.x & 31) == 0) atomicAnd(flag, 0);
+}
+cudaError_t launch_instance_pairs(const InstanceDataDev &I, int *flag, cudaStream_t stream) {
+  instance_pairs_kernel<<<148 * 4, 256, 0, stream>>>(I, flag);
+  return cudaGetLastError();
+}
+
 bool instance_reg_supports(int n, int m) { return n >= 1 && n <= kRegN && m >= 1 && m <= kRegM; }
 
 cudaError_t launch_admm_instance(const InstanceDataDev &I, const BatchDev &Bt, const SettingsDev &S, cudaStream_t stream, int prepare) {
   if (prepare && !(instance_reg_supports(I.n, I.m) && I.S0)) return cudaSuccess;   // nothing to prepare for the generic kernel
   if (instance_reg_supports(I.n, I.m)) {   // register-operator variant
-    const size_t per = ((instance_reg_warp_doubles(I.n, I.m) + 1) & ~(size_t)1) * sizeof(double);
+    const bool paired = I.paired != 0;
+    const size_t per = ((instance_reg_warp_doubles(I.n, I.m, paired) + 1) & ~(size_t)1) * sizeof(double);
     const int wpc = pick_wpc(per);
     const size_t smem = wpc * per;
     static bool attr_set = false;
     if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(admm_instance_reg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      cudaError_t e = cudaFuncSetAttribute(admm_instance_reg_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(admm_instance_reg_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
       if (e != cudaSuccess) return e;
       attr_set = true;
     }
-    admm_instance_reg_kernel<<<(Bt.B + wpc - 1) / wpc, wpc * 32, smem, stream>>>(I, Bt, S, wpc, prepare);
+    if (paired) admm_instance_reg_kernel<true><<<(Bt.B + wpc - 1) / wpc, wpc * 32, smem, stream>>>(I, Bt, S, wpc, prepare);
+    else admm_instance_reg_kernel<false><<<(Bt.B + wpc - 1) / wpc, wpc * 32, smem, stream>>>(I, Bt, S, wpc, prepare);
     return cudaGetLastError();
   }
   const size_t per = instance_warp_doubles(I.n, I.m) * sizeof(double);

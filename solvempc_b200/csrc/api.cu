@@ -397,7 +397,7 @@ int smpc_solver_create_batched(smpc_solver **out, int device, int n, int m, int 
     d.D = s->instbuf.take<double>(B * N); d.E = s->instbuf.take<double>(B * M ? B * M : 1); d.c = s->instbuf.take<double>(B);
     double *dl0 = s->instbuf.take<double>(M ? M : 1), *du0 = s->instbuf.take<double>(M ? M : 1);
     if (!du0) return fail(SMPC_ERR_CUDA, "internal: instance buffer carve-out overflow");
-    d.S0 = d.T = d.Minv0 = nullptr; d.rho_prepared = 0.0;
+    d.S0 = d.T = d.Minv0 = nullptr; d.rho_prepared = 0.0; d.paired = 0;
     if (prep) {
       d.S0 = s->instbuf.take<double>(B * tri); d.T = s->instbuf.take<double>(B * tri); d.Minv0 = s->instbuf.take<double>(B * N * 32);
       if (!d.Minv0) return fail(SMPC_ERR_CUDA, "internal: instance buffer carve-out overflow");
@@ -416,6 +416,15 @@ int smpc_solver_create_batched(smpc_solver **out, int device, int n, int m, int 
     }
     if (int rc = alloc_batch(s)) return rc;
     if (int rc = reset_state(s, true)) return rc;
+    if (prep && m >= 2 && m % 2 == 0) {   // [G; -G] rows in every instance?  (checked on the scaled data; d_status is free here)
+      int one = 1, flag = 0;
+      CK(cudaMemcpy(s->d_status, &one, sizeof(int), cudaMemcpyHostToDevice));
+      CK(smpc::launch_instance_pairs(d, s->d_status, nullptr));
+      s->launches++;
+      CK(cudaMemcpy(&flag, s->d_status, sizeof(int), cudaMemcpyDeviceToHost));
+      CK(cudaMemset(s->d_status, 0, sizeof(int)));
+      d.paired = flag;
+    }
     if (prep) {   // what osqp_setup does once per solver: the factorisation for rho0 (and the rho-independent parts of M)
       smpc::BatchDev pb{};
       pb.B = batch;
@@ -625,7 +634,11 @@ int smpc_solver_get_scaling(smpc_solver *s, double *D, double *E, double *c) {
 }
 
 long long smpc_solver_launch_count(const smpc_solver *s) { return s ? s->launches : 0; }
-int smpc_solver_row_pairs(const smpc_solver *s) { return (s && s->regime == 0 && s->kernel == 4) ? s->dtile.mp : 0; }
+int smpc_solver_row_pairs(const smpc_solver *s) {
+  if (!s) return 0;
+  if (s->regime == 1) return s->dinst.paired ? s->m / 2 : 0;
+  return s->kernel == 4 ? s->dtile.mp : 0;
+}
 const char *smpc_solver_kernel_name(const smpc_solver *s) {
   if (!s) return "";
   return s->regime == 1 ? "admm_instance_kernel" : s->kernel == 2 ? "admm_shared_small_kernel"

@@ -74,6 +74,7 @@ struct InstanceDataDev {
   // row classes of the setup bounds, packed lower triangles [B][n(n+1)/2], and the rows of M(rho_prepared)^-1, k-major [B][32][n]
   double *S0, *T, *Minv0;
   double rho_prepared;
+  int paired;           // 1: rows r and r + m/2 of every scaled A̅_i are exact negatives ([G; -G], cpp:335), checked at create time
 };
 
 // per-instance data and state, [B][len] contiguous

@@ -39,6 +39,7 @@ cudaError_t launch_ruiz_instance(const InstanceDataDev &I, int iters, cudaStream
 // prepare != 0: create-time pass of the register-operator kernel (fills I.S0, I.T, I.Minv0); no-op for other sizes
 cudaError_t launch_admm_instance(const InstanceDataDev &I, const BatchDev &Bt, const SettingsDev &S, cudaStream_t stream, int prepare = 0);
 bool instance_reg_supports(int n, int m);
+cudaError_t launch_instance_pairs(const InstanceDataDev &I, int *flag, cudaStream_t stream);   // *flag &= all instances are [G; -G]
 cudaError_t launch_warm_start_instance(const InstanceDataDev &I, const double *x, const double *y, double *xs, double *z,
                                        double *ys, cudaStream_t stream);
 bool instance_kernel_supports(int n, int m);
