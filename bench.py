@@ -86,13 +86,15 @@ class ClockSampler(threading.Thread):
                      "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
                      "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
                      "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
-            while not self._stop_evt.is_set():
+            while True:   # first sample at once, then every 2 ms, and one more after the stop request (short timed regions)
                 self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
                 r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
                 for k, bit in names.items():
                     if r & bit:
                         self.reasons.add(k)
-                time.sleep(0.01)
+                if self._stop_evt.is_set():
+                    break
+                time.sleep(0.002)
         except Exception as e:  # NVML missing: report that instead of inventing clocks
             self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
 
