@@ -945,13 +945,10 @@ cudaError_t launch_admm_instance(const InstanceDataDev &I, const BatchDev &Bt, c
     const size_t per = ((instance_reg_warp_doubles(I.n, I.m, paired) + 1) & ~(size_t)1) * sizeof(double);
     const int wpc = pick_wpc(per);
     const size_t smem = wpc * per;
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(admm_instance_reg_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(admm_instance_reg_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-      if (e != cudaSuccess) return e;
-      attr_set = true;
-    }
+    // (the attribute is per device: set it on every launch rather than once per process)
+    cudaError_t e = paired ? cudaFuncSetAttribute(admm_instance_reg_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                           : cudaFuncSetAttribute(admm_instance_reg_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
     if (paired) admm_instance_reg_kernel<true><<<(Bt.B + wpc - 1) / wpc, wpc * 32, smem, stream>>>(I, Bt, S, wpc, prepare);
     else admm_instance_reg_kernel<false><<<(Bt.B + wpc - 1) / wpc, wpc * 32, smem, stream>>>(I, Bt, S, wpc, prepare);
     return cudaGetLastError();

@@ -793,12 +793,9 @@ cudaError_t launch_admm_shared_small_mma(const SmallPackDev &K, const SharedPlan
   if (e != cudaSuccess) return e;
   int grid = (Bt.B + kSlots - 1) / kSlots;
   if (grid > num_sms * 4) grid = num_sms * 4;
-  static bool attr_set = false;
-  if (!attr_set) {
-    e = cudaFuncSetAttribute(admm_shared_small_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
+  // (the attribute is per device: set it on every launch rather than once per process)
+  e = cudaFuncSetAttribute(admm_shared_small_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
   admm_shared_small_mma_kernel<<<grid, 128, smem, stream>>>(K, P, Bt, S, queue, lists);
   return cudaGetLastError();
 }
