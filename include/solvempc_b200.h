@@ -261,6 +261,24 @@ int smpc_mimo_controller_step(smpc_mimo *m);
 int smpc_mimo_get_control(smpc_mimo *m, double *u0, int loc);
 long long smpc_mimo_launch_count(const smpc_mimo *m);
 
+/* ---------------------------------------------- wire format and asynchronous state feed (off the hot path) */
+/* One frame of the reference's ASCII protocol, parsed as SerialPort::getDataFromSerial does (src/SerialPort.cpp:106-138):
+ * five space-separated numbers "dt x1 x2 x3 x4" stored through float; frames of <= 30 bytes are rejected as readPort does
+ * (cpp:146).  Returns 1 when the frame is accepted, 0 otherwise.  dt is returned (the reference loses it: readPort takes it
+ * by value, cpp:142). */
+int smpc_wire_parse_frame(const char *buf, int nbytes, double *dt, double *X /* [4] */);
+/* The control as SerialPort::writePort formats it (std::to_string(U), cpp:165); max_chars = 8 reproduces the reference's
+ * sizeof(char*) truncation, <= 0 sends the whole number.  Returns the number of characters written (NUL excluded). */
+int smpc_wire_format_control(double U, char *out, int capacity, int max_chars);
+/* A reader thread on file descriptor fd (a serial port, pipe or pty the caller opened and configured) keeps the most recent
+ * accepted frame, so that one slow device never blocks the batch: smpc_feed_latest is non-blocking and returns 1 when a frame
+ * newer than *seq is available (then *seq, dt, X[4] are updated), 0 otherwise.  A frame ends at '\n' or at 42 bytes. */
+typedef struct smpc_feed smpc_feed;
+int smpc_feed_open(smpc_feed **out, int fd);
+int smpc_feed_latest(smpc_feed *f, long long *seq, double *dt, double *X /* [4] */);
+int smpc_feed_stats(smpc_feed *f, long long *accepted, long long *rejected);
+int smpc_feed_close(smpc_feed *f);   /* stops and joins the thread; does not close fd */
+
 #ifdef __cplusplus
 }
 #endif

@@ -113,6 +113,12 @@ SIGNATURES = {
     "smpc_mimo_controller_step": (_i, [_vp]),
     "smpc_mimo_get_control": (_i, [_vp, _dp, _i]),
     "smpc_mimo_launch_count": (C.c_longlong, [_vp]),
+    "smpc_wire_parse_frame": (_i, [C.c_char_p, _i, C.POINTER(C.c_double), _dp]),
+    "smpc_wire_format_control": (_i, [C.c_double, C.c_char_p, _i, _i]),
+    "smpc_feed_open": (_i, [C.POINTER(_vp), _i]),
+    "smpc_feed_latest": (_i, [_vp, C.POINTER(C.c_longlong), C.POINTER(C.c_double), _dp]),
+    "smpc_feed_stats": (_i, [_vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
+    "smpc_feed_close": (_i, [_vp]),
 }
 
 _lib = None
