@@ -231,6 +231,29 @@ admm_shared_tile_kernel(TilePackDev K, SharedPlanDev P, BatchDev Bt, SettingsDev
 
       for (int e = tid; e < N_COUNT * TB; e += kTileThreads) (&C.nmax[0][0])[e] = 0ull;
       for (int e = tid; e < S_COUNT * kTileWarps * TB; e += kTileThreads) (&C.psum[0][0][0])[e] = 0.0;
+      if (!initial) {
+        // The slots that finish at this event are refilled ~10^5 cycles from now with the next QPs of the queue.  Their rows
+        // (q, l, u and the warm-start state) are cold in HBM: pull the next 2 TB instances of the queue into L2 now (whichever
+        // tile pops them finds them there).  Speculative and read-only: results do not depend on it.
+        const int head = *reinterpret_cast<volatile int *>(queue);
+        const int lines_n = (n * 8 + 127) >> 7, lines_m = (m * 8 + 127) >> 7;          // 128-byte lines per row vector
+        const int per = (Bt.q ? lines_n : 0) + (Bt.l ? lines_m : 0) + (Bt.u ? lines_m : 0) + (warm ? lines_n + 2 * lines_m : 0);
+        for (int e = tid; e < 2 * TB * per; e += kTileThreads) {
+          const int b = head + e / per;
+          if (b >= Bt.B) break;
+          int j = e % per;
+          const double *p = nullptr;
+          if (Bt.q) { if (j < lines_n) p = Bt.q + (size_t)b * n + 16 * j; j -= lines_n; }
+          if (!p && Bt.l) { if (j < lines_m) p = Bt.l + (size_t)b * m + 16 * j; j -= lines_m; }
+          if (!p && Bt.u) { if (j < lines_m) p = Bt.u + (size_t)b * m + 16 * j; j -= lines_m; }
+          if (!p && warm) {
+            if (j < lines_n) p = Bt.xi + (size_t)b * n + 16 * j;
+            else if (j < lines_n + lines_m) p = Bt.z + (size_t)b * m + 16 * (j - lines_n);
+            else p = Bt.y + (size_t)b * m + 16 * (j - lines_n - lines_m);
+          }
+          if (p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+        }
+      }
       if (tid < TB) {
         int f = 0;
         if (C.inst[tid] >= 0) {
