@@ -19,6 +19,7 @@
 // Panel layout in shared memory: [nb][row][8] doubles (8-slot blocks), so a DMMA B-fragment load (4 k-rows x 8 slots)
 // is 32 consecutive doubles and the C-fragment of a thread is a double2 of the same panel layout.
 #include <cstdint>
+#include <cstdlib>
 #include <cstdio>
 
 #include "device_types.cuh"
@@ -52,10 +53,10 @@ __device__ __forceinline__ double2 ldg_stream(const double2 *p) {
 __device__ __forceinline__ double rho_of(int ct, double rho) { return ct == 0 ? rho : (ct == 1 ? kRhoEqOverIneq * rho : kRhoMin); }
 
 // per-tile bookkeeping in shared memory
-template <int TB>
+template <int TB, int W = kTileWarps>
 struct TileCtl {
   unsigned long long nmax[N_COUNT][TB];    // max-norms as IEEE bit patterns of non-negative doubles
-  double psum[S_COUNT][kTileWarps][TB];
+  double psum[S_COUNT][W][TB];
   double rho[TB], rinv[TB], rho_eq[TB], rinv_eq[TB];
   double obj[TB], pri[TB], dua[TB];
   int inst[TB];        // QP index of the slot, -1 = empty
@@ -75,9 +76,9 @@ enum SlotFlag { F_DUE_CHECK = 1, F_DUE_ADAPT = 2, F_AT_MAX = 4, F_PRIM_OK = 8, F
 // operator row-block; bp = panel + (lane&3)*8 + (lane>>2) (+ 64*first k-pair); nbs = doubles between 8-slot blocks.
 // The A fragments run kRing k-pairs ahead of their use in a register ring (covers the L2 latency); the main loop is
 // branch-free (prefetches past the end are clamped to the last k-pair).
-template <int NB, int NR>
+template <int NB, int NR, int RG>
 __device__ __forceinline__ void gemm_run(const double2 *__restrict__ opl, int kpt, int rb, int kp0, int cnt,
-                                         const double *bp, int nbs, double (&acc)[kRG][NB][2]) {
+                                         const double *bp, int nbs, double (&acc)[RG][NB][2]) {
   const double2 *ap[NR];
 #pragma unroll
   for (int r = 0; r < NR; ++r) ap[r] = opl + ((size_t)(rb + r) * kpt + kp0) * 32;
@@ -131,14 +132,16 @@ __device__ __forceinline__ void gemm_run(const double2 *__restrict__ opl, int kp
     }
 }
 // nr (1..kRG) row-blocks starting at rb: dispatch to the compile-time variants (nr is warp-uniform)
-template <int NB>
+template <int NB, int RG>
 __device__ __forceinline__ void gemm_seg(const double2 *__restrict__ opl, int kpt, int rb, int nr, int kp0, int cnt,
-                                         const double *bp, int nbs, double (&acc)[kRG][NB][2]) {
+                                         const double *bp, int nbs, double (&acc)[RG][NB][2]) {
   if (cnt <= 0) return;
-  if (nr >= 4) gemm_run<NB, 4>(opl, kpt, rb, kp0, cnt, bp, nbs, acc);
-  else if (nr == 3) gemm_run<NB, 3>(opl, kpt, rb, kp0, cnt, bp, nbs, acc);
-  else if (nr == 2) gemm_run<NB, 2>(opl, kpt, rb, kp0, cnt, bp, nbs, acc);
-  else gemm_run<NB, 1>(opl, kpt, rb, kp0, cnt, bp, nbs, acc);
+  if constexpr (RG >= 4) {
+    if (nr >= 4) { gemm_run<NB, 4, RG>(opl, kpt, rb, kp0, cnt, bp, nbs, acc); return; }
+    if (nr == 3) { gemm_run<NB, 3, RG>(opl, kpt, rb, kp0, cnt, bp, nbs, acc); return; }
+  }
+  if (nr >= 2) gemm_run<NB, 2, RG>(opl, kpt, rb, kp0, cnt, bp, nbs, acc);
+  else gemm_run<NB, 1, RG>(opl, kpt, rb, kp0, cnt, bp, nbs, acc);
 }
 
 // max over the 8 row-groups of a warp (lanes with equal lane&3 hold the same slot pair)
@@ -157,10 +160,13 @@ __device__ __forceinline__ double rsum8(double v) {
 
 enum PassId { P_XBAR, P_PX, P_ATY, P_AX, P_ATD, P_DX, P_PD, P_ADX, P_QH, P_COUNT };
 
-template <int NB, bool PAIRED>
-__global__ void __launch_bounds__(kTileThreads, 1)
+// WARPS = 8: two warps per SM sub-partition, up to 4 row-blocks per warp at once (254 registers);
+// WARPS = 16: four warps per sub-partition, up to 2 row-blocks at once (128 registers): more warps to cover LDS / L2 / barrier stalls
+template <int NB, bool PAIRED, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1)
 admm_shared_tile_kernel(TilePackDev K, SharedPlanDev P, BatchDev Bt, SettingsDev S, int *queue) {
   constexpr int TB = 8 * NB;
+  constexpr int kTileWarps = WARPS, kTileThreads = WARPS * 32, kRG = WARPS == 8 ? 4 : 2;   // (shadow the file-level defaults)
   extern __shared__ __align__(16) double smem[];
   const int n = P.n, m = P.m, n8 = K.n8, m8 = K.m8;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -171,7 +177,7 @@ admm_shared_tile_kernel(TilePackDev K, SharedPlanDev P, BatchDev Bt, SettingsDev
   double *cv = smem, *Tp = cv + cvr * TB, *qh = Tp + n8 * TB, *dinv = qh + n8 * TB, *Sp = dinv + n8 * TB, *Dp = Sp + n8 * TB;
   double *zp = Dp + n8 * TB, *yp = zp + m8 * TB, *lbp = yp + m8 * TB, *ubp = lbp + m8 * TB;
   const int bfrag = (lane & 3) * 8 + (lane >> 2);     // this lane's element of a B fragment
-  TileCtl<TB> &C = *reinterpret_cast<TileCtl<TB> *>(ubp + m8 * TB);
+  TileCtl<TB, WARPS> &C = *reinterpret_cast<TileCtl<TB, WARPS> *>(ubp + m8 * TB);
   const int NRB = n8 >> 3, MRB = m8 >> 3;
   const int nrb0 = (warp * NRB) / kTileWarps, nrb1 = ((warp + 1) * NRB) / kTileWarps;
   const int mrb0 = (warp * MRB) / kTileWarps, mrb1 = ((warp + 1) * MRB) / kTileWarps;
@@ -578,7 +584,7 @@ _Pragma("unroll 4")
         for (int rb = rb0; rb < rb1; rb += kRG) {
           double acc[kRG][NB][2];
           zero_acc(acc);
-          gemm_seg<NB>(op + lane, kpt, rb, min(kRG, rb1 - rb), 0, kpt, panel + bfrag, krows * 8, acc);
+          gemm_seg<NB, kRG>(op + lane, kpt, rb, min(kRG, rb1 - rb), 0, kpt, panel + bfrag, krows * 8, acc);
           double mx[NB][8][2], sm[NB][2];
 #pragma unroll
           for (int nb = 0; nb < NB; ++nb) {
@@ -735,7 +741,7 @@ _Pragma("unroll 4")
     for (int rb = nrb0; rb < nrb1; rb += kRG) {
       double acc[kRG][NB][2];
       zero_acc(acc);
-      gemm_seg<NB>(M1l, kp1, rb, min(kRG, nrb1 - rb), 0, kp1, cv + bfrag, cvr * 8, acc);
+      gemm_seg<NB, kRG>(M1l, kp1, rb, min(kRG, nrb1 - rb), 0, kp1, cv + bfrag, cvr * 8, acc);
 #pragma unroll
       for (int r = 0; r < kRG; ++r)
         if (rb + r < nrb1) {
@@ -766,7 +772,7 @@ _Pragma("unroll 4")
       for (int rb = prb0; rb < prb1; rb += kRG) {
         double acc[kRG][NB][2];
         zero_acc(acc);
-        gemm_seg<NB>(Wl, kpN, rb, min(kRG, prb1 - rb), 0, kpN, Tp + bfrag, n8 * 8, acc);
+        gemm_seg<NB, kRG>(Wl, kpN, rb, min(kRG, prb1 - rb), 0, kpN, Tp + bfrag, n8 * 8, acc);
 #pragma unroll
         for (int r = 0; r < kRG; ++r)
           if (rb + r < prb1) {
@@ -808,7 +814,7 @@ _Pragma("unroll 4")
     for (int rb = mrb0; rb < mrb1; rb += kRG) {
       double acc[kRG][NB][2];
       zero_acc(acc);
-      gemm_seg<NB>(Wl, kpN, rb, min(kRG, mrb1 - rb), 0, kpN, Tp + bfrag, n8 * 8, acc);
+      gemm_seg<NB, kRG>(Wl, kpN, rb, min(kRG, mrb1 - rb), 0, kpN, Tp + bfrag, n8 * 8, acc);
 #pragma unroll
       for (int r = 0; r < kRG; ++r)
         if (rb + r < mrb1) {
@@ -842,7 +848,7 @@ bool tile_kernel_supports(int n, int m) { return tile_kernel_nb(n, m) > 0; }
 
 size_t tile_smem_bytes(int n, int m, int nb) {
   const size_t n8 = (n + 7) & ~7, m8 = (m + 7) & ~7, TB = 8 * nb;
-  const size_t ctl = nb == 1 ? sizeof(TileCtl<8>) : sizeof(TileCtl<16>);
+  const size_t ctl = nb == 1 ? sizeof(TileCtl<8, 16>) : sizeof(TileCtl<16, 16>);   // (the larger of the 8- and 16-warp control blocks)
   return (6 * n8 + 5 * m8) * TB * sizeof(double) + ctl;
 }
 
@@ -869,15 +875,23 @@ cudaError_t launch_admm_shared_tile(const TilePackDev &K, const SharedPlanDev &P
   if (per_sm < 1) per_sm = 1;
   if (per_sm > 4) per_sm = 4;
   if (grid > num_sms * per_sm) grid = num_sms * per_sm;
+  // tiles that own an SM alone run 16 warps (4 per sub-partition cover each other's LDS / L2 / barrier stalls: +11 % at N = 100,
+  // +18 % on the quadrotor); smaller tiles keep 8 warps with 4 row-blocks per warp
+  int warps = per_sm == 1 ? 16 : 8;
+  if (const char *env = getenv("SMPC_TILE_WARPS")) warps = atoi(env) == 16 ? 16 : (atoi(env) == 8 ? 8 : warps);   // development knob
   auto go = [&](auto kernel) -> cudaError_t {
     cudaError_t e2 = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e2 != cudaSuccess) return e2;
-    kernel<<<grid, kTileThreads, smem, stream>>>(K, P, Bt, S, queue);
+    kernel<<<grid, warps * 32, smem, stream>>>(K, P, Bt, S, queue);
     return cudaGetLastError();
   };
   const bool paired = K.mp > 0;
-  if (nb == 1) return paired ? go(admm_shared_tile_kernel<1, true>) : go(admm_shared_tile_kernel<1, false>);
-  return paired ? go(admm_shared_tile_kernel<2, true>) : go(admm_shared_tile_kernel<2, false>);
+  if (warps == 16) {
+    if (nb == 1) return paired ? go(admm_shared_tile_kernel<1, true, 16>) : go(admm_shared_tile_kernel<1, false, 16>);
+    return paired ? go(admm_shared_tile_kernel<2, true, 16>) : go(admm_shared_tile_kernel<2, false, 16>);
+  }
+  if (nb == 1) return paired ? go(admm_shared_tile_kernel<1, true, 8>) : go(admm_shared_tile_kernel<1, false, 8>);
+  return paired ? go(admm_shared_tile_kernel<2, true, 8>) : go(admm_shared_tile_kernel<2, false, 8>);
 }
 
 }  // namespace smpc
