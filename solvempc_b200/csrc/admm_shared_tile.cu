@@ -877,7 +877,7 @@ cudaError_t launch_admm_shared_tile(const TilePackDev &K, const SharedPlanDev &P
   if (grid > num_sms * per_sm) grid = num_sms * per_sm;
   // tiles that own an SM alone run 16 warps (4 per sub-partition cover each other's LDS / L2 / barrier stalls: +11 % at N = 100,
   // +18 % on the quadrotor); smaller tiles keep 8 warps with 4 row-blocks per warp
-  int warps = per_sm == 1 ? 16 : 8;
+  int warps = (per_sm == 1 || K.n8 >= 48) ? 16 : 8;   // (with >= 6 row-blocks of n the 16 warps all have work; measured N = 30: 8 warps, N = 50: 16)
   if (const char *env = getenv("SMPC_TILE_WARPS")) warps = atoi(env) == 16 ? 16 : (atoi(env) == 8 ? 8 : warps);   // development knob
   auto go = [&](auto kernel) -> cudaError_t {
     cudaError_t e2 = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
