@@ -80,3 +80,57 @@ def test_c4_per_instance_plants_through_mpc_api(ref_mats):
             assert Uout[b] == U[b]
     assert ok == (nsolved == B) and nsolved >= B // 2
     mpc.close()
+
+
+@pytest.mark.parametrize("paired", [False, True])
+def test_bounds_that_change_a_row_class_fall_back_to_the_full_factorisation(ref_mats, paired):
+    """The factorisation prepared at create time (M = S0 + rho T for the setup bounds' row classes, M(rho0)^-1) must not be
+    used when an instance's own bounds turn an inequality row into an equality row: rho_vec changes, OSQP refactors."""
+    _, cfg = ref_mats
+    B = 24
+    if paired:      # [G; -G] rows (the reference's constraint form): per-instance plants through the MPC builders
+        N = 12
+        Ad, Bd = c4_plants(B, cfg, seed=5)
+        mats = [oracle.mpc_build(**{**cfg, "Ad": Ad[b], "Bd": Bd[b], "N": N}) for b in range(B)]
+        Ps, As = np.array([m["H"] for m in mats]), np.array([m["Gbar"] for m in mats])
+        n, m = N, 2 * N
+        l0, u0 = mats[0]["lb"], mats[0]["W0"]
+        X, U, ref = c2_batch(B, seed=77)
+        qs, us = [], []
+        for b in range(B):
+            f, ub = oracle.mpc_step_vectors(mats[b], X[b], U[b], ref[b])
+            qs.append(f); us.append(ub)
+        qs, us = np.array(qs), np.array(us)
+        ls = np.tile(l0, (B, 1))
+        ls[:, 3] = us[:, 3] = 0.0              # row 3 becomes an equality (its pair row 3 + N stays an inequality)
+    else:
+        n, m = 10, 16
+        Ps, As, qs = [], [], []
+        l0, u0 = np.full(m, -2.0), np.full(m, 2.0)   # wide enough to be feasible for every instance
+        for b in range(B):
+            P, q, A, _, _ = random_qp(n, m, seed=3000 + b)
+            Ps.append(P); As.append(A); qs.append(q)
+        Ps, As, qs = map(np.array, (Ps, As, qs))
+        ls, us = np.tile(l0, (B, 1)), np.tile(u0, (B, 1))
+        ls[:, 2] = us[:, 2] = 0.25             # inequality -> equality
+        ls[:, 5], us[:, 5] = -np.inf, np.inf   # inequality -> free
+    s = sm.BatchedSolver.batched(Ps, As, l0, u0, **EPS)
+    assert s.row_pairs == (m // 2 if paired else 0)
+    s.update_gradient(qs); s.update_bounds(ls, us); s.solve()
+    x, y = s.solution(); info = s.info()
+    for b in range(B):
+        so = oracle.Solver(Ps[b], np.zeros(n), As[b], l0, u0, **EPS)
+        so.update_lin_cost(qs[b]); so.update_bounds(ls[b], us[b])
+        r = so.solve()
+        assert info["status"][b] == r["status"] and info["iter"][b] == r["iter"], b
+        assert rel_err(x[b], r["x"]) < 1e-6
+    # back to the setup classes on the same handle: the prepared factorisation applies again, same answers as a fresh handle
+    s.update_bounds(np.tile(l0, (B, 1)), np.tile(u0, (B, 1)) if not paired else us * 0 + u0)
+    s.set_cold_solves(True); s.solve()
+    x2, _ = s.solution()
+    s2 = sm.BatchedSolver.batched(Ps, As, l0, u0, **EPS)
+    s2.update_gradient(qs); s2.solve()
+    x3, _ = s2.solution()
+    assert np.array_equal(x2, x3) and np.isfinite(x3).all()
+    assert (info["status"] == 1).mean() >= 0.5     # (forcing an equality makes a few of the paired instances infeasible: status parity above)
+    s.close(); s2.close()
