@@ -436,24 +436,34 @@ def run_ours(args, rank, local_rank, world):
         torch.cuda.synchronize()
         assert wl.solver.count_solved() == B, "warm-up solve did not reach SOLVED on every instance"
         iters = wl.solver.info()["iter"].astype(np.int64)
+
+        def timed_pass():
+            evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+            barrier()
+            w0 = time.perf_counter()
+            for e0, e1 in evs:
+                if flush is not None:
+                    flush.zero_()                 # evict the inputs from L2 between timed steps
+                e0.record(stream)
+                wl.step_device()
+                e1.record(stream)
+            barrier()
+            return np.array([a.elapsed_time(b) for a, b in evs]), 1e3 * (time.perf_counter() - w0)
+
+        # pass 1 (value): exactly K steps, nothing but the public calls inside the timed region.  Pass 2 (roofline): the same K
+        # steps with the library's CUDA events around the ADMM kernel -- they sit between the kernels of a step and switch off
+        # the programmatic-dependent-launch overlap, so they are kept out of the pass that produces `value`.
+        launches0 = wl.launches()
+        sampler.start()
+        step_ms, wall_ms = timed_pass()
+        launches = wl.launches() - launches0
         wl.solver.enable_timing(True)
         wl.solver.kernel_ms(reset=True)
-        launches0 = wl.launches()
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-        barrier()
-        sampler.start()
-        wall0 = time.perf_counter()
-        for e0, e1 in evs:
-            if flush is not None:
-                flush.zero_()                 # evict the inputs from L2 between timed steps
-            e0.record(stream)
-            wl.step_device()
-            e1.record(stream)
-        barrier()
-        wall_ms = 1e3 * (time.perf_counter() - wall0)
-        step_ms = np.array([a.elapsed_time(b) for a, b in evs])
+        step_ms_k, _ = timed_pass()
         prob_iters, iters_mean, iters_max = int(iters.sum()), float(iters.mean()), int(iters.max())
-    launches = wl.launches() - launches0
+    if closed_loop:
+        launches = wl.launches() - launches0
+        step_ms_k = step_ms
     kern_ms, kern_n = wl.solver.kernel_ms(reset=True)
     wl.solver.enable_timing(False)
     ms_per_step = float(step_ms.mean())
@@ -522,7 +532,9 @@ def run_ours(args, rank, local_rank, world):
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
                          "traffic": traffic, "traffic_unit": "bytes of DRAM read + written per launch", "traffic_source": traffic_src,
-                         "kernel": wl.solver.kernel_name, "kernel_ms": kms, "kernel_share_of_step": kms / float(step_ms.mean()),
+                         "kernel": wl.solver.kernel_name, "kernel_ms": kms, "kernel_share_of_step": kms / float(step_ms_k.mean()), "step_ms_in_kernel_timing_pass": float(step_ms_k.mean()),
+                         "kernel_timing": "CUDA events around the ADMM kernel inside the library, second pass of the same K steps"
+                                          if not closed_loop else "CUDA events around the ADMM kernel inside the library, same K steps",
                          "flops_per_launch": flops_per_launch, "executed_flops_per_launch": executed_per_launch,
                          "executed_frac": executed_per_launch / (kms * 1e-3) / 1e12 / fp64_peak,
                          "algorithmic_flops_per_instance_iteration": 2.0 * n * n + 4.0 * nnzA,

@@ -250,6 +250,10 @@ admm_shared_small_kernel(SmallPackDev K, SharedPlanDev P, BatchDev Bt, SettingsD
   const int check_every = S.check_every > 0 ? S.check_every : 0x7fffffff;
   const int adapt_every = (S.adaptive_rho && S.rho_interval > 0) ? S.rho_interval : 0x7fffffff;
   __syncthreads();
+  // Programmatic dependent launch: when the launcher allows it, this grid starts while the kernel before it in the stream (the
+  // MPC layer's step-vector / scheduling kernel) is still running; everything above reads only the constant operator packs.
+  // From here on the queue and the per-instance data written by that kernel are read: wait for it to complete (no-op otherwise).
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   for (;;) {
     // longest-expected-first: the queue walks the difficulty classes written by classify_small_kernel
@@ -810,8 +814,15 @@ cudaError_t launch_admm_shared_small(const SmallPackDev &K, const SharedPlanDev 
   int grid = (Bt.B + wpc - 1) / wpc;
   const int resident = num_sms * 3;   // __launch_bounds__(128, 3): three CTAs (12 warps) per SM
   if (grid > resident) grid = resident;
-  admm_shared_small_kernel<<<grid, wpc * 32, smem, stream>>>(K, P, Bt, S, queue, lists);
-  return cudaGetLastError();
+  // programmatic stream serialization: the prologue overlaps the tail of the preceding kernel (which must trigger it with
+  // griddepcontrol.launch_dependents, as the MPC layer's kernels do; otherwise this is an ordinary serialized launch)
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(wpc * 32); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, admm_shared_small_kernel, K, P, Bt, S, queue, (const int *)lists);
 }
 
 }  // namespace smpc

@@ -106,6 +106,10 @@ __global__ void mpc_step_classify_kernel(MpcDims d, int B, MpcMatsDev mt, const 
                                          const double *__restrict__ U, const double *__restrict__ ref,
                                          double *__restrict__ f, double *__restrict__ ub, SmallPackDev K, SharedPlanDev P,
                                          int *counts, int *lists) {
+  // let the ADMM kernel behind this one start its prologue now (programmatic dependent launch; it waits for this grid's
+  // completion before it reads f, ub and the scheduling lists), then wait for the set_state gather kernel in front
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const int lane = threadIdx.x & 31, b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (b >= B) return;
   const int N = d.N, nx = d.nx;
@@ -193,6 +197,7 @@ __global__ void mpc_advance_kernel(int B, int n, int nx, int per_instance, const
 __global__ void mpc_copy_state_kernel(int B, int nx, const double *__restrict__ X, const double *__restrict__ U,
                                       const double *__restrict__ ref, double *__restrict__ dX, double *__restrict__ dU,
                                       double *__restrict__ dref) {
+  asm volatile("griddepcontrol.launch_dependents;");   // the step-vector kernel may start; it waits for this grid's completion
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (X && e < B * nx) dX[e] = X[e];
   if (e < B) {
@@ -238,8 +243,13 @@ cudaError_t launch_mpc_step_classify(const MpcDims &d, int B, const MpcMatsDev &
                                      int *counts, int *lists, cudaStream_t stream) {
   if (d.N > 16 || P.n != d.N || P.m != 2 * d.N) return cudaErrorInvalidValue;
   const int wpc = 8;
-  mpc_step_classify_kernel<<<(B + wpc - 1) / wpc, wpc * 32, 0, stream>>>(d, B, mats, X, U, ref, f, ub, K, P, counts, lists);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((B + wpc - 1) / wpc); cfg.blockDim = dim3(wpc * 32); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, mpc_step_classify_kernel, d, B, mats, X, U, ref, f, ub, K, P, counts, lists);
 }
 cudaError_t launch_mpc_apply_control(int B, int n, const double *x, const int *status, double *U, cudaStream_t stream) {
   mpc_apply_control_kernel<<<(B + 255) / 256, 256, 0, stream>>>(B, n, x, status, U);

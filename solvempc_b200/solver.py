@@ -77,7 +77,10 @@ class BatchedSolver:
 
     def close(self):
         if getattr(self, "_h", None) and self._own:
-            L.lib().smpc_solver_destroy(self._h)
+            try:
+                L.lib().smpc_solver_destroy(self._h)
+            except TypeError:      # interpreter shutdown: the module globals are already gone
+                pass
         self._h = None
 
     __del__ = close
@@ -246,7 +249,10 @@ class BatchedModelPredictiveControlAPI:
 
     def close(self):
         if getattr(self, "_h", None):
-            L.lib().smpc_mpc_destroy(self._h)
+            try:
+                L.lib().smpc_mpc_destroy(self._h)
+            except TypeError:      # interpreter shutdown: the module globals are already gone
+                pass
         self._h = None
 
     __del__ = close
@@ -351,7 +357,10 @@ class BatchedMimoMPC:
 
     def close(self):
         if getattr(self, "_h", None):
-            L.lib().smpc_mimo_destroy(self._h)
+            try:
+                L.lib().smpc_mimo_destroy(self._h)
+            except TypeError:      # interpreter shutdown: the module globals are already gone
+                pass
         self._h = None
 
     __del__ = close
