@@ -75,3 +75,32 @@ def test_c4_per_instance_plants_at_full_size(ref_mats):
         if r["status"] == 1:
             assert np.abs(x[b] - r["x"]).max() <= 1e-6 * max(1e-9, np.abs(r["x"]).max())
     mpc.close()
+
+
+def test_c3_quadrotor_at_full_size(repo_root):
+    """One GPU's share of the 1M-instance batch of config 3 (131 072 quadrotor QPs, n = 200, m = 400): solver-independent
+    KKT properties of every instance; with a sample against the oracle."""
+    from problems import c3_batch
+    path = os.path.join(repo_root, "config", "quadrotor.json")
+    B = 131072
+    x0, xr = c3_batch(B, seed=11)
+    mpc = sm.BatchedMimoMPC(path, batch=B, **EPS)
+    assert mpc.solver.row_pairs == 200
+    mpc.set_state(x0=x0, xr=xr)
+    assert mpc.controllerStep()
+    x, y = mpc.solver.solution()
+    info = mpc.solver.info()
+    assert (info["iter"] % 25 == 0).all() and info["iter"].max() <= 500
+    H, A, ub = mpc.matrix("H"), mpc.matrix("A"), mpc.matrix("ub")
+    q = oracle.mimo_batch_vectors(dict(Fx=mpc.matrix("Fx"), Fr=mpc.matrix("Fr")), x0, xr)
+    Px, Aty, Ax = x @ H, y @ A, x @ A.T
+    stat = np.abs(Px + q + Aty).max(axis=1)
+    assert (stat <= 1e-5 + 1e-5 * np.maximum(np.maximum(np.abs(Px).max(axis=1), np.abs(Aty).max(axis=1)), np.abs(q).max(axis=1))).all()
+    assert ((Ax - ub).max(axis=1) <= 1e-5 + 1e-5 * np.abs(Ax).max(axis=1)).all()
+    assert (y >= -1e-9).all()
+    m = oracle.mimo_build(**oracle.load_mimo_config(path))
+    idx = np.arange(0, B, B // 8)
+    ora = oracle.solve_batch(H, A, m["lb"], ub, q[idx], np.tile(ub, (len(idx), 1)), nthreads=os.cpu_count() or 1, **EPS)
+    assert np.array_equal(info["status"][idx], ora["status"]) and np.array_equal(info["iter"][idx], ora["iter"])
+    assert (np.abs(x[idx] - ora["x"]).max(axis=1) / np.abs(ora["x"]).max(axis=1)).max() < 1e-4
+    mpc.close()
