@@ -67,6 +67,15 @@ struct smpc_mpc {
 
 namespace {
 
+// device view of a host pointer when it is pinned (cudaHostAlloc / cudaHostRegister) and mapped; NULL for pageable memory
+template <typename T>
+T *pinned_device_view(T *p) {
+  if (!p) return nullptr;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return (a.type == cudaMemoryTypeHost && a.devicePointer) ? static_cast<T *>(a.devicePointer) : nullptr;
+}
+
 smpc::SettingsDev to_dev(const smpc_settings &s) {
   smpc::SettingsDev d;
   d.rho0 = s.rho; d.sigma = s.sigma; d.alpha = s.alpha; d.eps_abs = s.eps_abs; d.eps_rel = s.eps_rel;
@@ -813,6 +822,14 @@ int smpc_mpc_set_state(smpc_mpc *M, const double *X, const double *U, const doub
     M->launches++;
     return SMPC_OK;
   }
+  // pinned host buffers: the gather kernel reads them over PCIe directly (one launch instead of up to three DMA copies);
+  // like cudaMemcpyAsync it reads the host memory asynchronously, on the stream
+  const double *vX = pinned_device_view(X), *vU = pinned_device_view(U), *vr = pinned_device_view(ref);
+  if ((!X || vX) && (!U || vU) && (!ref || vr) && (X || U || ref)) {
+    CK(smpc::launch_mpc_copy_state(M->B, M->dims.nx, vX, vU, vr, M->d_X, M->d_U, M->d_ref, M->stream));
+    M->launches++;
+    return SMPC_OK;
+  }
   if (X) CK(cudaMemcpyAsync(M->d_X, X, sizeof(double) * M->B * M->dims.nx, cudaMemcpyHostToDevice, M->stream));
   if (U) CK(cudaMemcpyAsync(M->d_U, U, sizeof(double) * M->B, cudaMemcpyHostToDevice, M->stream));
   if (ref) CK(cudaMemcpyAsync(M->d_ref, ref, sizeof(double) * M->B, cudaMemcpyHostToDevice, M->stream));
@@ -936,6 +953,16 @@ int smpc_mpc_get_control_status(smpc_mpc *M, double *U, int *status, int loc) {
   if (loc != SMPC_HOST && loc != SMPC_DEVICE) return fail(SMPC_ERR_ARG, "loc must be SMPC_HOST or SMPC_DEVICE");
   if (status && !M->solver->solved_once) return fail(SMPC_ERR_STATE, "status requested before the first controllerStep");
   CK(cudaSetDevice(M->device));
+  if (loc == SMPC_HOST) {
+    double *vU = pinned_device_view(U);
+    int *vs = pinned_device_view(status);
+    if ((!U || vU) && (!status || vs) && (U || status)) {   // pinned destinations: one export kernel writes them over PCIe
+      CK(smpc::launch_mpc_export(M->B, M->d_U, M->solver->d_status, vU, vs, M->stream));
+      M->launches++;
+      CK(cudaStreamSynchronize(M->stream));
+      return SMPC_OK;
+    }
+  }
   cudaMemcpyKind k = loc == SMPC_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
   if (U) CK(cudaMemcpyAsync(U, M->d_U, sizeof(double) * M->B, k, M->stream));
   if (status) CK(cudaMemcpyAsync(status, M->solver->d_status, sizeof(int) * M->B, k, M->stream));

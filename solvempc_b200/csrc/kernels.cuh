@@ -63,6 +63,8 @@ cudaError_t launch_mpc_copy_state(int B, int nx, const double *X, const double *
 cudaError_t launch_mpc_step_classify(const MpcDims &d, int B, const MpcMatsDev &mats, const double *X, const double *U,
                                      const double *ref, double *f, double *ub, const SmallPackDev &K, const SharedPlanDev &P,
                                      int *counts, int *lists, cudaStream_t stream);
+// results to (pinned, device-mapped) host memory in one launch: U and the per-instance status (either may be NULL)
+cudaError_t launch_mpc_export(int B, const double *U, const int *status, double *outU, int *outStatus, cudaStream_t stream);
 // U += dU[0]
 cudaError_t launch_mpc_apply_control(int B, int n, const double *x, const int *status, double *U, cudaStream_t stream);
 // X <- Ad X + Bd U

@@ -213,6 +213,18 @@ cudaError_t launch_mpc_copy_state(int B, int nx, const double *X, const double *
   return cudaGetLastError();
 }
 
+__global__ void mpc_export_kernel(int B, const double *__restrict__ U, const int *__restrict__ status, double *__restrict__ outU,
+                                  int *__restrict__ outStatus) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= B) return;
+  if (outU) outU[e] = U[e];
+  if (outStatus) outStatus[e] = status[e];
+}
+cudaError_t launch_mpc_export(int B, const double *U, const int *status, double *outU, int *outStatus, cudaStream_t stream) {
+  mpc_export_kernel<<<(B + 255) / 256, 256, 0, stream>>>(B, U, status, outU, outStatus);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_mpc_square_ref(int B, double amplitude, int period, const int *phase, const int *step, double *ref,
                                   cudaStream_t stream) {
   mpc_square_ref_kernel<<<(B + 255) / 256, 256, 0, stream>>>(B, amplitude, period, phase, step, ref);

@@ -394,3 +394,33 @@ def test_control_and_status_in_one_transfer(cfg_path):
     x, _ = mpc.solver.solution()
     assert np.array_equal(Uo, U + x[:, 0])
     mpc.close()
+
+
+def test_pinned_host_buffers_take_the_zero_copy_path(cfg_path):
+    """Pinned host buffers are gathered / exported by a kernel over PCIe, pageable ones by cudaMemcpyAsync: same results."""
+    import torch
+    B = 257
+    X, U, ref = c2_batch(B, seed=21)
+    out = []
+    for pinned in (False, True):
+        mpc = sm.BatchedModelPredictiveControlAPI(cfg_path, batch=B, **EPS)
+        if pinned:
+            hx, hu, hr = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in (X, U, ref)]
+            Uo, st = torch.empty(B, dtype=torch.float64).pin_memory(), torch.empty(B, dtype=torch.int32).pin_memory()
+            l0 = mpc.launches
+            mpc.set_state(X=hx, U=hu, ref=hr)
+            assert mpc.launches == l0 + 1                      # one gather kernel, no copy nodes
+            mpc.controller_step_async()
+            mpc.results_into(Uo, st)
+            out.append((Uo.numpy().copy(), st.numpy().copy()))
+            mpc.set_state(U=hu)                                # partial updates work too
+            mpc.results_into(Uo, st)
+            assert np.array_equal(Uo.numpy(), U)
+        else:
+            mpc.set_state(X=X, U=U, ref=ref)
+            mpc.controller_step_async()
+            Uo, st = np.empty(B), np.empty(B, np.int32)
+            mpc.results_into(Uo, st)
+            out.append((Uo, st))
+        mpc.close()
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1]) and (out[0][1] == 1).all()
