@@ -674,7 +674,7 @@ static int mpc_alloc(smpc_mpc *M, const smpc_mpc_config *cfg) {
   const size_t N = M->dims.N, nx = M->dims.nx, P = M->plants, B = M->B;
   size_t bytes = 0;
   for (size_t c : {P * nx * nx, P * nx, nx, nx, P * N * N, P * 2 * N * N, P * N * nx, P * N, P * N * N, P * 2 * N * nx, P * 2 * N,
-                   P * 2 * N, P * N * nx, P * N * N, P * N, B * nx, B, B}) bytes += DeviceBuf::need(c * sizeof(double));
+                   P * 2 * N, P * N * nx, P * N * N, P * N, P * N * N, B * nx, B, B}) bytes += DeviceBuf::need(c * sizeof(double));
   bytes += DeviceBuf::need(B * sizeof(int)) + DeviceBuf::need(sizeof(int)) + DeviceBuf::need(2 * sizeof(unsigned long long));
   CK(M->buf.alloc(bytes));
   DeviceBuf &b = M->buf;
@@ -682,7 +682,7 @@ static int mpc_alloc(smpc_mpc *M, const smpc_mpc_config *cfg) {
   smpc::MpcMatsDev &t = M->mats;
   t.H = b.take<double>(P * N * N); t.Gbar = b.take<double>(P * 2 * N * N); t.Fx = b.take<double>(P * N * nx); t.Fu = b.take<double>(P * N);
   t.Fr = b.take<double>(P * N * N); t.Sbar = b.take<double>(P * 2 * N * nx); t.Ku = b.take<double>(P * 2 * N); t.W0 = b.take<double>(P * 2 * N);
-  t.Sx = b.take<double>(P * N * nx); t.Su = b.take<double>(P * N * N); t.CAB = b.take<double>(P * N);
+  t.Sx = b.take<double>(P * N * nx); t.Su = b.take<double>(P * N * N); t.CAB = b.take<double>(P * N); t.FrT = b.take<double>(P * N * N);
   M->d_X = b.take<double>(B * nx); M->d_U = b.take<double>(B); M->d_ref = b.take<double>(B);
   M->d_phase = b.take<int>(B); M->d_step = b.take<int>(1); M->d_stats = b.take<unsigned long long>(2);
   if (!M->d_stats) return fail(SMPC_ERR_CUDA, "internal: mpc buffer carve-out overflow");

@@ -48,6 +48,7 @@ bool instance_kernel_supports(int n, int m);
 struct MpcDims { int N, nx, n_state_rows; double Q, R, RD, u_limit; };
 struct MpcMatsDev {   // per plant (index p): all row-major
   double *H, *Gbar, *Fx, *Fu, *Fr, *Sbar, *Ku, *W0, *Sx, *Su, *CAB;
+  double *FrT;   // Fr transposed (FrT[j][i] = Fr(i,j)): the per-step gradient sweeps Fr by rows with lane = row, coalesced through FrT
 };
 cudaError_t launch_mpc_assemble(const MpcDims &d, int plants, const double *Ad, const double *Bd,
                                 const double *Cd, const double *K, const MpcMatsDev &out, cudaStream_t stream);

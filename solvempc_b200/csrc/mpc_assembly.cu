@@ -65,7 +65,8 @@ __global__ void __launch_bounds__(256) mpc_assemble_kernel(MpcDims d, int plants
     for (int k = i; k < N; ++k) s += Su[(size_t)k * N + 0] * Su[(size_t)k * N + i];
     Fu[i] = 2.0 * (d.R + d.Q * s);
   }
-  for (int e = tid; e < N * N; e += nt) { int i = e / N, j = e % N; Fr[e] = -2.0 * d.Q * Su[(size_t)j * N + i]; }
+  double *FrT = o.FrT + (size_t)p * N * N;
+  for (int e = tid; e < N * N; e += nt) { int i = e / N, j = e % N; const double v = -2.0 * d.Q * Su[(size_t)j * N + i]; Fr[e] = v; FrT[(size_t)j * N + i] = v; }
   for (int e = tid; e < N * nx; e += nt) {
     int i = e / nx, c = e % nx; double s = 0;
     for (int k = i; k < N; ++k) s += Su[(size_t)k * N + i] * Sx[k * nx + c];
@@ -81,7 +82,7 @@ __global__ void mpc_step_vectors_kernel(MpcDims d, int B, int per_instance, MpcM
   if (b >= B) return;
   const int N = d.N, nx = d.nx;
   const size_t p = per_instance ? (size_t)b : 0;
-  const double *Fx = mt.Fx + p * N * nx, *Fu = mt.Fu + p * N, *Fr = mt.Fr + p * N * N;
+  const double *__restrict__ Fx = mt.Fx + p * N * nx, *__restrict__ Fu = mt.Fu + p * N, *__restrict__ FrT = mt.FrT + p * N * N;
   const double *Sbar = mt.Sbar + p * 2 * N * nx, *Ku = mt.Ku + p * 2 * N, *W0 = mt.W0 + p * 2 * N;
   const double *x = X + (size_t)b * nx;
   const double u = U[b], r = ref[b];
@@ -90,7 +91,8 @@ __global__ void mpc_step_vectors_kernel(MpcDims d, int B, int per_instance, MpcM
     for (int c = 0; c < nx; ++c) s += Fx[i * nx + c] * x[c];
     s += Fu[i] * u;
     double rr = 0;
-    for (int j = i; j < N; ++j) rr += Fr[(size_t)i * N + j] * r;   // Fr(i,j) = 0 for j < i
+#pragma unroll 8
+    for (int j = i; j < N; ++j) rr += __ldg(FrT + (size_t)j * N + i) * r;   // Fr(i,j) = 0 for j < i; same order of the sum, coalesced loads
     f[(size_t)b * N + i] = s + rr;
   }
   for (int i = lane; i < 2 * N; i += 32) {
@@ -122,7 +124,7 @@ __global__ void mpc_step_classify_kernel(MpcDims d, int B, MpcMatsDev mt, const 
     for (int c = 0; c < nx; ++c) s += mt.Fx[i * nx + c] * x[c];
     s += mt.Fu[i] * u;
     double rr = 0;
-    for (int j = i; j < N; ++j) rr += mt.Fr[(size_t)i * N + j] * r;   // Fr(i,j) = 0 for j < i
+    for (int j = i; j < N; ++j) rr += mt.FrT[(size_t)j * N + i] * r;   // Fr(i,j) = 0 for j < i
     f_i = s + rr;
     f[(size_t)b * N + i] = f_i;
   }
