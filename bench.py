@@ -510,7 +510,7 @@ def run_ours(args, rank, local_rank, world):
         n, m = wl.n, wl.m
         nnzA = wl.nnz_A()
         flops_per_launch = prob_iters * (2.0 * n * n + 4.0 * nnzA)       # 2 n^2 (KKT contraction) + 4 nnz(A) (A x, A'y)
-        m_exec = wl.solver.row_pairs or m                                # [G; -G] row pairs: the tile kernel multiplies the top half only
+        m_exec = wl.solver.row_pairs or m                                # [G; -G] row pairs: the tile and small-QP kernels multiply the top half only
         executed_per_launch = prob_iters * 2.0 * (n * n + 2 * m_exec * n)   # what the plan-coordinate iteration executes (dense W = A̅V)
         bytes_per_launch = prob_iters * 24.0 * (n + 2 * m)               # what one launch per iteration would stream
         kms = kern_ms / max(kern_n, 1)

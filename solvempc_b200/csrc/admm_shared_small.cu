@@ -219,14 +219,25 @@ __global__ void classify_small_kernel(SmallPackDev K, SharedPlanDev P, BatchDev 
   classify_instance(K, P, Bt.B, b, lane, q_i, lo, hi, counts, lists);
 }
 
+// PAIRED (the reference's two-sided limit [G; -G], cpp:335: row mp + i = -row i, m = 2 mp): W'w = W_top' (w_top - w_bot) and
+// z̃_bot = -z̃_top, so only the top half of W is multiplied.  Lane (h, i) then owns row h*mp + i: half-warp 0 sums
+// sigma*G xi and half-warp 1 W_top' wd (16 DFMA each instead of 24), both halves share the 16 products of z̃_top (8 DFMA
+// each instead of 16), each lane updates its own row and the pair's difference wd = w_top - w_bot goes back to shared memory.
+template <bool PAIRED>
 __global__ void __launch_bounds__(128, 3)
 admm_shared_small_kernel(SmallPackDev K, SharedPlanDev P, BatchDev Bt, SettingsDev S, int *queue, const int *lists) {
+  constexpr int K1 = PAIRED ? NP : KH;       // terms of t summed by one half-warp
+  constexpr int K2 = PAIRED ? NP / 2 : NP;   // terms of z̃ summed by one lane
   extern __shared__ __align__(16) double smem[];
   double *sV = smem + NP * NP * 2 + MP * NP;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double *cbuf = smem + kCtaMatDoubles + warp * kWarpDoubles, *tbuf = cbuf + NP + MP, *sbuf = tbuf + NP;
-  const int h = lane >> 4, i = lane & 15, r = lane;
-  const int n = P.n, m = P.m;
+  const int h = lane >> 4, i = lane & 15;
+  const int n = P.n, m = P.m, mp = m >> 1;
+  // r: the row this lane iterates on (MP = none); PAIRED: lane src holds row `lane` (check_step wants lane = row)
+  const int r = PAIRED ? (i < mp ? h * mp + i : MP) : lane;
+  const int rc = r < MP ? r : MP - 1;
+  const int src = lane < mp ? lane : (lane < m ? 16 + lane - mp : 15);
 
   for (int e = threadIdx.x; e < NP * NP; e += blockDim.x) {
     smem[e] = K.VT[e]; smem[NP * NP + e] = K.PVT[e]; sV[e] = K.V[e];
@@ -239,13 +250,16 @@ admm_shared_small_kernel(SmallPackDev K, SharedPlanDev P, BatchDev Bt, SettingsD
 
   const double lam_i = K.lam[i];
   LaneConst LC;
-  LC.D = K.D[i]; LC.Dinv = K.Dinv[i]; LC.E = K.E[r]; LC.Einv = K.Einv[r]; LC.ct = K.ctype[r];
+  LC.D = K.D[i]; LC.Dinv = K.Dinv[i]; LC.E = K.E[lane]; LC.Einv = K.Einv[lane]; LC.ct = K.ctype[lane];   // lane = row (check_step)
+  const double E_r = K.E[rc];
+  const int ct_r = K.ctype[rc];
   const double alpha = S.alpha, oma = 1.0 - S.alpha, c = P.c, cinv = P.cinv;
   const double qnan = __longlong_as_double(0x7ff8000000000000LL);
-  const uint32_t a_cv = (uint32_t)__cvta_generic_to_shared(cbuf + KH * h);   // this half-warp's 24 entries of [xi; w]
+  const uint32_t a_cv = (uint32_t)__cvta_generic_to_shared(cbuf + K1 * h);   // this half-warp's entries of [xi; w] / [xi; wd]
   const uint32_t a_tv = (uint32_t)__cvta_generic_to_shared(tbuf);
   const uint32_t a_xi = (uint32_t)__cvta_generic_to_shared(cbuf + i);
-  const uint32_t a_w = (uint32_t)__cvta_generic_to_shared(cbuf + NP + r);
+  const uint32_t a_w = (uint32_t)__cvta_generic_to_shared(cbuf + NP + (PAIRED ? i : lane));
+  const uint32_t a_tz = PAIRED ? a_tv + 8 * K2 * h : a_tv;   // this lane's terms of z̃
   const uint32_t a_t = (uint32_t)__cvta_generic_to_shared(tbuf + i);
   const int check_every = S.check_every > 0 ? S.check_every : 0x7fffffff;
   const int adapt_every = (S.adaptive_rho && S.rho_interval > 0) ? S.rho_interval : 0x7fffffff;
@@ -254,6 +268,13 @@ admm_shared_small_kernel(SmallPackDev K, SharedPlanDev P, BatchDev Bt, SettingsD
   // MPC layer's step-vector / scheduling kernel) is still running; everything above reads only the constant operator packs.
   // From here on the queue and the per-instance data written by that kernel are read: wait for it to complete (no-op otherwise).
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  auto store_w = [&](double w) {
+    if constexpr (PAIRED) {
+      const double wo = __shfl_xor_sync(kFull, w, 16);
+      if (h == 0) sts64(a_w, w - wo);
+    } else sts64(a_w, w);
+  };
+  auto by_row = [&](double v) { return PAIRED ? __shfl_sync(kFull, v, src) : v; };
 
   for (;;) {
     // longest-expected-first: the queue walks the difficulty classes written by classify_small_kernel
@@ -281,8 +302,8 @@ admm_shared_small_kernel(SmallPackDev K, SharedPlanDev P, BatchDev Bt, SettingsD
     double xi_i = (i < n && warm) ? Bt.xi[(size_t)b * n + i] : 0.0;
     double lb_r = -1.0, ub_r = 1.0, z_r = 0.0, y_r = 0.0;   // padded rows: A row = 0, never active
     if (r < m) {
-      lb_r = LC.E * (Bt.l ? Bt.l[(size_t)b * m + r] : P.l0[r]);
-      ub_r = LC.E * (Bt.u ? Bt.u[(size_t)b * m + r] : P.u0[r]);
+      lb_r = E_r * (Bt.l ? Bt.l[(size_t)b * m + r] : P.l0[r]);
+      ub_r = E_r * (Bt.u ? Bt.u[(size_t)b * m + r] : P.u0[r]);
       if (warm) { z_r = Bt.z[(size_t)b * m + r]; y_r = Bt.y[(size_t)b * m + r]; }
     }
     double rho = Bt.fresh ? fmin(fmax(S.rho0, kRhoMin), kRhoMax) : Bt.rho[b];
@@ -290,7 +311,7 @@ admm_shared_small_kernel(SmallPackDev K, SharedPlanDev P, BatchDev Bt, SettingsD
     // l > u (osqp_update_bounds refuses it) or a row whose class (equality / inequality / free) differs from the
     // shared plan's: the instance is left UNSOLVED (see admm_shared_generic.cu)
     const int ct_now = (lb_r < -kInfty * kMinScaling && ub_r > kInfty * kMinScaling) ? -1 : ((ub_r - lb_r < kRhoTolRow) ? 1 : 0);
-    const bool bad_bounds = __any_sync(kFull, r < m && (lb_r > ub_r || ct_now != LC.ct));
+    const bool bad_bounds = __any_sync(kFull, r < m && (lb_r > ub_r || ct_now != ct_r));
     // q̂ = V' q̄ ; lanes of the upper half-warp start their partial sum at 0, the lower half at -q̂
     if (h == 0) sbuf[i] = qb_i;
     __syncwarp();
@@ -302,13 +323,13 @@ admm_shared_small_kernel(SmallPackDev K, SharedPlanDev P, BatchDev Bt, SettingsD
       a += __shfl_xor_sync(kFull, a, 16);
       nqh_i = h == 0 ? -a : 0.0;
     }
-    double rv = rho_row(LC.ct, rho), rinv = 1.0 / rv;
+    double rv = rho_row(ct_r, rho), rinv = 1.0 / rv;
     double dinv_i = 1.0 / (1.0 + rho * lam_i);
     double dxi_i = 0.0, dy_r = 0.0;
     double base_r = fma(rinv, y_r, oma * z_r), om_xi = oma * xi_i;
     __syncwarp();
     if (h == 0) sts64(a_xi, xi_i);
-    sts64(a_w, rv * z_r - y_r);
+    store_w(rv * z_r - y_r);
     __syncwarp();
 
     int status = SMPC_UNSOLVED, iter = 0;
@@ -323,16 +344,19 @@ admm_shared_small_kernel(SmallPackDev K, SharedPlanDev P, BatchDev Bt, SettingsD
         // operators stay in registers; they are (re)loaded from L1/L2 here because check_step is out of line
         int steps = to_check < to_adapt ? to_check : to_adapt;
         if (steps > S.max_iter - iter) steps = S.max_iter - iter;
-        double m1[KH], wr[NP];
+        double m1[K1], wr[K2];
 #pragma unroll
-        for (int j = 0; j < KH; ++j) m1[j] = __ldg(K.M1T + (KH * h + j) * NP + i);
+        for (int j = 0; j < K1; ++j) m1[j] = __ldg(K.M1T + (K1 * h + j) * NP + i);
 #pragma unroll
-        for (int k = 0; k < NP; ++k) wr[k] = __ldg(K.WT + k * MP + r);
+        for (int k = 0; k < K2; ++k) {
+          if constexpr (PAIRED) wr[k] = i < mp ? __ldg(K.WT + (K2 * h + k) * MP + i) : 0.0;   // W_top(i, 8h + k)
+          else wr[k] = __ldg(K.WT + k * MP + r);
+        }
         for (int s = 0; s < steps; ++s) {
-          // ---- t = (sigma G xi + W' w - q̂) ./ (1 + rho lambda): each half-warp sums 24 of the 48 concatenated terms
+          // ---- t = (sigma G xi + W' w - q̂) ./ (1 + rho lambda): each half-warp sums half of the concatenated terms
           double a0 = nqh_i, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll
-          for (int j = 0; j < KH / 4; ++j) {
+          for (int j = 0; j < K1 / 4; ++j) {
             const double2 u0 = lds128(a_cv + 32 * j), u1 = lds128(a_cv + 32 * j + 16);
             a0 = fma(m1[4 * j + 0], u0.x, a0); a1 = fma(m1[4 * j + 1], u0.y, a1);
             a2 = fma(m1[4 * j + 2], u1.x, a2); a3 = fma(m1[4 * j + 3], u1.y, a3);
@@ -349,17 +373,21 @@ admm_shared_small_kernel(SmallPackDev K, SharedPlanDev P, BatchDev Bt, SettingsD
           // ---- z̃ = W t
           double b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
 #pragma unroll
-          for (int j = 0; j < NP / 4; ++j) {
-            const double2 u0 = lds128(a_tv + 32 * j), u1 = lds128(a_tv + 32 * j + 16);
+          for (int j = 0; j < K2 / 4; ++j) {
+            const double2 u0 = lds128(a_tz + 32 * j), u1 = lds128(a_tz + 32 * j + 16);
             b0 = fma(wr[4 * j + 0], u0.x, b0); b1 = fma(wr[4 * j + 1], u0.y, b1);
             b2 = fma(wr[4 * j + 2], u1.x, b2); b3 = fma(wr[4 * j + 3], u1.y, b3);
           }
-          const double zt = (b0 + b1) + (b2 + b3);
+          double zt = (b0 + b1) + (b2 + b3);
+          if constexpr (PAIRED) {
+            zt += __shfl_xor_sync(kFull, zt, 16);   // the same bits in both halves (a + b = b + a)
+            zt = h ? -zt : zt;                      // bottom row = -top row
+          }
           // ---- z, y updates (OSQP update_z / update_y re-associated, see the file header)
           const double v = fma(alpha, zt, base_r);
           const double zn = v < lb_r ? lb_r : (v > ub_r ? ub_r : v);
           const double yn = rv * (v - zn);
-          sts64(a_w, rv * fma(2.0, zn, -v));   // w' = rho z - y'
+          store_w(rv * fma(2.0, zn, -v));   // w' = rho z - y'
           dy_r = yn - y_r; y_r = yn; z_r = zn;
           base_r = fma(rinv, yn, oma * zn);
           __syncwarp();
@@ -370,24 +398,24 @@ admm_shared_small_kernel(SmallPackDev K, SharedPlanDev P, BatchDev Bt, SettingsD
         if (do_check) to_check = check_every;
         if (do_adapt) to_adapt = adapt_every;
         if (do_check || do_adapt) {
-          co = check_step(smem, cbuf, sbuf, S, n, m, c, cinv, LC, rho, qb_i, z_r, y_r, dy_r, dxi_i, lb_r, ub_r, do_check, false, do_adapt);
+          co = check_step(smem, cbuf, sbuf, S, n, m, c, cinv, LC, rho, qb_i, by_row(z_r), by_row(y_r), by_row(dy_r), dxi_i, by_row(lb_r), by_row(ub_r), do_check, false, do_adapt);
           if (co.status != SMPC_UNSOLVED) { status = co.status; break; }
           if (co.rho_changed) {
             rho = co.rho; ++rho_updates;
-            rv = rho_row(LC.ct, rho); rinv = 1.0 / rv; dinv_i = 1.0 / (1.0 + rho * lam_i);
+            rv = rho_row(ct_r, rho); rinv = 1.0 / rv; dinv_i = 1.0 / (1.0 + rho * lam_i);
             base_r = fma(rinv, y_r, oma * z_r);
-            sts64(a_w, rv * z_r - y_r);
+            store_w(rv * z_r - y_r);
             __syncwarp();
           }
         }
       }
       if (status == SMPC_UNSOLVED) {
         if (!checked_last) {
-          co = check_step(smem, cbuf, sbuf, S, n, m, c, cinv, LC, rho, qb_i, z_r, y_r, dy_r, dxi_i, lb_r, ub_r, true, false, false);
+          co = check_step(smem, cbuf, sbuf, S, n, m, c, cinv, LC, rho, qb_i, by_row(z_r), by_row(y_r), by_row(dy_r), dxi_i, by_row(lb_r), by_row(ub_r), true, false, false);
           status = co.status;
         }
         if (status == SMPC_UNSOLVED) {
-          const CheckOut ca = check_step(smem, cbuf, sbuf, S, n, m, c, cinv, LC, rho, qb_i, z_r, y_r, dy_r, dxi_i, lb_r, ub_r, true, true, false);
+          const CheckOut ca = check_step(smem, cbuf, sbuf, S, n, m, c, cinv, LC, rho, qb_i, by_row(z_r), by_row(y_r), by_row(dy_r), dxi_i, by_row(lb_r), by_row(ub_r), true, true, false);
           status = ca.status == SMPC_UNSOLVED ? SMPC_MAX_ITER_REACHED : ca.status;
           if (ca.status != SMPC_UNSOLVED) co.obj = ca.obj;
         }
@@ -403,7 +431,7 @@ admm_shared_small_kernel(SmallPackDev K, SharedPlanDev P, BatchDev Bt, SettingsD
       Bt.xi[(size_t)b * n + i] = has_sol ? xi_i : 0.0;
     }
     if (r < m) {
-      if (Bt.y_out) Bt.y_out[(size_t)b * m + r] = has_sol ? cinv * (LC.E * y_r) : qnan;
+      if (Bt.y_out) Bt.y_out[(size_t)b * m + r] = has_sol ? cinv * (E_r * y_r) : qnan;
       Bt.z[(size_t)b * m + r] = has_sol ? z_r : 0.0;
       Bt.y[(size_t)b * m + r] = has_sol ? y_r : 0.0;
     }
@@ -822,7 +850,8 @@ cudaError_t launch_admm_shared_small(const SmallPackDev &K, const SharedPlanDev 
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, admm_shared_small_kernel, K, P, Bt, S, queue, (const int *)lists);
+  if (K.mp > 0 && 2 * K.mp == P.m) return cudaLaunchKernelEx(&cfg, admm_shared_small_kernel<true>, K, P, Bt, S, queue, (const int *)lists);
+  return cudaLaunchKernelEx(&cfg, admm_shared_small_kernel<false>, K, P, Bt, S, queue, (const int *)lists);
 }
 
 }  // namespace smpc

@@ -169,6 +169,7 @@ int upload_small_pack(smpc_solver *s) {
   int *dct = s->packbuf.take<int>(MP);
   CK(cudaMemcpy(dct, ct.data(), MP * sizeof(int), cudaMemcpyHostToDevice));
   k.ctype = dct;
+  k.mp = (p.pairs > 0 && 2 * p.pairs == p.m && !getenv("SMPC_SMALL_NO_PAIRS")) ? p.pairs : 0;
   s->d_queue = s->packbuf.take<int>(smpc::small_queue_ints());
   s->d_lists = s->packbuf.take<int>((size_t)(smpc::small_queue_ints() - 1) * s->B);
   if (!s->d_lists) return fail(SMPC_ERR_CUDA, "internal: pack buffer carve-out overflow");
@@ -646,7 +647,7 @@ long long smpc_solver_launch_count(const smpc_solver *s) { return s ? s->launche
 int smpc_solver_row_pairs(const smpc_solver *s) {
   if (!s) return 0;
   if (s->regime == 1) return s->dinst.paired ? s->m / 2 : 0;
-  return s->kernel == 4 ? s->dtile.mp : 0;
+  return s->kernel == 4 ? s->dtile.mp : s->kernel == 2 ? s->dpack.mp : 0;
 }
 const char *smpc_solver_kernel_name(const smpc_solver *s) {
   if (!s) return "";

@@ -41,6 +41,7 @@ struct SmallPackDev {
   const double *lam, *D, *Dinv;   // [16]
   const double *E, *Einv;         // [32]
   const int *ctype;               // [32]
+  int mp;                         // > 0: rows are [G; -G] with mp = m / 2 pairs (row mp + i = -row i), else 0
 };
 
 // DMMA A-fragment packs of the plan for the tile kernel (admm_shared_tile.cu).  An operator Op (rows x K, both
