@@ -202,6 +202,38 @@ def _random_qps(n, m, B, kernel):
     s.close()
 
 
+@pytest.mark.parametrize("n,mp,B", [(3, 2, 9), (10, 10, 64), (16, 16, 64), (15, 15, 48), (12, 7, 33)])
+def test_small_kernel_row_pairs(n, mp, B):
+    """A = [G; -G] (the reference's two-sided limit, cpp:335): the one-warp kernel multiplies the top half of W only.
+    Pairs below, at and above the lane-mapping edges (mp < 15, mp = 16), per-instance bounds that make some pairs
+    inconsistent (u_top + u_bot < 0: primal infeasible) and +inf upper bounds on a few rows."""
+    P, q0, G, _, _ = random_qp(n, mp, seed=31 * n + mp)
+    A = np.vstack([G, -G])
+    m = 2 * mp
+    rng = np.random.default_rng(n * mp)
+    u0 = np.concatenate([1.0 + rng.random(mp), 1.0 + rng.random(mp)])
+    l0 = np.full(m, -np.inf)
+    q = q0[None, :] + 0.5 * rng.standard_normal((B, n))
+    u = u0[None, :] + 0.4 * rng.standard_normal((B, m))
+    u[1::7, 0] = -2.0; u[1::7, mp] = -2.0          # G x <= -2 and -G x <= -2: infeasible pair
+    s = sm.BatchedSolver(P, A, l0, u0, batch=B, kernel=2, **EPS)
+    assert s.kernel_name == KERNEL_NAMES[2] and s.row_pairs == mp
+    s.update_gradient(q); s.update_upper_bound(u); s.solve()
+    x, y = s.solution(); info = s.info()
+    ora = oracle.solve_batch(P, A, l0, u0, q, u, nthreads=os.cpu_count() or 1, **EPS)
+    assert np.array_equal(info["status"], ora["status"]) and np.array_equal(info["iter"], ora["iter"])
+    ok = ora["status"] == 1
+    assert ok.sum() >= B // 2 and (ora["status"][1::7] == sm.PRIMAL_INFEASIBLE).all()
+    assert rel_err(x[ok], ora["x"][ok]) < TIGHT and rel_err(y[ok], ora["y"][ok]) < 1e-5
+    assert np.isnan(x[~ok]).all()
+    # generic kernel (no pair exploitation) on the same data: same statuses and iteration counts
+    g = sm.BatchedSolver(P, A, l0, u0, batch=B, kernel=1, **EPS)
+    g.update_gradient(q); g.update_upper_bound(u); g.solve()
+    gi = g.info()
+    assert g.row_pairs == 0 and np.array_equal(gi["status"], info["status"]) and np.array_equal(gi["iter"], info["iter"])
+    s.close(); g.close()
+
+
 @pytest.mark.parametrize("kernel", [1, 2, 4, 5])
 @pytest.mark.parametrize("opts", [dict(adaptive_rho=0), dict(scaling=0), dict(scaled_termination=1),
                                   dict(adaptive_rho_interval=50), dict(check_termination=10, adaptive_rho_interval=30),
