@@ -17,6 +17,7 @@
 // out-of-line routine that reads its operators from shared memory.
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 
 #include "classify.cuh"
 #include "device_types.cuh"
@@ -51,7 +52,24 @@ __device__ __forceinline__ double wsum(double v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
   return v;
 }
-// queue layout: [0] work counter, [1..kClasses] class sizes, [1 + kClasses] warps / CTAs that finished
+// queue layout: [0] work counter, [1..kClasses] class sizes, [1 + kClasses] warps / CTAs that finished,
+// [kQHard] counter of the hardest class's quiet share, [kQSeen] SMs seen, [kQRank + smid] CTAs arrived on an SM,
+// [kQTicket + smid] 1 + arrival order of the SM (quiet-SM scheduling of admm_shared_small_kernel)
+constexpr int kQHard = 2 + kClasses, kQSeen = 3 + kClasses, kQRank = 16, kSmSlots = 512, kQTicket = kQRank + kSmSlots;
+constexpr int kQueueInts = kQTicket + kSmSlots;
+// the last warp to leave clears the whole queue block (all lanes of the warp call this)
+__device__ __forceinline__ void release_queue_warp(int *queue, int participants, int lane) {
+  int last = 0;
+  if (lane == 0) {
+    __threadfence();
+    last = atomicAdd(queue + 1 + kClasses, 1) == participants - 1;
+  }
+  last = __shfl_sync(kFull, last, 0);
+  if (last) {
+    for (int k = lane; k < kQueueInts; k += 32) queue[k] = 0;
+    __threadfence();
+  }
+}
 __device__ __forceinline__ void release_queue(int *queue, int participants) {
   __threadfence();
   if (atomicAdd(queue + 1 + kClasses, 1) == participants - 1) {
@@ -77,6 +95,9 @@ struct CheckOut {
   int rho_changed;
 };
 
+__device__ __forceinline__ bool prim_inf_status(int st) { return st == SMPC_PRIMAL_INFEASIBLE || st == SMPC_PRIMAL_INFEASIBLE_INACCURATE; }
+__device__ __forceinline__ bool dual_inf_status(int st) { return st == SMPC_DUAL_INFEASIBLE || st == SMPC_DUAL_INFEASIBLE_INACCURATE; }
+
 struct LaneConst {          // per-lane constants of the plan
   double D, Dinv, E, Einv;
   int ct;
@@ -87,7 +108,7 @@ struct LaneConst {          // per-lane constants of the plan
 __device__ __noinline__ CheckOut check_step(const double *sm, double *cbuf, double *sbuf, const SettingsDev &S, int n, int m,
                                             double c, double cinv, LaneConst L, double rho, double qb_i, double z_r,
                                             double y_r, double dy_r, double dxi_i, double lb_r, double ub_r,
-                                            bool do_check, bool approx, bool do_adapt) {
+                                            bool do_check, bool approx, bool do_adapt, bool want_obj) {
   const double *sVT = sm, *sPVT = sVT + NP * NP, *sAb = sPVT + NP * NP, *sAbT = sAb + MP * NP + NP * NP;
   const int lane = threadIdx.x & 31, h = lane >> 4, i = lane & 15, r = lane;
   const bool unscale = !S.scaled_termination;
@@ -118,19 +139,16 @@ __device__ __noinline__ CheckOut check_step(const double *sm, double *cbuf, doub
   const double rp = Ax_r - z_r, rd = (qb_i + apx) + aty;
   const double s_rp = wmax_nn(fabs(rp)), s_z = wmax_nn(fabs(z_r)), s_Ax = wmax_nn(fabs(Ax_r));
   const double s_rd = wmax_nn(fabs(rd)), s_q = wmax_nn(fabs(qb_i)), s_Aty = wmax_nn(fabs(aty)), s_Px = wmax_nn(fabs(apx));
-  double pri_res, dua_res, nEz, nEAx, nDq, nDAty, nDPx, obj;
-  const double ob = h == 0 ? 0.5 * ax * apx + qb_i * ax : 0.0;
+  double pri_res, dua_res, nEz, nEAx, nDq, nDAty, nDPx;
   if (unscale) {
     pri_res = wmax_nn(fabs(L.Einv * rp)); nEz = wmax_nn(fabs(L.Einv * z_r)); nEAx = wmax_nn(fabs(L.Einv * Ax_r));
     dua_res = cinv * wmax_nn(fabs(L.Dinv * rd)); nDq = wmax_nn(fabs(L.Dinv * qb_i));
     nDAty = wmax_nn(fabs(L.Dinv * aty)); nDPx = wmax_nn(fabs(L.Dinv * apx));
-    obj = cinv * wsum(ob);
   } else {
     pri_res = s_rp; nEz = s_z; nEAx = s_Ax; dua_res = s_rd; nDq = s_q; nDAty = s_Aty; nDPx = s_Px;
-    obj = wsum(ob);
   }
   if (m == 0) pri_res = 0.0;
-  o.obj = obj; o.pri_res = pri_res; o.dua_res = dua_res;
+  o.obj = 0.0; o.pri_res = pri_res; o.dua_res = dua_res;
 
   if (do_check) {
     double ea = S.eps_abs, er = S.eps_rel, epi = S.eps_prim_inf, edi = S.eps_dual_inf;
@@ -165,36 +183,42 @@ __device__ __noinline__ CheckOut check_step(const double *sm, double *cbuf, doub
     if (dua_res < ea + er * (unscale ? cinv : 1.0) * fmax(fmax(nDq, nDAty), nDPx)) dual_ok = true;
     else {
       // is_dual_infeasible on delta_x = V delta_xi
+      // (the three conditions in OSQP's order, each computed only when the one before it holds: all warp-uniform)
       if (h == 0) sbuf[i] = dxi_i;
       __syncwarp();
-      double dx = 0.0, pd = 0.0;
+      double dx = 0.0;
 #pragma unroll
-      for (int k = 0; k < NP / 2; ++k) {
-        const double dk = sbuf[8 * h + k];
-        dx = fma(sVT[(8 * h + k) * NP + i], dk, dx);
-        pd = fma(sPVT[(8 * h + k) * NP + i], dk, pd);
-      }
+      for (int k = 0; k < NP / 2; ++k) dx = fma(sVT[(8 * h + k) * NP + i], sbuf[8 * h + k], dx);
       dx += __shfl_xor_sync(kFull, dx, 16);
-      pd += __shfl_xor_sync(kFull, pd, 16);
-      __syncwarp();
-      if (h == 0) sbuf[i] = dx;
-      __syncwarp();
-      double ad = 0.0;
-#pragma unroll
-      for (int k = 0; k < NP; ++k) ad = fma(sAbT[k * MP + r], sbuf[k], ad);
-      __syncwarp();
       const double nd = wmax_nn(fabs(unscale ? L.D * dx : dx));
-      const double qd = wsum(h == 0 ? qb_i * dx : 0.0);
       const double cs = unscale ? c : 1.0;
-      if (nd > edi && qd < -cs * edi * nd && wmax_nn(fabs(unscale ? L.Dinv * pd : pd)) < cs * edi * nd) {
-        if (unscale) ad *= L.Einv;
-        const int bad = ((ub_r < kInfty * kMinScaling) && (ad > edi * nd)) || ((lb_r > -kInfty * kMinScaling) && (ad < -edi * nd));
-        dual_inf = !__any_sync(kFull, bad && r < m);
+      if (nd > edi && wsum(h == 0 ? qb_i * dx : 0.0) < -cs * edi * nd) {
+        double pd = 0.0;
+#pragma unroll
+        for (int k = 0; k < NP / 2; ++k) pd = fma(sPVT[(8 * h + k) * NP + i], sbuf[8 * h + k], pd);
+        pd += __shfl_xor_sync(kFull, pd, 16);
+        if (wmax_nn(fabs(unscale ? L.Dinv * pd : pd)) < cs * edi * nd) {
+          __syncwarp();
+          if (h == 0) sbuf[i] = dx;
+          __syncwarp();
+          double ad = 0.0;
+#pragma unroll
+          for (int k = 0; k < NP; ++k) ad = fma(sAbT[k * MP + r], sbuf[k], ad);
+          if (unscale) ad *= L.Einv;
+          const int bad = ((ub_r < kInfty * kMinScaling) && (ad > edi * nd)) || ((lb_r > -kInfty * kMinScaling) && (ad < -edi * nd));
+          dual_inf = !__any_sync(kFull, bad && r < m);
+        }
       }
+      __syncwarp();
     }
     if (prim_ok && dual_ok) o.status = approx ? SMPC_SOLVED_INACCURATE : SMPC_SOLVED;
-    else if (prim_inf) { o.status = approx ? SMPC_PRIMAL_INFEASIBLE_INACCURATE : SMPC_PRIMAL_INFEASIBLE; o.obj = kInfty; }
-    else if (dual_inf) { o.status = approx ? SMPC_DUAL_INFEASIBLE_INACCURATE : SMPC_DUAL_INFEASIBLE; o.obj = -kInfty; }
+    else if (prim_inf) o.status = approx ? SMPC_PRIMAL_INFEASIBLE_INACCURATE : SMPC_PRIMAL_INFEASIBLE;
+    else if (dual_inf) o.status = approx ? SMPC_DUAL_INFEASIBLE_INACCURATE : SMPC_DUAL_INFEASIBLE;
+  }
+  // the objective is reported, never tested: only when the solve ends here (or the caller is at max_iter)
+  if (o.status != SMPC_UNSOLVED || want_obj) {
+    const double ob = wsum(h == 0 ? 0.5 * ax * apx + qb_i * ax : 0.0);
+    o.obj = prim_inf_status(o.status) ? kInfty : (dual_inf_status(o.status) ? -kInfty : (unscale ? cinv * ob : ob));
   }
   if (do_adapt && o.status == SMPC_UNSOLVED) {
     // compute_rho_estimate / adapt_rho on the SCALED residual norms
@@ -223,14 +247,33 @@ __global__ void classify_small_kernel(SmallPackDev K, SharedPlanDev P, BatchDev 
 // z̃_bot = -z̃_top, so only the top half of W is multiplied.  Lane (h, i) then owns row h*mp + i: half-warp 0 sums
 // sigma*G xi and half-warp 1 W_top' wd (16 DFMA each instead of 24), both halves share the 16 products of z̃_top (8 DFMA
 // each instead of 16), each lane updates its own row and the pair's difference wd = w_top - w_bot goes back to shared memory.
+#ifndef SMPC_SMALL_SPLIT_Z
+#define SMPC_SMALL_SPLIT_Z 1
+#endif
+constexpr bool kSplitZ = SMPC_SMALL_SPLIT_Z;   // PAIRED: 1 = the half-warps share z̃_top's products (8 DFMA + shuffle), 0 = both sum all 16
 template <bool PAIRED>
 __global__ void __launch_bounds__(128, 3)
-admm_shared_small_kernel(SmallPackDev K, SharedPlanDev P, BatchDev Bt, SettingsDev S, int *queue, const int *lists) {
+admm_shared_small_kernel(SmallPackDev K, SharedPlanDev P, BatchDev Bt, SettingsDev S, int *queue, const int *lists, int quiet_cap) {
   constexpr int K1 = PAIRED ? NP : KH;       // terms of t summed by one half-warp
-  constexpr int K2 = PAIRED ? NP / 2 : NP;   // terms of z̃ summed by one lane
+  constexpr int K2 = (PAIRED && kSplitZ) ? NP / 2 : NP;   // terms of z̃ summed by one lane
   extern __shared__ __align__(16) double smem[];
+  __shared__ int s_rank, s_ticket;
   double *sV = smem + NP * NP * 2 + MP * NP;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // Quiet-SM scheduling (quiet_cap > 0: the grid fills every SM with three CTAs and the batch is a few waves, so the solve
+  // ends with its longest instances): the first Sq SMs to arrive keep ONE CTA (one warp per sub-partition, an
+  // iteration takes ~490 instead of ~740 cycles) and those warps take the hardest class first; the other two CTAs of a
+  // quiet SM leave at once.  Sq = ceil(min(size of the hardest class, 4 quiet_cap) / 4).  Only the schedule changes.
+  if (quiet_cap > 0 && threadIdx.x == 0) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    smid &= kSmSlots - 1;
+    const int rank = atomicAdd(queue + kQRank + smid, 1);
+    int t;
+    if (rank == 0) { t = atomicAdd(queue + kQSeen, 1); atomicExch(queue + kQTicket + smid, t + 1); }
+    else { do { t = atomicAdd(queue + kQTicket + smid, 0); } while (t == 0); t -= 1; }
+    s_rank = rank; s_ticket = t;
+  }
   double *cbuf = smem + kCtaMatDoubles + warp * kWarpDoubles, *tbuf = cbuf + NP + MP, *sbuf = tbuf + NP;
   const int h = lane >> 4, i = lane & 15;
   const int n = P.n, m = P.m, mp = m >> 1;
@@ -254,12 +297,13 @@ admm_shared_small_kernel(SmallPackDev K, SharedPlanDev P, BatchDev Bt, SettingsD
   const double E_r = K.E[rc];
   const int ct_r = K.ctype[rc];
   const double alpha = S.alpha, oma = 1.0 - S.alpha, c = P.c, cinv = P.cinv;
+  const double alpha_r = (PAIRED && h) ? -alpha : alpha;   // bottom row of a pair: z̃ = -z̃_top, (-alpha) z̃_top = alpha (-z̃_top) exactly
   const double qnan = __longlong_as_double(0x7ff8000000000000LL);
   const uint32_t a_cv = (uint32_t)__cvta_generic_to_shared(cbuf + K1 * h);   // this half-warp's entries of [xi; w] / [xi; wd]
   const uint32_t a_tv = (uint32_t)__cvta_generic_to_shared(tbuf);
   const uint32_t a_xi = (uint32_t)__cvta_generic_to_shared(cbuf + i);
   const uint32_t a_w = (uint32_t)__cvta_generic_to_shared(cbuf + NP + (PAIRED ? i : lane));
-  const uint32_t a_tz = PAIRED ? a_tv + 8 * K2 * h : a_tv;   // this lane's terms of z̃
+  const uint32_t a_tz = (PAIRED && kSplitZ) ? a_tv + 8 * K2 * h : a_tv;   // this lane's terms of z̃
   const uint32_t a_t = (uint32_t)__cvta_generic_to_shared(tbuf + i);
   const int check_every = S.check_every > 0 ? S.check_every : 0x7fffffff;
   const int adapt_every = (S.adaptive_rho && S.rho_interval > 0) ? S.rho_interval : 0x7fffffff;
@@ -275,26 +319,45 @@ admm_shared_small_kernel(SmallPackDev K, SharedPlanDev P, BatchDev Bt, SettingsD
     } else sts64(a_w, w);
   };
   auto by_row = [&](double v) { return PAIRED ? __shfl_sync(kFull, v, src) : v; };
+  int n_quiet = 0;            // instances of the hardest class reserved for the quiet SMs
+  bool quiet_warp = false;
+  if (quiet_cap > 0 && lists != nullptr) {
+    n_quiet = min(queue[1], 4 * quiet_cap);
+    const int sq = (n_quiet + 3) >> 2;
+    quiet_warp = s_ticket < sq && s_rank == 0;
+    if (s_ticket < sq && s_rank != 0) { release_queue_warp(queue, gridDim.x * (blockDim.x >> 5), lane); return; }
+  }
 
   for (;;) {
-    // longest-expected-first: the queue walks the difficulty classes written by classify_small_kernel
+    // longest-expected-first: the queue walks the difficulty classes written by classify_small_kernel (the first n_quiet
+    // instances of class 0 go to the quiet warps)
     int b = 0;
     if (lane == 0) {
-      int q = atomicAdd(queue, 1);
       b = -1;
-      if (q < Bt.B) {
-        if (lists == nullptr) b = q;
-        else {
+      if (quiet_warp) {
+        const int qh = atomicAdd(queue + kQHard, 1);
+        if (qh < n_quiet) b = lists[qh]; else quiet_warp = false;
+      }
+      if (b < 0) {
+        int q = atomicAdd(queue, 1);
+        if (q < Bt.B - n_quiet) {
+          if (lists == nullptr) b = q;
+          else {
 #pragma unroll
-          for (int k = 0; k < kClasses; ++k) {
-            const int cnt = queue[1 + k];
-            if (b < 0) { if (q < cnt) b = lists[(size_t)k * Bt.B + q]; else q -= cnt; }
+            for (int k = 0; k < kClasses; ++k) {
+              const int skip = k == 0 ? n_quiet : 0, cnt = queue[1 + k] - skip;
+              if (b < 0) { if (q < cnt) b = lists[(size_t)k * Bt.B + skip + q]; else q -= cnt; }
+            }
           }
         }
       }
     }
     b = __shfl_sync(kFull, b, 0);
     if (b < 0) break;
+#ifdef SMPC_SMALL_TIMELINE
+    unsigned long long tl0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tl0));
+#endif
 
     // ---- load the instance (osqp_update_lin_cost / osqp_update_bounds scaling)
     const bool warm = S.warm_start && !Bt.fresh;
@@ -349,7 +412,7 @@ admm_shared_small_kernel(SmallPackDev K, SharedPlanDev P, BatchDev Bt, SettingsD
         for (int j = 0; j < K1; ++j) m1[j] = __ldg(K.M1T + (K1 * h + j) * NP + i);
 #pragma unroll
         for (int k = 0; k < K2; ++k) {
-          if constexpr (PAIRED) wr[k] = i < mp ? __ldg(K.WT + (K2 * h + k) * MP + i) : 0.0;   // W_top(i, 8h + k)
+          if constexpr (PAIRED) wr[k] = i < mp ? __ldg(K.WT + ((kSplitZ ? K2 * h : 0) + k) * MP + i) : 0.0;   // W_top(i, k)
           else wr[k] = __ldg(K.WT + k * MP + r);
         }
         for (int s = 0; s < steps; ++s) {
@@ -379,12 +442,9 @@ admm_shared_small_kernel(SmallPackDev K, SharedPlanDev P, BatchDev Bt, SettingsD
             b2 = fma(wr[4 * j + 2], u1.x, b2); b3 = fma(wr[4 * j + 3], u1.y, b3);
           }
           double zt = (b0 + b1) + (b2 + b3);
-          if constexpr (PAIRED) {
-            zt += __shfl_xor_sync(kFull, zt, 16);   // the same bits in both halves (a + b = b + a)
-            zt = h ? -zt : zt;                      // bottom row = -top row
-          }
+          if constexpr (PAIRED && kSplitZ) zt += __shfl_xor_sync(kFull, zt, 16);   // the same bits in both halves (a + b = b + a)
           // ---- z, y updates (OSQP update_z / update_y re-associated, see the file header)
-          const double v = fma(alpha, zt, base_r);
+          const double v = fma(alpha_r, zt, base_r);
           const double zn = v < lb_r ? lb_r : (v > ub_r ? ub_r : v);
           const double yn = rv * (v - zn);
           store_w(rv * fma(2.0, zn, -v));   // w' = rho z - y'
@@ -398,7 +458,7 @@ admm_shared_small_kernel(SmallPackDev K, SharedPlanDev P, BatchDev Bt, SettingsD
         if (do_check) to_check = check_every;
         if (do_adapt) to_adapt = adapt_every;
         if (do_check || do_adapt) {
-          co = check_step(smem, cbuf, sbuf, S, n, m, c, cinv, LC, rho, qb_i, by_row(z_r), by_row(y_r), by_row(dy_r), dxi_i, by_row(lb_r), by_row(ub_r), do_check, false, do_adapt);
+          co = check_step(smem, cbuf, sbuf, S, n, m, c, cinv, LC, rho, qb_i, by_row(z_r), by_row(y_r), by_row(dy_r), dxi_i, by_row(lb_r), by_row(ub_r), do_check, false, do_adapt, iter >= S.max_iter);
           if (co.status != SMPC_UNSOLVED) { status = co.status; break; }
           if (co.rho_changed) {
             rho = co.rho; ++rho_updates;
@@ -411,11 +471,11 @@ admm_shared_small_kernel(SmallPackDev K, SharedPlanDev P, BatchDev Bt, SettingsD
       }
       if (status == SMPC_UNSOLVED) {
         if (!checked_last) {
-          co = check_step(smem, cbuf, sbuf, S, n, m, c, cinv, LC, rho, qb_i, by_row(z_r), by_row(y_r), by_row(dy_r), dxi_i, by_row(lb_r), by_row(ub_r), true, false, false);
+          co = check_step(smem, cbuf, sbuf, S, n, m, c, cinv, LC, rho, qb_i, by_row(z_r), by_row(y_r), by_row(dy_r), dxi_i, by_row(lb_r), by_row(ub_r), true, false, false, true);
           status = co.status;
         }
         if (status == SMPC_UNSOLVED) {
-          const CheckOut ca = check_step(smem, cbuf, sbuf, S, n, m, c, cinv, LC, rho, qb_i, by_row(z_r), by_row(y_r), by_row(dy_r), dxi_i, by_row(lb_r), by_row(ub_r), true, true, false);
+          const CheckOut ca = check_step(smem, cbuf, sbuf, S, n, m, c, cinv, LC, rho, qb_i, by_row(z_r), by_row(y_r), by_row(dy_r), dxi_i, by_row(lb_r), by_row(ub_r), true, true, false, true);
           status = ca.status == SMPC_UNSOLVED ? SMPC_MAX_ITER_REACHED : ca.status;
           if (ca.status != SMPC_UNSOLVED) co.obj = ca.obj;
         }
@@ -439,11 +499,20 @@ admm_shared_small_kernel(SmallPackDev K, SharedPlanDev P, BatchDev Bt, SettingsD
       Bt.rho[b] = rho;
       Bt.status[b] = status; Bt.iter[b] = iter; Bt.rho_updates[b] = rho_updates;
       Bt.obj[b] = co.obj; Bt.pri_res[b] = co.pri_res; Bt.dua_res[b] = co.dua_res;
+#ifdef SMPC_SMALL_TIMELINE
+      // development build (tests/dev/dev_small_timeline.py): start / end time and placement of every instance
+      unsigned long long tl1;
+      unsigned smid_tl;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tl1));
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid_tl));
+      Bt.pri_res[b] = (double)(tl0 & 0xffffffffffull); Bt.dua_res[b] = (double)(tl1 & 0xffffffffffull);
+      Bt.obj[b] = (double)(smid_tl * 2048 + blockIdx.x * 4 + warp) + (quiet_warp ? 0.5 : 0.0);
+#endif
       if (Bt.u_apply && status == SMPC_SOLVED) Bt.u_apply[b] = __dadd_rn(Bt.u_apply[b], __dmul_rn(LC.D, co.xbar));   // U += dU*[0] (cpp:105): x[0] rounded first, no FMA
     }
   }
   // the last warp of the grid to leave re-arms the queue for the next launch (no memset node per solve)
-  if (lane == 0) release_queue(queue, gridDim.x * (blockDim.x >> 5));
+  release_queue_warp(queue, gridDim.x * (blockDim.x >> 5), lane);
 }
 
 // =====================================================================================================================
@@ -615,7 +684,7 @@ admm_shared_small_mma_kernel(SmallPackDev K, SharedPlanDev P, BatchDev Bt, Setti
 #ifdef SMPC_PROFILE
               const long long tc = clock64();
 #endif
-              co = check_step(smem, cbuf, sbuf, S, n, m, c, cinv, LC, rho, qb_i, z_r, y_r, dy_r, dxi_i, lb_r, ub_r, do_check, false, do_adapt);
+              co = check_step(smem, cbuf, sbuf, S, n, m, c, cinv, LC, rho, qb_i, z_r, y_r, dy_r, dxi_i, lb_r, ub_r, do_check, false, do_adapt, at_max);
               status = co.status;
 #ifdef SMPC_PROFILE
               pf_chk += clock64() - tc;
@@ -628,11 +697,11 @@ admm_shared_small_mma_kernel(SmallPackDev K, SharedPlanDev P, BatchDev Bt, Setti
             }
             if (at_max && status == SMPC_UNSOLVED) {
               if (!do_check) {
-                co = check_step(smem, cbuf, sbuf, S, n, m, c, cinv, LC, rho, qb_i, z_r, y_r, dy_r, dxi_i, lb_r, ub_r, true, false, false);
+                co = check_step(smem, cbuf, sbuf, S, n, m, c, cinv, LC, rho, qb_i, z_r, y_r, dy_r, dxi_i, lb_r, ub_r, true, false, false, true);
                 status = co.status;
               }
               if (status == SMPC_UNSOLVED) {
-                const CheckOut ca = check_step(smem, cbuf, sbuf, S, n, m, c, cinv, LC, rho, qb_i, z_r, y_r, dy_r, dxi_i, lb_r, ub_r, true, true, false);
+                const CheckOut ca = check_step(smem, cbuf, sbuf, S, n, m, c, cinv, LC, rho, qb_i, z_r, y_r, dy_r, dxi_i, lb_r, ub_r, true, true, false, true);
                 status = ca.status == SMPC_UNSOLVED ? SMPC_MAX_ITER_REACHED : ca.status;
                 if (ca.status != SMPC_UNSOLVED) co.obj = ca.obj;
               }
@@ -807,7 +876,8 @@ bool small_kernel_supports(int n, int m) { return n >= 1 && n <= NP && m >= 0 &&
 
 size_t small_pack_doubles() { return (size_t)(NP + MP) * NP + NP * MP + 3 * NP * NP + MP * NP + 3 * NP + 2 * MP; }
 
-int small_queue_ints() { return 2 + kClasses; }
+int small_queue_ints() { return kQueueInts; }
+int small_sched_classes() { return kClasses; }
 
 // scheduling pre-pass: fills the class lists and sizes (the queue is zero on entry: cleared at upload and re-armed by
 // the last warp of every solve, see release_queue)
@@ -840,7 +910,8 @@ cudaError_t launch_admm_shared_small(const SmallPackDev &K, const SharedPlanDev 
   cudaError_t e = (lists && !classified) ? launch_classify_small(K, P, Bt, queue, lists, stream) : cudaSuccess;
   if (e != cudaSuccess) return e;
   int grid = (Bt.B + wpc - 1) / wpc;
-  const int resident = num_sms * 3;   // __launch_bounds__(128, 3): three CTAs (12 warps) per SM
+  static const int ctas_per_sm = [] { const char *e = getenv("SMPC_SMALL_CTAS"); const int v = e ? atoi(e) : 3; return v >= 1 && v <= 3 ? v : 3; }();
+  const int resident = num_sms * ctas_per_sm;   // __launch_bounds__(128, 3): at most three CTAs (12 warps) per SM
   if (grid > resident) grid = resident;
   // programmatic stream serialization: the prologue overlaps the tail of the preceding kernel (which must trigger it with
   // griddepcontrol.launch_dependents, as the MPC layer's kernels do; otherwise this is an ordinary serialized launch)
@@ -850,8 +921,12 @@ cudaError_t launch_admm_shared_small(const SmallPackDev &K, const SharedPlanDev 
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  if (K.mp > 0 && 2 * K.mp == P.m) return cudaLaunchKernelEx(&cfg, admm_shared_small_kernel<true>, K, P, Bt, S, queue, (const int *)lists);
-  return cudaLaunchKernelEx(&cfg, admm_shared_small_kernel<false>, K, P, Bt, S, queue, (const int *)lists);
+  // quiet SMs for the hardest class when the batch is a few waves of a full grid (the tail of the longest instances sets
+  // the time); deeper batches are throughput-bound and keep every warp slot busy
+  static const bool quiet_on = [] { const char *e = getenv("SMPC_SMALL_QUIET"); return !e || atoi(e) != 0; }();
+  const int quiet_cap = (quiet_on && lists && ctas_per_sm == 3 && grid == resident && Bt.B <= 4 * resident * wpc) ? (num_sms + 5) / 6 : 0;
+  if (K.mp > 0 && 2 * K.mp == P.m) return cudaLaunchKernelEx(&cfg, admm_shared_small_kernel<true>, K, P, Bt, S, queue, (const int *)lists, quiet_cap);
+  return cudaLaunchKernelEx(&cfg, admm_shared_small_kernel<false>, K, P, Bt, S, queue, (const int *)lists, quiet_cap);
 }
 
 }  // namespace smpc

@@ -156,7 +156,7 @@ int upload_small_pack(smpc_solver *s) {
   for (size_t c : {M1T.size(), WT.size(), VT.size(), PVT.size(), Ab.size(), V.size(), lam.size(), D.size(), Dinv.size(), E.size(), Einv.size()})
     bytes += DeviceBuf::need(c * sizeof(double));
   bytes += DeviceBuf::need(MP * sizeof(int)) + DeviceBuf::need(sizeof(int) * smpc::small_queue_ints()) +
-           DeviceBuf::need(sizeof(int) * (size_t)(smpc::small_queue_ints() - 1) * s->B);
+           DeviceBuf::need(sizeof(int) * (size_t)smpc::small_sched_classes() * s->B);
   CK(s->packbuf.alloc(bytes));
   auto put = [&](const std::vector<double> &v, const double **dst) -> cudaError_t {
     double *d = s->packbuf.take<double>(v.size());
@@ -171,7 +171,7 @@ int upload_small_pack(smpc_solver *s) {
   k.ctype = dct;
   k.mp = (p.pairs > 0 && 2 * p.pairs == p.m && !getenv("SMPC_SMALL_NO_PAIRS")) ? p.pairs : 0;
   s->d_queue = s->packbuf.take<int>(smpc::small_queue_ints());
-  s->d_lists = s->packbuf.take<int>((size_t)(smpc::small_queue_ints() - 1) * s->B);
+  s->d_lists = s->packbuf.take<int>((size_t)smpc::small_sched_classes() * s->B);
   if (!s->d_lists) return fail(SMPC_ERR_CUDA, "internal: pack buffer carve-out overflow");
   CK(cudaMemset(s->d_queue, 0, sizeof(int) * smpc::small_queue_ints()));
   int sms = 0;

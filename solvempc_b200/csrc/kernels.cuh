@@ -18,6 +18,7 @@ cudaError_t launch_warm_start(const SharedPlanDev &P, int B, const double *x, co
 bool small_kernel_supports(int n, int m);
 size_t small_pack_doubles();
 int small_queue_ints();
+int small_sched_classes();
 // lists != nullptr: longest-expected-first order; classified: the class lists were already filled for this solve (fused
 // into the MPC layer's step-vector kernel), so the stand-alone pre-pass is skipped
 cudaError_t launch_admm_shared_small(const SmallPackDev &K, const SharedPlanDev &P, const BatchDev &Bt,
