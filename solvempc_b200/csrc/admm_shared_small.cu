@@ -17,6 +17,7 @@
 // out-of-line routine that reads its operators from shared memory.
 #include <cstdint>
 #include <cstdio>
+#include <type_traits>
 #include <cstdlib>
 
 #include "classify.cuh"
@@ -415,7 +416,12 @@ admm_shared_small_kernel(SmallPackDev K, SharedPlanDev P, BatchDev Bt, SettingsD
           if constexpr (PAIRED) wr[k] = i < mp ? __ldg(K.WT + ((kSplitZ ? K2 * h : 0) + k) * MP + i) : 0.0;   // W_top(i, k)
           else wr[k] = __ldg(K.WT + k * MP + r);
         }
-        for (int s = 0; s < steps; ++s) {
+        // one ADMM iteration; LAST (the iteration a check follows) also leaves delta_xi, delta_y and y for check_step.
+        // In between y is carried as d = v - z (y = rho d, and y / rho = d goes straight into the next base).
+        double d_r = 0.0;
+        bool have_d = false;
+        auto iteration = [&](auto last) {
+          constexpr bool LAST = decltype(last)::value;
           // ---- t = (sigma G xi + W' w - q̂) ./ (1 + rho lambda): each half-warp sums half of the concatenated terms
           double a0 = nqh_i, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll
@@ -431,7 +437,8 @@ admm_shared_small_kernel(SmallPackDev K, SharedPlanDev P, BatchDev Bt, SettingsD
           __syncwarp();
           // x update (off the critical path of z̃)
           const double xn = fma(alpha, t_i, om_xi);
-          dxi_i = xn - xi_i; xi_i = xn; om_xi = oma * xn;
+          if constexpr (LAST) dxi_i = xn - xi_i;
+          xi_i = xn; om_xi = oma * xn;
           if (h == 0) sts64(a_xi, xn);
           // ---- z̃ = W t
           double b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
@@ -446,12 +453,18 @@ admm_shared_small_kernel(SmallPackDev K, SharedPlanDev P, BatchDev Bt, SettingsD
           // ---- z, y updates (OSQP update_z / update_y re-associated, see the file header)
           const double v = fma(alpha_r, zt, base_r);
           const double zn = v < lb_r ? lb_r : (v > ub_r ? ub_r : v);
-          const double yn = rv * (v - zn);
+          const double dn = v - zn;
           store_w(rv * fma(2.0, zn, -v));   // w' = rho z - y'
-          dy_r = yn - y_r; y_r = yn; z_r = zn;
-          base_r = fma(rinv, yn, oma * zn);
+          if constexpr (LAST) {
+            const double yo = have_d ? rv * d_r : y_r, yn = rv * dn;
+            dy_r = yn - yo; y_r = yn;
+          }
+          d_r = dn; z_r = zn;
+          base_r = fma(oma, zn, dn);
           __syncwarp();
-        }
+        };
+        for (int s = 0; s < steps - 1; ++s) { iteration(std::false_type{}); have_d = true; }
+        iteration(std::true_type{});
         iter += steps; to_check -= steps; to_adapt -= steps;
         const bool do_check = to_check == 0, do_adapt = to_adapt == 0;
         checked_last = do_check;
