@@ -35,6 +35,14 @@ warp = place.astype(np.int64)
 per = {}
 for b in range(len(it)):
     per.setdefault(int(warp[b]) % 2048, []).append(b)
+gaps = []
+for v in per.values():
+    v = sorted(v, key=lambda b: t0[b])
+    gaps += [t0[v[k + 1]] - t1[v[k]] for k in range(len(v) - 1)]
+gaps = np.array(gaps)
+print(f"gap between the end of an instance and the start of the warp's next: mean {gaps.mean():.2f} us, median {np.median(gaps):.2f}, p90 {np.percentile(gaps, 90):.2f}, max {gaps.max():.2f} ({len(gaps)} gaps)")
+first = np.array([min(t0[b] for b in v) for v in per.values()])
+print(f"first start per warp: median {np.median(first):.2f} us, max {first.max():.2f}")
 tot = np.array([sum(it[v]) for v in per.values()])
 print(f"warps used {len(per)}; iterations per warp mean {tot.mean():.0f} max {tot.max()} min {tot.min()}")
 s.close()
