@@ -9,7 +9,7 @@ JSON contract (c3: 12-state quadrotor N = 50, 131072 controllers per GPU = the 1
 per-instance plants N = 30; c5: warm-started closed loop of 65536 controllers, N = 100).  Weak scaling: every rank
 owns its own instances, no data-path collective; NCCL carries only the barrier and the max-over-ranks.
 
-  value        device-resident: inputs already in HBM; per step set_state (device) + controllerStep
+  value        device-resident: inputs already in HBM; per step set_state (device) + controllerStep (config 2: the one-call form controller_step_from)
   e2e          the same public call with HOST (pinned) inputs in and the control / status out inside the timed region
   roofline     the ADMM kernel against the FP64 pipe (DFMA / DMMA, one shared peak on B200; measured in this run);
                it keeps all iterates on chip, so HBM is touched once per solve -- the HBM-equivalent of a
@@ -152,13 +152,12 @@ class C2(Workload):
         self.d2h = int(self.B * 8 + self.B * 4)
 
     def step_device(self):
-        self.mpc.set_state(X=self.dev[0], U=self.dev[1], ref=self.dev[2])
-        self.mpc.controller_step_async()
+        # the body of the reference's loop (solver.cpp:45-55): write X, U, ref and run controllerStep, one public call
+        self.mpc.controller_step_from(self.dev[0], self.dev[1], self.dev[2])
 
     def step_e2e(self):
-        self.mpc.set_state(X=self.pin[0], U=self.pin[1], ref=self.pin[2])   # H2D from pinned memory
-        self.mpc.controller_step_async()
-        self.mpc.results_into(self.out_u, self.out_st)                      # D2H of the control and the status (one sync)
+        self.mpc.controller_step_from(self.pin[0], self.pin[1], self.pin[2])   # H2D from pinned memory (read by the step's first kernel)
+        self.mpc.results_into(self.out_u, self.out_st)                         # D2H of the control and the status (one sync)
 
     def nnz_A(self):
         return int(np.count_nonzero(self.mpc.matrix("Gbar")))

@@ -204,6 +204,12 @@ int smpc_mpc_set_state(smpc_mpc *m, const double *X, const double *U, const doub
 /* controllerStep (cpp:81-108): f and ub from X,U,ref -> updateGradient -> updateUpperBound ->
  * solve -> U += dU[0].  Asynchronous on the stream. */
 int smpc_mpc_controller_step(smpc_mpc *m);
+/* One iteration of main()'s loop body up to the solve (src/solver.cpp:45-55: write X, U, ref, then controllerStep) in one
+ * call: equivalent to smpc_mpc_set_state(m, X, U, ref, loc) + smpc_mpc_controller_step(m), all three arrays required.
+ * Device buffers and pinned host buffers are read where they lie by the step's first kernel (no gather launch in front; the
+ * controller's own X, U, ref are updated by that kernel); they must stay unchanged until the stream has run the step.
+ * Pageable host buffers, per-instance plants and the larger-QP kernels take the two-call path internally. */
+int smpc_mpc_controller_step_from(smpc_mpc *m, const double *X, const double *U, const double *ref, int loc);
 /* synthetic plant for closed-loop runs (the reference's plant is hardware): X <- Ad X + Bd U */
 int smpc_mpc_plant_step(smpc_mpc *m);
 /* Closed-loop driver: the reference's main loop (src/solver.cpp:43-74: read state -> controllerStep -> write U) for the

@@ -837,16 +837,47 @@ int smpc_mpc_set_state(smpc_mpc *M, const double *X, const double *U, const doub
   return SMPC_OK;
 }
 
+namespace {
+// the small-QP kernels' step: f, ub and the scheduling lists in one launch
+bool fused_step_available(const smpc_mpc *M) {
+  const smpc_solver *s = M->solver;
+  const bool small = s->regime == 0 && (s->kernel == 2 || s->kernel == 5);
+  return small && s->schedule && !M->per_instance && !s->have_l && M->dims.N <= 16;
+}
+// controllerStep reading the state from (X, U, ref); `keep`: they are the caller's buffers, copy them into the controller's own
+int mpc_step_impl(smpc_mpc *M, const double *X, const double *U, const double *ref, bool keep);
+}  // namespace
+
 int smpc_mpc_controller_step(smpc_mpc *M) {
   if (!M) return fail(SMPC_ERR_ARG, "null handle");
   CK(cudaSetDevice(M->device));
+  return mpc_step_impl(M, M->d_X, M->d_U, M->d_ref, false);
+}
+
+int smpc_mpc_controller_step_from(smpc_mpc *M, const double *X, const double *U, const double *ref, int loc) {
+  if (!M) return fail(SMPC_ERR_ARG, "null handle");
+  if (loc != SMPC_HOST && loc != SMPC_DEVICE) return fail(SMPC_ERR_ARG, "loc must be SMPC_HOST or SMPC_DEVICE");
+  if (!X || !U || !ref) return fail(SMPC_ERR_ARG, "controller_step_from: X, U and ref are all required");
+  CK(cudaSetDevice(M->device));
+  if (fused_step_available(M)) {
+    // device buffers, or pinned host buffers through their device view: the step's first kernel reads them where they lie
+    const double *vX = loc == SMPC_DEVICE ? X : pinned_device_view(X), *vU = loc == SMPC_DEVICE ? U : pinned_device_view(U),
+                 *vr = loc == SMPC_DEVICE ? ref : pinned_device_view(ref);
+    if (vX && vU && vr) return mpc_step_impl(M, vX, vU, vr, true);
+  }
+  const int rc = smpc_mpc_set_state(M, X, U, ref, loc);
+  return rc ? rc : mpc_step_impl(M, M->d_X, M->d_U, M->d_ref, false);
+}
+
+namespace {
+int mpc_step_impl(smpc_mpc *M, const double *X, const double *U, const double *ref, bool keep) {
   smpc_solver *s = M->solver;
   // setF (cpp:90), W0 + Sbar X + Ku U (cpp:99) written straight into the solver's q / u (updateGradient, updateUpperBound);
   // for the small-QP kernels the same launch also fills their longest-expected-first scheduling lists
-  const bool small = s->regime == 0 && (s->kernel == 2 || s->kernel == 5);
-  if (small && s->schedule && !M->per_instance && !s->have_l && M->dims.N <= 16) {
-    CK(smpc::launch_mpc_step_classify(M->dims, M->B, M->mats, M->d_X, M->d_U, M->d_ref, s->d_q, s->d_u, s->dpack, s->dplan,
-                                      s->d_queue + 1, s->d_lists, M->stream));
+  if (fused_step_available(M)) {
+    CK(smpc::launch_mpc_step_classify(M->dims, M->B, M->mats, X, U, ref, s->d_q, s->d_u, s->dpack, s->dplan,
+                                      s->d_queue + 1, s->d_lists, keep ? M->d_X : nullptr, keep ? M->d_U : nullptr,
+                                      keep ? M->d_ref : nullptr, M->stream));
     s->classified = true;
   } else {
     CK(smpc::launch_mpc_step_vectors(M->dims, M->B, M->per_instance, M->mats, M->d_X, M->d_U, M->d_ref, s->d_q, s->d_u, M->stream));
@@ -865,6 +896,7 @@ int smpc_mpc_controller_step(smpc_mpc *M) {
   }
   return SMPC_OK;
 }
+}  // namespace
 
 int smpc_mpc_plant_step(smpc_mpc *M) {
   if (!M) return fail(SMPC_ERR_ARG, "null handle");

@@ -64,7 +64,8 @@ cudaError_t launch_mpc_copy_state(int B, int nx, const double *X, const double *
 // counts = queue + 1, lists as launch_admm_shared_small takes them; lower bounds are the plan's (P.l0)
 cudaError_t launch_mpc_step_classify(const MpcDims &d, int B, const MpcMatsDev &mats, const double *X, const double *U,
                                      const double *ref, double *f, double *ub, const SmallPackDev &K, const SharedPlanDev &P,
-                                     int *counts, int *lists, cudaStream_t stream);
+                                     int *counts, int *lists, double *keepX, double *keepU, double *keepRef, cudaStream_t stream);
+// (keepX / keepU / keepRef != nullptr: X, U, ref are the caller's buffers and are also copied into the controller's own)
 // results to (pinned, device-mapped) host memory in one launch: U and the per-instance status (either may be NULL)
 cudaError_t launch_mpc_export(int B, const double *U, const int *status, double *outU, int *outStatus, cudaStream_t stream);
 // U += dU[0]

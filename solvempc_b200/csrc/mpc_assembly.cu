@@ -107,7 +107,8 @@ __global__ void mpc_step_vectors_kernel(MpcDims d, int B, int per_instance, MpcM
 __global__ void mpc_step_classify_kernel(MpcDims d, int B, MpcMatsDev mt, const double *__restrict__ X,
                                          const double *__restrict__ U, const double *__restrict__ ref,
                                          double *__restrict__ f, double *__restrict__ ub, SmallPackDev K, SharedPlanDev P,
-                                         int *counts, int *lists) {
+                                         int *counts, int *lists, double *__restrict__ keepX, double *__restrict__ keepU,
+                                         double *__restrict__ keepRef) {
   // let the ADMM kernel behind this one start its prologue now (programmatic dependent launch; it waits for this grid's
   // completion before it reads f, ub and the scheduling lists), then wait for the set_state gather kernel in front
   asm volatile("griddepcontrol.launch_dependents;");
@@ -128,6 +129,12 @@ __global__ void mpc_step_classify_kernel(MpcDims d, int B, MpcMatsDev mt, const 
   const int N = d.N, nx = d.nx;
   const double *x = X + (size_t)b * nx;
   const double u = U[b], r = ref[b];
+  // smpc_mpc_controller_step_from: X, U, ref are the caller's buffers (device or pinned host read over PCIe); the
+  // controller's own copies (the members X, U and the reference, h:186-187) are written here instead of by a gather kernel
+  if (keepX != nullptr) {
+    for (int c = lane; c < nx; c += 32) keepX[(size_t)b * nx + c] = x[c];
+    if (lane == 0) { keepU[b] = u; keepRef[b] = r; }
+  }
   double f_i = 0.0, ub_r = 0.0;
   if (lane < N) {
     const int i = lane;
@@ -265,7 +272,7 @@ cudaError_t launch_mpc_step_vectors(const MpcDims &d, int B, int per_instance, c
 }
 cudaError_t launch_mpc_step_classify(const MpcDims &d, int B, const MpcMatsDev &mats, const double *X, const double *U,
                                      const double *ref, double *f, double *ub, const SmallPackDev &K, const SharedPlanDev &P,
-                                     int *counts, int *lists, cudaStream_t stream) {
+                                     int *counts, int *lists, double *keepX, double *keepU, double *keepRef, cudaStream_t stream) {
   if (d.N > 16 || P.n != d.N || P.m != 2 * d.N) return cudaErrorInvalidValue;
   const int wpc = 8;
   cudaLaunchConfig_t cfg = {};
@@ -274,7 +281,7 @@ cudaError_t launch_mpc_step_classify(const MpcDims &d, int B, const MpcMatsDev &
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, mpc_step_classify_kernel, d, B, mats, X, U, ref, f, ub, K, P, counts, lists);
+  return cudaLaunchKernelEx(&cfg, mpc_step_classify_kernel, d, B, mats, X, U, ref, f, ub, K, P, counts, lists, keepX, keepU, keepRef);
 }
 cudaError_t launch_mpc_apply_control(int B, int n, const double *x, const int *status, double *U, cudaStream_t stream) {
   mpc_apply_control_kernel<<<(B + 255) / 256, 256, 0, stream>>>(B, n, x, status, U);

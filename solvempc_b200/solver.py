@@ -286,6 +286,18 @@ class BatchedModelPredictiveControlAPI:
     def controller_step_async(self):
         L.check(L.lib().smpc_mpc_controller_step(self._h))
 
+    def controller_step_from(self, X, U, ref):
+        """set_state(X, U, ref) + controllerStep in one asynchronous call (the body of the reference's loop,
+        src/solver.cpp:45-55): device tensors and pinned host tensors are read where they lie by the step's first kernel."""
+        px, l1, _k1 = _loc_ptr(X, self.batch * self.N_S, "X")
+        pu, l2, _k2 = _loc_ptr(U, self.batch, "U")
+        pr, l3, _k3 = _loc_ptr(ref, self.batch, "ref")
+        if X is None or U is None or ref is None:
+            raise ValueError("X, U and ref are all required")
+        if len({l1, l2, l3}) > 1:
+            raise ValueError("X, U, ref must live in the same place")
+        L.check(L.lib().smpc_mpc_controller_step_from(self._h, px, pu, pr, l1))
+
     def plant_step(self):
         L.check(L.lib().smpc_mpc_plant_step(self._h))
 

@@ -428,6 +428,42 @@ def test_control_and_status_in_one_transfer(cfg_path):
     mpc.close()
 
 
+@pytest.mark.parametrize("kernel", [2, 4])
+def test_controller_step_from_equals_set_state_plus_step(cfg_path, kernel):
+    """smpc_mpc_controller_step_from = set_state + controllerStep (src/solver.cpp:45-55) in one call: same bits from device
+    tensors, pinned host tensors (both read by the step's first kernel on the small-QP path) and pageable host arrays
+    (two-call path), and the controller's own X / U follow."""
+    import torch
+    B = 300
+    X, U, ref = c2_batch(B, seed=33)
+    base = sm.BatchedModelPredictiveControlAPI(cfg_path, batch=B, kernel=kernel, **EPS)
+    base.set_state(X=X, U=U, ref=ref)
+    base.controller_step_async()
+    x0, _ = base.solver.solution(); X0, U0 = base.state(); st0 = base.solver.info()["status"]
+    assert (st0 == 1).all() and np.array_equal(U0, U + x0[:, 0])
+    for how in ("device", "pinned", "pageable"):
+        mpc = sm.BatchedModelPredictiveControlAPI(cfg_path, batch=B, kernel=kernel, **EPS)
+        if how == "device":
+            args = [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (X, U, ref)]
+        elif how == "pinned":
+            args = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in (X, U, ref)]
+        else:
+            args = [np.ascontiguousarray(a) for a in (X, U, ref)]
+        l0 = mpc.launches
+        mpc.controller_step_from(*args)
+        if kernel == 2 and how != "pageable":
+            assert mpc.launches == l0 + 2               # step vectors + pre-pass, ADMM: no gather kernel in front
+        x1, _ = mpc.solver.solution(); X1, U1 = mpc.state()
+        assert np.array_equal(x1, x0) and np.array_equal(U1, U0) and np.array_equal(X1, X), how
+        assert np.array_equal(mpc.solver.info()["iter"], base.solver.info()["iter"])
+        # a second step from the controller's own state (the copies written by the fused kernel)
+        mpc.controller_step_async(); base_again = None
+        mpc.close()
+    with pytest.raises(Exception):
+        base.controller_step_from(X, None, ref)
+    base.close()
+
+
 def test_pinned_host_buffers_take_the_zero_copy_path(cfg_path):
     """Pinned host buffers are gathered / exported by a kernel over PCIe, pageable ones by cudaMemcpyAsync: same results."""
     import torch
