@@ -210,6 +210,13 @@ int smpc_mpc_controller_step(smpc_mpc *m);
  * controller's own X, U, ref are updated by that kernel); they must stay unchanged until the stream has run the step.
  * Pageable host buffers, per-instance plants and the larger-QP kernels take the two-call path internally. */
 int smpc_mpc_controller_step_from(smpc_mpc *m, const double *X, const double *U, const double *ref, int loc);
+/* What main() reads after controllerStep (src/solver.cpp:55-60: the flag and U), delivered by the step itself: every later
+ * controllerStep also writes U:[batch] (after U += dU[0]) and status:[batch] (OSQP numbers) to these buffers -- device
+ * memory or PINNED host memory (pageable host memory is refused: SMPC_ERR_ARG); either may be NULL, both NULL unbinds.  The
+ * one-warp small-QP kernel stores them as each instance ends, the other kernels are followed by one export launch.
+ * They are valid once the stream has run the step: smpc_mpc_sync. */
+int smpc_mpc_bind_results(smpc_mpc *m, double *U, int *status, int loc);
+int smpc_mpc_sync(smpc_mpc *m);
 /* synthetic plant for closed-loop runs (the reference's plant is hardware): X <- Ad X + Bd U */
 int smpc_mpc_plant_step(smpc_mpc *m);
 /* Closed-loop driver: the reference's main loop (src/solver.cpp:43-74: read state -> controllerStep -> write U) for the

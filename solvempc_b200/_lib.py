@@ -97,6 +97,8 @@ SIGNATURES = {
     "smpc_mpc_set_state": (_i, [_vp, _dp, _dp, _dp, _i]),
     "smpc_mpc_controller_step": (_i, [_vp]),
     "smpc_mpc_controller_step_from": (_i, [_vp, _dp, _dp, _dp, _i]),
+    "smpc_mpc_bind_results": (_i, [_vp, _vp, _vp, _i]),
+    "smpc_mpc_sync": (_i, [_vp]),
     "smpc_mpc_plant_step": (_i, [_vp]),
     "smpc_mpc_closed_loop": (_i, [_vp, _i, C.c_double, _i, _vp, _i, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
     "smpc_mpc_get_state": (_i, [_vp, _dp, _dp, _i]),

@@ -521,7 +521,13 @@ admm_shared_small_kernel(SmallPackDev K, SharedPlanDev P, BatchDev Bt, SettingsD
       Bt.pri_res[b] = (double)(tl0 & 0xffffffffffull); Bt.dua_res[b] = (double)(tl1 & 0xffffffffffull);
       Bt.obj[b] = (double)(smid_tl * 2048 + blockIdx.x * 4 + warp) + (quiet_warp ? 0.5 : 0.0);
 #endif
-      if (Bt.u_apply && status == SMPC_SOLVED) Bt.u_apply[b] = __dadd_rn(Bt.u_apply[b], __dmul_rn(LC.D, co.xbar));   // U += dU*[0] (cpp:105): x[0] rounded first, no FMA
+      if (Bt.u_apply) {
+        double un = 0.0;
+        if (status == SMPC_SOLVED || Bt.u_export) un = Bt.u_apply[b];
+        if (status == SMPC_SOLVED) { un = __dadd_rn(un, __dmul_rn(LC.D, co.xbar)); Bt.u_apply[b] = un; }   // U += dU*[0] (cpp:105): x[0] rounded first, no FMA
+        if (Bt.u_export) Bt.u_export[b] = un;                                                             // straight to the caller's (pinned) buffer
+      }
+      if (Bt.status_export) Bt.status_export[b] = status;
     }
   }
   // the last warp of the grid to leave re-arms the queue for the next launch (no memset node per solve)

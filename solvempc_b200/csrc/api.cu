@@ -62,6 +62,8 @@ struct smpc_mpc {
   int *d_phase = nullptr, *d_step = nullptr;          // closed-loop driver: per-instance phase, device step counter
   unsigned long long *d_stats = nullptr;              // [0] solves that did not reach SOLVED, [1] ADMM iterations
   smpc_solver *solver = nullptr;
+  double *bound_U = nullptr;       // smpc_mpc_bind_results: device views of the caller's result buffers
+  int *bound_status = nullptr;
   long long launches = 0;
 };
 
@@ -529,6 +531,8 @@ int smpc_solver_solve(smpc_solver *s) {
   b.obj = s->d_obj; b.pri_res = s->d_pri; b.dua_res = s->d_dua;
   b.fresh = s->cold_solves ? 1 : 0;
   b.u_apply = (s->regime == 0 && (s->kernel == 2 || s->kernel == 5)) ? s->u_apply : nullptr;
+  b.u_export = (s->regime == 0 && s->kernel == 2 && b.u_apply) ? s->u_export : nullptr;
+  b.status_export = (s->regime == 0 && s->kernel == 2) ? s->status_export : nullptr;
   smpc::SettingsDev sd = to_dev(s->st);
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   if (s->timing) {
@@ -886,12 +890,21 @@ int mpc_step_impl(smpc_mpc *M, const double *X, const double *U, const double *r
   s->have_q = true; s->have_u = true;
   // cpp:102 solve, cpp:105 U += dU*[0]: inside the small-QP kernels' store_solution, a separate kernel otherwise
   const bool fused = s->regime == 0 && (s->kernel == 2 || s->kernel == 5);
+  // bound result buffers (smpc_mpc_bind_results): written by the one-warp kernel as each instance ends, by an export
+  // kernel behind the solve otherwise
+  const bool bound = M->bound_U || M->bound_status, export_fused = bound && s->regime == 0 && s->kernel == 2;
   s->u_apply = fused ? M->d_U : nullptr;
+  s->u_export = export_fused ? M->bound_U : nullptr;
+  s->status_export = export_fused ? M->bound_status : nullptr;
   const int rc = smpc_solver_solve(s);
-  s->u_apply = nullptr;
+  s->u_apply = nullptr; s->u_export = nullptr; s->status_export = nullptr;
   if (rc) return rc;
   if (!fused) {
     CK(smpc::launch_mpc_apply_control(M->B, s->n, s->d_x, s->d_status, M->d_U, M->stream));
+    M->launches++;
+  }
+  if (bound && !export_fused) {
+    CK(smpc::launch_mpc_export(M->B, M->d_U, s->d_status, M->bound_U, M->bound_status, M->stream));
     M->launches++;
   }
   return SMPC_OK;
@@ -1000,6 +1013,28 @@ int smpc_mpc_get_control_status(smpc_mpc *M, double *U, int *status, int loc) {
   if (U) CK(cudaMemcpyAsync(U, M->d_U, sizeof(double) * M->B, k, M->stream));
   if (status) CK(cudaMemcpyAsync(status, M->solver->d_status, sizeof(int) * M->B, k, M->stream));
   if (loc == SMPC_HOST) CK(cudaStreamSynchronize(M->stream));
+  return SMPC_OK;
+}
+
+int smpc_mpc_bind_results(smpc_mpc *M, double *U, int *status, int loc) {
+  if (!M) return fail(SMPC_ERR_ARG, "null handle");
+  if (loc != SMPC_HOST && loc != SMPC_DEVICE) return fail(SMPC_ERR_ARG, "loc must be SMPC_HOST or SMPC_DEVICE");
+  CK(cudaSetDevice(M->device));
+  double *vU = U;
+  int *vs = status;
+  if (loc == SMPC_HOST) {
+    vU = pinned_device_view(U); vs = pinned_device_view(status);
+    if ((U && !vU) || (status && !vs))
+      return fail(SMPC_ERR_ARG, "bind_results: host buffers must be pinned (cudaHostAlloc / cudaHostRegister); use smpc_mpc_get_control_status for pageable memory");
+  }
+  M->bound_U = vU; M->bound_status = vs;
+  return SMPC_OK;
+}
+
+int smpc_mpc_sync(smpc_mpc *M) {
+  if (!M) return fail(SMPC_ERR_ARG, "null handle");
+  CK(cudaSetDevice(M->device));
+  CK(cudaStreamSynchronize(M->stream));
   return SMPC_OK;
 }
 

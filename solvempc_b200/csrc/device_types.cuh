@@ -92,6 +92,8 @@ struct BatchDev {
   double *obj, *pri_res, *dua_res;       // [B]
   double *u_apply;      // [B] or NULL: MPC layer's U, incremented by x[0] of every instance that ends SOLVED (cpp:105);
                         // honoured by the small-QP kernels only (the API launches mpc_apply_control_kernel otherwise)
+  double *u_export;     // [B] or NULL: where the caller wants U after the step (device or pinned host, smpc_mpc_bind_results) and
+  int *status_export;   // [B] or NULL: the statuses; written by admm_shared_small_kernel as each instance ends
 };
 
 }  // namespace smpc

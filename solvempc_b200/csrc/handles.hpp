@@ -67,6 +67,8 @@ struct smpc_solver {
   int kernel = 1;
   bool classified = false;     // the scheduling lists of the next solve were filled by the MPC layer's fused step-vector kernel
   double *u_apply = nullptr;   // MPC layer: U to increment inside the small-QP kernels' store (cpp:105), else NULL
+  double *u_export = nullptr;  // MPC layer: bound result buffers (smpc_mpc_bind_results) for this solve, kernel 2 only
+  int *status_export = nullptr;
   bool solved_once = false;
   bool cold_solves = false, timing = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;   // pending kernel timings

@@ -332,6 +332,28 @@ class BatchedModelPredictiveControlAPI:
             raise ValueError("U and status must live in the same place")
         L.check(L.lib().smpc_mpc_get_control_status(self._h, pu, ps, l1))
 
+    def bind_results(self, U=None, status=None):
+        """Every later controllerStep also writes U (float64) and the statuses (int32) to these device or PINNED host tensors
+        (what the reference's loop reads after the step, src/solver.cpp:55-60); valid after sync().  None, None unbinds."""
+        self._bound = (U, status)                       # keep the buffers alive
+        if U is None and status is None:
+            L.check(L.lib().smpc_mpc_bind_results(self._h, None, None, L.HOST))
+            return
+        pu, l1, _k1 = _loc_ptr(U, self.batch, "U") if U is not None else (None, None, None)
+        ps, l2 = None, None
+        if status is not None:
+            if hasattr(status, "data_ptr"):
+                ps, l2 = status.data_ptr(), (L.DEVICE if status.is_cuda else L.HOST)
+            else:
+                ps, l2 = status.ctypes.data, L.HOST
+        locs = {l for l in (l1, l2) if l is not None}
+        if len(locs) > 1:
+            raise ValueError("U and status must live in the same place")
+        L.check(L.lib().smpc_mpc_bind_results(self._h, pu, ps, locs.pop()))
+
+    def sync(self):
+        L.check(L.lib().smpc_mpc_sync(self._h))
+
     def step_vectors(self):
         f, ub = np.empty((self.batch, self.n_variables)), np.empty((self.batch, self.n_constraints))
         L.check(L.lib().smpc_mpc_get_step_vectors(self._h, f.ctypes.data, ub.ctypes.data, L.HOST))

@@ -464,6 +464,46 @@ def test_controller_step_from_equals_set_state_plus_step(cfg_path, kernel):
     base.close()
 
 
+@pytest.mark.parametrize("kernel", [2, 4])
+def test_bound_results_follow_every_step(cfg_path, kernel):
+    """smpc_mpc_bind_results: U and the statuses land in the caller's pinned (or device) buffers with the step itself -- stored by
+    the one-warp kernel as each instance ends, by one export launch behind the other kernels -- and equal what
+    get_control_status returns; pageable host memory is refused."""
+    import torch
+    B = 513
+    X, U, ref = c2_batch(B, seed=5)
+    mpc = sm.BatchedModelPredictiveControlAPI(cfg_path, batch=B, kernel=kernel, **EPS)
+    Uo, st = torch.zeros(B, dtype=torch.float64).pin_memory(), torch.zeros(B, dtype=torch.int32).pin_memory()
+    mpc.bind_results(Uo, st)
+    mpc.controller_step_from(X, U, ref)
+    mpc.sync()
+    U1, s1 = np.empty(B), np.empty(B, np.int32)
+    mpc.results_into(U1, s1)
+    x, _ = mpc.solver.solution()
+    assert np.array_equal(Uo.numpy(), U1) and np.array_equal(st.numpy(), s1) and (s1 == 1).all()
+    assert np.array_equal(U1, U + x[:, 0])
+    # a state far outside the operating range: whatever the status, the buffers still equal the controller's own U / status
+    Xb = X.copy(); Xb[7] = [50.0, 0.0, 50.0, 0.0]
+    mpc.controller_step_from(Xb, U, ref)
+    mpc.sync()
+    mpc.results_into(U1, s1)
+    assert np.array_equal(Uo.numpy(), U1) and np.array_equal(st.numpy(), s1)
+    if s1[7] != 1:
+        assert U1[7] == U[7]
+    dU, ds = torch.zeros(B, dtype=torch.float64, device="cuda"), torch.zeros(B, dtype=torch.int32, device="cuda")
+    mpc.bind_results(dU, ds)
+    mpc.controller_step_from(X, U, ref); mpc.sync()
+    mpc.results_into(U1, s1)
+    assert np.array_equal(dU.cpu().numpy(), U1) and np.array_equal(ds.cpu().numpy(), s1)
+    with pytest.raises(Exception):
+        mpc.bind_results(np.zeros(B), np.zeros(B, np.int32))          # pageable host memory
+    mpc.bind_results(None, None)
+    Uo.zero_()
+    mpc.controller_step_from(X, U, ref); mpc.sync()
+    assert (Uo.numpy() == 0).all()                                     # unbound
+    mpc.close()
+
+
 def test_pinned_host_buffers_take_the_zero_copy_path(cfg_path):
     """Pinned host buffers are gathered / exported by a kernel over PCIe, pageable ones by cudaMemcpyAsync: same results."""
     import torch
