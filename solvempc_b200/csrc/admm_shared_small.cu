@@ -106,37 +106,73 @@ struct LaneConst {          // per-lane constants of the plan
 
 // OSQP update_info + check_termination (+ is_primal_infeasible / is_dual_infeasible) + adapt_rho for one QP.
 // Everything it returns except xbar is uniform across the warp.  cbuf[0..15] must hold the current xi.
+// PM = false: lane = row (L.E, L.Einv, z_r, ... of row `lane`).
+// PM = true (row pairs [G; -G], the lane mapping of admm_shared_small_kernel<true>): lane (h, i) owns row h*mp + i for
+// i < mp (L.E, L.Einv, z_r, ... of THAT row; padded lanes carry z = y = 0, l = -1, u = 1) and the products use the pairs:
+// A̅'y = A̅_top'(y_top - y_bot), (A̅ v)_bot = -(A̅ v)_top, 8 terms per half-warp.
+// dot of 8 operator entries op[(8h + k) * stride + i] with vec[8h + k], two accumulators (vec read as LDS.128)
+__device__ __forceinline__ double half_dot8(const double *op, int stride, const double *vec, int h, int i) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(vec + 8 * h);
+  double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const double2 v = lds128(a + 16 * j);
+    s0 = fma(op[(8 * h + 2 * j) * stride + i], v.x, s0);
+    s1 = fma(op[(8 * h + 2 * j + 1) * stride + i], v.y, s1);
+  }
+  const double s = s0 + s1;
+  return s + __shfl_xor_sync(kFull, s, 16);
+}
+template <bool PM>
 __device__ __noinline__ CheckOut check_step(const double *sm, double *cbuf, double *sbuf, const SettingsDev &S, int n, int m,
                                             double c, double cinv, LaneConst L, double rho, double qb_i, double z_r,
                                             double y_r, double dy_r, double dxi_i, double lb_r, double ub_r,
                                             bool do_check, bool approx, bool do_adapt, bool want_obj) {
   const double *sVT = sm, *sPVT = sVT + NP * NP, *sAb = sPVT + NP * NP, *sAbT = sAb + MP * NP + NP * NP;
   const int lane = threadIdx.x & 31, h = lane >> 4, i = lane & 15, r = lane;
+  const bool row_ok = PM ? i < (m >> 1) : r < m;    // this lane owns a row
   const bool unscale = !S.scaled_termination;
   CheckOut o;
   o.rho = rho; o.status = SMPC_UNSOLVED; o.rho_changed = 0;
-  sbuf[r] = y_r;
-  __syncwarp();
-  double ax = 0.0, apx = 0.0, aty = 0.0;
+  double ax, apx, aty, Ax_r;
+  if constexpr (PM) {
+    const double yo = __shfl_xor_sync(kFull, y_r, 16);
+    if (h == 0) sbuf[i] = y_r - yo;                  // y_top - y_bot of pair i (0 on padded lanes)
+    __syncwarp();
+    ax = half_dot8(sVT, NP, cbuf, h, i);
+    apx = half_dot8(sPVT, NP, cbuf, h, i);
+    aty = half_dot8(sAb, NP, sbuf, h, i);            // rows 0 .. mp-1 of A̅ are the top rows
+    o.xbar = ax;
+    __syncwarp();
+    if (h == 0) sbuf[i] = ax;                        // x̄ for A̅ x̄
+    __syncwarp();
+    const double at = half_dot8(sAbT, MP, sbuf, h, i);
+    Ax_r = row_ok ? (h ? -at : at) : 0.0;
+    __syncwarp();
+  } else {
+    sbuf[r] = y_r;
+    __syncwarp();
+    ax = 0.0; apx = 0.0; aty = 0.0;
 #pragma unroll
-  for (int k = 0; k < NP / 2; ++k) {
-    const double xk = cbuf[8 * h + k];
-    ax = fma(sVT[(8 * h + k) * NP + i], xk, ax);
-    apx = fma(sPVT[(8 * h + k) * NP + i], xk, apx);
+    for (int k = 0; k < NP / 2; ++k) {
+      const double xk = cbuf[8 * h + k];
+      ax = fma(sVT[(8 * h + k) * NP + i], xk, ax);
+      apx = fma(sPVT[(8 * h + k) * NP + i], xk, apx);
+    }
+#pragma unroll
+    for (int k = 0; k < MP / 2; ++k) aty = fma(sAb[(16 * h + k) * NP + i], sbuf[16 * h + k], aty);
+    ax += __shfl_xor_sync(kFull, ax, 16);
+    apx += __shfl_xor_sync(kFull, apx, 16);
+    aty += __shfl_xor_sync(kFull, aty, 16);
+    o.xbar = ax;
+    __syncwarp();
+    if (h == 0) sbuf[i] = ax;          // x̄ for A̅ x̄
+    __syncwarp();
+    Ax_r = 0.0;
+#pragma unroll
+    for (int k = 0; k < NP; ++k) Ax_r = fma(sAbT[k * MP + r], sbuf[k], Ax_r);
+    __syncwarp();
   }
-#pragma unroll
-  for (int k = 0; k < MP / 2; ++k) aty = fma(sAb[(16 * h + k) * NP + i], sbuf[16 * h + k], aty);
-  ax += __shfl_xor_sync(kFull, ax, 16);
-  apx += __shfl_xor_sync(kFull, apx, 16);
-  aty += __shfl_xor_sync(kFull, aty, 16);
-  o.xbar = ax;
-  __syncwarp();
-  if (h == 0) sbuf[i] = ax;          // x̄ for A̅ x̄
-  __syncwarp();
-  double Ax_r = 0.0;
-#pragma unroll
-  for (int k = 0; k < NP; ++k) Ax_r = fma(sAbT[k * MP + r], sbuf[k], Ax_r);
-  __syncwarp();
   const double rp = Ax_r - z_r, rd = (qb_i + apx) + aty;
   const double s_rp = wmax_nn(fabs(rp)), s_z = wmax_nn(fabs(z_r)), s_Ax = wmax_nn(fabs(Ax_r));
   const double s_rd = wmax_nn(fabs(rd)), s_q = wmax_nn(fabs(qb_i)), s_Aty = wmax_nn(fabs(aty)), s_Px = wmax_nn(fabs(apx));
@@ -170,12 +206,19 @@ __device__ __noinline__ CheckOut check_step(const double *sm, double *cbuf, doub
         if (dm != 0.0) lhs += lb_r * dm;
         lhs = wsum(lhs);
         if (lhs < -epi * nd) {
-          sbuf[r] = d;
-          __syncwarp();
           double a = 0.0;
+          if constexpr (PM) {
+            const double d_other = __shfl_xor_sync(kFull, d, 16);
+            if (h == 0) sbuf[i] = d - d_other;
+            __syncwarp();
+            a = half_dot8(sAb, NP, sbuf, h, i);
+          } else {
+            sbuf[r] = d;
+            __syncwarp();
 #pragma unroll
-          for (int k = 0; k < MP / 2; ++k) a = fma(sAb[(16 * h + k) * NP + i], sbuf[16 * h + k], a);
-          a += __shfl_xor_sync(kFull, a, 16);
+            for (int k = 0; k < MP / 2; ++k) a = fma(sAb[(16 * h + k) * NP + i], sbuf[16 * h + k], a);
+            a += __shfl_xor_sync(kFull, a, 16);
+          }
           __syncwarp();
           prim_inf = wmax_nn(fabs(unscale ? L.Dinv * a : a)) < epi * nd;
         }
@@ -188,26 +231,37 @@ __device__ __noinline__ CheckOut check_step(const double *sm, double *cbuf, doub
       if (h == 0) sbuf[i] = dxi_i;
       __syncwarp();
       double dx = 0.0;
+      if constexpr (PM) dx = half_dot8(sVT, NP, sbuf, h, i);
+      else {
 #pragma unroll
-      for (int k = 0; k < NP / 2; ++k) dx = fma(sVT[(8 * h + k) * NP + i], sbuf[8 * h + k], dx);
-      dx += __shfl_xor_sync(kFull, dx, 16);
+        for (int k = 0; k < NP / 2; ++k) dx = fma(sVT[(8 * h + k) * NP + i], sbuf[8 * h + k], dx);
+        dx += __shfl_xor_sync(kFull, dx, 16);
+      }
       const double nd = wmax_nn(fabs(unscale ? L.D * dx : dx));
       const double cs = unscale ? c : 1.0;
       if (nd > edi && wsum(h == 0 ? qb_i * dx : 0.0) < -cs * edi * nd) {
         double pd = 0.0;
+        if constexpr (PM) pd = half_dot8(sPVT, NP, sbuf, h, i);
+        else {
 #pragma unroll
-        for (int k = 0; k < NP / 2; ++k) pd = fma(sPVT[(8 * h + k) * NP + i], sbuf[8 * h + k], pd);
-        pd += __shfl_xor_sync(kFull, pd, 16);
+          for (int k = 0; k < NP / 2; ++k) pd = fma(sPVT[(8 * h + k) * NP + i], sbuf[8 * h + k], pd);
+          pd += __shfl_xor_sync(kFull, pd, 16);
+        }
         if (wmax_nn(fabs(unscale ? L.Dinv * pd : pd)) < cs * edi * nd) {
           __syncwarp();
           if (h == 0) sbuf[i] = dx;
           __syncwarp();
           double ad = 0.0;
+          if constexpr (PM) {
+            const double at = half_dot8(sAbT, MP, sbuf, h, i);
+            ad = h ? -at : at;
+          } else {
 #pragma unroll
-          for (int k = 0; k < NP; ++k) ad = fma(sAbT[k * MP + r], sbuf[k], ad);
+            for (int k = 0; k < NP; ++k) ad = fma(sAbT[k * MP + r], sbuf[k], ad);
+          }
           if (unscale) ad *= L.Einv;
           const int bad = ((ub_r < kInfty * kMinScaling) && (ad > edi * nd)) || ((lb_r > -kInfty * kMinScaling) && (ad < -edi * nd));
-          dual_inf = !__any_sync(kFull, bad && r < m);
+          dual_inf = !__any_sync(kFull, bad && row_ok);
         }
       }
       __syncwarp();
@@ -278,10 +332,9 @@ admm_shared_small_kernel(SmallPackDev K, SharedPlanDev P, BatchDev Bt, SettingsD
   double *cbuf = smem + kCtaMatDoubles + warp * kWarpDoubles, *tbuf = cbuf + NP + MP, *sbuf = tbuf + NP;
   const int h = lane >> 4, i = lane & 15;
   const int n = P.n, m = P.m, mp = m >> 1;
-  // r: the row this lane iterates on (MP = none); PAIRED: lane src holds row `lane` (check_step wants lane = row)
+  // r: the row this lane owns (MP = none)
   const int r = PAIRED ? (i < mp ? h * mp + i : MP) : lane;
   const int rc = r < MP ? r : MP - 1;
-  const int src = lane < mp ? lane : (lane < m ? 16 + lane - mp : 15);
 
   for (int e = threadIdx.x; e < NP * NP; e += blockDim.x) {
     smem[e] = K.VT[e]; smem[NP * NP + e] = K.PVT[e]; sV[e] = K.V[e];
@@ -294,9 +347,9 @@ admm_shared_small_kernel(SmallPackDev K, SharedPlanDev P, BatchDev Bt, SettingsD
 
   const double lam_i = K.lam[i];
   LaneConst LC;
-  LC.D = K.D[i]; LC.Dinv = K.Dinv[i]; LC.E = K.E[lane]; LC.Einv = K.Einv[lane]; LC.ct = K.ctype[lane];   // lane = row (check_step)
-  const double E_r = K.E[rc];
-  const int ct_r = K.ctype[rc];
+  LC.D = K.D[i]; LC.Dinv = K.Dinv[i]; LC.E = K.E[rc]; LC.Einv = K.Einv[rc]; LC.ct = K.ctype[rc];   // of the lane's own row
+  const double E_r = LC.E;
+  const int ct_r = LC.ct;
   const double alpha = S.alpha, oma = 1.0 - S.alpha, c = P.c, cinv = P.cinv;
   const double alpha_r = (PAIRED && h) ? -alpha : alpha;   // bottom row of a pair: z̃ = -z̃_top, (-alpha) z̃_top = alpha (-z̃_top) exactly
   const double qnan = __longlong_as_double(0x7ff8000000000000LL);
@@ -319,7 +372,6 @@ admm_shared_small_kernel(SmallPackDev K, SharedPlanDev P, BatchDev Bt, SettingsD
       if (h == 0) sts64(a_w, w - wo);
     } else sts64(a_w, w);
   };
-  auto by_row = [&](double v) { return PAIRED ? __shfl_sync(kFull, v, src) : v; };
   int n_quiet = 0;            // instances of the hardest class reserved for the quiet SMs
   bool quiet_warp = false;
   if (quiet_cap > 0 && lists != nullptr) {
@@ -471,7 +523,7 @@ admm_shared_small_kernel(SmallPackDev K, SharedPlanDev P, BatchDev Bt, SettingsD
         if (do_check) to_check = check_every;
         if (do_adapt) to_adapt = adapt_every;
         if (do_check || do_adapt) {
-          co = check_step(smem, cbuf, sbuf, S, n, m, c, cinv, LC, rho, qb_i, by_row(z_r), by_row(y_r), by_row(dy_r), dxi_i, by_row(lb_r), by_row(ub_r), do_check, false, do_adapt, iter >= S.max_iter);
+          co = check_step<PAIRED>(smem, cbuf, sbuf, S, n, m, c, cinv, LC, rho, qb_i, z_r, y_r, dy_r, dxi_i, lb_r, ub_r, do_check, false, do_adapt, iter >= S.max_iter);
           if (co.status != SMPC_UNSOLVED) { status = co.status; break; }
           if (co.rho_changed) {
             rho = co.rho; ++rho_updates;
@@ -484,11 +536,11 @@ admm_shared_small_kernel(SmallPackDev K, SharedPlanDev P, BatchDev Bt, SettingsD
       }
       if (status == SMPC_UNSOLVED) {
         if (!checked_last) {
-          co = check_step(smem, cbuf, sbuf, S, n, m, c, cinv, LC, rho, qb_i, by_row(z_r), by_row(y_r), by_row(dy_r), dxi_i, by_row(lb_r), by_row(ub_r), true, false, false, true);
+          co = check_step<PAIRED>(smem, cbuf, sbuf, S, n, m, c, cinv, LC, rho, qb_i, z_r, y_r, dy_r, dxi_i, lb_r, ub_r, true, false, false, true);
           status = co.status;
         }
         if (status == SMPC_UNSOLVED) {
-          const CheckOut ca = check_step(smem, cbuf, sbuf, S, n, m, c, cinv, LC, rho, qb_i, by_row(z_r), by_row(y_r), by_row(dy_r), dxi_i, by_row(lb_r), by_row(ub_r), true, true, false, true);
+          const CheckOut ca = check_step<PAIRED>(smem, cbuf, sbuf, S, n, m, c, cinv, LC, rho, qb_i, z_r, y_r, dy_r, dxi_i, lb_r, ub_r, true, true, false, true);
           status = ca.status == SMPC_UNSOLVED ? SMPC_MAX_ITER_REACHED : ca.status;
           if (ca.status != SMPC_UNSOLVED) co.obj = ca.obj;
         }
@@ -703,7 +755,7 @@ admm_shared_small_mma_kernel(SmallPackDev K, SharedPlanDev P, BatchDev Bt, Setti
 #ifdef SMPC_PROFILE
               const long long tc = clock64();
 #endif
-              co = check_step(smem, cbuf, sbuf, S, n, m, c, cinv, LC, rho, qb_i, z_r, y_r, dy_r, dxi_i, lb_r, ub_r, do_check, false, do_adapt, at_max);
+              co = check_step<false>(smem, cbuf, sbuf, S, n, m, c, cinv, LC, rho, qb_i, z_r, y_r, dy_r, dxi_i, lb_r, ub_r, do_check, false, do_adapt, at_max);
               status = co.status;
 #ifdef SMPC_PROFILE
               pf_chk += clock64() - tc;
@@ -716,11 +768,11 @@ admm_shared_small_mma_kernel(SmallPackDev K, SharedPlanDev P, BatchDev Bt, Setti
             }
             if (at_max && status == SMPC_UNSOLVED) {
               if (!do_check) {
-                co = check_step(smem, cbuf, sbuf, S, n, m, c, cinv, LC, rho, qb_i, z_r, y_r, dy_r, dxi_i, lb_r, ub_r, true, false, false, true);
+                co = check_step<false>(smem, cbuf, sbuf, S, n, m, c, cinv, LC, rho, qb_i, z_r, y_r, dy_r, dxi_i, lb_r, ub_r, true, false, false, true);
                 status = co.status;
               }
               if (status == SMPC_UNSOLVED) {
-                const CheckOut ca = check_step(smem, cbuf, sbuf, S, n, m, c, cinv, LC, rho, qb_i, z_r, y_r, dy_r, dxi_i, lb_r, ub_r, true, true, false, true);
+                const CheckOut ca = check_step<false>(smem, cbuf, sbuf, S, n, m, c, cinv, LC, rho, qb_i, z_r, y_r, dy_r, dxi_i, lb_r, ub_r, true, true, false, true);
                 status = ca.status == SMPC_UNSOLVED ? SMPC_MAX_ITER_REACHED : ca.status;
                 if (ca.status != SMPC_UNSOLVED) co.obj = ca.obj;
               }
