@@ -15,6 +15,13 @@
 // re-associated; y' is exactly 0 on rows that are not clipped).
 // Termination checks / rho adaptation (every check_termination / adaptive_rho_interval iterations) are an
 // out-of-line routine that reads its operators from shared memory.
+// When the constraint rows are [G; -G] (the reference's two-sided limit, cpp:335) the PAIRED instantiation multiplies the
+// top half of W only (16 + 8 DFMA per lane-iteration, lane (h, i) owns row h*mp + i; see the kernel's comment).
+// Scheduling: the queue walks the difficulty classes of classify.cuh longest-expected-first; when the batch is only a few
+// waves of a full grid, the hardest class runs on "quiet" SMs that keep one warp per sub-partition (see the kernel).
+// Development knobs (environment, read once per process): SMPC_SMALL_QUIET=0 switches the quiet SMs off, SMPC_SMALL_CTAS=1..3
+// limits the resident CTAs per SM, SMPC_SMALL_NO_PAIRS=1 (at solver creation) selects the unpaired instantiation;
+// -DSMPC_SMALL_TIMELINE builds the per-instance timeline of tests/dev/dev_small_timeline.py (it overwrites obj / residuals).
 #include <cstdint>
 #include <cstdio>
 #include <type_traits>
