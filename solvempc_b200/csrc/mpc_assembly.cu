@@ -102,6 +102,63 @@ __global__ void mpc_step_vectors_kernel(MpcDims d, int B, int per_instance, MpcM
   }
 }
 
+// Shared plant: one warp carries G consecutive instances through the same sweep, so every operator entry is loaded once per G
+// instances (the sweep of Fr is L1-bandwidth bound otherwise).  Per instance the operations and their order are those of
+// mpc_step_vectors_kernel: same bits.
+template <int G>
+__global__ void mpc_step_vectors_shared_kernel(MpcDims d, int B, MpcMatsDev mt, const double *__restrict__ X,
+                                               const double *__restrict__ U, const double *__restrict__ ref,
+                                               double *__restrict__ f, double *__restrict__ ub) {
+  const int lane = threadIdx.x & 31, b0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * G;
+  if (b0 >= B) return;
+  const int N = d.N, nx = d.nx;
+  const double *__restrict__ Fx = mt.Fx, *__restrict__ Fu = mt.Fu, *__restrict__ FrT = mt.FrT;
+  const double *__restrict__ Sbar = mt.Sbar, *__restrict__ Ku = mt.Ku, *__restrict__ W0 = mt.W0;
+  size_t bg[G];
+  double u[G], r[G];
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    bg[g] = (size_t)min(b0 + g, B - 1);      // the tail warp repeats the last instance (stores are guarded)
+    u[g] = U[bg[g]]; r[g] = ref[bg[g]];
+  }
+  for (int i = lane; i < N; i += 32) {
+    double s[G], rr[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) { s[g] = 0.0; rr[g] = 0.0; }
+    for (int c = 0; c < nx; ++c) {
+      const double fx = Fx[i * nx + c];
+#pragma unroll
+      for (int g = 0; g < G; ++g) s[g] += fx * X[bg[g] * nx + c];
+    }
+    const double fu = Fu[i];
+#pragma unroll
+    for (int g = 0; g < G; ++g) s[g] += fu * u[g];
+#pragma unroll 4
+    for (int j = i; j < N; ++j) {
+      const double v = __ldg(FrT + (size_t)j * N + i);   // Fr(i,j) = 0 for j < i
+#pragma unroll
+      for (int g = 0; g < G; ++g) rr[g] += v * r[g];
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+      if (b0 + g < B) f[bg[g] * N + i] = s[g] + rr[g];
+  }
+  for (int i = lane; i < 2 * N; i += 32) {
+    double s[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) s[g] = 0.0;
+    for (int c = 0; c < nx; ++c) {
+      const double sb = Sbar[i * nx + c];
+#pragma unroll
+      for (int g = 0; g < G; ++g) s[g] += sb * X[bg[g] * nx + c];
+    }
+    const double w0 = W0[i], ku = Ku[i];
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+      if (b0 + g < B) ub[bg[g] * 2 * N + i] = (w0 + s[g]) + ku * u[g];
+  }
+}
+
 // The same for a shared plant with N <= 16 (n = N <= 16, m = 2N <= 32: lane = row), fused with the scheduling pre-pass of
 // the small-QP kernels: the warp that produced f and ub classifies its instance at once.
 __global__ void mpc_step_classify_kernel(MpcDims d, int B, MpcMatsDev mt, const double *__restrict__ X,
@@ -267,6 +324,12 @@ cudaError_t launch_mpc_assemble(const MpcDims &d, int plants, const double *Ad, 
 cudaError_t launch_mpc_step_vectors(const MpcDims &d, int B, int per_instance, const MpcMatsDev &mats, const double *X,
                                     const double *U, const double *ref, double *f, double *ub, cudaStream_t stream) {
   const int wpc = 8;
+  if (!per_instance && d.N > 32) {   // long horizons: four instances per warp share the operator loads
+    constexpr int G = 4;
+    const int warps = (B + G - 1) / G;
+    mpc_step_vectors_shared_kernel<G><<<(warps + wpc - 1) / wpc, wpc * 32, 0, stream>>>(d, B, mats, X, U, ref, f, ub);
+    return cudaGetLastError();
+  }
   mpc_step_vectors_kernel<<<(B + wpc - 1) / wpc, wpc * 32, 0, stream>>>(d, B, per_instance, mats, X, U, ref, f, ub);
   return cudaGetLastError();
 }
