@@ -214,7 +214,8 @@ int smpc_mpc_controller_step_from(smpc_mpc *m, const double *X, const double *U,
  * controllerStep also writes U:[batch] (after U += dU[0]) and status:[batch] (OSQP numbers) to these buffers -- device
  * memory or PINNED host memory (pageable host memory is refused: SMPC_ERR_ARG); either may be NULL, both NULL unbinds.  The
  * one-warp small-QP kernel stores them as each instance ends, the other kernels are followed by one export launch.
- * They are valid once the stream has run the step: smpc_mpc_sync. */
+ * They are valid once the stream has run the step: smpc_mpc_sync.  (smpc_mpc_closed_loop keeps everything on the device and
+ * does not write them.) */
 int smpc_mpc_bind_results(smpc_mpc *m, double *U, int *status, int loc);
 int smpc_mpc_sync(smpc_mpc *m);
 /* synthetic plant for closed-loop runs (the reference's plant is hardware): X <- Ad X + Bd U */
