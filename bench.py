@@ -18,6 +18,12 @@ owns its own instances, no data-path collective; NCCL carries only t
                here) on the host cores, one solver per core, bounded sample
 
 `--impl reference` times that CPU path alone with the same metric / config (rank 0 only).
+
+With no `--config` (the driver's call) the line is config 2 and carries a `configs` object with the other BASELINE
+configurations measured in the same run at reduced step counts -- c1 (single controller: latency), c3, c4, c5, each with the
+same fields (value, ms_per_step, e2e, roofline, cpu_baseline, clocks) -- so that every configuration is driver-visible at
+every N; `--config cK` runs one configuration alone.  The CPU arm is the perf build of the port (oracle.PERF_FLAGS, built on
+this host), one controller per core on all host threads, for every configuration.
 """
 import argparse
 import json
@@ -34,7 +40,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 EPS = 1e-5
 METRIC = "QP solves/sec (eps 1e-5)"
-CPU_NOTE = "one OSQP-equivalent solver per core (oracle/osqp_port.c; osqp-eigen is not installable offline)"
+CPU_NOTE = "one OSQP-equivalent solver per core (oracle/osqp_port.c, perf build; osqp-eigen is not installable offline)"
 
 
 def load_plant(path):
@@ -117,9 +123,13 @@ class Workload:
     def __init__(self, batch, rank):
         self.B, self.rank = batch, rank
 
-    # -- CPU side (oracle): returns (solves, seconds) for `count` QPs of this workload on `threads` cores
+    # -- CPU side (oracle): returns (solves, seconds, cores) for `count` QPs of this workload on `threads` cores
     def cpu_solve(self, count, threads):
         raise NotImplementedError
+
+    def executed_flops(self, n, m_exec):
+        """flops one instance-iteration of the kernel executes: n x n KKT product + the two products with the m_exec stored rows"""
+        return 2.0 * (n * n + 2 * m_exec * n)
 
 
 class C2(Workload):
@@ -177,7 +187,7 @@ class C2(Workload):
         m = oracle.mpc_build(**{**cfg, "N": self.N})
         X, U, ref = self._inputs(count, 0)
         f, ub = oracle.mpc_batch_vectors(m, X, U, ref)
-        out = oracle.solve_batch(m["H"], m["Gbar"], m["lb"], m["W0"], f, ub, settings=oracle.default_settings(eps_abs=EPS, eps_rel=EPS), nthreads=threads)
+        out = oracle.solve_batch(m["H"], m["Gbar"], m["lb"], m["W0"], f, ub, settings=oracle.default_settings(eps_abs=EPS, eps_rel=EPS), nthreads=threads, perf=True)
         return count, out["seconds"], threads
 
 
@@ -232,7 +242,7 @@ class C3(Workload):
         x0, xr = c3_batch(count, seed=0)
         q = oracle.mimo_batch_vectors(m, x0, xr)
         out = oracle.solve_batch(m["H"], m["A"], m["lb"], m["ub"], q, np.tile(m["ub"], (count, 1)),
-                                 settings=oracle.default_settings(eps_abs=EPS, eps_rel=EPS), nthreads=threads)
+                                 settings=oracle.default_settings(eps_abs=EPS, eps_rel=EPS), nthreads=threads, perf=True)
         return count, out["seconds"], threads
 
 
@@ -272,15 +282,11 @@ class C4(C2):
         cfg = oracle.load_config(self._conf())
         Ad, Bd = c4_plants(count, cfg, seed=2)
         X, U, ref = self._inputs(count, 31)
-        st = oracle.default_settings(eps_abs=EPS, eps_rel=EPS)
-        t0 = time.perf_counter()   # ONE core: setup (assembly, scaling, factor) + solve per instance, as a per-plant controller pays it
-        for b in range(count):
-            mats = oracle.mpc_build(**{**cfg, "Ad": Ad[b], "Bd": Bd[b], "N": self.N})
-            f, ub = oracle.mpc_step_vectors(mats, X[b], U[b], ref[b])
-            so = oracle.Solver(mats["H"], np.zeros(self.N), mats["Gbar"], mats["lb"], mats["W0"], settings=st)
-            so.update_lin_cost(f); so.update_upper_bound(ub)
-            so.solve()
-        return count, time.perf_counter() - t0, 1
+        # one controller per plant and per core: constructor (builders, scaling, factor) + controllerStep, as a per-plant
+        # ModelPredictiveControlAPI object pays it (oracle/batch_drivers.c)
+        out = oracle.plant_batch(cfg, Ad, Bd, X, U, ref, self.N, settings=oracle.default_settings(eps_abs=EPS, eps_rel=EPS),
+                                 nthreads=threads, perf=True)
+        return count, out["seconds"], threads
 
 
 class C5(C2):
@@ -326,33 +332,21 @@ class C5(C2):
     def cpu_solve(self, count, threads):
         import oracle
         cfg = oracle.load_config(self._conf())
-        m = oracle.mpc_build(**{**cfg, "N": self.N})
-        X, U, ref = self._inputs(count, 31)
-        X, U = X * 0.2, U * 0.1
-        st = oracle.default_settings(eps_abs=EPS, eps_rel=EPS)
-        solvers = [oracle.Solver(m["H"], np.zeros(self.N), m["Gbar"], m["lb"], m["W0"], settings=st) for _ in range(count)]
-        steps, secs = 5, 0.0
-        for k in range(steps + 1):           # step 0 is the cold solve (not counted), then warm-started steps
-            t0 = time.perf_counter()
-            for b, so in enumerate(solvers):
-                f, ub = oracle.mpc_step_vectors(m, X[b], U[b], self.AMP)
-                so.update_lin_cost(f); so.update_upper_bound(ub)
-                r = so.solve()
-                U[b] += r["x"][0]
-                X[b] = cfg["Ad"] @ X[b] + cfg["Bd"] * U[b]
-            if k:
-                secs += time.perf_counter() - t0
-        return count * steps, secs, 1
+        X, U, _ = self._inputs(count, 31)
+        phase = np.random.default_rng(5).integers(0, self.PERIOD, count).astype(np.int32)
+        steps = 6                           # step 0 is the cold solve (run, not counted), then warm-started steps
+        out = oracle.closed_loop(cfg, X * 0.2, U * 0.1, self.N, steps, self.AMP, self.PERIOD, phase, skip=1,
+                                 settings=oracle.default_settings(eps_abs=EPS, eps_rel=EPS), nthreads=threads, perf=True)
+        return count * (steps - 1), out["seconds"], threads
 
 
 WORKLOADS = {w.key: w for w in (C2, C3, C4, C5)}
 
 
 def cpu_solves_per_s(wl, min_seconds, threads, first=None):
-    """The CPU oracle on this workload's QPs; bounded sample.  Returns (solves/s, solves, seconds, cores used):
-    c2 / c3 run one solver per core on all host threads; c4 / c5 (per-instance setup, closed loop) drive the scalar
-    port from one core."""
-    count = first or {"c2": 4096, "c3": 8 * threads, "c4": 256, "c5": 16}[wl.key]
+    """The CPU oracle (perf build) on this workload's QPs, one controller per core on all host threads; bounded sample.
+    Returns (solves/s, solves, seconds, cores used)."""
+    count = first or {"c2": 4096, "c3": 8 * threads, "c4": 64 * threads, "c5": 8 * threads}[wl.key]
     done, secs, cores = 0, 0.0, 1
     while done == 0 or secs < min_seconds:
         c, s, cores = wl.cpu_solve(count, threads)
@@ -361,198 +355,445 @@ def cpu_solves_per_s(wl, min_seconds, threads, first=None):
     return done / secs, done, secs, cores
 
 
+SUB_STEPS = {"c2": 50, "c3": 3, "c4": 5, "c5": 20}      # timed steps of a configuration measured inside the all-configs line
+BOUND = {"c2": "fp64", "c3": "tensor", "c4": "fp64", "c5": "tensor"}   # DFMA kernels vs the DMMA (FP64 tensor pipe) tile kernel
+C1_CASES = [dict(X=[.01, 0, .02, 0], U=0.0, ref=0.0), dict(X=[0, 0, .05, 0], U=0.0, ref=0.0),
+            dict(X=[.02, -.1, .03, .2], U=0.5, ref=0.25), dict(X=[.1, .5, .08, -.2], U=-1.0, ref=-0.3)]   # SURVEY 8(c) cases A-D
+C1_WORKLOAD = ("config1: shipped config/MPC_API.json plant and horizon (n=15, m=30), ONE controller (batch 1): latency of "
+               "controllerStep in a warm-started closed loop (square-wave reference +-0.1, period 200, synthetic plant) and of a "
+               "cold controllerStep from the states of SURVEY 8(c) cases A-D")
+
+
+def cpu_c1_latency(steps):
+    """Config 1 on the CPU port (perf build, one core): microseconds per controllerStep, warm closed loop and cold cases."""
+    import oracle
+    cfg = oracle.load_config(os.path.join(ROOT, "config", "MPC_API.json"))
+    st = oracle.default_settings(eps_abs=EPS, eps_rel=EPS)
+    out = oracle.closed_loop(cfg, np.array([[0.0, 0.0, 0.05, 0.0]]), np.zeros(1), 15, 20 + steps, 0.1, 200, None, skip=20,
+                             settings=st, nthreads=1, perf=True)
+    warm = 1e6 * out["step_seconds"][20:]
+    cold = []
+    for _ in range(max(1, steps // 8)):
+        for c in C1_CASES:
+            o = oracle.closed_loop(cfg, np.array([c["X"]]), np.array([c["U"]]), 15, 1, c["ref"], 0, None, skip=0, settings=st,
+                                   nthreads=1, perf=True)
+            cold.append(1e6 * o["step_seconds"][0])     # timed around the step only (the constructor is outside)
+    return float(np.mean(warm)), float(np.median(warm)), float(np.mean(cold)), out["iterations"] / steps
+
+
+def reference_sample(key, threads, batch=None):
+    """Workload `key` and the size of one bounded CPU sample of it (a `step` of the reference arm)."""
+    wl = WORKLOADS[key](batch or WORKLOADS[key].default_batch, 0)
+    return wl, {"c2": wl.B, "c3": 4 * threads, "c4": 32 * threads, "c5": 4 * threads}[key]
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    wl = WORKLOADS[args.config](args.batch or WORKLOADS[args.config].default_batch, 0)
     threads = os.cpu_count() or 1
-    per_step, solves = [], 0
-    for i in range(args.warmup + args.steps):
-        c, s, cores = wl.cpu_solve({"c2": wl.B, "c3": 4 * threads, "c4": 128, "c5": 8}[wl.key], threads)   # one bounded sample per step
-        if i >= args.warmup:
-            per_step.append(s)
-            solves = c
-    ms = 1e3 * float(np.mean(per_step))
-    value = solves / (ms / 1e3)
-    sample = f"{args.steps} samples of {solves} solves of this workload, {CPU_NOTE}"
-    line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl.describe(), "eps_abs": EPS, "eps_rel": EPS, "solves_per_step": solves},
-        "cpu_baseline": {"value": value, "unit": "solves/s", "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
-    }
+    import oracle
+    flags = oracle.PERF_FLAGS
+
+    def arm(key, steps, warmup):
+        wl, count = reference_sample(key, threads, args.batch if args.config == key else None)
+        per_step, solves, cores = [], 0, threads
+        for i in range(warmup + steps):
+            c, s, cores = wl.cpu_solve(count, threads)     # one bounded sample of the workload per step
+            if i >= warmup:
+                per_step.append(s)
+                solves = c
+        ms = 1e3 * float(np.mean(per_step))
+        value = solves / (ms / 1e3)
+        sample = f"{steps} samples of {solves} solves of this workload, {CPU_NOTE}, gcc {flags}"
+        return {"value": value, "unit": "solves/s", "ms_per_step": ms, "steps": steps, "warmup": warmup,
+                "config": {"workload": wl.describe(), "eps_abs": EPS, "eps_rel": EPS, "solves_per_step": solves},
+                "cpu_baseline": {"value": value, "unit": "solves/s", "cores": cores, "kind": "port", "sample": sample, "flags": flags},
+                "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+    head_key = "c2" if args.config == "all" else args.config
+    r = arm(head_key, args.steps, args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "solves/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": r["config"],
+            "cpu_baseline": r["cpu_baseline"], "e2e": r["e2e"], "gpu_launches": 0}
+    if args.config == "all":
+        cfgs = {}
+        for key in ("c3", "c4", "c5"):
+            cfgs[key] = arm(key, 3, 1)
+        wm, wmed, cold, its = cpu_c1_latency(400)
+        cfgs["c1"] = {"config": {"workload": C1_WORKLOAD}, "latency_us": {"cpu": wm, "cpu_median": wmed, "cpu_cold": cold},
+                      "value": 1e6 / wm, "unit": "solves/s", "iters_mean": its,
+                      "cpu_baseline": {"value": 1e6 / wm, "unit": "solves/s", "cores": 1, "kind": "port",
+                                       "sample": f"400 warm closed-loop steps of one controller, {CPU_NOTE}, gcc {flags}", "flags": flags}}
+        line["configs"] = cfgs
     print(json.dumps(line), flush=True)
 
 
-def run_ours(args, rank, local_rank, world):
-    import torch
-    import torch.distributed as dist
-    import solvempc_b200 as sm
+class Bench:
+    """The GPU arm: owns the process group, the stream and the timing helpers; measure() runs one configuration."""
 
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: solvempc_b200 has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    wl = WORKLOADS[args.config](args.batch or WORKLOADS[args.config].default_batch, rank)
-    B = wl.B
-    wl.setup(sm, torch, local_rank, args.kernel)
-    stream = torch.cuda.current_stream()
-    wl.mpc.set_stream(stream.cuda_stream)
-    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda") if wl.flush_l2 else None   # 256 MB > 126 MB L2
-    closed_loop = wl.key == "c5"
-
-    def barrier():
-        torch.cuda.synchronize()
+    def __init__(self, args, rank, local_rank, world):
+        import torch
+        import torch.distributed as dist
+        import solvempc_b200 as sm
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: solvempc_b200 has no CPU fallback")
+        self.torch, self.dist, self.sm = torch, dist, sm
+        self.args, self.rank, self.local_rank, self.world = args, rank, local_rank, world
+        torch.cuda.set_device(local_rank)
         if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        self.stream = torch.cuda.current_stream()
+        self.flush = None
+        self.fp64_peak = None
+        self._pending_cpu = []
 
-    sampler = ClockSampler(local_rank)
-    # ---- device-resident value
-    if closed_loop:
-        bad, _ = wl.closed_loop(max(args.warmup, 3), graph=True)
-        assert bad == 0, "warm-up closed-loop steps did not reach SOLVED on every instance"
-        wl.solver.enable_timing(True)
-        wl.solver.kernel_ms(reset=True)
-        launches0 = wl.launches()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        sampler.start()
-        wall0 = time.perf_counter()
-        e0.record(stream)
-        bad, total_iters = wl.closed_loop(args.steps, graph=False)   # (kernel timing events cannot be captured into a graph)
-        e1.record(stream)
-        barrier()
-        wall_ms = 1e3 * (time.perf_counter() - wall0)
-        assert bad == 0
-        step_ms = np.array([e0.elapsed_time(e1) / args.steps])
-        prob_iters = total_iters / args.steps                          # per step
-        iters_mean, iters_max = total_iters / (args.steps * B), None
-    else:
-        for _ in range(args.warmup):
-            wl.step_device()
-        torch.cuda.synchronize()
-        assert wl.solver.count_solved() == B, "warm-up solve did not reach SOLVED on every instance"
-        iters = wl.solver.info()["iter"].astype(np.int64)
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
 
-        def timed_pass():
-            evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-            barrier()
-            w0 = time.perf_counter()
-            for e0, e1 in evs:
-                if flush is not None:
-                    flush.zero_()                 # evict the inputs from L2 between timed steps
-                e0.record(stream)
-                wl.step_device()
-                e1.record(stream)
-            barrier()
-            return np.array([a.elapsed_time(b) for a, b in evs]), 1e3 * (time.perf_counter() - w0)
+    def max_over_ranks(self, v):
+        if self.world == 1:
+            return v
+        t = self.torch.tensor([v], device="cuda", dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
 
-        # pass 1 (value): exactly K steps, nothing but the public calls inside the timed region.  Pass 2 (roofline): the same K
-        # steps with the library's CUDA events around the ADMM kernel -- they sit between the kernels of a step and switch off
-        # the programmatic-dependent-launch overlap, so they are kept out of the pass that produces `value`.
-        launches0 = wl.launches()
-        sampler.start()
-        step_ms, wall_ms = timed_pass()
-        launches = wl.launches() - launches0
-        wl.solver.enable_timing(True)
-        wl.solver.kernel_ms(reset=True)
-        step_ms_k, _ = timed_pass()
-        prob_iters, iters_mean, iters_max = int(iters.sum()), float(iters.mean()), int(iters.max())
-    if closed_loop:
-        launches = wl.launches() - launches0
-        step_ms_k = step_ms
-    kern_ms, kern_n = wl.solver.kernel_ms(reset=True)
-    wl.solver.enable_timing(False)
-    ms_per_step = float(step_ms.mean())
-    if world > 1:
-        t = torch.tensor([ms_per_step], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_per_step = float(t.item())
-    value = world * B / (ms_per_step / 1e3)
+    def dgemm_peak(self):
+        """FP64 denominator: MEASURED_PEAKS.json has none, so a cuBLAS DGEMM is measured here."""
+        if self.fp64_peak is None:
+            torch = self.torch
+            a = torch.randn(4096, 4096, dtype=torch.float64, device="cuda")
+            b = torch.randn(4096, 4096, dtype=torch.float64, device="cuda")
+            best = 1e9
+            for _ in range(6):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); torch.matmul(a, b); e1.record(); torch.cuda.synchronize()
+                best = min(best, e0.elapsed_time(e1))
+            self.fp64_peak = 2 * 4096 ** 3 / (best * 1e-3) / 1e12
+        return self.fp64_peak
 
-    # ---- end to end through the public call with host buffers
-    for _ in range(max(3, args.warmup)):
-        wl.step_e2e()
-    barrier()
-    t_e2e = []
-    for _ in range(args.steps):
-        if flush is not None:
-            flush.zero_()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        wl.step_e2e()
-        torch.cuda.synchronize()
-        t_e2e.append(time.perf_counter() - t0)
-    barrier()
-    clocks = sampler.stop()
-    assert (wl.out_st.numpy() == 1).all()
-    e2e_ms = 1e3 * float(np.mean(t_e2e))
-    if world > 1:
-        t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
-    e2e_value = world * B / (e2e_ms / 1e3)
-
-    if rank == 0:
-        peaks, peak_src = load_peaks()
-        # FP64 denominator: MEASURED_PEAKS.json has none, so a cuBLAS DGEMM is measured here
-        a = torch.randn(4096, 4096, dtype=torch.float64, device="cuda")
-        b = torch.randn(4096, 4096, dtype=torch.float64, device="cuda")
-        best = 1e9
-        for _ in range(6):
+    # ------------------------------------------------------------------------------------------ one configuration
+    def measure(self, key, steps, warmup, batch=0, cpu_seconds=10.0):
+        torch, args, world, rank = self.torch, self.args, self.world, self.rank
+        wl = WORKLOADS[key](batch or WORKLOADS[key].default_batch, rank)
+        B = wl.B
+        wl.setup(self.sm, torch, self.local_rank, args.kernel)
+        stream = self.stream
+        wl.mpc.set_stream(stream.cuda_stream)
+        if wl.flush_l2 and self.flush is None:
+            self.flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")   # 256 MB > 126 MB L2
+        flush = self.flush if wl.flush_l2 else None
+        closed_loop = key == "c5"
+        barrier = self.barrier
+        sampler = ClockSampler(self.local_rank)
+        fresh = None
+        # ---- device-resident value
+        if closed_loop:
+            bad, _ = wl.closed_loop(max(warmup, 3), graph=True)
+            assert bad == 0, "warm-up closed-loop steps did not reach SOLVED on every instance"
+            wl.solver.enable_timing(True)
+            wl.solver.kernel_ms(reset=True)
+            launches0 = wl.launches()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(); torch.matmul(a, b); e1.record(); torch.cuda.synchronize()
-            best = min(best, e0.elapsed_time(e1))
-        fp64_peak = 2 * 4096 ** 3 / (best * 1e-3) / 1e12
-        n, m = wl.n, wl.m
-        nnzA = wl.nnz_A()
-        flops_per_launch = prob_iters * (2.0 * n * n + 4.0 * nnzA)       # 2 n^2 (KKT contraction) + 4 nnz(A) (A x, A'y)
-        m_exec = wl.solver.row_pairs or m                                # [G; -G] row pairs: the tile and small-QP kernels multiply the top half only
-        executed_per_launch = prob_iters * 2.0 * (n * n + 2 * m_exec * n)   # what the plan-coordinate iteration executes (dense W = A̅V)
-        bytes_per_launch = prob_iters * 24.0 * (n + 2 * m)               # what one launch per iteration would stream
-        kms = kern_ms / max(kern_n, 1)
-        achieved = flops_per_launch / (kms * 1e-3) / 1e12
-        cpu_threads = os.cpu_count() or 1
-        cpu_v, cpu_done, cpu_secs, cpu_cores = cpu_solves_per_s(wl, args.cpu_seconds, cpu_threads)
-        traffic, traffic_src = load_traffic(wl.key, B)
-        line = {
-            "metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic",
-            "config": {"workload": wl.describe(), "batch_per_gpu": B, "eps_abs": EPS, "eps_rel": EPS, "adaptive_rho_interval": 25,
-                       "l2": wl.l2_note, "kernel": wl.solver.kernel_name, "row_pairs_exploited": wl.solver.row_pairs,
-                       "iters_mean": iters_mean, "iters_max": iters_max,
-                       "wall_ms_timed_region": wall_ms},
-            "e2e": {"value": e2e_value, "unit": "solves/s", "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": wl.h2d, "d2h_bytes_per_step": wl.d2h},
-            "gpu_launches": int(launches),
-            "clocks": clocks,
-            "roofline": {"bound": "tensor", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
-                         "traffic": traffic, "traffic_unit": "bytes of DRAM read + written per launch", "traffic_source": traffic_src,
-                         "kernel": wl.solver.kernel_name, "kernel_ms": kms, "kernel_share_of_step": kms / float(step_ms_k.mean()), "step_ms_in_kernel_timing_pass": float(step_ms_k.mean()),
-                         "kernel_timing": "CUDA events around the ADMM kernel inside the library, second pass of the same K steps"
-                                          if not closed_loop else "CUDA events around the ADMM kernel inside the library, same K steps",
-                         "flops_per_launch": flops_per_launch, "executed_flops_per_launch": executed_per_launch,
-                         "executed_frac": executed_per_launch / (kms * 1e-3) / 1e12 / fp64_peak,
-                         "algorithmic_flops_per_instance_iteration": 2.0 * n * n + 4.0 * nnzA,
-                         "peak_source": "FP64 pipe (DFMA and DMMA share one peak on B200): cuBLAS DGEMM 4096^3 measured in this run "
-                                        "(MEASURED_PEAKS.json has no fp64 entry)",
-                         "hbm_equivalent": {"achieved": bytes_per_launch / (kms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                                            "frac": bytes_per_launch / (kms * 1e-3) / 1e9 / peaks["hbm_gbs"], "peak_source": peak_src,
-                                            "note": "24(n+2m) B per problem-iteration that a one-launch-per-iteration kernel would stream; "
-                                                    "this kernel keeps the iterates on chip and reads/writes HBM once per solve"}},
-            "cpu_baseline": {"value": cpu_v, "unit": "solves/s", "cores": cpu_cores, "kind": "port",
-                             "sample": f"{cpu_done} solves of this workload's QPs in {cpu_secs:.1f} s, {CPU_NOTE}"},
-        }
-        print(json.dumps(line), flush=True)
-    wl.close()
+            barrier()
+            sampler.start()
+            wall0 = time.perf_counter()
+            e0.record(stream)
+            bad, total_iters = wl.closed_loop(steps, graph=False)   # (kernel timing events cannot be captured into a graph)
+            e1.record(stream)
+            barrier()
+            wall_ms = 1e3 * (time.perf_counter() - wall0)
+            assert bad == 0
+            step_ms = np.array([e0.elapsed_time(e1) / steps])
+            prob_iters = total_iters / steps                          # per step
+            iters_mean, iters_max = total_iters / (steps * B), None
+        else:
+            for _ in range(warmup):
+                wl.step_device()
+            torch.cuda.synchronize()
+            assert wl.solver.count_solved() == B, "warm-up solve did not reach SOLVED on every instance"
+            iters = wl.solver.info()["iter"].astype(np.int64)
+
+            def timed_pass(step):
+                evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+                barrier()
+                w0 = time.perf_counter()
+                for k, (e0, e1) in enumerate(evs):
+                    if flush is not None:
+                        flush.zero_()                 # evict the inputs from L2 between timed steps
+                    e0.record(stream)
+                    step(k)
+                    e1.record(stream)
+                barrier()
+                return np.array([a.elapsed_time(b) for a, b in evs]), 1e3 * (time.perf_counter() - w0)
+
+            # pass 1 (value): exactly K steps, nothing but the public calls inside the timed region.  Pass 2 (roofline): the same K
+            # steps with the library's CUDA events around the ADMM kernel -- they sit between the kernels of a step and switch off
+            # the programmatic-dependent-launch overlap, so they are kept out of the pass that produces `value`.
+            launches0 = wl.launches()
+            sampler.start()
+            step_ms, wall_ms = timed_pass(lambda k: wl.step_device())
+            launches = wl.launches() - launches0
+            if key == "c2":
+                # pass 1b: the same K steps, every step on inputs it has never seen (fresh seeds): the scheduler's difficulty classes
+                # and the queue order are recomputed per step anyway; this shows ms_per_step does not lean on a repeated batch
+                sets = [[torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in wl._inputs(B, 777 + 1000 * rank + 17 * k)] for k in range(steps)]
+                wl.mpc.controller_step_from(*sets[0]); torch.cuda.synchronize()
+                fr_ms, _ = timed_pass(lambda k: wl.mpc.controller_step_from(*sets[k]))
+                torch.cuda.synchronize()
+                fresh = {"ms_per_step": float(fr_ms.mean()), "value": world * B / (float(fr_ms.mean()) / 1e3),
+                         "solved_last_step": int(wl.solver.count_solved()),
+                         "note": "every timed step on a batch drawn from its own seed (never seen before)"}
+                wl.step_device(); torch.cuda.synchronize()
+            wl.solver.enable_timing(True)
+            wl.solver.kernel_ms(reset=True)
+            step_ms_k, _ = timed_pass(lambda k: wl.step_device())
+            prob_iters, iters_mean, iters_max = int(iters.sum()), float(iters.mean()), int(iters.max())
+        if closed_loop:
+            launches = wl.launches() - launches0
+            step_ms_k = step_ms
+        kern_ms, kern_n = wl.solver.kernel_ms(reset=True)
+        wl.solver.enable_timing(False)
+        ms_per_step = self.max_over_ranks(float(step_ms.mean()))
+        value = world * B / (ms_per_step / 1e3)
+
+        # ---- end to end through the public call with host buffers
+        for _ in range(max(3, warmup)):
+            wl.step_e2e()
+        barrier()
+        t_e2e = []
+        for _ in range(steps):
+            if flush is not None:
+                flush.zero_()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            wl.step_e2e()
+            torch.cuda.synchronize()
+            t_e2e.append(time.perf_counter() - t0)
+        barrier()
+        clocks = sampler.stop()
+        assert (wl.out_st.numpy() == 1).all()
+        e2e_ms = self.max_over_ranks(1e3 * float(np.mean(t_e2e)))
+        e2e_value = world * B / (e2e_ms / 1e3)
+
+        res = None
+        if rank == 0:
+            peaks, peak_src = load_peaks()
+            fp64_peak = self.dgemm_peak()
+            n, m = wl.n, wl.m
+            nnzA = wl.nnz_A()
+            flops_per_launch = prob_iters * (2.0 * n * n + 4.0 * nnzA)       # SURVEY 8(d): 2 n^2 (KKT contraction) + 4 nnz(A) (A x, A'y)
+            m_exec = wl.solver.row_pairs or m                                # [G; -G] row pairs: the kernels multiply the top half only
+            executed_per_launch = prob_iters * wl.executed_flops(n, m_exec)  # what the kernel's iteration executes
+            bytes_per_launch = prob_iters * 24.0 * (n + 2 * m)               # SURVEY 8d: what one launch per iteration would stream
+            kms = kern_ms / max(kern_n, 1)
+            achieved = flops_per_launch / (kms * 1e-3) / 1e12
+            traffic, traffic_src = load_traffic(wl.key, B)
+            res = {
+                "value": value, "unit": "solves/s", "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_per_step,
+                "config": {"workload": wl.describe(), "batch_per_gpu": B, "eps_abs": EPS, "eps_rel": EPS, "adaptive_rho_interval": 25,
+                           "l2": wl.l2_note, "kernel": wl.solver.kernel_name, "row_pairs_exploited": wl.solver.row_pairs,
+                           "iters_mean": iters_mean, "iters_max": iters_max, "wall_ms_timed_region": wall_ms},
+                "e2e": {"value": e2e_value, "unit": "solves/s", "ms_per_step": e2e_ms,
+                        "h2d_bytes_per_step": wl.h2d, "d2h_bytes_per_step": wl.d2h},
+                "gpu_launches": int(launches),
+                "clocks": clocks,
+                "roofline": {"bound": BOUND[key], "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
+                             "traffic": traffic, "traffic_unit": "bytes of DRAM read + written per launch", "traffic_source": traffic_src,
+                             "kernel": wl.solver.kernel_name, "kernel_ms": kms, "kernel_share_of_step": kms / float(step_ms_k.mean()),
+                             "step_ms_in_kernel_timing_pass": float(step_ms_k.mean()),
+                             "kernel_timing": "CUDA events around the ADMM kernel inside the library, second pass of the same K steps"
+                                              if not closed_loop else "CUDA events around the ADMM kernel inside the library, same K steps",
+                             "flops_per_launch": flops_per_launch, "executed_flops_per_launch": executed_per_launch,
+                             "executed_frac": executed_per_launch / (kms * 1e-3) / 1e12 / fp64_peak,
+                             "algorithmic_flops_per_instance_iteration": 2.0 * n * n + 4.0 * nnzA,
+                             "bound_note": "fp64 = FP64 DFMA pipe, tensor = FP64 DMMA (mma.sync.m8n8k4.f64) pipe; the two share one measured peak on B200",
+                             "peak_source": "cuBLAS DGEMM 4096^3 measured in this run (MEASURED_PEAKS.json has no fp64 entry)",
+                             "hbm_equivalent": {"achieved": bytes_per_launch / (kms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                                "frac": bytes_per_launch / (kms * 1e-3) / 1e9 / peaks["hbm_gbs"], "peak_source": peak_src,
+                                                "note": "24(n+2m) B per problem-iteration that a one-launch-per-iteration kernel would stream; "
+                                                        "this kernel keeps the iterates on chip and reads/writes HBM once per solve"}},
+            }
+            if fresh is not None:
+                res["fresh_inputs"] = fresh
+            self._pending_cpu.append((res, wl.__class__, B, cpu_seconds))
+        wl.close()
+        del wl
+        torch.cuda.empty_cache()
+        return res
+
+    def cpu_legs(self):
+        """The CPU arm of every measured configuration, after all GPU work (rank 0; the other ranks have nothing to wait for)."""
+        import oracle
+        threads = os.cpu_count() or 1
+        for res, cls, B, secs in self._pending_cpu:
+            wl = cls(B, 0)
+            cpu_v, cpu_done, cpu_secs, cpu_cores = cpu_solves_per_s(wl, secs, threads)
+            res["cpu_baseline"] = {"value": cpu_v, "unit": "solves/s", "cores": cpu_cores, "kind": "port", "flags": oracle.PERF_FLAGS,
+                                   "sample": f"{cpu_done} solves of this workload's QPs in {cpu_secs:.1f} s, {CPU_NOTE}, gcc {oracle.PERF_FLAGS}"}
+        self._pending_cpu = []
+
+    # ------------------------------------------------------------------------------------------ one global batch over the ranks
+    def sharded_batch_check(self, per_rank=4096):
+        """ONE global config-2 batch split contiguously over the ranks (solvempc_b200.sharding.shard_bounds), every
+        rank steps its shard on its own GPU, the controls and statuses are gathered over NCCL (the optional final gather), and
+        rank 0 compares them bitwise with the whole batch stepped on its GPU alone.  Outside every timed region."""
+        from solvempc_b200.sharding import gather_results, shard_arrays
+        torch, sm = self.torch, self.sm
+        wl = C2(per_rank, 0)
+        total = per_rank * self.world + 3                       # ragged on purpose
+        X, U, ref = wl._inputs(total, 4242)
+
+        def step(Xs, Us, rs):
+            mpc = sm.BatchedModelPredictiveControlAPI(wl._conf(), batch=Xs.shape[0], device=self.local_rank, eps_abs=EPS, eps_rel=EPS, kernel=self.args.kernel)
+            mpc.set_stream(self.stream.cuda_stream)
+            mpc.set_state(X=np.ascontiguousarray(Xs), U=np.ascontiguousarray(Us), ref=np.ascontiguousarray(rs))
+            mpc.controllerStep()
+            _, Uo = mpc.state()
+            st = mpc.solver.info()["status"]
+            mpc.close()
+            return Uo, st
+
+        Us, st = step(*shard_arrays((X, U, ref), self.world, self.rank))
+        Ug, stg = gather_results(Us, total), gather_results(st, total)
+        if self.rank != 0:
+            return None
+        U1, st1 = step(X, U, ref)
+        return {"global_batch": total, "ranks": self.world, "gather": "nccl all_gather (solvempc_b200.sharding.gather_results)",
+                "bitwise_equal_to_single_gpu": bool(np.array_equal(Ug, U1) and np.array_equal(stg, st1)),
+                "solved": int((stg == 1).sum())}
+
+    # ------------------------------------------------------------------------------------------ config 1: latency
+    def measure_c1(self, steps):
+        """BASELINE config 1 (parity and latency only): one controller, microseconds per controllerStep through
+        (i) the C ABI with pinned host state in / control + status out, (ii) the reference's own unmodified class on the shim
+        (oracle/_ref/ref_mpc_gpu, built in the build container), (iii) the device-resident CUDA-graph closed loop."""
+        torch, sm = self.torch, self.sm
+        if self.rank != 0:
+            return None
+        conf = os.path.join(ROOT, "config", "MPC_API.json")
+        cfg = load_plant(conf)
+        mpc = sm.BatchedModelPredictiveControlAPI(conf, batch=1, device=self.local_rank, eps_abs=EPS, eps_rel=EPS, kernel=self.args.kernel)
+        mpc.set_stream(self.stream.cuda_stream)
+        X = torch.tensor([[0.0, 0.0, 0.05, 0.0]], dtype=torch.float64).pin_memory()
+        U = torch.zeros(1, dtype=torch.float64).pin_memory()
+        ref = torch.zeros(1, dtype=torch.float64).pin_memory()
+        out_u = torch.zeros(1, dtype=torch.float64).pin_memory()
+        out_st = torch.zeros(1, dtype=torch.int32).pin_memory()
+        mpc.bind_results(out_u, out_st)
+        Xn, Un = X.numpy(), U.numpy()
+        lat, its, bad = [], 0, 0
+        launches0 = mpc.launches
+        for s in range(20 + steps):
+            ref[0] = 0.1 if 2 * (s % 200) < 200 else -0.1
+            t0 = time.perf_counter()
+            mpc.controller_step_from(X, U, ref)
+            mpc.sync()
+            t1 = time.perf_counter()
+            if s >= 20:
+                lat.append(1e6 * (t1 - t0))
+                bad += int(out_st[0] != 1)
+            Un[0] = out_u[0]
+            Xn[0] = cfg["Ad"] @ Xn[0] + cfg["Bd"] * Un[0]
+        launches = mpc.launches - launches0
+        its = float(mpc.solver.info()["iter"][0])
+        # cold controllerStep from the known-answer states (every solve from x = z = y = 0, rho = rho0)
+        mpc.solver.set_cold_solves(True)
+        cold = []
+        for k in range(max(4, steps // 2)):
+            c = C1_CASES[k % 4]
+            Xn[0] = c["X"]; Un[0] = c["U"]; ref[0] = c["ref"]
+            t0 = time.perf_counter()
+            mpc.controller_step_from(X, U, ref)
+            mpc.sync()
+            cold.append(1e6 * (time.perf_counter() - t0))
+        mpc.solver.set_cold_solves(False)
+        mpc.bind_results(None, None)
+        # device-resident closed loop, one CUDA-graph replay per step (no host round trip)
+        mpc.set_state(X=np.array([[0.0, 0.0, 0.05, 0.0]]), U=np.zeros(1), ref=np.zeros(1))
+        mpc.closed_loop(20, 0.1, 200, None, use_graph=True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record(self.stream)
+        gbad, git = mpc.closed_loop(steps, 0.1, 200, None, use_graph=True)
+        e1.record(self.stream)
+        torch.cuda.synchronize()
+        graph_us = 1e3 * e0.elapsed_time(e1) / steps
+        kname = mpc.solver.kernel_name
+        mpc.close()
+        shim, shim_note = None, "oracle/_ref/ref_mpc_gpu not present (built only where /root/reference exists)"
+        exe = os.path.join(ROOT, "oracle", "_ref", "ref_mpc_gpu")
+        if os.path.exists(exe):
+            import subprocess
+            try:
+                out = subprocess.run([exe, "latency", str(steps)], cwd=ROOT, env=dict(os.environ, SOLVEMPC_EPS=str(EPS), SOLVEMPC_DEVICE=str(self.local_rank)),
+                                     capture_output=True, text=True, timeout=300)
+                shim = json.loads(out.stdout)
+                shim_note = "the reference's unmodified ModelPredictiveControlAPI.cpp + include/OsqpEigen shim + libsolvempc_b200.so, timed around controllerStep()"
+            except Exception as e:   # report instead of failing the whole line
+                shim_note = f"ref_mpc_gpu failed: {type(e).__name__}"
+        lat = np.array(lat)
+        res = {"config": {"workload": C1_WORKLOAD, "kernel": kname, "eps_abs": EPS, "eps_rel": EPS},
+               "value": 1e6 / float(lat.mean()), "unit": "solves/s", "steps": steps, "iters_last_step": its, "not_solved": bad + int(gbad),
+               "latency_us": {"gpu": float(lat.mean()), "gpu_median": float(np.median(lat)), "gpu_cold": float(np.mean(cold)),
+                              "gpu_graph_closed_loop": graph_us,
+                              "gpu_shim": None if shim is None else shim["latency_us_mean"],
+                              "gpu_shim_median": None if shim is None else shim["latency_us_median"]},
+               "latency_notes": {"gpu": "smpc_mpc_controller_step_from (pinned X, U, ref read in place; U + status written to bound pinned buffers) + smpc_mpc_sync, host clock, ctypes call overhead included",
+                                 "gpu_graph_closed_loop": "smpc_mpc_closed_loop(use_graph=1): device-resident, CUDA events / steps (graph instantiation included)",
+                                 "gpu_shim": shim_note},
+               "e2e": {"value": 1e6 / float(lat.mean()), "unit": "solves/s", "h2d_bytes_per_step": 48, "d2h_bytes_per_step": 12},
+               "gpu_launches": int(launches)}
+        self._c1 = res
+        return res
+
+    def c1_cpu(self, res, steps):
+        wm, wmed, cold, its = cpu_c1_latency(steps)
+        import oracle
+        res["latency_us"].update({"cpu": wm, "cpu_median": wmed, "cpu_cold": cold})
+        res["cpu_baseline"] = {"value": 1e6 / wm, "unit": "solves/s", "cores": 1, "kind": "port", "flags": oracle.PERF_FLAGS,
+                               "sample": f"{steps} warm closed-loop steps of one controller (mean {its:.1f} iterations), {CPU_NOTE}, gcc {oracle.PERF_FLAGS}"}
+
+
+def run_ours(args, rank, local_rank, world):
+    bench = Bench(args, rank, local_rank, world)
+    head_key = "c2" if args.config == "all" else args.config
+    if head_key == "c1":
+        res = bench.measure_c1(args.steps)
+        if rank == 0:
+            bench.c1_cpu(res, args.steps)
+            print(json.dumps({"metric": "controllerStep latency (eps 1e-5)", "higher_is_better": True, "n_gpus": 1, "dtype": "f64", "data": "synthetic", **res}), flush=True)
+        return
+    head = bench.measure(head_key, args.steps, args.warmup, args.batch, args.cpu_seconds)
+    subs = {}
+    if args.config == "all":
+        for key in ("c3", "c4", "c5"):
+            subs[key] = bench.measure(key, SUB_STEPS[key], 3, 0, args.cpu_seconds)
+        subs["c1"] = bench.measure_c1(300)
+    shard = None
     if world > 1:
-        dist.destroy_process_group()
+        bench.barrier()
+        shard = bench.sharded_batch_check()
+        bench.barrier()
+        bench.dist.destroy_process_group()
+    if rank == 0:
+        bench.cpu_legs()
+        if "c1" in subs:
+            bench.c1_cpu(subs["c1"], 300)
+        line = {"metric": METRIC, "value": head["value"], "unit": "solves/s", "n_gpus": world, "steps": head["steps"],
+                "warmup": head["warmup"], "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic"}
+        line.update({k: v for k, v in head.items() if k not in line})
+        if subs:
+            for v in subs.values():
+                v.update({"metric": METRIC, "scaling": "weak", "dtype": "f64", "data": "synthetic", "higher_is_better": True})
+            line["configs"] = subs
+        if shard is not None:
+            line["sharded_batch_check"] = shard
+        print(json.dumps(line), flush=True)
 
 
 def main():
@@ -561,13 +802,14 @@ def main():
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--config", default="all", choices=["all", "c1"] + sorted(WORKLOADS),
+                    help="all (default): config 2 as the headline + a `configs` object with c1, c3, c4, c5; cK: that configuration alone")
     ap.add_argument("--batch", type=int, default=0, help="instances per GPU (0 = the configuration's own size)")
     ap.add_argument("--kernel", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     args = ap.parse_args()
     if args.steps is None:
-        args.steps = {"c2": 50, "c3": 10, "c4": 10, "c5": 50}[args.config]
+        args.steps = {"all": 50, "c1": 300, "c2": 50, "c3": 10, "c4": 10, "c5": 50}[args.config]
     args.warmup = max(args.warmup, 3)
     rank, local_rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     if args.impl == "reference":

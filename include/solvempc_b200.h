@@ -271,7 +271,9 @@ int smpc_mimo_get_matrix(smpc_mimo *m, const char *name, double *out, int capaci
 int smpc_mimo_set_state(smpc_mimo *m, const double *x0, const double *xr, int loc);
 /* one controller step for every instance: q = Fx x0 + Fr xr -> updateGradient -> solve; asynchronous */
 int smpc_mimo_controller_step(smpc_mimo *m);
-/* the first move u_0 of every instance, u0:[batch][nu] (NaN where the solve did not end SOLVED) */
+/* the first move u_0 of every instance, u0:[batch][nu]: the solver's iterate for SOLVED / SOLVED_INACCURATE /
+ * MAX_ITER_REACHED (check the status from smpc_solver_get_info before applying it), NaN for the infeasible statuses
+ * (OSQP stores no solution there) */
 int smpc_mimo_get_control(smpc_mimo *m, double *u0, int loc);
 long long smpc_mimo_launch_count(const smpc_mimo *m);
 

@@ -31,51 +31,93 @@ class Settings(C.Structure):
     ]
 
 
+_SOURCES = ("osqp_port.c", "mpc_assembly.c", "batch_drivers.c", "osqp_port.h", "mpc_assembly.h")
+
+
+def _stale(target):
+    return not os.path.exists(target) or any(
+        os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(target) for f in _SOURCES)
+
+
 def build(force=False):
     """Compile the C oracle (gcc) into oracle/_build/; and oracle/_ref when the reference is present."""
-    if force or not os.path.exists(_LIB) or any(
-        os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(_LIB)
-        for f in ("osqp_port.c", "mpc_assembly.c", "osqp_port.h", "mpc_assembly.h")
-    ):
+    if force or _stale(_LIB):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return _LIB
 
 
+PERF_FLAGS = "-O3 -march=native -ffp-contract=fast -fassociative-math -fno-signed-zeros -fno-trapping-math -fno-math-errno"
+
+
+def build_perf():
+    """The same sources compiled for speed (PERF_FLAGS) ON this machine: used only by bench.py's CPU arm.  The file is
+    named after the host's CPU flags so that a library built in one container is never loaded on another CPU."""
+    import hashlib
+    try:
+        with open("/proc/cpuinfo") as f:
+            flags = next((ln for ln in f if ln.startswith("flags")), "")
+    except OSError:
+        flags = ""
+    out = os.path.join(_HERE, "_build", "liboracle_perf_%s.so" % hashlib.sha1(flags.encode()).hexdigest()[:10])
+    if _stale(out):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "perf", "PERF_OUT=" + out, "PERF_CFLAGS=" + PERF_FLAGS + " -fPIC -std=gnu11"])
+    return out
+
+
 _lib = None
+_perf = None
+
+
+def _bind(L):
+    dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+    L.orc_default_settings.argtypes = [C.POINTER(Settings)]
+    L.orc_setup.restype = C.c_void_p
+    L.orc_setup.argtypes = [C.c_int, C.c_int, dp, dp, dp, dp, dp, C.POINTER(Settings)]
+    L.orc_cleanup.argtypes = [C.c_void_p]
+    for f in ("orc_update_lin_cost", "orc_update_lower_bound", "orc_update_upper_bound"):
+        getattr(L, f).argtypes = [C.c_void_p, dp]
+        getattr(L, f).restype = C.c_int
+    L.orc_update_bounds.argtypes = [C.c_void_p, dp, dp]
+    L.orc_warm_start.argtypes = [C.c_void_p, dp, dp]
+    L.orc_cold_start.argtypes = [C.c_void_p]
+    L.orc_reset.argtypes = [C.c_void_p]
+    L.orc_solve.argtypes = [C.c_void_p]
+    L.orc_get_solution.argtypes = [C.c_void_p, dp, dp]
+    L.orc_get_info.argtypes = [C.c_void_p, dp]
+    L.orc_get_scaling.argtypes = [C.c_void_p, dp, dp, dp]
+    L.orc_get_scaled_data.argtypes = [C.c_void_p, dp, dp]
+    L.orc_get_iterates.argtypes = [C.c_void_p, dp, dp, dp]
+    L.orc_solve_batch.restype = C.c_double
+    L.orc_solve_batch.argtypes = [C.c_int, C.c_int, dp, dp, dp, dp, C.POINTER(Settings), C.c_int,
+                                  dp, dp, dp, C.c_int, dp, dp, ip, ip]
+    L.orc_mpc_build.argtypes = [C.c_int, C.c_int, dp, dp, dp, dp, C.c_double, C.c_double, C.c_double,
+                                C.c_int, C.c_double] + [dp] * 11
+    L.orc_mpc_step_vectors.argtypes = [C.c_int, C.c_int] + [dp] * 7 + [C.c_double, dp, dp, dp]
+    L.orc_mpc_lower_bound.restype = C.c_double
+    L.orc_plant_batch.restype = C.c_double
+    L.orc_plant_batch.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp, dp, dp, C.c_double, C.c_double, C.c_double, C.c_int,
+                                  C.c_double, dp, dp, dp, C.POINTER(Settings), C.c_int, dp, ip, ip]
+    L.orc_closed_loop.restype = C.c_double
+    L.orc_closed_loop.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp, dp, dp, C.c_double, C.c_double, C.c_double, C.c_int,
+                                  C.c_double, dp, dp, C.c_double, C.c_int, ip, C.c_int, C.c_int, C.POINTER(Settings), C.c_int,
+                                  C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), dp]
+    return L
 
 
 def lib():
     global _lib
     if _lib is None:
         build()
-        L = C.CDLL(_LIB)
-        dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
-        L.orc_default_settings.argtypes = [C.POINTER(Settings)]
-        L.orc_setup.restype = C.c_void_p
-        L.orc_setup.argtypes = [C.c_int, C.c_int, dp, dp, dp, dp, dp, C.POINTER(Settings)]
-        L.orc_cleanup.argtypes = [C.c_void_p]
-        for f in ("orc_update_lin_cost", "orc_update_lower_bound", "orc_update_upper_bound"):
-            getattr(L, f).argtypes = [C.c_void_p, dp]
-            getattr(L, f).restype = C.c_int
-        L.orc_update_bounds.argtypes = [C.c_void_p, dp, dp]
-        L.orc_warm_start.argtypes = [C.c_void_p, dp, dp]
-        L.orc_cold_start.argtypes = [C.c_void_p]
-        L.orc_reset.argtypes = [C.c_void_p]
-        L.orc_solve.argtypes = [C.c_void_p]
-        L.orc_get_solution.argtypes = [C.c_void_p, dp, dp]
-        L.orc_get_info.argtypes = [C.c_void_p, dp]
-        L.orc_get_scaling.argtypes = [C.c_void_p, dp, dp, dp]
-        L.orc_get_scaled_data.argtypes = [C.c_void_p, dp, dp]
-        L.orc_get_iterates.argtypes = [C.c_void_p, dp, dp, dp]
-        L.orc_solve_batch.restype = C.c_double
-        L.orc_solve_batch.argtypes = [C.c_int, C.c_int, dp, dp, dp, dp, C.POINTER(Settings), C.c_int,
-                                      dp, dp, dp, C.c_int, dp, dp, ip, ip]
-        L.orc_mpc_build.argtypes = [C.c_int, C.c_int, dp, dp, dp, dp, C.c_double, C.c_double, C.c_double,
-                                    C.c_int, C.c_double] + [dp] * 11
-        L.orc_mpc_step_vectors.argtypes = [C.c_int, C.c_int] + [dp] * 7 + [C.c_double, dp, dp, dp]
-        L.orc_mpc_lower_bound.restype = C.c_double
-        _lib = L
+        _lib = _bind(C.CDLL(_LIB))
     return _lib
+
+
+def perf_lib():
+    """liboracle built with PERF_FLAGS on this host (bench.py's CPU arm); the parity tests use lib()."""
+    global _perf
+    if _perf is None:
+        _perf = _bind(C.CDLL(build_perf()))
+    return _perf
 
 
 def _p(a):
@@ -158,7 +200,7 @@ class Solver:
         return x, z, y
 
 
-def solve_batch(P, A, l0, u0, q, u, l=None, settings=None, nthreads=1, **kw):
+def solve_batch(P, A, l0, u0, q, u, l=None, settings=None, nthreads=1, perf=False, **kw):
     """'One solver per core' batch of independent cold solves; returns dict with seconds."""
     P, A, q, u = _c(P), _c(A), _c(q), _c(u)
     l0, u0, l = _c(l0), _c(u0), _c(l)
@@ -166,7 +208,7 @@ def solve_batch(P, A, l0, u0, q, u, l=None, settings=None, nthreads=1, **kw):
     s = settings if settings is not None else default_settings(**kw)
     x, y = np.empty((B, n)), np.empty((B, m))
     st, it = np.empty(B, dtype=np.int32), np.empty(B, dtype=np.int32)
-    secs = lib().orc_solve_batch(n, m, _p(P), _p(A), _p(l0), _p(u0), C.byref(s), B, _p(q), _p(l), _p(u),
+    secs = (perf_lib() if perf else lib()).orc_solve_batch(n, m, _p(P), _p(A), _p(l0), _p(u0), C.byref(s), B, _p(q), _p(l), _p(u),
                                  nthreads, _p(x), _p(y), st.ctypes.data_as(C.POINTER(C.c_int)),
                                  it.ctypes.data_as(C.POINTER(C.c_int)))
     return dict(x=x, y=y, status=st, iter=it, seconds=secs)
@@ -220,6 +262,40 @@ def mpc_batch_vectors(mats, X, U, ref):
     f = (X @ mats["Fx"].T + U[:, None] * mats["Fu"][None, :]) + ref @ mats["Fr"].T
     ub = (mats["W0"][None, :] + X @ mats["Sbar"].T) + U[:, None] * mats["Ku"][None, :]
     return f, ub
+
+
+def plant_batch(cfg, Ad, Bd, X, U, ref, N, settings=None, nthreads=1, perf=False, **kw):
+    """One controller PER PLANT (BASELINE config 4): constructor (builders + solver setup) and one controllerStep for every
+    instance, one controller per core.  Ad [B][nx][nx], Bd [B][nx].  Returns dict with x, status, iter, seconds."""
+    Ad, Bd, X, U, ref = _c(Ad), _c(Bd), _c(X), _c(U), _c(ref)
+    B, nx = Ad.shape[0], Ad.shape[1]
+    s = settings if settings is not None else default_settings(**kw)
+    x = np.empty((B, N))
+    st, it = np.empty(B, dtype=np.int32), np.empty(B, dtype=np.int32)
+    ip = C.POINTER(C.c_int)
+    secs = (perf_lib() if perf else lib()).orc_plant_batch(
+        N, nx, B, _p(Ad), _p(Bd), _p(_c(cfg["Cd"])), _p(_c(cfg["K"])), cfg["Q"], cfg["R"], cfg["RD"],
+        int(cfg.get("n_state_rows", 10)), float(cfg.get("u_limit", 255.0)), _p(X), _p(U), _p(ref), C.byref(s), nthreads,
+        _p(x), st.ctypes.data_as(ip), it.ctypes.data_as(ip))
+    return dict(x=x, status=st, iter=it, seconds=secs)
+
+
+def closed_loop(cfg, X, U, N, steps, amp, period=0, phase=None, skip=0, settings=None, nthreads=1, perf=False, **kw):
+    """Warm-started closed loop (the reference's main loop, src/solver.cpp:43-74, with a synthetic plant) of B controllers
+    sharing the plant, one controller per core.  Returns dict with X, U, not_solved, iterations, seconds (timed steps =
+    steps - skip), step_seconds (thread 0)."""
+    X, U = _c(X).copy(), _c(U).copy()
+    B, nx = X.shape
+    s = settings if settings is not None else default_settings(**kw)
+    ph = None if phase is None else np.ascontiguousarray(phase, dtype=np.int32)
+    bad, it = C.c_longlong(), C.c_longlong()
+    step_secs = np.zeros(steps)
+    secs = (perf_lib() if perf else lib()).orc_closed_loop(
+        N, nx, B, _p(_c(cfg["Ad"])), _p(_c(cfg["Bd"]).reshape(-1)), _p(_c(cfg["Cd"])), _p(_c(cfg["K"])), cfg["Q"], cfg["R"],
+        cfg["RD"], int(cfg.get("n_state_rows", 10)), float(cfg.get("u_limit", 255.0)), _p(X), _p(U), float(amp), int(period),
+        None if ph is None else ph.ctypes.data_as(C.POINTER(C.c_int)), int(steps), int(skip), C.byref(s), nthreads,
+        C.byref(bad), C.byref(it), _p(step_secs))
+    return dict(X=X, U=U, not_solved=bad.value, iterations=it.value, seconds=secs, step_seconds=step_secs)
 
 
 # --------------------------------------------------------------------------- exact KKT (solver independent)

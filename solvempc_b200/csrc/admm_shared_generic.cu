@@ -319,11 +319,9 @@ cudaError_t launch_admm_shared_generic(const SharedPlanDev &P, const BatchDev &B
   while (wpc > 1 && generic_smem_bytes(P.n, P.m, wpc) > 200 * 1024) --wpc;
   size_t smem = generic_smem_bytes(P.n, P.m, wpc);
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
+  if (smem > 48 * 1024) {   // the attribute is per device: set it on every launch (cheap), as the other launchers do
     cudaError_t e = cudaFuncSetAttribute(admm_shared_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured = smem;
   }
   int grid = (Bt.B + wpc - 1) / wpc;
   admm_shared_generic_kernel<<<grid, wpc * 32, smem, stream>>>(P, Bt, S, wpc);

@@ -898,7 +898,11 @@ int mpc_step_impl(smpc_mpc *M, const double *X, const double *U, const double *r
   s->status_export = export_fused ? M->bound_status : nullptr;
   const int rc = smpc_solver_solve(s);
   s->u_apply = nullptr; s->u_export = nullptr; s->status_export = nullptr;
-  if (rc) return rc;
+  if (rc) {
+    // the ADMM kernel's last warp zeroes the class counters; if it never ran they must not survive into the next step
+    if (s->classified) { cudaMemsetAsync(s->d_queue, 0, sizeof(int) * smpc::small_queue_ints(), M->stream); s->classified = false; }
+    return rc;
+  }
   if (!fused) {
     CK(smpc::launch_mpc_apply_control(M->B, s->n, s->d_x, s->d_status, M->d_U, M->stream));
     M->launches++;

@@ -39,7 +39,8 @@ __device__ __forceinline__ void classify_instance(const SmallPackDev &K, const S
   if (lane == 0) {
     const double ratio = key / fmax(ref, 1e-300);
     const int cls = !(key > 0.0) ? 4 : (ratio <= 0.02 ? 0 : (ratio <= 0.05 ? 1 : (ratio <= 0.15 ? 2 : 3)));
-    lists[(size_t)cls * B + atomicAdd(counts + cls, 1)] = b;
+    const int slot = atomicAdd(counts + cls, 1);
+    if (slot < B) lists[(size_t)cls * B + slot] = b;   // (slot >= B only if stale counters survived a failed step)
   }
 }
 

@@ -131,13 +131,16 @@ __global__ void __launch_bounds__(256) mimo_step_vectors_kernel(MimoDims d, int 
   }
 }
 
-// u0[b][:] = z_b[0:nu] when the solve ended SOLVED, else NaN
+// u0[b][:] = z_b[0:nu]: the first move of the solver's iterate for every status that has one (SOLVED, SOLVED_INACCURATE,
+// MAX_ITER_REACHED -- read the status next to it); NaN only where OSQP stores no solution (the infeasible statuses)
 __global__ void mimo_first_move_kernel(int B, int n, int nu, const double *__restrict__ x, const int *__restrict__ status,
                                        double *__restrict__ u0) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= B * nu) return;
   const int b = e / nu, c = e % nu;
-  u0[e] = status[b] == SMPC_SOLVED ? x[(size_t)b * n + c] : __longlong_as_double(0x7ff8000000000000LL);
+  const int st = status[b];
+  const bool has_solution = st == SMPC_SOLVED || st == SMPC_SOLVED_INACCURATE || st == SMPC_MAX_ITER_REACHED;
+  u0[e] = has_solution ? x[(size_t)b * n + c] : __longlong_as_double(0x7ff8000000000000LL);
 }
 
 cudaError_t launch_mimo_assemble(const MimoDims &d, const double *Ad, const double *Bd, const double *Q, const double *R,

@@ -73,11 +73,11 @@ void jacobi_eigh(int n, std::vector<double> &C, std::vector<double> &w, std::vec
     double off = 0.0;
     for (int i = 0; i < n; ++i)
       for (int j = i + 1; j < n; ++j) off = std::max(off, std::fabs(at(i, j)));
-    if (off <= 1e-18 * scale) break;
+    if (off <= 1e-15 * scale) break;   // reachable in double: the rotations leave off-diagonals at round-off level
     for (int p = 0; p < n - 1; ++p) {
       for (int q = p + 1; q < n; ++q) {
         double apq = at(p, q);
-        if (std::fabs(apq) <= 1e-300) continue;
+        if (std::fabs(apq) <= 1e-17 * scale) { at(p, q) = at(q, p) = 0.0; continue; }
         double app = at(p, p), aqq = at(q, q);
         double theta = (aqq - app) / (2.0 * apq);
         double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
@@ -92,6 +92,7 @@ void jacobi_eigh(int n, std::vector<double> &C, std::vector<double> &w, std::vec
           at(p, k) = cs * apk - sn * aqk;
           at(q, k) = sn * apk + cs * aqk;
         }
+        at(p, q) = at(q, p) = 0.0;   // annihilated exactly by this rotation
         for (int k = 0; k < n; ++k) {
           double qkp = Q[(size_t)k * n + p], qkq = Q[(size_t)k * n + q];
           Q[(size_t)k * n + p] = cs * qkp - sn * qkq;

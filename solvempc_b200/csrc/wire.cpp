@@ -35,10 +35,9 @@ struct smpc_feed {
   long long seq = 0, accepted = 0, rejected = 0;
 };
 
-extern "C" {
-
-int smpc_wire_parse_frame(const char *buf, int nbytes, double *dt, double *X) {
-  if (!buf || nbytes <= kMinFrame) return 0;                       // cpp:146
+// length_checked != 0: the caller (the reader thread) has already applied readPort's byte-count test to the raw read
+static int parse_frame_impl(const char *buf, int nbytes, double *dt, double *X, int length_checked) {
+  if (!buf || nbytes <= 0 || (!length_checked && nbytes <= kMinFrame)) return 0;   // cpp:146
   // getDataFromSerial: strtok on " ", atof, stored through float ref[5]; a field that parses to 0 leaves the 0 default
   char tmp[256];
   const int len = nbytes < (int)sizeof(tmp) - 1 ? nbytes : (int)sizeof(tmp) - 1;
@@ -57,6 +56,10 @@ int smpc_wire_parse_frame(const char *buf, int nbytes, double *dt, double *X) {
   return 1;
 }
 
+extern "C" {
+
+int smpc_wire_parse_frame(const char *buf, int nbytes, double *dt, double *X) { return parse_frame_impl(buf, nbytes, dt, X, 0); }
+
 int smpc_wire_format_control(double U, char *out, int capacity, int max_chars) {
   if (!out || capacity <= 0) return 0;
   const std::string s = std::to_string(U);                         // cpp:165
@@ -72,9 +75,10 @@ static void *feed_main(void *arg) {
   smpc_feed *f = static_cast<smpc_feed *>(arg);
   char line[kFrameBuf + 1];
   int fill = 0;
-  auto flush = [&]() {
+  auto flush = [&](int terminator) {
     double dt, X[4];
-    const int ok = smpc_wire_parse_frame(line, fill, &dt, X);
+    // readPort tests the raw byte count of read(), the terminator included (src/SerialPort.cpp:146: num_bytes > 30)
+    const int ok = (fill + terminator > kMinFrame) ? parse_frame_impl(line, fill, &dt, X, 1) : 0;
     std::lock_guard<std::mutex> g(f->mu);
     if (ok) { f->dt = dt; std::memcpy(f->X, X, sizeof(X)); ++f->seq; ++f->accepted; }
     else if (fill > 0) ++f->rejected;
@@ -90,9 +94,9 @@ static void *feed_main(void *arg) {
     if (got <= 0) { if (p.revents & POLLHUP) break; continue; }
     for (ssize_t k = 0; k < got; ++k) {
       // a frame ends at a newline or when the reference's 42-byte buffer is full
-      if (chunk[k] == '\n') { flush(); continue; }
+      if (chunk[k] == '\n') { flush(1); continue; }
       line[fill++] = chunk[k];
-      if (fill == kFrameBuf) flush();
+      if (fill == kFrameBuf) flush(0);
     }
   }
   return nullptr;

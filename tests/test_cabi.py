@@ -79,7 +79,7 @@ def test_plan_scaling_matches_oracle_bitwise(ref_mats):
     assert (pl["ctype"] == 0).all()
 
 
-def _plan_identities(P, A, l0, u0, **kw):
+def _plan_identities(P, A, l0, u0, tol=1.0, **kw):
     s = oracle.Solver(P, np.zeros(P.shape[0]), A, l0, u0, **kw)
     Pb, Ab = s.scaled_data()
     pl = sm.shared_plan_inspect(P, A, l0, u0, **kw)
@@ -90,16 +90,16 @@ def _plan_identities(P, A, l0, u0, **kw):
     free = pl["ctype"] == -1
     S = Pb + sigma * np.eye(n) + 1e-6 * Ab[free].T @ Ab[free]
     T = Ab.T @ (kap[:, None] * Ab)
-    assert np.abs(V.T @ S @ V - np.eye(n)).max() < 1e-12
+    assert np.abs(V.T @ S @ V - np.eye(n)).max() < 1e-12 * tol
     assert np.abs(V.T @ T @ V - np.diag(lam)).max() < 1e-10 * max(1.0, lam.max())
-    assert np.abs(pl["SG"] - sigma * V.T @ V).max() < 1e-18
-    assert np.abs(pl["W"] - Ab @ V).max() < 1e-12 * max(1.0, np.abs(Ab).max())
-    assert np.abs(pl["PVT"].T - Pb @ V).max() < 1e-12
-    assert np.abs(pl["VinvT"].T @ V - np.eye(n)).max() < 1e-11
+    assert np.abs(pl["SG"] - sigma * V.T @ V).max() < 1e-18 * tol * tol
+    assert np.abs(pl["W"] - Ab @ V).max() < 1e-12 * tol * max(1.0, np.abs(Ab).max())
+    assert np.abs(pl["PVT"].T - Pb @ V).max() < 1e-12 * tol
+    assert np.abs(pl["VinvT"].T @ V - np.eye(n)).max() < 1e-11 * tol
     for rho in (1e-6, 0.1, 37.0, 1e6):   # M(rho)^-1 = V diag(1/(1+rho lam)) V'
         M = S + rho * T
         Minv = V @ np.diag(1.0 / (1.0 + rho * lam)) @ V.T
-        assert np.abs(M @ Minv - np.eye(n)).max() < 1e-9
+        assert np.abs(M @ Minv - np.eye(n)).max() < 1e-9 * tol
     return pl
 
 
@@ -113,6 +113,17 @@ def test_plan_pencil_identities(ref_mats):
         pl = _plan_identities(P, A, l, u)
         assert (pl["ctype"][: mm // 4] == 1).all() and pl["ctype"][mm // 4] == -1
     _plan_identities(*[random_qp(8, 10, 5)[k] for k in (0, 2, 3, 4)], scaling=0)
+
+
+def test_plan_pencil_identities_at_config3_size():
+    """n = 200, m = 400 (BASELINE config 3): the Jacobi sweep must converge (not run out its sweep limit with a residual) and
+    build in seconds, not minutes."""
+    import time
+    m3 = oracle.mimo_build(**oracle.load_mimo_config(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "config", "quadrotor.json")))
+    t0 = time.time()
+    pl = _plan_identities(m3["H"], m3["A"], m3["lb"], m3["ub"], tol=2e3)   # cond(S) = 5e7 here: residuals ~ cond * eps
+    assert time.time() - t0 < 60.0
+    assert pl["lam"].min() > 0
 
 
 def _emulate_device_iteration(pl, Ab, qbar, lbar, ubar, eps, c, D, E, rho0=0.1, sigma=1e-6, alpha=1.6, max_iter=4000):

@@ -77,3 +77,27 @@ def test_async_feed_keeps_the_latest_frame_without_blocking():
     finally:
         feed.close()
         os.close(r); os.close(w)
+
+
+def test_feed_length_test_counts_the_terminator_like_readPort():
+    """readPort tests the raw byte count of read(), newline included (src/SerialPort.cpp:146: num_bytes > 30): a 30-byte payload
+    + '\\n' (31 bytes) is accepted, a 29-byte payload + '\\n' (30 bytes) is rejected."""
+    r, w = os.pipe()
+    feed = wire.StateFeed(r)
+    try:
+        f30 = b"0.0150 0.0100 0.0000 0.02 0.04"       # 30 bytes
+        f29 = b"0.0150 0.0100 0.0000 0.02 0.4"        # 29 bytes
+        assert len(f30) == 30 and len(f29) == 29
+        os.write(w, f29 + b"\n")
+        os.write(w, f30 + b"\n")
+        deadline = time.time() + 5.0
+        while time.time() < deadline and sum(feed.stats()) < 2:
+            time.sleep(0.005)
+        assert feed.stats() == (1, 1)
+        dt, X = feed.latest()
+        assert dt == np.float32(0.015) and X[3] == np.float32(0.04)
+        # the stand-alone parser sees the raw frame, terminator included
+        assert wire.parse_frame(f30.decode() + "\n") is not None and wire.parse_frame(f29.decode() + "\n") is None
+    finally:
+        feed.close()
+        os.close(r); os.close(w)
