@@ -1,0 +1,641 @@
+// admm_instance_pair.cu -- per-instance regime (every QP has its OWN P_i, A_i: BASELINE config 4) for the reference's
+// constraint form A = [G; -G] (two-sided limit as row pairs, src/ModelPredictiveControlAPI.cpp:335), n <= 32, m = 2 mp <= 64.
+// Replaces what the reference reaches through solver.initSolver() / solver.solve() (cpp:64,102) for distinct P, A.
+//
+// One CTA of TWO warps owns one QP at a time (persistent CTAs, device ticket queue: no CTA waits for a slow neighbour):
+//   x-warp (warp 0), lane i:  x_i, q_i and row i of M^-1          in registers
+//   z-warp (warp 1), lane r:  z, y of rows r and r + mp, row r of K = G M^-1   in registers
+//   both warps:               half a row of G' each (lane i: G(16 w .. 16 w + 15, i))
+// One OSQP iteration (x-space, same steps and order as osqp_solve):
+//   phase 1   rhs = sigma x - q + G' wd,           wd = (rho_vec z - y)_top - (rho_vec z - y)_bot      (two half dot products)
+//   phase 2   x~ = M^-1 rhs (x-warp)   ||   z~_top = K rhs = G x~ (z-warp), z~_bot = -z~_top            (independent)
+//   then relaxation, clip to [l, u], dual update in the z-warp's registers; x update in the x-warp's.
+// Three CTA barriers of 64 threads per iteration; 96 DFMA + 24 LDS.128 per thread-pair-iteration; no operator is read from
+// shared memory inside the iteration.
+//
+// Operands are staged by TMA: every instance has a prepared PACK in HBM (written once at create time by the same kernel
+// with prepare = 1, as osqp_setup factors once): G' (padded rows of 34 doubles), M(rho)^-1 and K for the rho it was last
+// factored with, and the rho-independent split M(rho) = S0 + rho T.  While a QP iterates, thread 0 has already drawn the
+// NEXT ticket, issued cp.async.bulk (global -> the second G' stage in shared memory, completion on an mbarrier) and an L2
+// prefetch of the rest of that pack, so a solve starts with its operands on chip.
+// Refactorisation (every rho update, exactly when OSQP refactors): M = S0 + rho T, left-looking Cholesky in shared memory,
+// lane c solves L L' v = e_c in registers (row c of M^-1), then the z-warp forms its rows of K = G M^-1.
+#include <cstdint>
+#include <cstdlib>
+
+#include "device_types.cuh"
+#include "kernels.cuh"
+
+namespace smpc {
+
+namespace {
+
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kPN = 32;    // max n and mp
+constexpr int kPLD = 34;   // padded row stride in doubles: 16-byte row sweeps of a quarter warp hit 8 different bank groups
+
+__device__ __forceinline__ double wmax(double v) {   // exact max over the warp of NON-NEGATIVE doubles (IEEE bit patterns order them)
+  const unsigned hi = (unsigned)__double2hiint(v);
+  const unsigned mh = __reduce_max_sync(kFull, hi);
+  const unsigned lo = hi == mh ? (unsigned)__double2loint(v) : 0u;
+  const unsigned ml = __reduce_max_sync(kFull, lo);
+  return __hiloint2double((int)mh, (int)ml);
+}
+__device__ __forceinline__ double wsum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+
+// ---- TMA (1-D bulk copy) + mbarrier, raw PTX (SASS: UBLKCP.S.G, UBLKPF.L2, SYNCS.*)
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+               "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_prefetch_l2(const void *src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+// sum_{k < 32} reg[k] * vec[k]: the row in registers, vec (zero padded to 32) broadcast from shared memory with LDS.128
+__device__ __forceinline__ double dot_reg32(const double (&reg)[kPN], const double *vec) {
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+  for (int k = 0; k < kPN; k += 4) {
+    const double2 v0 = *reinterpret_cast<const double2 *>(vec + k), v1 = *reinterpret_cast<const double2 *>(vec + k + 2);
+    a0 = fma(reg[k], v0.x, a0); a1 = fma(reg[k + 1], v0.y, a1); a2 = fma(reg[k + 2], v1.x, a2); a3 = fma(reg[k + 3], v1.y, a3);
+  }
+  return (a0 + a1) + (a2 + a3);
+}
+__device__ __forceinline__ double dot_reg16(const double (&reg)[16], const double *vec) {
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+  for (int k = 0; k < 16; k += 4) {
+    const double2 v0 = *reinterpret_cast<const double2 *>(vec + k), v1 = *reinterpret_cast<const double2 *>(vec + k + 2);
+    a0 = fma(reg[k], v0.x, a0); a1 = fma(reg[k + 1], v0.y, a1); a2 = fma(reg[k + 2], v1.x, a2); a3 = fma(reg[k + 3], v1.y, a3);
+  }
+  return (a0 + a1) + (a2 + a3);
+}
+
+__device__ __forceinline__ int row_class(double lo, double hi) {   // -1 free, 0 inequality, 1 equality (OSQP constr_type)
+  return (lo < -kInfty * kMinScaling && hi > kInfty * kMinScaling) ? -1 : ((hi - lo < kRhoTolRow) ? 1 : 0);
+}
+
+// indices into the CTA-wide scalar exchange red[]
+enum { R_SRP, R_SZ, R_SAX, R_URP, R_UZ, R_UAX, R_PIND, R_PILHS, R_SRD, R_SQ, R_SATY, R_SPX, R_URD, R_UQ, R_UATY, R_UPX, R_OB, R_DIND,
+       R_DIQD, R_RARE0, R_RARE1, R_FLAG0, R_FLAG1, R_COUNT };
+
+}  // namespace
+
+__host__ __device__ inline int pair_tri2(int n) { return ((n * (n + 1) / 2) + 1) & ~1; }
+// pack of one instance (doubles): G' | M^-1 | K (kPN rows of kPLD each) | S0 | T (packed lower triangles)
+size_t instance_pair_pack_doubles(int n) { return 3 * (size_t)kPN * kPLD + 2 * (size_t)pair_tri2(n); }
+bool instance_pair_supports(int n, int m) { return n >= 1 && n <= kPN && m >= 2 && m % 2 == 0 && m / 2 <= kPN; }
+static size_t pair_smem_bytes(int n) { return ((size_t)3 * n * kPLD + 20 * kPN) * sizeof(double) + 4 * sizeof(uint64_t); }
+
+template <int CTAS_PER_SM>
+__global__ void __launch_bounds__(64, CTAS_PER_SM) admm_instance_pair_kernel(InstanceDataDev I, BatchDev Bt, SettingsDev S, int *queue, int prepare) {
+  extern __shared__ __align__(16) double smem[];
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const bool xw = w == 0;
+  const int n = I.n, m = I.m, mp = m >> 1, B = Bt.B;
+  const int tri = n * (n + 1) / 2, tri2 = pair_tri2(n);
+  const size_t pack_stride = 3 * (size_t)kPN * kPLD + 2 * (size_t)tri2;
+  double *const Gt0 = smem, *const Gt1 = smem + n * kPLD;
+  double *Sc = smem + 2 * n * kPLD;
+  double *wd = Sc + n * kPLD, *p1 = wd + kPN, *rhs = p1 + kPN, *xs = rhs + kPN, *ubt = xs + kPN, *ubb = ubt + kPN, *lbt = ubb + kPN,
+         *lbb = lbt + kPN, *t0 = lbb + kPN, *t1 = t0 + kPN, *evt = t1 + kPN, *evb = evt + kPN, *dl0 = evb + kPN, *dl1 = dl0 + kPN,
+         *dl2 = dl1 + kPN, *rvt = dl2 + kPN, *rvb = rvt + kPN, *rit = rvb + kPN, *rib = rit + kPN, *red = rib + kPN;
+  // dl0 / dl1: delta_y (top, bottom), dl2: delta_x of the iteration before a check; rvt .. rib: rho_vec and 1 / rho_vec per row
+  uint64_t *mbar = reinterpret_cast<uint64_t *>(red + kPN);   // [0], [1]: the two G' stages
+  __shared__ int s_ticket;
+
+  const double alpha = S.alpha, sigma = S.sigma;
+  const bool unscale = !S.scaled_termination;
+  const uint32_t gt_bytes = (uint32_t)(n * kPLD * sizeof(double));
+
+  if (tid == 0) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); mbar_fence_init(); }
+  for (int e = tid; e < 20 * kPN; e += 64) wd[e] = 0.0;
+  __syncthreads();
+  // first ticket + its G' stage
+  if (tid == 0) {
+    const int t = atomicAdd(queue, 1);
+    s_ticket = t;
+    if (t < B && !prepare) { fence_proxy_async(); mbar_expect_tx(&mbar[0], gt_bytes); bulk_g2s(Gt0, I.pack + (size_t)t * pack_stride, gt_bytes, &mbar[0]); }
+  }
+  __syncthreads();
+  int cur = s_ticket, stage = 0;
+  uint32_t phase0 = 0u, phase1 = 0u;
+
+  while (cur < B) {
+    const int b = cur;
+    __syncthreads();                       // everyone has read s_ticket / finished the previous solve
+    if (tid == 0) {                        // draw the next ticket now: its operands travel while this QP is solved
+      const int t = atomicAdd(queue, 1);
+      s_ticket = t;
+      if (t < B && !prepare) {
+        const double *pk = I.pack + (size_t)t * pack_stride;
+        fence_proxy_async();                                                                       // the other stage was read with LDS until a moment ago
+        mbar_expect_tx(&mbar[stage ^ 1], gt_bytes);
+        bulk_g2s(stage ? Gt0 : Gt1, pk, gt_bytes, &mbar[stage ^ 1]);
+        bulk_prefetch_l2(pk + kPN * kPLD, (uint32_t)((kPN + n) * kPLD * sizeof(double)));          // M^-1 and the first n rows of K
+        bulk_prefetch_l2(pk + 3 * kPN * kPLD, (uint32_t)(2 * tri2 * sizeof(double)));              // S0, T
+        const uintptr_t pa = reinterpret_cast<uintptr_t>(I.P + (size_t)t * n * n) & ~(uintptr_t)15;
+        bulk_prefetch_l2(reinterpret_cast<const void *>(pa), (uint32_t)((n * n * sizeof(double) + 15) & ~(size_t)15));   // P̄ (termination checks)
+      }
+    }
+    double *Gt = stage ? Gt1 : Gt0;
+    double *pack = I.pack + (size_t)b * pack_stride;
+    const double *gP = I.P + (size_t)b * n * n;
+    const double c = I.c[b], cinv = 1.0 / c;
+    const bool warm = S.warm_start && !Bt.fresh && !prepare;
+
+    // ---- per-instance vectors into registers
+    // four state registers per thread, by role.  x-warp (lane < n): x, q̄, D, -.  z-warp (lane < mp): z_top, z_bot, y_top, y_bot.
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#define X_ s0
+#define Q_ s1
+#define DV_ s2
+#define ZT_ s0
+#define ZB_ s1
+#define YT_ s2
+#define YB_ s3
+    int cls_t = 0, cls_b = 0, flag_bad = 0, flag_diff = 0;
+    if (tid < 32) { dl0[lane] = 0.0; dl1[lane] = 0.0; dl2[lane] = 0.0; }
+    if (xw) {
+      if (lane < n) {
+        DV_ = I.D[(size_t)b * n + lane];
+        Q_ = Bt.q ? c * (DV_ * Bt.q[(size_t)b * n + lane]) : 0.0;
+        X_ = warm ? Bt.xi[(size_t)b * n + lane] : 0.0;
+      }
+    } else {
+      double lt = -1.0, lb_ = -1.0, ut = 1.0, ub_ = 1.0, et = 1.0, eb = 1.0;
+      if (lane < mp) {
+        const size_t rt = (size_t)b * m + lane, rb = rt + mp;
+        et = I.E[rt]; eb = I.E[rb];
+        lt = et * (Bt.l ? Bt.l[rt] : I.l0[lane]); lb_ = eb * (Bt.l ? Bt.l[rb] : I.l0[lane + mp]);
+        ut = et * (Bt.u ? Bt.u[rt] : I.u0[lane]); ub_ = eb * (Bt.u ? Bt.u[rb] : I.u0[lane + mp]);
+        if (warm) { ZT_ = Bt.z[rt]; ZB_ = Bt.z[rb]; YT_ = Bt.y[rt]; YB_ = Bt.y[rb]; }
+        flag_bad = (lt > ut) || (lb_ > ub_);
+        cls_t = row_class(lt, ut); cls_b = row_class(lb_, ub_);
+        flag_diff = (cls_t != row_class(et * I.l0[lane], et * I.u0[lane])) || (cls_b != row_class(eb * I.l0[lane + mp], eb * I.u0[lane + mp]));
+      }
+      lbt[lane] = lt; lbb[lane] = lb_; ubt[lane] = ut; ubb[lane] = ub_; evt[lane] = et; evb[lane] = eb;
+      flag_bad = __any_sync(kFull, flag_bad); flag_diff = __any_sync(kFull, flag_diff);
+      if (lane == 0) { red[R_FLAG0] = flag_bad ? 1.0 : 0.0; red[R_FLAG1] = flag_diff ? 1.0 : 0.0; }
+    }
+    double rho = (Bt.fresh || prepare) ? fmin(fmax(S.rho0, kRhoMin), kRhoMax) : Bt.rho[b];
+    if (prepare) {   // build G' (padded) from the scaled A̅ of this instance; everything else of the pack follows below
+      const double *gA = I.A + (size_t)b * m * n;
+      for (int e = tid; e < n * kPLD; e += 64) Gt[e] = 0.0;
+      __syncthreads();
+      for (int e = tid; e < mp * n; e += 64) { const int r = e / n, i = e % n; Gt[i * kPLD + r] = gA[e]; }
+      __syncthreads();
+      for (int e = tid; e < n * kPLD; e += 64) pack[e] = Gt[e];
+    } else {
+      mbar_wait(&mbar[stage], stage ? phase1 : phase0);   // G' of this instance has landed (issued one solve ago)
+      if (stage) phase1 ^= 1u; else phase0 ^= 1u;
+    }
+    __syncthreads();
+    const bool bad_bounds = red[R_FLAG0] != 0.0;
+    bool split_ok = red[R_FLAG1] == 0.0;     // the pack's S0 / T / M^-1 / K hold for the row classes of the SETUP bounds only
+
+    // ---- operators into registers
+    double gt[16], op[kPN];
+#pragma unroll
+    for (int j = 0; j < 16; j += 2) {
+      const double2 v = lane < n ? *reinterpret_cast<const double2 *>(Gt + lane * kPLD + 16 * w + j) : make_double2(0.0, 0.0);
+      gt[j] = v.x; gt[j + 1] = v.y;
+    }
+#pragma unroll
+    for (int k = 0; k < kPN; ++k) op[k] = 0.0;
+
+    // OSQP set_rho_vec / update_rho_vec for this solve's row classes (z-warp lanes own their rows' entries)
+    auto set_rho = [&]() {
+      if (!xw) {
+        const double rho_eq = kRhoEqOverIneq * rho;
+        const double vt = cls_t < 0 ? kRhoMin : (cls_t == 1 ? rho_eq : rho), vb = cls_b < 0 ? kRhoMin : (cls_b == 1 ? rho_eq : rho);
+        rvt[lane] = vt; rvb[lane] = vb; rit[lane] = 1.0 / vt; rib[lane] = 1.0 / vb;
+      }
+    };
+    set_rho();
+
+    // (A̅' v)_lane for v = top - bottom given in t0[] (valid on the x-warp's lanes < n).  Two barriers.
+    auto AT_dot_t0 = [&]() -> double {
+      const double part = dot_reg16(gt, t0 + 16 * w);
+      if (!xw) p1[lane] = part;
+      __syncthreads();
+      const double full = part + p1[lane];
+      __syncthreads();
+      return full;
+    };
+
+    // M (lower triangle) -> Sc; Cholesky; rows of M^-1 -> x-warp registers; rows of K = G M^-1 -> z-warp registers.
+    // mode 0: M = S0 + rho T from the pack; 1: assembled from G and this solve's rho_vec; 2 (prepare): also writes S0, T.
+    auto refactor = [&](int mode) -> bool {
+      if (mode != 0 && !xw) {   // per-row weights of G_r' G_r: t0 = kappa_top + kappa_bot (times rho), t1 = the free rows' rho_min
+        if (mode == 2) {
+          t0[lane] = lane < mp ? ((cls_t < 0 ? 0.0 : (cls_t == 1 ? kRhoEqOverIneq : 1.0)) + (cls_b < 0 ? 0.0 : (cls_b == 1 ? kRhoEqOverIneq : 1.0))) : 0.0;
+          t1[lane] = lane < mp ? ((cls_t < 0 ? kRhoMin : 0.0) + (cls_b < 0 ? kRhoMin : 0.0)) : 0.0;
+        } else {
+          t0[lane] = lane < mp ? rvt[lane] + rvb[lane] : 0.0;
+        }
+      }
+      __syncthreads();
+      for (int e = tid; e < tri; e += 64) {
+        int i = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
+        while ((i + 1) * (i + 2) / 2 <= e) ++i;
+        while (i * (i + 1) / 2 > e) --i;
+        const int j = e - i * (i + 1) / 2;
+        double mij;
+        if (mode == 0) {
+          mij = fma(rho, pack[3 * kPN * kPLD + tri2 + e], pack[3 * kPN * kPLD + e]);
+        } else {
+          const double *gi = Gt + i * kPLD, *gj = Gt + j * kPLD;
+          double s0 = gP[i * n + j] + (i == j ? sigma : 0.0), tt = 0.0;
+          if (mode == 2) {
+            for (int r = 0; r < mp; ++r) { const double aa = gi[r] * gj[r]; s0 = fma(t1[r], aa, s0); tt = fma(t0[r], aa, tt); }
+            pack[3 * kPN * kPLD + e] = s0; pack[3 * kPN * kPLD + tri2 + e] = tt;
+            mij = fma(rho, tt, s0);
+          } else {
+            for (int r = 0; r < mp; ++r) s0 = fma(t0[r] * gi[r], gj[r], s0);
+            mij = s0;
+          }
+        }
+        Sc[i * kPLD + j] = mij;
+      }
+      __syncthreads();
+      // left-looking Cholesky by the x-warp, lower triangle of Sc in place; t1[j] = 1 / L_jj; rhs[] is scratch
+      if (xw) {
+        int ok = 1;
+        for (int j = 0; j < n; ++j) {
+          if (lane >= j && lane < n) {
+            const double *ri = Sc + lane * kPLD, *rj = Sc + j * kPLD;
+            double s0 = ri[j], s1 = 0.0;
+            int k = 0;
+            for (; k + 2 <= j; k += 2) {
+              const double2 a = *reinterpret_cast<const double2 *>(ri + k), c2 = *reinterpret_cast<const double2 *>(rj + k);
+              s0 = fma(-a.x, c2.x, s0); s1 = fma(-a.y, c2.y, s1);
+            }
+            if (k < j) s0 = fma(-ri[k], rj[k], s0);
+            rhs[lane] = s0 + s1;
+          }
+          __syncwarp();
+          const double d = rhs[j];
+          if (!(d > 0.0)) { ok = 0; break; }
+          const double sd = sqrt(d);
+          if (lane >= j && lane < n) Sc[lane * kPLD + j] = lane == j ? sd : rhs[lane] / sd;
+          if (lane == 0) t1[j] = 1.0 / sd;
+          __syncwarp();
+        }
+        if (lane == 0) red[R_FLAG0] = ok ? 0.0 : 1.0;
+        if (ok) {
+          // forward substitution L v = e_lane, then backward L' u = v, in registers; L is read with warp-uniform addresses
+#pragma unroll
+          for (int i = 0; i < kPN; ++i) {
+            if (i < n) {
+              double s0 = i == lane ? 1.0 : 0.0, s1 = 0.0;
+#pragma unroll
+              for (int k = 0; k + 1 < i; k += 2) {
+                const double2 l = *reinterpret_cast<const double2 *>(Sc + i * kPLD + k);
+                s0 = fma(-l.x, op[k], s0); s1 = fma(-l.y, op[k + 1], s1);
+              }
+              if (i & 1) s0 = fma(-Sc[i * kPLD + i - 1], op[i - 1], s0);
+              op[i] = (s0 + s1) * t1[i];
+            } else {
+              op[i] = 0.0;
+            }
+          }
+#pragma unroll
+          for (int i = kPN - 1; i >= 0; --i) {
+            if (i < n) {
+              double s0 = op[i], s1 = 0.0;
+#pragma unroll
+              for (int k = i + 1; k < kPN; ++k) {
+                if (k < n) {
+                  if (k & 1) s1 = fma(-Sc[k * kPLD + i], op[k], s1); else s0 = fma(-Sc[k * kPLD + i], op[k], s0);
+                }
+              }
+              op[i] = (s0 + s1) * t1[i];
+            }
+          }
+          if (lane >= n) {
+#pragma unroll
+            for (int k = 0; k < kPN; ++k) op[k] = 0.0;
+          }
+          __syncwarp();   // every lane is done with L: Sc now receives M^-1 for the z-warp
+          if (lane < n) {
+#pragma unroll
+            for (int k = 0; k < kPN; k += 2) *reinterpret_cast<double2 *>(Sc + lane * kPLD + k) = make_double2(op[k], op[k + 1]);
+          }
+        }
+      }
+      __syncthreads();
+      if (red[R_FLAG0] != 0.0) return false;
+      if (!xw) {   // K_r = sum_k G(r, k) M^-1(k, :)
+#pragma unroll
+        for (int k = 0; k < kPN; ++k) op[k] = 0.0;
+        for (int k = 0; k < n; ++k) {
+          const double g = lane < mp ? Gt[k * kPLD + lane] : 0.0;
+          const double *row = Sc + k * kPLD;
+#pragma unroll
+          for (int c2 = 0; c2 < kPN; c2 += 2) {
+            const double2 v = *reinterpret_cast<const double2 *>(row + c2);
+            op[c2] = fma(g, v.x, op[c2]); op[c2 + 1] = fma(g, v.y, op[c2 + 1]);
+          }
+        }
+      }
+      __syncthreads();
+      return true;
+    };
+
+    int status = SMPC_UNSOLVED, iter = 0, rho_updates = 0;
+    bool can_check = false, factor_ok = true, refactored = false;
+    double F_pri = 0.0, F_dua = 0.0, F_obj = 0.0;
+
+    // OSQP update_info: residuals, their norms, the objective -- and the first, cheap tests of both infeasibility checks
+    auto update_info = [&]() {
+      if (xw) xs[lane] = X_; else t0[lane] = YT_ - YB_;
+      __syncthreads();
+      double Px = 0.0, Ax = 0.0;
+      if (xw) {
+        if (lane < n) for (int k = 0; k < n; ++k) Px = fma(gP[k * n + lane], xs[k], Px);   // P̄ is stored full symmetric: column sweep = coalesced
+      } else {
+        if (lane < mp) for (int k = 0; k < n; ++k) Ax = fma(Gt[k * kPLD + lane], xs[k], Ax);
+      }
+      const double Aty = AT_dot_t0();
+      if (xw) {
+        double rd = 0.0, ob = 0.0, u_rd = 0.0, u_q = 0.0, u_Aty = 0.0, u_Px = 0.0, nd = 0.0, qd = 0.0;
+        double a_q = 0.0, a_Aty = 0.0, a_Px = 0.0;
+        if (lane < n) {
+          const double x = X_, q = Q_, Dinv = 1.0 / DV_, dx = dl2[lane];
+          rd = fabs((q + Px) + Aty); a_q = fabs(q); a_Aty = fabs(Aty); a_Px = fabs(Px);
+          u_rd = fabs(Dinv * ((q + Px) + Aty)); u_q = fabs(Dinv * q); u_Aty = fabs(Dinv * Aty); u_Px = fabs(Dinv * Px);
+          ob = 0.5 * x * Px + q * x;
+          nd = fabs(unscale ? DV_ * dx : dx); qd = q * dx;
+        }
+        rd = wmax(rd); a_q = wmax(a_q); a_Aty = wmax(a_Aty); a_Px = wmax(a_Px);
+        u_rd = wmax(u_rd); u_q = wmax(u_q); u_Aty = wmax(u_Aty); u_Px = wmax(u_Px);
+        ob = wsum(ob); nd = wmax(nd); qd = wsum(qd);
+        if (lane == 0) {
+          red[R_SRD] = rd; red[R_SQ] = a_q; red[R_SATY] = a_Aty; red[R_SPX] = a_Px;
+          red[R_URD] = u_rd; red[R_UQ] = u_q; red[R_UATY] = u_Aty; red[R_UPX] = u_Px; red[R_OB] = ob; red[R_DIND] = nd; red[R_DIQD] = qd;
+        }
+      } else {
+        double a_rp = 0.0, a_z = 0.0, a_Ax = 0.0, u_rp = 0.0, u_z = 0.0, u_Ax = 0.0, nd = 0.0, lhs = 0.0;
+        if (lane < mp) {
+          const double et = evt[lane], eb = evb[lane], eit = 1.0 / et, eib = 1.0 / eb;
+          const double zt = ZT_, zb = ZB_;
+          const double rpt = Ax - zt, rpb = -Ax - zb;
+          a_rp = fmax(fabs(rpt), fabs(rpb)); a_z = fmax(fabs(zt), fabs(zb)); a_Ax = fabs(Ax);
+          u_rp = fmax(fabs(eit * rpt), fabs(eib * rpb)); u_z = fmax(fabs(eit * zt), fabs(eib * zb)); u_Ax = fmax(fabs(eit * Ax), fabs(eib * Ax));
+          // is_primal_infeasible, first part: project delta_y on the recession directions, its norm and u' dy+ + l' dy-
+          const double lt = lbt[lane], lb_ = lbb[lane], ut = ubt[lane], ub_ = ubb[lane];
+          double dt = dl0[lane], db = dl1[lane];
+          const bool uti = ut > kInfty * kMinScaling, lti = lt < -kInfty * kMinScaling, ubi = ub_ > kInfty * kMinScaling, lbi = lb_ < -kInfty * kMinScaling;
+          if (uti) dt = lti ? 0.0 : fmin(dt, 0.0); else if (lti) dt = fmax(dt, 0.0);
+          if (ubi) db = lbi ? 0.0 : fmin(db, 0.0); else if (lbi) db = fmax(db, 0.0);
+          dl0[lane] = dt; dl1[lane] = db;
+          nd = fmax(fabs(unscale ? et * dt : dt), fabs(unscale ? eb * db : db));
+          const double dpt = fmax(dt, 0.0), dmt = fmin(dt, 0.0), dpb = fmax(db, 0.0), dmb = fmin(db, 0.0);
+          if (dpt != 0.0) lhs += ut * dpt;
+          if (dmt != 0.0) lhs += lt * dmt;
+          if (dpb != 0.0) lhs += ub_ * dpb;
+          if (dmb != 0.0) lhs += lb_ * dmb;
+        }
+        a_rp = wmax(a_rp); a_z = wmax(a_z); a_Ax = wmax(a_Ax); u_rp = wmax(u_rp); u_z = wmax(u_z); u_Ax = wmax(u_Ax);
+        nd = wmax(nd); lhs = wsum(lhs);
+        if (lane == 0) {
+          red[R_SRP] = a_rp; red[R_SZ] = a_z; red[R_SAX] = a_Ax; red[R_URP] = u_rp; red[R_UZ] = u_z; red[R_UAX] = u_Ax;
+          red[R_PIND] = nd; red[R_PILHS] = lhs;
+        }
+      }
+      __syncthreads();
+      if (unscale) { F_pri = red[R_URP]; F_dua = cinv * red[R_URD]; F_obj = cinv * red[R_OB]; }
+      else { F_pri = red[R_SRP]; F_dua = red[R_SRD]; F_obj = red[R_OB]; }
+    };
+
+    auto primal_infeasible = [&](double eps) -> bool {   // uniform over the CTA
+      const double nd = red[R_PIND], lhs = red[R_PILHS];
+      if (!(nd > eps)) return false;
+      if (!(lhs < -eps * nd)) return false;
+      if (!xw) t0[lane] = dl0[lane] - dl1[lane];
+      __syncthreads();
+      const double v = AT_dot_t0();
+      if (xw) {
+        const double na = wmax(lane < n ? fabs(unscale ? (1.0 / DV_) * v : v) : 0.0);
+        if (lane == 0) red[R_RARE0] = na;
+      }
+      __syncthreads();
+      return red[R_RARE0] < eps * nd;
+    };
+
+    auto dual_infeasible = [&](double eps) -> bool {   // uniform over the CTA
+      const double nd = red[R_DIND], qd = red[R_DIQD];
+      const double cs = unscale ? c : 1.0;
+      if (!(nd > eps)) return false;
+      if (!(qd < -cs * eps * nd)) return false;
+      if (xw) {
+        double s = 0.0;
+        if (lane < n) for (int k = 0; k < n; ++k) s = fma(gP[k * n + lane], dl2[k], s);
+        const double np = wmax(lane < n ? fabs(unscale ? (1.0 / DV_) * s : s) : 0.0);
+        if (lane == 0) red[R_RARE0] = np;
+      } else {
+        int bad = 0;
+        if (lane < mp) {
+          double v = 0.0;
+          for (int k = 0; k < n; ++k) v = fma(Gt[k * kPLD + lane], dl2[k], v);
+          const double vt = unscale ? v / evt[lane] : v, vb = unscale ? -v / evb[lane] : -v;
+          if (((ubt[lane] < kInfty * kMinScaling) && (vt > eps * nd)) || ((lbt[lane] > -kInfty * kMinScaling) && (vt < -eps * nd))) bad = 1;
+          if (((ubb[lane] < kInfty * kMinScaling) && (vb > eps * nd)) || ((lbb[lane] > -kInfty * kMinScaling) && (vb < -eps * nd))) bad = 1;
+        }
+        bad = __any_sync(kFull, bad);
+        if (lane == 0) red[R_RARE1] = bad ? 1.0 : 0.0;
+      }
+      __syncthreads();
+      return (red[R_RARE0] < cs * eps * nd) && red[R_RARE1] == 0.0;
+    };
+
+    auto check_termination = [&](bool approx) -> bool {   // uniform over the CTA
+      double ea = S.eps_abs, er = S.eps_rel, epi = S.eps_prim_inf, edi = S.eps_dual_inf;
+      if (approx) { ea *= 10; er *= 10; epi *= 10; edi *= 10; }
+      const double nEz = unscale ? red[R_UZ] : red[R_SZ], nEAx = unscale ? red[R_UAX] : red[R_SAX];
+      const double nDq = unscale ? red[R_UQ] : red[R_SQ], nDAty = unscale ? red[R_UATY] : red[R_SATY], nDPx = unscale ? red[R_UPX] : red[R_SPX];
+      bool prim_ok = false, dual_ok = false, prim_inf = false, dual_inf = false;
+      if (F_pri < ea + er * fmax(nEz, nEAx)) prim_ok = true;
+      else prim_inf = primal_infeasible(epi);
+      if (F_dua < ea + er * (unscale ? cinv : 1.0) * fmax(fmax(nDq, nDAty), nDPx)) dual_ok = true;
+      else dual_inf = dual_infeasible(edi);
+      if (prim_ok && dual_ok) { status = approx ? SMPC_SOLVED_INACCURATE : SMPC_SOLVED; return true; }
+      if (prim_inf) { status = approx ? SMPC_PRIMAL_INFEASIBLE_INACCURATE : SMPC_PRIMAL_INFEASIBLE; F_obj = kInfty; return true; }
+      if (dual_inf) { status = approx ? SMPC_DUAL_INFEASIBLE_INACCURATE : SMPC_DUAL_INFEASIBLE; F_obj = -kInfty; return true; }
+      return false;
+    };
+
+    // ---- factorisation for this solve's rho: the pack's (osqp_setup / the last refactorisation that was stored), or a new one
+    // at the top of the first iteration (one call site for setup, rho updates and the prepare pass)
+    bool need_factor = !bad_bounds;
+    if (!prepare && !bad_bounds && split_ok && rho == I.pack_rho[b]) {
+      need_factor = false;
+      if (lane < (xw ? n : mp)) {
+        const double *src = pack + (xw ? 1 : 2) * kPN * kPLD + lane * kPLD;
+#pragma unroll
+        for (int k = 0; k < kPN; k += 2) { const double2 v = *reinterpret_cast<const double2 *>(src + k); op[k] = v.x; op[k + 1] = v.y; }
+      }
+    }
+    // wd for the first iteration
+    if (!xw) wd[lane] = lane < mp ? (rvt[lane] * ZT_ - YT_) - (rvb[lane] * ZB_ - YB_) : 0.0;
+    int to_check = S.check_every ? S.check_every : -1, to_adapt = (S.adaptive_rho && S.rho_interval) ? S.rho_interval : -1;   // countdowns instead of iter % interval
+
+    for (iter = 1; iter <= S.max_iter && !bad_bounds && factor_ok; ++iter) {
+      if (need_factor) {
+        factor_ok = refactor(prepare ? 2 : (split_ok ? 0 : 1));
+        need_factor = false; refactored = true;
+        if (prepare || !factor_ok) break;
+      }
+      __syncthreads();                                                                  // wd is visible
+      const double part = dot_reg16(gt, wd + 16 * w);                                   // half of (G' wd)_lane
+      if (!xw) p1[lane] = part;
+      __syncthreads();
+      if (xw) rhs[lane] = lane < n ? (sigma * X_ - Q_) + (part + p1[lane]) : 0.0;
+      __syncthreads();
+      const double acc = dot_reg32(op, rhs);                                            // x~_lane (x-warp) | (G x~)_lane (z-warp)
+      can_check = --to_check == 0;
+      const bool adapt = --to_adapt == 0;
+      if (can_check) to_check = S.check_every;
+      if (adapt) to_adapt = S.rho_interval;
+      const bool keep_deltas = can_check || adapt || iter == S.max_iter;                // delta_x, delta_y feed the infeasibility tests only
+      if (xw) {
+        const double xn = alpha * acc + (1.0 - alpha) * X_;
+        if (keep_deltas) dl2[lane] = xn - X_;
+        X_ = xn;
+      } else if (lane < mp) {
+        {
+          const double zr = alpha * acc + (1.0 - alpha) * ZT_;
+          const double zn = fmin(fmax(zr + rit[lane] * YT_, lbt[lane]), ubt[lane]);
+          const double d = rvt[lane] * (zr - zn);
+          ZT_ = zn; YT_ += d;
+          if (keep_deltas) dl0[lane] = d;
+        }
+        {
+          const double zr = alpha * (-acc) + (1.0 - alpha) * ZB_;
+          const double zn = fmin(fmax(zr + rib[lane] * YB_, lbb[lane]), ubb[lane]);
+          const double d = rvb[lane] * (zr - zn);
+          ZB_ = zn; YB_ += d;
+          if (keep_deltas) dl1[lane] = d;
+        }
+      }
+      if (can_check || adapt) {
+        update_info();
+        if (can_check && check_termination(false)) break;
+        if (adapt) {
+          const double pr = red[R_SRP] / (fmax(red[R_SZ], red[R_SAX]) + kDivTol);
+          const double dr = red[R_SRD] / (fmax(fmax(red[R_SQ], red[R_SATY]), red[R_SPX]) + kDivTol);
+          const double rn = fmin(fmax(rho * sqrt(pr / (dr + kDivTol)), kRhoMin), kRhoMax);
+          if (rn > rho * S.rho_tol || rn < rho / S.rho_tol) {
+            rho = rn; ++rho_updates;
+            set_rho();
+            need_factor = true;
+          }
+        }
+      }
+      if (!xw) wd[lane] = lane < mp ? (rvt[lane] * ZT_ - YT_) - (rvb[lane] * ZB_ - YB_) : 0.0;
+    }
+    if (prepare) {   // create-time pass: the pack now holds G', S0, T; add M(rho0)^-1 and K and leave
+      const bool ok = !bad_bounds && factor_ok;
+      if (ok && lane < (xw ? n : mp)) {
+        double *dst = pack + (xw ? 1 : 2) * kPN * kPLD + lane * kPLD;
+#pragma unroll
+        for (int k = 0; k < kPN; k += 2) *reinterpret_cast<double2 *>(dst + k) = make_double2(op[k], op[k + 1]);
+      }
+      if (tid == 0) I.pack_rho[b] = ok ? rho : -1.0;   // -1: no usable factorisation in the pack
+      __syncthreads();
+      cur = s_ticket;
+      continue;
+    }
+    if (iter > S.max_iter) iter = S.max_iter;
+    if (bad_bounds || !factor_ok) iter = 0;
+    else {
+      if (!can_check) { update_info(); check_termination(false); }
+      if (status == SMPC_UNSOLVED) { if (!check_termination(true)) status = SMPC_MAX_ITER_REACHED; }
+    }
+
+    const bool has_sol = !bad_bounds && factor_ok && !(status == SMPC_PRIMAL_INFEASIBLE || status == SMPC_PRIMAL_INFEASIBLE_INACCURATE ||
+                                                       status == SMPC_DUAL_INFEASIBLE || status == SMPC_DUAL_INFEASIBLE_INACCURATE);
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    if (xw) {
+      if (lane < n) {
+        if (Bt.x_out) Bt.x_out[(size_t)b * n + lane] = has_sol ? DV_ * X_ : qnan;
+        Bt.xi[(size_t)b * n + lane] = has_sol ? X_ : 0.0;
+      }
+    } else if (lane < mp) {
+      const size_t rt = (size_t)b * m + lane, rb = rt + mp;
+      if (Bt.y_out) { Bt.y_out[rt] = has_sol ? cinv * (evt[lane] * YT_) : qnan; Bt.y_out[rb] = has_sol ? cinv * (evb[lane] * YB_) : qnan; }
+      Bt.z[rt] = has_sol ? ZT_ : 0.0; Bt.z[rb] = has_sol ? ZB_ : 0.0;
+      Bt.y[rt] = has_sol ? YT_ : 0.0; Bt.y[rb] = has_sol ? YB_ : 0.0;
+    }
+    // OSQP keeps its factorisation between solves: store the one for the final rho (warm solves restart from it)
+    if (refactored && factor_ok && split_ok && !Bt.fresh) {
+      if (lane < (xw ? n : mp)) {
+        double *dst = pack + (xw ? 1 : 2) * kPN * kPLD + lane * kPLD;
+#pragma unroll
+        for (int k = 0; k < kPN; k += 2) *reinterpret_cast<double2 *>(dst + k) = make_double2(op[k], op[k + 1]);
+      }
+      if (tid == 0) I.pack_rho[b] = rho;
+    }
+    if (tid == 0) {
+      Bt.rho[b] = rho;
+      Bt.status[b] = status; Bt.iter[b] = iter; Bt.rho_updates[b] = rho_updates;
+      Bt.obj[b] = F_obj; Bt.pri_res[b] = F_pri; Bt.dua_res[b] = F_dua;
+    }
+    __syncthreads();
+    cur = s_ticket;
+    stage ^= 1;
+  }
+  // the last CTA to leave re-arms the ticket counter for the next launch
+  if (tid == 0) {
+    __threadfence();
+    const int done = atomicAdd(queue + 1, 1);
+    if (done == (int)gridDim.x - 1) { queue[0] = 0; queue[1] = 0; __threadfence(); }
+  }
+}
+
+template <int CTAS_PER_SM>
+static cudaError_t launch_pair(const InstanceDataDev &I, const BatchDev &Bt, const SettingsDev &S, int num_sms, cudaStream_t stream, int prepare) {
+  const size_t smem = pair_smem_bytes(I.n);
+  cudaError_t e = cudaFuncSetAttribute(admm_instance_pair_kernel<CTAS_PER_SM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // per device: every launch
+  if (e != cudaSuccess) return e;
+  int per_sm = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, admm_instance_pair_kernel<CTAS_PER_SM>, 64, smem);
+  if (e != cudaSuccess) return e;
+  if (per_sm < 1) return cudaErrorInvalidValue;
+  int grid = num_sms * per_sm;
+  if (grid > Bt.B) grid = Bt.B;
+  admm_instance_pair_kernel<CTAS_PER_SM><<<grid, 64, smem, stream>>>(I, Bt, S, I.queue, prepare);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_admm_instance_pair(const InstanceDataDev &I, const BatchDev &Bt, const SettingsDev &S, int num_sms, cudaStream_t stream,
+                                      int prepare) {
+  static const int ctas = getenv("SMPC_PAIR_CTAS") ? atoi(getenv("SMPC_PAIR_CTAS")) : 6;   // register budget per thread: 6 -> 168, 7 -> 144, 5 -> 200
+  if (ctas == 7) return launch_pair<7>(I, Bt, S, num_sms, stream, prepare);
+  if (ctas == 5) return launch_pair<5>(I, Bt, S, num_sms, stream, prepare);
+  return launch_pair<6>(I, Bt, S, num_sms, stream, prepare);
+}
+
+}  // namespace smpc

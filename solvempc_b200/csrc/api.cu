@@ -399,9 +399,6 @@ int smpc_solver_create_batched(smpc_solver **out, int device, int n, int m, int 
     const size_t N = n, M = m, B = batch;
     size_t bytes = 0;
     for (size_t c : {B * N * N, B * M * N, B * N, B * M, B, M, M}) bytes += DeviceBuf::need(c * sizeof(double));
-    const bool prep = smpc::instance_reg_supports(n, m);
-    const size_t tri = N * (N + 1) / 2;
-    if (prep) for (size_t c : {B * tri, B * tri, B * N * 32}) bytes += DeviceBuf::need(c * sizeof(double));
     CK(s->instbuf.alloc(bytes));
     smpc::InstanceDataDev &d = s->dinst;
     d.n = n; d.m = m; d.B = batch;
@@ -410,11 +407,7 @@ int smpc_solver_create_batched(smpc_solver **out, int device, int n, int m, int 
     double *dl0 = s->instbuf.take<double>(M ? M : 1), *du0 = s->instbuf.take<double>(M ? M : 1);
     if (!du0) return fail(SMPC_ERR_CUDA, "internal: instance buffer carve-out overflow");
     d.S0 = d.T = d.Minv0 = nullptr; d.rho_prepared = 0.0; d.paired = 0;
-    if (prep) {
-      d.S0 = s->instbuf.take<double>(B * tri); d.T = s->instbuf.take<double>(B * tri); d.Minv0 = s->instbuf.take<double>(B * N * 32);
-      if (!d.Minv0) return fail(SMPC_ERR_CUDA, "internal: instance buffer carve-out overflow");
-      d.rho_prepared = std::min(std::max(s->st.rho, smpc::kRhoMin), smpc::kRhoMax);
-    }
+    d.pack = d.pack_rho = nullptr; d.queue = nullptr;
     std::vector<double> hl(M), hu(M);
     for (size_t i = 0; i < M; ++i) { hl[i] = l0 ? l0[i] : -INFINITY; hu[i] = u0 ? u0[i] : INFINITY; }
     if (M) { CK(cudaMemcpy(dl0, hl.data(), M * sizeof(double), cudaMemcpyHostToDevice)); CK(cudaMemcpy(du0, hu.data(), M * sizeof(double), cudaMemcpyHostToDevice)); }
@@ -422,12 +415,11 @@ int smpc_solver_create_batched(smpc_solver **out, int device, int n, int m, int 
     cudaMemcpyKind k = loc == SMPC_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
     CK(cudaMemcpy(d.P, P, B * N * N * sizeof(double), k));
     if (M) CK(cudaMemcpy(d.A, A, B * M * N * sizeof(double), k));
-    if (s->st.scaling > 0) { CK(smpc::launch_ruiz_instance(d, s->st.scaling, nullptr)); s->launches++; }
-    else {
-      CK(smpc::launch_ruiz_instance(d, 0, nullptr)); s->launches++;   // zero passes: mirrors P's upper triangle, D = E = c = 1
-    }
+    // scale_data per instance (scaling == 0: zero passes, which still mirror P's upper triangle and set D = E = c = 1)
+    CK(smpc::launch_ruiz_instance(d, s->st.scaling > 0 ? s->st.scaling : 0, nullptr)); s->launches++;
     if (int rc = alloc_batch(s)) return rc;
     if (int rc = reset_state(s, true)) return rc;
+    const bool prep = smpc::instance_reg_supports(n, m);
     if (prep && m >= 2 && m % 2 == 0) {   // [G; -G] rows in every instance?  (checked on the scaled data; d_status is free here)
       int one = 1, flag = 0;
       CK(cudaMemcpy(s->d_status, &one, sizeof(int), cudaMemcpyHostToDevice));
@@ -437,17 +429,39 @@ int smpc_solver_create_batched(smpc_solver **out, int device, int n, int m, int 
       CK(cudaMemset(s->d_status, 0, sizeof(int)));
       d.paired = flag;
     }
-    if (prep) {   // what osqp_setup does once per solver: the factorisation for rho0 (and the rho-independent parts of M)
+    // what osqp_setup does once per solver -- the factorisation for rho0 and the rho-independent parts of M -- is prepared
+    // here, in the layout of the kernel that will run the solves
+    const bool pair_kernel = d.paired && smpc::instance_pair_supports(n, m) && !getenv("SMPC_INSTANCE_NO_PAIR_KERNEL");
+    const size_t tri = N * (N + 1) / 2;
+    if (pair_kernel) {
+      const size_t pk = smpc::instance_pair_pack_doubles(n);
+      CK(s->prepbuf.alloc(DeviceBuf::need(B * pk * sizeof(double)) + DeviceBuf::need(B * sizeof(double)) + DeviceBuf::need(2 * sizeof(int))));
+      d.pack = s->prepbuf.take<double>(B * pk); d.pack_rho = s->prepbuf.take<double>(B); d.queue = s->prepbuf.take<int>(2);
+      if (!d.queue) return fail(SMPC_ERR_CUDA, "internal: instance pack carve-out overflow");
+      CK(cudaMemset(d.queue, 0, 2 * sizeof(int)));
+      int sms = 0;
+      CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+      s->num_sms = sms > 0 ? sms : 148;
+    } else if (prep) {
+      size_t pb = 0;
+      for (size_t c : {B * tri, B * tri, B * N * 32}) pb += DeviceBuf::need(c * sizeof(double));
+      CK(s->prepbuf.alloc(pb));
+      d.S0 = s->prepbuf.take<double>(B * tri); d.T = s->prepbuf.take<double>(B * tri); d.Minv0 = s->prepbuf.take<double>(B * N * 32);
+      if (!d.Minv0) return fail(SMPC_ERR_CUDA, "internal: instance buffer carve-out overflow");
+      d.rho_prepared = std::min(std::max(s->st.rho, smpc::kRhoMin), smpc::kRhoMax);
+    }
+    if (pair_kernel || prep) {
       smpc::BatchDev pb{};
       pb.B = batch;
-      CK(smpc::launch_admm_instance(d, pb, to_dev(s->st), nullptr, 1));
+      CK(pair_kernel ? smpc::launch_admm_instance_pair(d, pb, to_dev(s->st), s->num_sms, nullptr, 1)
+                     : smpc::launch_admm_instance(d, pb, to_dev(s->st), nullptr, 1));
       s->launches++;
     }
     CK(cudaDeviceSynchronize());
     return SMPC_OK;
   };
   int rc = body();
-  if (rc != SMPC_OK) { s->instbuf.release(); s->batchbuf.release(); delete s; return rc; }
+  if (rc != SMPC_OK) { s->instbuf.release(); s->prepbuf.release(); s->batchbuf.release(); delete s; return rc; }
   *out = s;
   return SMPC_OK;
 }
@@ -456,7 +470,7 @@ int smpc_solver_destroy(smpc_solver *s) {
   if (!s) return SMPC_OK;
   cudaSetDevice(s->device);
   cudaStreamSynchronize(s->stream);
-  s->planbuf.release(); s->batchbuf.release(); s->packbuf.release(); s->instbuf.release(); s->tilebuf.release();
+  s->planbuf.release(); s->batchbuf.release(); s->packbuf.release(); s->instbuf.release(); s->prepbuf.release(); s->tilebuf.release();
   delete s;
   return SMPC_OK;
 }
@@ -539,7 +553,8 @@ int smpc_solver_solve(smpc_solver *s) {
     CK(cudaEventCreate(&ev0)); CK(cudaEventCreate(&ev1));
     CK(cudaEventRecord(ev0, s->stream));
   }
-  cudaError_t e = s->regime == 1 ? smpc::launch_admm_instance(s->dinst, b, sd, s->stream)
+  cudaError_t e = s->regime == 1 ? (s->dinst.pack ? smpc::launch_admm_instance_pair(s->dinst, b, sd, s->num_sms, s->stream, 0)
+                                                  : smpc::launch_admm_instance(s->dinst, b, sd, s->stream))
                   : s->kernel == 2 ? smpc::launch_admm_shared_small(s->dpack, s->dplan, b, sd, s->d_queue, s->schedule ? s->d_lists : nullptr, s->classified, s->num_sms, s->stream)
                   : s->kernel == 5 ? smpc::launch_admm_shared_small_mma(s->dpack, s->dplan, b, sd, s->d_queue, s->schedule ? s->d_lists : nullptr, s->classified, s->num_sms, s->stream)
                   : s->kernel == 4 ? smpc::launch_admm_shared_tile(s->dtile, s->dplan, b, sd, s->d_queue, s->tile_nb, s->num_sms, s->stream)
@@ -655,7 +670,7 @@ int smpc_solver_row_pairs(const smpc_solver *s) {
 }
 const char *smpc_solver_kernel_name(const smpc_solver *s) {
   if (!s) return "";
-  return s->regime == 1 ? "admm_instance_kernel" : s->kernel == 2 ? "admm_shared_small_kernel"
+  return s->regime == 1 ? (s->dinst.pack ? "admm_instance_pair_kernel" : "admm_instance_kernel") : s->kernel == 2 ? "admm_shared_small_kernel"
          : s->kernel == 4 ? "admm_shared_tile_kernel" : s->kernel == 5 ? "admm_shared_small_mma_kernel" : "admm_shared_generic_kernel";
 }
 

@@ -76,6 +76,11 @@ struct InstanceDataDev {
   double *S0, *T, *Minv0;
   double rho_prepared;
   int paired;           // 1: rows r and r + m/2 of every scaled A̅_i are exact negatives ([G; -G], cpp:335), checked at create time
+  // two-warp kernel for paired instances (admm_instance_pair.cu), NULL when it does not apply: per-instance pack
+  // [G' | M(pack_rho)^-1 | K = G M^-1 | S0 | T] (instance_pair_pack_doubles(n) doubles each), the rho each pack was last factored
+  // with, and the ticket queue (2 ints)
+  double *pack, *pack_rho;
+  int *queue;
 };
 
 // per-instance data and state, [B][len] contiguous

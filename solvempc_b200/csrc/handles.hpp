@@ -54,6 +54,7 @@ struct smpc_solver {
   int *d_status = nullptr, *d_iter = nullptr, *d_rhoup = nullptr;
   double *d_stage_x = nullptr, *d_stage_y = nullptr;  // warm-start staging
   smpc::DeviceBuf instbuf;                                  // per-instance regime: P̄, A̅, D, E, c
+  smpc::DeviceBuf prepbuf;                                  // per-instance regime: what osqp_setup prepares (factor for rho0, S0 / T split)
   smpc::InstanceDataDev dinst{};
   smpc::DeviceBuf packbuf;                                  // small-kernel operator pack + work queue
   smpc::SmallPackDev dpack{};

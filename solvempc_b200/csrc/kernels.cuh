@@ -44,6 +44,11 @@ cudaError_t launch_instance_pairs(const InstanceDataDev &I, int *flag, cudaStrea
 cudaError_t launch_warm_start_instance(const InstanceDataDev &I, const double *x, const double *y, double *xs, double *z,
                                        double *ys, cudaStream_t stream);
 bool instance_kernel_supports(int n, int m);
+// admm_instance_pair.cu : two warps per QP for [G; -G] instances, TMA-staged operands, persistent CTAs
+bool instance_pair_supports(int n, int m);
+size_t instance_pair_pack_doubles(int n);
+cudaError_t launch_admm_instance_pair(const InstanceDataDev &I, const BatchDev &Bt, const SettingsDev &S, int num_sms, cudaStream_t stream,
+                                      int prepare);
 
 // mpc_assembly.cu
 struct MpcDims { int N, nx, n_state_rows; double Q, R, RD, u_limit; };

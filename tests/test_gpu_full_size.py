@@ -54,7 +54,7 @@ def test_c4_per_instance_plants_at_full_size(ref_mats):
     Ad, Bd = c4_plants(B, cfg, seed=2)
     conf = dict(Ad=Ad, Bd=Bd, Cd=cfg["Cd"], K=cfg["K"], Q=cfg["Q"], R=cfg["R"], RD=cfg["RD"], horizon=N, per_instance=1)
     mpc = sm.BatchedModelPredictiveControlAPI(conf, batch=B, **EPS)
-    assert mpc.solver.kernel_name == "admm_instance_kernel" and mpc.solver.row_pairs == N
+    assert mpc.solver.kernel_name == "admm_instance_pair_kernel" and mpc.solver.row_pairs == N
     X, U, ref = c2_batch(B, seed=31)
     mpc.set_state(X=X, U=U, ref=ref)
     mpc.controller_step_async()

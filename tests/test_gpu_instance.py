@@ -53,7 +53,7 @@ def test_c4_per_instance_plants_through_mpc_api(ref_mats):
     Ad, Bd = c4_plants(B, cfg, seed=2)
     conf = dict(Ad=Ad, Bd=Bd, Cd=cfg["Cd"], K=cfg["K"], Q=cfg["Q"], R=cfg["R"], RD=cfg["RD"], horizon=N, per_instance=1)
     mpc = sm.BatchedModelPredictiveControlAPI(conf, batch=B, **EPS)
-    assert (mpc.n_variables, mpc.n_constraints) == (30, 60) and mpc.solver.kernel_name == "admm_instance_kernel"
+    assert (mpc.n_variables, mpc.n_constraints) == (30, 60) and mpc.solver.kernel_name == "admm_instance_pair_kernel"
     X, U, ref = c2_batch(B, seed=31)
     mpc.set_state(X=X, U=U, ref=ref)
     ok = mpc.controllerStep()
@@ -134,3 +134,54 @@ def test_bounds_that_change_a_row_class_fall_back_to_the_full_factorisation(ref_
     assert np.array_equal(x2, x3) and np.isfinite(x3).all()
     assert (info["status"] == 1).mean() >= 0.5     # (forcing an equality makes a few of the paired instances infeasible: status parity above)
     s.close(); s2.close()
+
+
+@pytest.mark.parametrize("N", [12, 15, 30, 32])
+def test_pair_kernel_matches_the_one_warp_kernel_and_the_oracle(ref_mats, monkeypatch, N):
+    """[G; -G] instances run on the two-warp TMA-staged kernel (admm_instance_pair.cu); SMPC_INSTANCE_NO_PAIR_KERNEL keeps them on
+    the one-warp register kernel.  Same statuses and iteration counts, solutions to round-off; warm second solve (the stored
+    factorisation of the final rho is reused) and a cold third solve (rho0: the prepared pack again) agree as well."""
+    _, cfg = ref_mats
+    B = 40
+    Ad, Bd = c4_plants(B, cfg, seed=9)
+    conf = dict(Ad=Ad, Bd=Bd, Cd=cfg["Cd"], K=cfg["K"], Q=cfg["Q"], R=cfg["R"], RD=cfg["RD"], horizon=N, per_instance=1)
+    X, U, ref = c2_batch(B, seed=13)
+    out = {}
+    for name, env in (("pair", None), ("warp", "1")):
+        if env:
+            monkeypatch.setenv("SMPC_INSTANCE_NO_PAIR_KERNEL", env)
+        else:
+            monkeypatch.delenv("SMPC_INSTANCE_NO_PAIR_KERNEL", raising=False)
+        mpc = sm.BatchedModelPredictiveControlAPI(conf, batch=B, **EPS)
+        assert mpc.solver.kernel_name == ("admm_instance_pair_kernel" if name == "pair" else "admm_instance_kernel")
+        res = []
+        mpc.set_state(X=X, U=U, ref=ref)
+        mpc.controller_step_async()
+        res.append((mpc.solver.solution(), mpc.solver.info(), mpc.state()[1]))
+        mpc.set_state(X=X * 0.9)
+        mpc.controller_step_async()                      # warm: iterates, rho and the factorisation persist
+        res.append((mpc.solver.solution(), mpc.solver.info(), mpc.state()[1]))
+        mpc.solver.set_cold_solves(True)
+        mpc.set_state(X=X, U=U, ref=ref)
+        mpc.controller_step_async()                      # cold again: bitwise the first solve
+        res.append((mpc.solver.solution(), mpc.solver.info(), mpc.state()[1]))
+        out[name] = res
+        mpc.close()
+    for k in range(3):
+        (xp, yp), ip, up = out["pair"][k]
+        (xw, yw), iw, uw = out["warp"][k]
+        assert np.array_equal(ip["status"], iw["status"]) and np.array_equal(ip["iter"], iw["iter"]), k
+        assert np.array_equal(ip["rho_updates"], iw["rho_updates"])
+        assert rel_err(xp, xw) < 1e-7 and rel_err(yp, yw) < 1e-6
+        assert np.abs(up - uw).max() < 1e-9
+    assert np.array_equal(out["pair"][0][0][0], out["pair"][2][0][0])
+    # and the oracle on a few instances
+    (xp, _), ip, _ = out["pair"][0]
+    for b in range(0, B, 8):
+        mats = oracle.mpc_build(**{**cfg, "Ad": Ad[b], "Bd": Bd[b], "N": N})
+        f, ub = oracle.mpc_step_vectors(mats, X[b], U[b], ref[b])
+        so = oracle.Solver(mats["H"], np.zeros(N), mats["Gbar"], mats["lb"], mats["W0"], **EPS)
+        so.update_lin_cost(f); so.update_upper_bound(ub)
+        r = so.solve()
+        assert ip["status"][b] == r["status"] and ip["iter"][b] == r["iter"]
+        assert rel_err(xp[b], r["x"]) < 1e-6
