@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsolvempc_b200.so")
+LIB_PATH = os.environ.get("SOLVEMPC_B200_LIB") or os.path.join(_HERE, "libsolvempc_b200.so")   # (the override is for A/B builds in development)
 
 HOST, DEVICE = 0, 1
 OK, ERR_ARG, ERR_DATA, ERR_CUDA, ERR_STATE, ERR_IO = 0, 1, 2, 3, 4, 5

@@ -21,6 +21,7 @@
 // Refactorisation (every rho update, exactly when OSQP refactors): M = S0 + rho T, left-looking Cholesky in shared memory,
 // lane c solves L L' v = e_c in registers (row c of M^-1), then the z-warp forms its rows of K = G M^-1.
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 
 #include "device_types.cuh"
@@ -92,6 +93,31 @@ __device__ __forceinline__ double dot_reg16(const double (&reg)[16], const doubl
   return (a0 + a1) + (a2 + a3);
 }
 
+// Reciprocal, quotient and square root without the library's out-of-line slow path (a CALL in the middle of the solve makes
+// ptxas keep a quarter of the register-resident operator rows in local memory): hardware seed + Newton steps, accurate to
+// the last bit or two for the normal, finite operands that occur here (scalings, rho, pivots of a positive definite matrix).
+__device__ __forceinline__ double fast_rcp(double b) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+  double e = fma(-b, r, 1.0); r = fma(r, e, r);
+  e = fma(-b, r, 1.0); r = fma(r, e, r);
+  e = fma(-b, r, 1.0); r = fma(r, e, r);
+  return r;
+}
+__device__ __forceinline__ double fast_div(double a, double b) {
+  const double r = fast_rcp(b);
+  const double q = a * r;
+  return fma(fma(-b, q, a), r, q);
+}
+__device__ __forceinline__ double fast_sqrt(double d) {   // d > 0
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+  double g = d * y, h = 0.5 * y;
+  double r = fma(-h, g, 0.5); g = fma(g, r, g); h = fma(h, r, h);
+  r = fma(-h, g, 0.5); g = fma(g, r, g); h = fma(h, r, h);
+  return fma(fma(-g, g, d), h, g);
+}
+
 __device__ __forceinline__ int row_class(double lo, double hi) {   // -1 free, 0 inequality, 1 equality (OSQP constr_type)
   return (lo < -kInfty * kMinScaling && hi > kInfty * kMinScaling) ? -1 : ((hi - lo < kRhoTolRow) ? 1 : 0);
 }
@@ -141,6 +167,13 @@ __global__ void __launch_bounds__(64, CTAS_PER_SM) admm_instance_pair_kernel(Ins
   __syncthreads();
   int cur = s_ticket, stage = 0;
   uint32_t phase0 = 0u, phase1 = 0u;
+#ifdef SMPC_PAIR_PROFILE
+  long long pf[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, pc = clock64();
+  int pf_solves = 0, pf_iters = 0, pf_refac = 0;
+#define PFI(i) { const long long tt = clock64(); pf[i] += tt - pc; pc = tt; }
+#else
+#define PFI(i)
+#endif
 
   while (cur < B) {
     const int b = cur;
@@ -162,7 +195,7 @@ __global__ void __launch_bounds__(64, CTAS_PER_SM) admm_instance_pair_kernel(Ins
     double *Gt = stage ? Gt1 : Gt0;
     double *pack = I.pack + (size_t)b * pack_stride;
     const double *gP = I.P + (size_t)b * n * n;
-    const double c = I.c[b], cinv = 1.0 / c;
+    const double c = I.c[b], cinv = fast_rcp(c);
     const bool warm = S.warm_start && !Bt.fresh && !prepare;
 
     // ---- per-instance vectors into registers
@@ -230,7 +263,7 @@ __global__ void __launch_bounds__(64, CTAS_PER_SM) admm_instance_pair_kernel(Ins
       if (!xw) {
         const double rho_eq = kRhoEqOverIneq * rho;
         const double vt = cls_t < 0 ? kRhoMin : (cls_t == 1 ? rho_eq : rho), vb = cls_b < 0 ? kRhoMin : (cls_b == 1 ? rho_eq : rho);
-        rvt[lane] = vt; rvb[lane] = vb; rit[lane] = 1.0 / vt; rib[lane] = 1.0 / vb;
+        rvt[lane] = vt; rvb[lane] = vb; rit[lane] = fast_rcp(vt); rib[lane] = fast_rcp(vb);
       }
     };
     set_rho();
@@ -245,109 +278,103 @@ __global__ void __launch_bounds__(64, CTAS_PER_SM) admm_instance_pair_kernel(Ins
       return full;
     };
 
-    // M (lower triangle) -> Sc; Cholesky; rows of M^-1 -> x-warp registers; rows of K = G M^-1 -> z-warp registers.
+    // Factorisation and inverse of M = P̄ + sigma I + A̅' diag(rho_vec) A̅ by pivot-free Gauss-Jordan sweeps IN REGISTERS: thread (w, i)
+    // holds M(i, 16 w .. 16 w + 15).  Sweep k uses the k-th LDL' pivot d_k (the pivots QDLDL / a Cholesky factorisation produce;
+    // d_k > 0 for all k <=> M positive definite), broadcasts the pivot row and column through shared memory (double buffered:
+    // one CTA barrier per sweep) and updates 16 entries per thread; after n sweeps the registers hold M^-1.  All 64 threads
+    // work in every sweep and the dependent chain per sweep is one reciprocal + one FMA.  Then rows of M^-1 -> x-warp registers,
+    // rows of K = G M^-1 -> z-warp registers.
     // mode 0: M = S0 + rho T from the pack; 1: assembled from G and this solve's rho_vec; 2 (prepare): also writes S0, T.
     auto refactor = [&](int mode) -> bool {
-      if (mode != 0 && !xw) {   // per-row weights of G_r' G_r: t0 = kappa_top + kappa_bot (times rho), t1 = the free rows' rho_min
-        if (mode == 2) {
-          t0[lane] = lane < mp ? ((cls_t < 0 ? 0.0 : (cls_t == 1 ? kRhoEqOverIneq : 1.0)) + (cls_b < 0 ? 0.0 : (cls_b == 1 ? kRhoEqOverIneq : 1.0))) : 0.0;
-          t1[lane] = lane < mp ? ((cls_t < 0 ? kRhoMin : 0.0) + (cls_b < 0 ? kRhoMin : 0.0)) : 0.0;
-        } else {
-          t0[lane] = lane < mp ? rvt[lane] + rvb[lane] : 0.0;
+      double *row = Sc + lane * kPLD + 16 * w;      // this thread's 16 entries of M (rows >= n are never touched)
+      if (mode == 0) {
+        const double *S0 = pack + 3 * kPN * kPLD, *T = S0 + tri2;
+        if (lane < n) {
+#pragma unroll
+          for (int jj = 0; jj < 16; ++jj) {
+            const int j = 16 * w + jj;
+            double v = 0.0;
+            if (j < n) {
+              const int hi_ = lane > j ? lane : j, lo_ = lane > j ? j : lane, e = hi_ * (hi_ + 1) / 2 + lo_;
+              v = fma(rho, T[e], S0[e]);
+            }
+            row[jj] = v;
+          }
         }
-      }
-      __syncthreads();
-      for (int e = tid; e < tri; e += 64) {
-        int i = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
-        while ((i + 1) * (i + 2) / 2 <= e) ++i;
-        while (i * (i + 1) / 2 > e) --i;
-        const int j = e - i * (i + 1) / 2;
-        double mij;
-        if (mode == 0) {
-          mij = fma(rho, pack[3 * kPN * kPLD + tri2 + e], pack[3 * kPN * kPLD + e]);
-        } else {
-          const double *gi = Gt + i * kPLD, *gj = Gt + j * kPLD;
-          double s0 = gP[i * n + j] + (i == j ? sigma : 0.0), tt = 0.0;
+      } else {
+        // per-row weights of G_r' G_r: t0 = kappa_top + kappa_bot (times rho), t1 = the free rows' rho_min
+        if (!xw) {
           if (mode == 2) {
-            for (int r = 0; r < mp; ++r) { const double aa = gi[r] * gj[r]; s0 = fma(t1[r], aa, s0); tt = fma(t0[r], aa, tt); }
-            pack[3 * kPN * kPLD + e] = s0; pack[3 * kPN * kPLD + tri2 + e] = tt;
-            mij = fma(rho, tt, s0);
+            t0[lane] = lane < mp ? ((cls_t < 0 ? 0.0 : (cls_t == 1 ? kRhoEqOverIneq : 1.0)) + (cls_b < 0 ? 0.0 : (cls_b == 1 ? kRhoEqOverIneq : 1.0))) : 0.0;
+            t1[lane] = lane < mp ? ((cls_t < 0 ? kRhoMin : 0.0) + (cls_b < 0 ? kRhoMin : 0.0)) : 0.0;
           } else {
-            for (int r = 0; r < mp; ++r) s0 = fma(t0[r] * gi[r], gj[r], s0);
-            mij = s0;
+            t0[lane] = lane < mp ? rvt[lane] + rvb[lane] : 0.0;
           }
         }
-        Sc[i * kPLD + j] = mij;
-      }
-      __syncthreads();
-      // left-looking Cholesky by the x-warp, lower triangle of Sc in place; t1[j] = 1 / L_jj; rhs[] is scratch
-      if (xw) {
-        int ok = 1;
-        for (int j = 0; j < n; ++j) {
-          if (lane >= j && lane < n) {
-            const double *ri = Sc + lane * kPLD, *rj = Sc + j * kPLD;
-            double s0 = ri[j], s1 = 0.0;
-            int k = 0;
-            for (; k + 2 <= j; k += 2) {
-              const double2 a = *reinterpret_cast<const double2 *>(ri + k), c2 = *reinterpret_cast<const double2 *>(rj + k);
-              s0 = fma(-a.x, c2.x, s0); s1 = fma(-a.y, c2.y, s1);
-            }
-            if (k < j) s0 = fma(-ri[k], rj[k], s0);
-            rhs[lane] = s0 + s1;
-          }
-          __syncwarp();
-          const double d = rhs[j];
-          if (!(d > 0.0)) { ok = 0; break; }
-          const double sd = sqrt(d);
-          if (lane >= j && lane < n) Sc[lane * kPLD + j] = lane == j ? sd : rhs[lane] / sd;
-          if (lane == 0) t1[j] = 1.0 / sd;
-          __syncwarp();
-        }
-        if (lane == 0) red[R_FLAG0] = ok ? 0.0 : 1.0;
-        if (ok) {
-          // forward substitution L v = e_lane, then backward L' u = v, in registers; L is read with warp-uniform addresses
-#pragma unroll
-          for (int i = 0; i < kPN; ++i) {
-            if (i < n) {
-              double s0 = i == lane ? 1.0 : 0.0, s1 = 0.0;
-#pragma unroll
-              for (int k = 0; k + 1 < i; k += 2) {
-                const double2 l = *reinterpret_cast<const double2 *>(Sc + i * kPLD + k);
-                s0 = fma(-l.x, op[k], s0); s1 = fma(-l.y, op[k + 1], s1);
-              }
-              if (i & 1) s0 = fma(-Sc[i * kPLD + i - 1], op[i - 1], s0);
-              op[i] = (s0 + s1) * t1[i];
+        __syncthreads();
+        for (int e = tid; e < n * kPN; e += 64) {      // full symmetric M, columns >= n zero
+          const int i = e >> 5, j = e & 31;
+          double mij = 0.0;
+          if (j < n) {
+            const double *gi = Gt + i * kPLD, *gj = Gt + j * kPLD;
+            double s0 = gP[i * n + j] + (i == j ? sigma : 0.0), tt = 0.0;
+            if (mode == 2) {
+              for (int r = 0; r < mp; ++r) { const double aa = gi[r] * gj[r]; s0 = fma(t1[r], aa, s0); tt = fma(t0[r], aa, tt); }
+              if (j <= i) { pack[3 * kPN * kPLD + i * (i + 1) / 2 + j] = s0; pack[3 * kPN * kPLD + tri2 + i * (i + 1) / 2 + j] = tt; }
+              mij = fma(rho, tt, s0);
             } else {
-              op[i] = 0.0;
+              for (int r = 0; r < mp; ++r) s0 = fma(t0[r] * gi[r], gj[r], s0);
+              mij = s0;
             }
           }
-#pragma unroll
-          for (int i = kPN - 1; i >= 0; --i) {
-            if (i < n) {
-              double s0 = op[i], s1 = 0.0;
-#pragma unroll
-              for (int k = i + 1; k < kPN; ++k) {
-                if (k < n) {
-                  if (k & 1) s1 = fma(-Sc[k * kPLD + i], op[k], s1); else s0 = fma(-Sc[k * kPLD + i], op[k], s0);
-                }
-              }
-              op[i] = (s0 + s1) * t1[i];
-            }
-          }
-          if (lane >= n) {
-#pragma unroll
-            for (int k = 0; k < kPN; ++k) op[k] = 0.0;
-          }
-          __syncwarp();   // every lane is done with L: Sc now receives M^-1 for the z-warp
-          if (lane < n) {
-#pragma unroll
-            for (int k = 0; k < kPN; k += 2) *reinterpret_cast<double2 *>(Sc + lane * kPLD + k) = make_double2(op[k], op[k + 1]);
-          }
+          Sc[i * kPLD + j] = mij;
         }
       }
       __syncthreads();
-      if (red[R_FLAG0] != 0.0) return false;
-      if (!xw) {   // K_r = sum_k G(r, k) M^-1(k, :)
+      PFI(5)
+      // Gauss-Jordan sweeps in place (shared memory); the scaled pivot row goes through a double-buffered broadcast row
+      int ok = 1;
+      const bool live = lane < n;
+      for (int k = 0; k < n; ++k) {
+        double *prow = ((k & 1) ? xs : rhs) + 16 * w;                      // this warp's half of the broadcast row
+        const double d = Sc[k * kPLD + k];
+        if (!(d > 0.0)) ok = 0;                                             // LDL' pivot: M is not positive definite
+        const double pv = fast_rcp(d);
+        // Nothing of M is written before the barrier: every thread still reads the pivot d and its column-k entry f.
+        const double f = live ? Sc[lane * kPLD + k] : 0.0;
+        if (lane == k) {                                                    // pivot row, scaled, into the broadcast buffer
+#pragma unroll
+          for (int jj = 0; jj < 16; jj += 2) {
+            double2 r2 = *reinterpret_cast<const double2 *>(row + jj);
+            r2.x *= pv; r2.y *= pv;
+            *reinterpret_cast<double2 *>(prow + jj) = r2;
+          }
+        }
+        __syncthreads();
+        if (live) {                                                         // row_i <- row_i - f * (row_k / d); row_k <- row_k / d
+          const double g = lane == k ? 0.0 : -f;                           // (the pivot row: 0 * x + copy of the scaled row)
+#pragma unroll
+          for (int jj = 0; jj < 16; jj += 2) {
+            const double2 p2 = *reinterpret_cast<const double2 *>(prow + jj);
+            double2 r2 = *reinterpret_cast<const double2 *>(row + jj);
+            r2.x = lane == k ? p2.x : fma(g, p2.x, r2.x);
+            r2.y = lane == k ? p2.y : fma(g, p2.y, r2.y);
+            *reinterpret_cast<double2 *>(row + jj) = r2;
+          }
+          if (w == (k >> 4)) row[k & 15] = lane == k ? pv : g * pv;          // column k: 1 / d on the pivot row, -f / d elsewhere
+        }
+        __syncthreads();
+      }
+      PFI(6)
+      if (!ok) return false;                                               // (uniform: every thread saw the same pivots)
+      PFI(7)
+      if (xw) {
+#pragma unroll
+        for (int k = 0; k < kPN; k += 2) {
+          const double2 v = lane < n ? *reinterpret_cast<const double2 *>(Sc + lane * kPLD + k) : make_double2(0.0, 0.0);
+          op[k] = v.x; op[k + 1] = v.y;
+        }
+      } else {   // K_r = sum_k G(r, k) M^-1(k, :)
 #pragma unroll
         for (int k = 0; k < kPN; ++k) op[k] = 0.0;
         for (int k = 0; k < n; ++k) {
@@ -361,6 +388,7 @@ __global__ void __launch_bounds__(64, CTAS_PER_SM) admm_instance_pair_kernel(Ins
         }
       }
       __syncthreads();
+      PFI(9)
       return true;
     };
 
@@ -372,18 +400,33 @@ __global__ void __launch_bounds__(64, CTAS_PER_SM) admm_instance_pair_kernel(Ins
     auto update_info = [&]() {
       if (xw) xs[lane] = X_; else t0[lane] = YT_ - YB_;
       __syncthreads();
+      // P̄ x: P̄ is stored full symmetric, so the column sweep is coalesced; each warp takes half of the sum (16 independent loads)
       double Px = 0.0, Ax = 0.0;
-      if (xw) {
-        if (lane < n) for (int k = 0; k < n; ++k) Px = fma(gP[k * n + lane], xs[k], Px);   // P̄ is stored full symmetric: column sweep = coalesced
-      } else {
-        if (lane < mp) for (int k = 0; k < n; ++k) Ax = fma(Gt[k * kPLD + lane], xs[k], Ax);
+      {
+        double pv[16];
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) { const int k = 16 * w + kk; pv[kk] = (lane < n && k < n) ? gP[k * n + lane] : 0.0; }
+        double p0 = 0.0, p1_ = 0.0;
+#pragma unroll
+        for (int kk = 0; kk < 16; kk += 2) { p0 = fma(pv[kk], xs[16 * w + kk], p0); p1_ = fma(pv[kk + 1], xs[16 * w + kk + 1], p1_); }
+        Px = p0 + p1_;
       }
-      const double Aty = AT_dot_t0();
+      if (!xw && lane < mp) {
+        double a0 = 0.0, a1 = 0.0;
+        int k = 0;
+        for (; k + 2 <= n; k += 2) { a0 = fma(Gt[k * kPLD + lane], xs[k], a0); a1 = fma(Gt[(k + 1) * kPLD + lane], xs[k + 1], a1); }
+        if (k < n) a0 = fma(Gt[k * kPLD + lane], xs[k], a0);
+        Ax = a0 + a1;
+      }
+      double Aty = dot_reg16(gt, t0 + 16 * w);
+      if (!xw) { p1[lane] = Aty; t1[lane] = Px; }
+      __syncthreads();
+      if (xw) { Aty += p1[lane]; Px += t1[lane]; }
       if (xw) {
         double rd = 0.0, ob = 0.0, u_rd = 0.0, u_q = 0.0, u_Aty = 0.0, u_Px = 0.0, nd = 0.0, qd = 0.0;
         double a_q = 0.0, a_Aty = 0.0, a_Px = 0.0;
         if (lane < n) {
-          const double x = X_, q = Q_, Dinv = 1.0 / DV_, dx = dl2[lane];
+          const double x = X_, q = Q_, Dinv = fast_rcp(DV_), dx = dl2[lane];
           rd = fabs((q + Px) + Aty); a_q = fabs(q); a_Aty = fabs(Aty); a_Px = fabs(Px);
           u_rd = fabs(Dinv * ((q + Px) + Aty)); u_q = fabs(Dinv * q); u_Aty = fabs(Dinv * Aty); u_Px = fabs(Dinv * Px);
           ob = 0.5 * x * Px + q * x;
@@ -399,7 +442,7 @@ __global__ void __launch_bounds__(64, CTAS_PER_SM) admm_instance_pair_kernel(Ins
       } else {
         double a_rp = 0.0, a_z = 0.0, a_Ax = 0.0, u_rp = 0.0, u_z = 0.0, u_Ax = 0.0, nd = 0.0, lhs = 0.0;
         if (lane < mp) {
-          const double et = evt[lane], eb = evb[lane], eit = 1.0 / et, eib = 1.0 / eb;
+          const double et = evt[lane], eb = evb[lane], eit = fast_rcp(et), eib = fast_rcp(eb);
           const double zt = ZT_, zb = ZB_;
           const double rpt = Ax - zt, rpb = -Ax - zb;
           a_rp = fmax(fabs(rpt), fabs(rpb)); a_z = fmax(fabs(zt), fabs(zb)); a_Ax = fabs(Ax);
@@ -438,7 +481,7 @@ __global__ void __launch_bounds__(64, CTAS_PER_SM) admm_instance_pair_kernel(Ins
       __syncthreads();
       const double v = AT_dot_t0();
       if (xw) {
-        const double na = wmax(lane < n ? fabs(unscale ? (1.0 / DV_) * v : v) : 0.0);
+        const double na = wmax(lane < n ? fabs(unscale ? fast_rcp(DV_) * v : v) : 0.0);
         if (lane == 0) red[R_RARE0] = na;
       }
       __syncthreads();
@@ -453,14 +496,14 @@ __global__ void __launch_bounds__(64, CTAS_PER_SM) admm_instance_pair_kernel(Ins
       if (xw) {
         double s = 0.0;
         if (lane < n) for (int k = 0; k < n; ++k) s = fma(gP[k * n + lane], dl2[k], s);
-        const double np = wmax(lane < n ? fabs(unscale ? (1.0 / DV_) * s : s) : 0.0);
+        const double np = wmax(lane < n ? fabs(unscale ? fast_rcp(DV_) * s : s) : 0.0);
         if (lane == 0) red[R_RARE0] = np;
       } else {
         int bad = 0;
         if (lane < mp) {
           double v = 0.0;
           for (int k = 0; k < n; ++k) v = fma(Gt[k * kPLD + lane], dl2[k], v);
-          const double vt = unscale ? v / evt[lane] : v, vb = unscale ? -v / evb[lane] : -v;
+          const double vt = unscale ? v * fast_rcp(evt[lane]) : v, vb = unscale ? -v * fast_rcp(evb[lane]) : -v;
           if (((ubt[lane] < kInfty * kMinScaling) && (vt > eps * nd)) || ((lbt[lane] > -kInfty * kMinScaling) && (vt < -eps * nd))) bad = 1;
           if (((ubb[lane] < kInfty * kMinScaling) && (vb > eps * nd)) || ((lbb[lane] > -kInfty * kMinScaling) && (vb < -eps * nd))) bad = 1;
         }
@@ -500,61 +543,84 @@ __global__ void __launch_bounds__(64, CTAS_PER_SM) admm_instance_pair_kernel(Ins
     }
     // wd for the first iteration
     if (!xw) wd[lane] = lane < mp ? (rvt[lane] * ZT_ - YT_) - (rvb[lane] * ZB_ - YB_) : 0.0;
-    int to_check = S.check_every ? S.check_every : -1, to_adapt = (S.adaptive_rho && S.rho_interval) ? S.rho_interval : -1;   // countdowns instead of iter % interval
-
-    for (iter = 1; iter <= S.max_iter && !bad_bounds && factor_ok; ++iter) {
+    // Iterations run in stretches that end at the next event (termination check, rho adaptation, max_iter): the hot loop is a
+    // plain counted loop with nothing but the iteration in it, so the operator rows stay in registers across it.
+    const int kNever = 0x3fffffff;
+    int to_check = S.check_every ? S.check_every : kNever, to_adapt = (S.adaptive_rho && S.rho_interval) ? S.rho_interval : kNever;
+    iter = 0;
+    PFI(0)
+    while (!bad_bounds) {
       if (need_factor) {
+        PFI(2)
         factor_ok = refactor(prepare ? 2 : (split_ok ? 0 : 1));
+#ifdef SMPC_PAIR_PROFILE
+        ++pf_refac;
+#endif
         need_factor = false; refactored = true;
         if (prepare || !factor_ok) break;
       }
-      __syncthreads();                                                                  // wd is visible
-      const double part = dot_reg16(gt, wd + 16 * w);                                   // half of (G' wd)_lane
-      if (!xw) p1[lane] = part;
-      __syncthreads();
-      if (xw) rhs[lane] = lane < n ? (sigma * X_ - Q_) + (part + p1[lane]) : 0.0;
-      __syncthreads();
-      const double acc = dot_reg32(op, rhs);                                            // x~_lane (x-warp) | (G x~)_lane (z-warp)
-      can_check = --to_check == 0;
-      const bool adapt = --to_adapt == 0;
+      const int run = min(min(to_check, to_adapt), S.max_iter - iter);
+      for (int k = run; k > 0; --k) {
+        __syncthreads();                                                                  // wd is visible
+        const double part = dot_reg16(gt, wd + 16 * w);                                   // half of (G' wd)_lane
+        if (!xw) p1[lane] = part;
+        __syncthreads();
+        if (xw) rhs[lane] = lane < n ? (sigma * X_ - Q_) + (part + p1[lane]) : 0.0;
+        __syncthreads();
+        const double acc = dot_reg32(op, rhs);                                            // x~_lane (x-warp) | (G x~)_lane (z-warp)
+        const bool keep_deltas = k == 1;                                                  // delta_x, delta_y feed the infeasibility tests only
+        if (xw) {
+          const double xn = alpha * acc + (1.0 - alpha) * X_;
+          if (keep_deltas) dl2[lane] = xn - X_;
+          X_ = xn;
+        } else if (lane < mp) {
+          {
+            const double zr = alpha * acc + (1.0 - alpha) * ZT_;
+            const double zn = fmin(fmax(zr + rit[lane] * YT_, lbt[lane]), ubt[lane]);
+            const double d = rvt[lane] * (zr - zn);
+            ZT_ = zn; YT_ += d;
+            if (keep_deltas) dl0[lane] = d;
+          }
+          {
+            const double zr = alpha * (-acc) + (1.0 - alpha) * ZB_;
+            const double zn = fmin(fmax(zr + rib[lane] * YB_, lbb[lane]), ubb[lane]);
+            const double d = rvb[lane] * (zr - zn);
+            ZB_ = zn; YB_ += d;
+            if (keep_deltas) dl1[lane] = d;
+          }
+          wd[lane] = (rvt[lane] * ZT_ - YT_) - (rvb[lane] * ZB_ - YB_);
+        }
+      }
+      PFI(2)
+      iter += run; to_check -= run; to_adapt -= run;
+      can_check = to_check == 0;
+      const bool adapt = to_adapt == 0, last = iter >= S.max_iter;
       if (can_check) to_check = S.check_every;
       if (adapt) to_adapt = S.rho_interval;
-      const bool keep_deltas = can_check || adapt || iter == S.max_iter;                // delta_x, delta_y feed the infeasibility tests only
-      if (xw) {
-        const double xn = alpha * acc + (1.0 - alpha) * X_;
-        if (keep_deltas) dl2[lane] = xn - X_;
-        X_ = xn;
-      } else if (lane < mp) {
-        {
-          const double zr = alpha * acc + (1.0 - alpha) * ZT_;
-          const double zn = fmin(fmax(zr + rit[lane] * YT_, lbt[lane]), ubt[lane]);
-          const double d = rvt[lane] * (zr - zn);
-          ZT_ = zn; YT_ += d;
-          if (keep_deltas) dl0[lane] = d;
-        }
-        {
-          const double zr = alpha * (-acc) + (1.0 - alpha) * ZB_;
-          const double zn = fmin(fmax(zr + rib[lane] * YB_, lbb[lane]), ubb[lane]);
-          const double d = rvb[lane] * (zr - zn);
-          ZB_ = zn; YB_ += d;
-          if (keep_deltas) dl1[lane] = d;
-        }
-      }
-      if (can_check || adapt) {
+      bool done = false;
+      if (can_check || adapt || last) {
         update_info();
-        if (can_check && check_termination(false)) break;
-        if (adapt) {
-          const double pr = red[R_SRP] / (fmax(red[R_SZ], red[R_SAX]) + kDivTol);
-          const double dr = red[R_SRD] / (fmax(fmax(red[R_SQ], red[R_SATY]), red[R_SPX]) + kDivTol);
-          const double rn = fmin(fmax(rho * sqrt(pr / (dr + kDivTol)), kRhoMin), kRhoMax);
-          if (rn > rho * S.rho_tol || rn < rho / S.rho_tol) {
-            rho = rn; ++rho_updates;
-            set_rho();
-            need_factor = true;
+        // one call site for the termination test: pass 0 = osqp_solve's check inside the loop (and, at max_iter, the one behind
+        // it), then rho adaptation, pass 1 (max_iter only) = the approximate test with 10 x tolerances
+        for (int pass = 0; pass < 2 && !done; ++pass) {
+          if (pass == 0 ? (can_check || last) : last) done = check_termination(pass == 1);
+          if (pass == 0 && !done && adapt) {
+            const double pr = fast_div(red[R_SRP], fmax(red[R_SZ], red[R_SAX]) + kDivTol);
+            const double dr = fast_div(red[R_SRD], fmax(fmax(red[R_SQ], red[R_SATY]), red[R_SPX]) + kDivTol);
+            const double ratio = fast_div(pr, dr + kDivTol);
+            const double rn = fmin(fmax(rho * (ratio > 0.0 ? fast_sqrt(ratio) : 0.0), kRhoMin), kRhoMax);
+            if (rn > rho * S.rho_tol || rn * S.rho_tol < rho) {
+              rho = rn; ++rho_updates;
+              set_rho();
+              need_factor = !last;
+              if (!xw && lane < mp) wd[lane] = (rvt[lane] * ZT_ - YT_) - (rvb[lane] * ZB_ - YB_);   // rho_vec changed
+            }
           }
         }
+        if (last && !done) { status = SMPC_MAX_ITER_REACHED; done = true; }
       }
-      if (!xw) wd[lane] = lane < mp ? (rvt[lane] * ZT_ - YT_) - (rvb[lane] * ZB_ - YB_) : 0.0;
+      PFI(3)
+      if (done) break;
     }
     if (prepare) {   // create-time pass: the pack now holds G', S0, T; add M(rho0)^-1 and K and leave
       const bool ok = !bad_bounds && factor_ok;
@@ -568,12 +634,7 @@ __global__ void __launch_bounds__(64, CTAS_PER_SM) admm_instance_pair_kernel(Ins
       cur = s_ticket;
       continue;
     }
-    if (iter > S.max_iter) iter = S.max_iter;
     if (bad_bounds || !factor_ok) iter = 0;
-    else {
-      if (!can_check) { update_info(); check_termination(false); }
-      if (status == SMPC_UNSOLVED) { if (!check_termination(true)) status = SMPC_MAX_ITER_REACHED; }
-    }
 
     const bool has_sol = !bad_bounds && factor_ok && !(status == SMPC_PRIMAL_INFEASIBLE || status == SMPC_PRIMAL_INFEASIBLE_INACCURATE ||
                                                        status == SMPC_DUAL_INFEASIBLE || status == SMPC_DUAL_INFEASIBLE_INACCURATE);
@@ -606,7 +667,16 @@ __global__ void __launch_bounds__(64, CTAS_PER_SM) admm_instance_pair_kernel(Ins
     __syncthreads();
     cur = s_ticket;
     stage ^= 1;
+    PFI(4)
+#ifdef SMPC_PAIR_PROFILE
+    ++pf_solves; pf_iters += iter;
+#endif
   }
+#ifdef SMPC_PAIR_PROFILE
+  if (blockIdx.x == 0 && tid == 0 && !prepare)
+    printf("pair profile (cycles, CTA 0): prologue %lld, refactor (%d): assembly %lld cholesky %lld Linv %lld Minv %lld K %lld, iterations %lld (%d), checks %lld, epilogue %lld; solves %d\n",
+           pf[0], pf_refac, pf[5], pf[6], pf[7], pf[8], pf[9], pf[2], pf_iters, pf[3], pf[4], pf_solves);
+#endif
   // the last CTA to leave re-arms the ticket counter for the next launch
   if (tid == 0) {
     __threadfence();
@@ -632,9 +702,10 @@ static cudaError_t launch_pair(const InstanceDataDev &I, const BatchDev &Bt, con
 
 cudaError_t launch_admm_instance_pair(const InstanceDataDev &I, const BatchDev &Bt, const SettingsDev &S, int num_sms, cudaStream_t stream,
                                       int prepare) {
-  static const int ctas = getenv("SMPC_PAIR_CTAS") ? atoi(getenv("SMPC_PAIR_CTAS")) : 6;   // register budget per thread: 6 -> 168, 7 -> 144, 5 -> 200
+  static const int ctas = getenv("SMPC_PAIR_CTAS") ? atoi(getenv("SMPC_PAIR_CTAS")) : 5;   // register budget per thread: 6 -> 168, 7 -> 144, 5 -> 200
   if (ctas == 7) return launch_pair<7>(I, Bt, S, num_sms, stream, prepare);
   if (ctas == 5) return launch_pair<5>(I, Bt, S, num_sms, stream, prepare);
+  if (ctas == 4) return launch_pair<4>(I, Bt, S, num_sms, stream, prepare);
   return launch_pair<6>(I, Bt, S, num_sms, stream, prepare);
 }
 
