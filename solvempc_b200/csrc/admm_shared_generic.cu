@@ -292,7 +292,7 @@ __global__ void fill_kernel(double *p, double v, size_t count) {
 
 // osqp_warm_start: x̄ = D^-1 x, xi = Vinv x̄, z = A̅ x̄ = W xi, ȳ = c E^-1 y.  One warp per instance.
 __global__ void warm_start_kernel(SharedPlanDev P, int B, const double *x, const double *y,
-                                  double *xi, double *z, double *ys) {
+                                  double *xi, double *z, double *ys, int xspace) {
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
   const int b = blockIdx.x * wpc + warp;
@@ -303,7 +303,7 @@ __global__ void warm_start_kernel(SharedPlanDev P, int B, const double *x, const
   __syncwarp();
   for (int i = lane; i < n; i += 32) { double s = 0; for (int k = 0; k < n; ++k) s = fma(P.VinvT[(size_t)k * n + i], xb[k], s); xv[i] = s; }
   __syncwarp();
-  for (int i = lane; i < n; i += 32) xi[(size_t)b * n + i] = xv[i];
+  for (int i = lane; i < n; i += 32) xi[(size_t)b * n + i] = xspace ? xb[i] : xv[i];   // x-space kernels keep x̄ itself
   for (int r = lane; r < m; r += 32) {
     double s = 0; for (int k = 0; k < n; ++k) s = fma(P.WT[(size_t)k * m + r], xv[k], s);
     z[(size_t)b * m + r] = s;
@@ -335,10 +335,10 @@ cudaError_t launch_fill(double *p, double v, size_t count, cudaStream_t stream) 
 }
 
 cudaError_t launch_warm_start(const SharedPlanDev &P, int B, const double *x, const double *y, double *xi,
-                              double *z, double *ys, cudaStream_t stream) {
+                              double *z, double *ys, cudaStream_t stream, bool xspace) {
   int wpc = 4;
   size_t smem = (size_t)wpc * 2 * P.n * sizeof(double);
-  warm_start_kernel<<<(B + wpc - 1) / wpc, wpc * 32, smem, stream>>>(P, B, x, y, xi, z, ys);
+  warm_start_kernel<<<(B + wpc - 1) / wpc, wpc * 32, smem, stream>>>(P, B, x, y, xi, z, ys, xspace ? 1 : 0);
   return cudaGetLastError();
 }
 

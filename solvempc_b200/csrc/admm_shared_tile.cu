@@ -162,9 +162,16 @@ enum PassId { P_XBAR, P_PX, P_ATY, P_AX, P_ATD, P_DX, P_PD, P_ADX, P_QH, P_COUNT
 
 // WARPS = 8: two warps per SM sub-partition, up to 4 row-blocks per warp at once (254 registers);
 // WARPS = 16: four warps per sub-partition, up to 2 row-blocks at once (128 registers): more warps to cover LDS / L2 / barrier stalls
-template <int NB, bool PAIRED, int WARPS>
+// XD ("x-space, diagonal"): the rows come as [G; -G] with G = diag(a) after scaling (a two-sided box on the variables, e.g. the
+// input limits of the condensed multi-input MPC, BASELINE config 3).  Then W = A̅V is dense for no reason: the iteration runs in
+// x-space instead,   x~ = V (dinv .* (V' rhs)),   rhs = sigma x - q̄ + a .* wd,   z~_top = a .* x~,
+// two n x n GEMMs (2 n^2 MACs per instance-iteration instead of n^2 + 2 m n = 3 n^2 with pairs), every product with A̅ or A̅' is
+// element-wise in an epilogue, and a check needs ONE panel GEMM (P̄ x) instead of four.  Panels: cv's first n8 rows hold x̄, Sp the
+// right-hand side between events, qh holds q̄.
+template <int NB, bool PAIRED, int WARPS, bool XD = false>
 __global__ void __launch_bounds__(WARPS * 32, 1)
 admm_shared_tile_kernel(TilePackDev K, SharedPlanDev P, BatchDev Bt, SettingsDev S, int *queue) {
+  static_assert(!XD || PAIRED, "the x-space variant is for paired rows");
   constexpr int TB = 8 * NB;
   constexpr int kTileWarps = WARPS, kTileThreads = WARPS * 32, kRG = WARPS == 8 ? 4 : 2;   // (shadow the file-level defaults)
   extern __shared__ __align__(16) double smem[];
@@ -278,8 +285,16 @@ admm_shared_tile_kernel(TilePackDev K, SharedPlanDev P, BatchDev Bt, SettingsDev
       for (int pass = 0; pass < P_COUNT; ++pass) {
         // ---------- what runs before the GEMM of this pass (block-uniform control flow)
         bool run = false;
-        if (pass <= P_AX) run = !initial;
-        else if (pass == P_ATD) {
+        if (pass <= P_AX) {
+          run = !initial;
+          if (XD && pass == P_XBAR) {   // x̄ is the iterate itself: copy it where the later passes and the store expect it
+            run = false;
+            if (!initial) {
+              for (int e = tid; e < n8 * TB; e += kTileThreads) Tp[e] = cv[xi_at(e)];
+              __syncthreads();
+            }
+          }
+        } else if (pass == P_ATD) {
           if (!initial) {
             __syncthreads();   // norms of the four update_info passes are complete
             // per-slot: update_info results, convergence tests with the plain tolerances
@@ -366,7 +381,7 @@ admm_shared_tile_kernel(TilePackDev K, SharedPlanDev P, BatchDev Bt, SettingsDev
               }
             }
             __syncthreads();
-            if (tid < TB && (C.flags[tid] & F_NEED_DINF) && 1.000001 * P.dx_bound * nrm(N_DXI, tid) <= S.eps_dual_inf) C.flags[tid] &= ~F_NEED_DINF;
+            if (tid < TB && (C.flags[tid] & F_NEED_DINF) && 1.000001 * (XD ? K.dmax : P.dx_bound) * nrm(N_DXI, tid) <= S.eps_dual_inf) C.flags[tid] &= ~F_NEED_DINF;
             __syncthreads();
             any = any_flags();
           }
@@ -569,12 +584,12 @@ _Pragma("unroll 4")
         const double2 *op; const double *panel; int kpt, rb0, rb1, krows;   // krows: panel rows per 8-slot block
         switch (pass) {
           case P_XBAR: op = reinterpret_cast<const double2 *>(K.Vp);  kpt = kpN; panel = cv;          krows = cvr; rb0 = nrb0; rb1 = nrb1; break;
-          case P_PX:   op = reinterpret_cast<const double2 *>(K.PVp); kpt = kpN; panel = cv;          krows = cvr; rb0 = nrb0; rb1 = nrb1; break;
+          case P_PX:   op = reinterpret_cast<const double2 *>(XD ? K.Pp : K.PVp); kpt = kpN; panel = cv; krows = cvr; rb0 = nrb0; rb1 = nrb1; break;
           case P_ATY:  op = reinterpret_cast<const double2 *>(K.ATp); kpt = kpM; panel = yp;          krows = m8;  rb0 = nrb0; rb1 = nrb1; break;
           case P_AX:   op = reinterpret_cast<const double2 *>(K.Wp);  kpt = kpN; panel = cv;          krows = cvr; rb0 = mrb0; rb1 = mrb1; break;
           case P_ATD:  op = reinterpret_cast<const double2 *>(K.ATp); kpt = kpM; panel = cv + n8 * 8; krows = cvr; rb0 = nrb0; rb1 = nrb1; break;
           case P_DX:   op = reinterpret_cast<const double2 *>(K.Vp);  kpt = kpN; panel = Dp;          krows = n8;  rb0 = nrb0; rb1 = nrb1; break;
-          case P_PD:   op = reinterpret_cast<const double2 *>(K.PVp); kpt = kpN; panel = Dp;          krows = n8;  rb0 = nrb0; rb1 = nrb1; break;
+          case P_PD:   op = reinterpret_cast<const double2 *>(XD ? K.Pp : K.PVp); kpt = kpN; panel = Dp; krows = n8;  rb0 = nrb0; rb1 = nrb1; break;
           case P_ADX:  op = reinterpret_cast<const double2 *>(K.Wp);  kpt = kpN; panel = Dp;          krows = n8;  rb0 = mrb0; rb1 = mrb1; break;
           default:     op = reinterpret_cast<const double2 *>(K.VTp); kpt = kpN; panel = Sp;          krows = n8;  rb0 = nrb0; rb1 = nrb1; break;
         }
@@ -584,7 +599,40 @@ _Pragma("unroll 4")
         for (int rb = rb0; rb < rb1; rb += kRG) {
           double acc[kRG][NB][2];
           zero_acc(acc);
-          gemm_seg<NB, kRG>(op + lane, kpt, rb, min(kRG, rb1 - rb), 0, kpt, panel + bfrag, krows * 8, acc);
+          if (XD && pass != P_PX && pass != P_PD) {
+            // products with A̅ = [diag(a); -diag(a)] (or the identity) are element-wise: fill the accumulators directly
+#pragma unroll
+            for (int r = 0; r < kRG; ++r) {
+              if (rb + r >= rb1) continue;
+              const int row = 8 * (rb + r) + g;
+#pragma unroll
+              for (int nb = 0; nb < NB; ++nb) {
+                double2 v = make_double2(0.0, 0.0);
+                if (pass == P_ATY || pass == P_ATD) {            // A̅' y = a .* (y_top - y_bot); A̅' delta_y likewise (delta_y is in the w part of cv)
+                  if (row < n) {
+                    const double a = __ldg(K.adiag + row);
+                    const double2 t = pass == P_ATY ? *reinterpret_cast<const double2 *>(yp + pidx(m8, nb, row)) : *reinterpret_cast<const double2 *>(cv + pidx(cvr, nb, n8 + row));
+                    const double2 b = pass == P_ATY ? *reinterpret_cast<const double2 *>(yp + pidx(m8, nb, row + mp)) : *reinterpret_cast<const double2 *>(cv + pidx(cvr, nb, n8 + row + mp));
+                    v = make_double2(a * (t.x - b.x), a * (t.y - b.y));
+                  }
+                } else if (pass == P_AX || pass == P_ADX) {      // A̅ x̄ (rows over m): +a x on the top half, -a x on the bottom half
+                  if (row < m) {
+                    const int col = row < mp ? row : row - mp;
+                    const double a = row < mp ? __ldg(K.adiag + col) : -__ldg(K.adiag + col);
+                    const double2 x2 = pass == P_AX ? *reinterpret_cast<const double2 *>(cv + pidx(cvr, nb, col)) : *reinterpret_cast<const double2 *>(Dp + pidx(n8, nb, col));
+                    v = make_double2(a * x2.x, a * x2.y);
+                  }
+                } else if (pass == P_DX) {                       // delta_x is the Dp panel itself
+                  v = *reinterpret_cast<const double2 *>(Dp + pidx(n8, nb, row));
+                } else {                                         // P_QH: q̄ itself
+                  v = *reinterpret_cast<const double2 *>(Sp + pidx(n8, nb, row));
+                }
+                acc[r][nb][0] = v.x; acc[r][nb][1] = v.y;
+              }
+            }
+          } else {
+            gemm_seg<NB, kRG>(op + lane, kpt, rb, min(kRG, rb1 - rb), 0, kpt, panel + bfrag, krows * 8, acc);
+          }
           double mx[NB][8][2], sm[NB][2];
 #pragma unroll
           for (int nb = 0; nb < NB; ++nb) {
@@ -688,7 +736,18 @@ _Pragma("unroll 4")
 #pragma unroll
         for (int nb = 0; nb < NB; ++nb) {
           const double rho_s = C.rho[nb * 8 + s8];
-          if (PAIRED) {
+          if (XD) {   // rhs = sigma x - q̄ + a .* ((rho_vec z - y)_top - (rho_vec z - y)_bot) into the Sp panel
+            for (int r = tid >> 3; r < n8; r += kTileThreads / 8) {
+              double v = 0.0;
+              if (r < n) {
+                const int e1 = (nb * m8 + r) * 8 + s8, e2 = e1 + mp * 8, en = (nb * n8 + r) * 8 + s8;
+                const double w1 = rho_of((int)__ldg(P.ctype + r), rho_s) * zp[e1] - yp[e1];
+                const double w2 = rho_of((int)__ldg(P.ctype + r + mp), rho_s) * zp[e2] - yp[e2];
+                v = (S.sigma * cv[xi_at(en)] - qh[en]) + __ldg(K.adiag + r) * (w1 - w2);
+              }
+              Sp[(nb * n8 + r) * 8 + s8] = v;
+            }
+          } else if (PAIRED) {
             for (int r = tid >> 3; r < mp; r += kTileThreads / 8) {
               const int e1 = (nb * m8 + r) * 8 + s8, e2 = e1 + mp * 8;
               const double w1 = rho_of((int)__ldg(P.ctype + r), rho_s) * zp[e1] - yp[e1];
@@ -734,6 +793,74 @@ _Pragma("unroll 4")
     // ================= one ADMM iteration for the whole tile
     ++k;
     event = (k == C.next_event);
+    if constexpr (XD) {
+      const double2 *VTl = reinterpret_cast<const double2 *>(K.VTp) + lane, *Vl = reinterpret_cast<const double2 *>(K.Vp) + lane;
+      // ---- GEMM 1: u = dinv .* (V' rhs)
+      for (int rb = nrb0; rb < nrb1; rb += kRG) {
+        double acc[kRG][NB][2];
+        zero_acc(acc);
+        gemm_seg<NB, kRG>(VTl, kpN, rb, min(kRG, nrb1 - rb), 0, kpN, Sp + bfrag, n8 * 8, acc);
+#pragma unroll
+        for (int r = 0; r < kRG; ++r)
+          if (rb + r < nrb1) {
+#pragma unroll
+            for (int nb = 0; nb < NB; ++nb) {
+              const int pi = pidx(n8, nb, 8 * (rb + r) + g);
+              const double2 dv = *reinterpret_cast<const double2 *>(dinv + pi);
+              *reinterpret_cast<double2 *>(Tp + pi) = make_double2(acc[r][nb][0] * dv.x, acc[r][nb][1] * dv.y);
+            }
+          }
+      }
+      __syncthreads();
+      // ---- GEMM 2: x~ = V u; then, per row i (the owner of x_i also owns constraint rows i and i + mp): x update, z~ = +-a_i x~_i,
+      //      z / y updates (OSQP update_z / update_y), next right-hand side
+      for (int rb = nrb0; rb < nrb1; rb += kRG) {
+        double acc[kRG][NB][2];
+        zero_acc(acc);
+        gemm_seg<NB, kRG>(Vl, kpN, rb, min(kRG, nrb1 - rb), 0, kpN, Tp + bfrag, n8 * 8, acc);
+#pragma unroll
+        for (int r = 0; r < kRG; ++r)
+          if (rb + r < nrb1) {
+            const int row = 8 * (rb + r) + g;
+            if (row < n) {
+              const int ct1 = (int)__ldg(P.ctype + row), ct2 = (int)__ldg(P.ctype + row + mp);
+              const double a = __ldg(K.adiag + row);
+#pragma unroll
+              for (int nb = 0; nb < NB; ++nb) {
+                const int s = nb * 8 + q2, pn = pidx(n8, nb, row), ci = pidx(cvr, nb, row);
+                const double2 xo = *reinterpret_cast<const double2 *>(cv + ci), qv = *reinterpret_cast<const double2 *>(qh + pn);
+                const double x0 = alpha * acc[r][nb][0] + oma * xo.x, x1 = alpha * acc[r][nb][1] + oma * xo.y;
+                *reinterpret_cast<double2 *>(cv + ci) = make_double2(x0, x1);
+                if (event) *reinterpret_cast<double2 *>(Dp + pn) = make_double2(x0 - xo.x, x1 - xo.y);
+                const double zt0 = a * acc[r][nb][0], zt1 = a * acc[r][nb][1];
+                double wsum2[2] = {0.0, 0.0};
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                  const int rr = row + half * mp, ct = half ? ct2 : ct1, pi = pidx(m8, nb, rr);
+                  const double sg = half ? -1.0 : 1.0;
+                  const double2 zo = *reinterpret_cast<const double2 *>(zp + pi), yo = *reinterpret_cast<const double2 *>(yp + pi);
+                  const double2 lo = *reinterpret_cast<const double2 *>(lbp + pi), hi = *reinterpret_cast<const double2 *>(ubp + pi);
+                  double rv0, rv1, ri0, ri1;
+                  if (ct == 0) { rv0 = C.rho[s]; rv1 = C.rho[s + 1]; ri0 = C.rinv[s]; ri1 = C.rinv[s + 1]; }
+                  else if (ct == 1) { rv0 = C.rho_eq[s]; rv1 = C.rho_eq[s + 1]; ri0 = C.rinv_eq[s]; ri1 = C.rinv_eq[s + 1]; }
+                  else { rv0 = rv1 = kRhoMin; ri0 = ri1 = 1.0 / kRhoMin; }
+                  const double zr0 = alpha * (sg * zt0) + oma * zo.x, zr1 = alpha * (sg * zt1) + oma * zo.y;
+                  const double zn0 = fmin(fmax(zr0 + ri0 * yo.x, lo.x), hi.x), zn1 = fmin(fmax(zr1 + ri1 * yo.y, lo.y), hi.y);
+                  const double d0 = rv0 * (zr0 - zn0), d1 = rv1 * (zr1 - zn1);
+                  const double yn0 = yo.x + d0, yn1 = yo.y + d1;
+                  *reinterpret_cast<double2 *>(zp + pi) = make_double2(zn0, zn1);
+                  *reinterpret_cast<double2 *>(yp + pi) = make_double2(yn0, yn1);
+                  if (event) *reinterpret_cast<double2 *>(cv + pidx(cvr, nb, n8 + rr)) = make_double2(d0, d1);   // delta_y for is_primal_infeasible
+                  wsum2[0] += sg * (rv0 * zn0 - yn0); wsum2[1] += sg * (rv1 * zn1 - yn1);
+                }
+                *reinterpret_cast<double2 *>(Sp + pn) = make_double2((S.sigma * x0 - qv.x) + a * wsum2[0], (S.sigma * x1 - qv.y) + a * wsum2[1]);
+              }
+            }
+          }
+      }
+      __syncthreads();
+      continue;
+    }
     const double2 *M1l = reinterpret_cast<const double2 *>(PAIRED ? K.M1p : K.M1) + lane;
     const double2 *Wl = reinterpret_cast<const double2 *>(PAIRED ? K.Wtop : K.Wp) + lane;
     const int kp1 = kpN + (PAIRED ? kpMp : kpM);      // k-pairs of GEMM 1
@@ -886,6 +1013,10 @@ cudaError_t launch_admm_shared_tile(const TilePackDev &K, const SharedPlanDev &P
     return cudaGetLastError();
   };
   const bool paired = K.mp > 0;
+  if (K.xd && paired) {
+    if (warps == 16) return nb == 1 ? go(admm_shared_tile_kernel<1, true, 16, true>) : go(admm_shared_tile_kernel<2, true, 16, true>);
+    return nb == 1 ? go(admm_shared_tile_kernel<1, true, 8, true>) : go(admm_shared_tile_kernel<2, true, 8, true>);
+  }
   if (warps == 16) {
     if (nb == 1) return paired ? go(admm_shared_tile_kernel<1, true, 16>) : go(admm_shared_tile_kernel<1, false, 16>);
     return paired ? go(admm_shared_tile_kernel<2, true, 16>) : go(admm_shared_tile_kernel<2, false, 16>);

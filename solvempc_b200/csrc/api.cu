@@ -219,8 +219,18 @@ int upload_tile_pack(smpc_solver *s) {
     });
     Wtop = pack(mp8, n8, [&](int r, int k) -> double { return (r < mp && k < n) ? p.W[(size_t)r * n + k] : 0.0; });
   }
+  // x-space variant: P̄ itself (termination checks) and the diagonal of the top block
+  const bool xd = !p.xdiag.empty() && !getenv("SMPC_TILE_NO_XSPACE");
+  std::vector<double> Pp, adiag;
+  double dmax = 1.0;
+  if (xd) {
+    Pp = pack(n8, n8, [&](int i, int k) -> double { return (i < n && k < n) ? p.Pbar[(size_t)i * n + k] : 0.0; });
+    adiag.assign(n8, 0.0);
+    for (int i = 0; i < n; ++i) adiag[i] = p.xdiag[i];
+    if (!s->st.scaled_termination) { dmax = 0.0; for (int i = 0; i < n; ++i) dmax = std::max(dmax, p.D[i]); }
+  }
   size_t bytes = DeviceBuf::need(sizeof(int) * 4);
-  for (const std::vector<double> *v : {&M1, &Wp, &VTp, &Vp, &PVp, &ATp, &M1p, &Wtop}) bytes += DeviceBuf::need((v->size() ? v->size() : 1) * sizeof(double));
+  for (const std::vector<double> *v : {&M1, &Wp, &VTp, &Vp, &PVp, &ATp, &M1p, &Wtop, &Pp, &adiag}) bytes += DeviceBuf::need((v->size() ? v->size() : 1) * sizeof(double));
   CK(s->tilebuf.alloc(bytes));
   auto put = [&](const std::vector<double> &v, const double **dst) -> cudaError_t {
     double *d = s->tilebuf.take<double>(v.size() ? v.size() : 1);
@@ -233,6 +243,8 @@ int upload_tile_pack(smpc_solver *s) {
   CK(put(M1, &k.M1)); CK(put(Wp, &k.Wp)); CK(put(VTp, &k.VTp)); CK(put(Vp, &k.Vp)); CK(put(PVp, &k.PVp)); CK(put(ATp, &k.ATp));
   k.mp = mp; k.mp8 = mp8;
   CK(put(M1p, &k.M1p)); CK(put(Wtop, &k.Wtop));
+  k.xd = xd ? 1 : 0; k.dmax = dmax;
+  CK(put(Pp, &k.Pp)); CK(put(adiag, &k.adiag));
   s->d_queue = s->tilebuf.take<int>(4);
   if (!s->d_queue) return fail(SMPC_ERR_CUDA, "internal: tile buffer carve-out overflow");
   CK(cudaMemset(s->d_queue, 0, sizeof(int) * 4));
@@ -519,7 +531,7 @@ int smpc_solver_warm_start(smpc_solver *s, const double *x, const double *y, int
   if (int rc = copy_in(s, s->d_stage_x, x, (size_t)s->B * s->n, loc)) return rc;
   if (int rc = copy_in(s, s->d_stage_y, y, (size_t)s->B * s->m, loc)) return rc;
   if (s->regime == 1) CK(smpc::launch_warm_start_instance(s->dinst, s->d_stage_x, s->d_stage_y, s->d_xi, s->d_z, s->d_y, s->stream));
-  else CK(smpc::launch_warm_start(s->dplan, s->B, s->d_stage_x, s->d_stage_y, s->d_xi, s->d_z, s->d_y, s->stream));
+  else CK(smpc::launch_warm_start(s->dplan, s->B, s->d_stage_x, s->d_stage_y, s->d_xi, s->d_z, s->d_y, s->stream, s->kernel == 4 && s->dtile.xd));
   s->launches++;
   return SMPC_OK;
 }
@@ -671,7 +683,7 @@ int smpc_solver_row_pairs(const smpc_solver *s) {
 const char *smpc_solver_kernel_name(const smpc_solver *s) {
   if (!s) return "";
   return s->regime == 1 ? (s->dinst.pack ? "admm_instance_pair_kernel" : "admm_instance_kernel") : s->kernel == 2 ? "admm_shared_small_kernel"
-         : s->kernel == 4 ? "admm_shared_tile_kernel" : s->kernel == 5 ? "admm_shared_small_mma_kernel" : "admm_shared_generic_kernel";
+         : s->kernel == 4 ? (s->dtile.xd ? "admm_shared_tile_kernel<x-space>" : "admm_shared_tile_kernel") : s->kernel == 5 ? "admm_shared_small_mma_kernel" : "admm_shared_generic_kernel";
 }
 
 /* host-only inspection of the shared plan (no device needed): used by the CPU tests of the host logic */

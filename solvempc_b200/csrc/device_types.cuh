@@ -62,6 +62,12 @@ struct TilePackDev {
   int mp, mp8;
   const double *M1p;   // [sigma*G | Wtop']  n8 x (n8 + mp8)
   const double *Wtop;  // first mp rows of W  mp8 x n8
+  // x-space variant (xd != 0): paired rows whose top block is DIAGONAL after scaling, A̅ = [diag(adiag); -diag(adiag)] (mp == n):
+  // the iteration multiplies by V' and V only (2 n^2 MACs) and needs P̄ for the checks
+  int xd;
+  const double *Pp;     // P̄  n8 x n8 (fragment pack)
+  const double *adiag;  // n8 (zero padded)
+  double dmax;          // max_i D_i (unscaled termination) or 1: ||delta_x||_inf <= dmax ||delta_x̄||_inf
 };
 
 // per-instance regime: every QP has its own (scaled) P̄_i, A̅_i and scaling

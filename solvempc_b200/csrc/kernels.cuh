@@ -11,8 +11,9 @@ namespace smpc {
 cudaError_t launch_admm_shared_generic(const SharedPlanDev &P, const BatchDev &Bt, const SettingsDev &S,
                                        cudaStream_t stream);
 cudaError_t launch_fill(double *p, double v, size_t count, cudaStream_t stream);
+// xspace != 0: the handle's kernel keeps the scaled iterate x̄ itself as its state (tile kernel, x-space variant), not xi = V^-1 x̄
 cudaError_t launch_warm_start(const SharedPlanDev &P, int B, const double *x, const double *y, double *xi,
-                              double *z, double *ys, cudaStream_t stream);
+                              double *z, double *ys, cudaStream_t stream, bool xspace = false);
 
 // admm_shared_small.cu : register-resident kernel for small QPs (n <= 16, m <= 32)
 bool small_kernel_supports(int n, int m);

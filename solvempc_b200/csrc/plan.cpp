@@ -244,6 +244,14 @@ int build_shared_plan(int n, int m, const double *P_in, const double *A_in, cons
     }
     if (ok == h) pl.pairs = h;
   }
+  // paired rows whose top block is diagonal (a two-sided box on the variables): the tile kernel can iterate in x-space
+  pl.xdiag.clear();
+  if (pl.pairs == n && n > 0) {
+    bool diag = true;
+    for (int r = 0; r < n && diag; ++r)
+      for (int j = 0; j < n && diag; ++j) diag = (j == r) || Ab[(size_t)r * n + j] == 0.0;
+    if (diag) { pl.xdiag.resize(n); for (int r = 0; r < n; ++r) pl.xdiag[r] = Ab[(size_t)r * n + r]; }
+  }
   return SMPC_OK;
 }
 

@@ -34,6 +34,7 @@ struct SharedPlan {
   std::vector<double> PVT;                  // (P̄ V)' (n*n)
   std::vector<double> VinvT;                // (V' S)' = S V (n*n): xi = Vinv x̄
   int pairs = 0;                            // rows r, r+m/2 with A[r+m/2] == -A[r] (diagnostic)
+  std::vector<double> xdiag;                // non-empty: pairs == n and the top block of A̅ is diag(xdiag) (x-space tile iteration)
 };
 
 // OSQP scale_data (modified Ruiz + cost scaling) on (P, A, q): returns D, E, c and scaled P̄, A̅.
