@@ -52,12 +52,20 @@ class Settings {
   void setDualInfeasibilityTollerance(double v) { m_s.eps_dual_inf = v; }
   void setCheckTermination(int v) { m_s.check_termination = v; }
   void setScaledTerimination(bool v) { m_s.scaled_termination = v ? 1 : 0; }
+  void setPolish(bool v) { m_polish = v; }
+  void setDelta(double v) { m_delta = v; }
+  void setPolishRefineIter(int v) { m_refine = v; }
+  bool polish() const { return m_polish; }
+  double delta() const { return m_delta; }
+  int polishRefineIter() const { return m_refine; }
   const smpc_settings *getSettings() const { return &m_s; }
   bool verbose() const { return m_verbose; }
 
  private:
   smpc_settings m_s;
-  bool m_verbose = false;
+  bool m_verbose = false, m_polish = false;
+  double m_delta = 1e-6;
+  int m_refine = 3;
 };
 
 class Data {
@@ -129,7 +137,8 @@ class Solver {
     int rc = smpc_solver_create_shared_csc(&m_h, device, d.m_n, d.m_m, 1, d.m_Pp.data(), d.m_Pi.data(), d.m_Px.data(),
                                            d.m_Ap.data(), d.m_Ai.data(), d.m_Ax.data(), d.m_q.data(), d.m_l.data(), d.m_u.data(),
                                            m_settings->getSettings());
-    if (rc != SMPC_OK) { std::cerr << "[OsqpEigen shim] " << smpc_last_error() << "\n"; m_h = nullptr; return false; }
+    if (rc == SMPC_OK && m_settings->polish()) rc = smpc_solver_set_polish(m_h, 1, m_settings->delta(), m_settings->polishRefineIter());
+    if (rc != SMPC_OK) { std::cerr << "[OsqpEigen shim] " << smpc_last_error() << "\n"; if (m_h) smpc_solver_destroy(m_h); m_h = nullptr; return false; }
     m_x = Eigen::VectorXd::Zero(d.m_n);
     m_y = Eigen::VectorXd::Zero(d.m_m);
     return true;

@@ -129,6 +129,16 @@ int smpc_solver_set_scheduling(smpc_solver *s, int on);
 int smpc_solver_enable_timing(smpc_solver *s, int on);
 int smpc_solver_kernel_ms(smpc_solver *s, double *total_ms, int *launches, int reset);
 
+/* solver.settings()->setPolish / setDelta / setPolishRefineIter (osqp-eigen Settings; OSQP polish.c): after the ADMM loop every
+ * instance that ended SOLVED guesses its active set from (z, y), solves the regularised reduced KKT system
+ * [P + delta I, Ared'; Ared, -delta I] with `refine_iter` steps of iterative refinement and keeps the polished point when it
+ * lowers the residuals.  Off by default -- the reference never enables it (cpp:51-52); OSQP defaults delta = 1e-6, 3 steps.
+ * One extra kernel launch per solve.  Both regimes. */
+int smpc_solver_set_polish(smpc_solver *s, int on, double delta, int refine_iter);
+/* info->status_polish of every instance after the last solve: 1 polished, -1 polish unsuccessful (ADMM solution kept),
+ * 0 not run (polish off, or the instance did not end SOLVED) */
+int smpc_solver_get_polish_status(smpc_solver *s, int *status_polish, int loc);
+
 /* solver.solve() (cpp:102) -> osqp_solve for every instance; asynchronous on the stream */
 int smpc_solver_solve(smpc_solver *s);
 /* solver.getSolution() (cpp:105): x:[batch][n]; y:[batch][m] duals (either may be NULL).

@@ -28,6 +28,7 @@ class Settings(C.Structure):
         ("max_iter", C.c_int), ("check_termination", C.c_int), ("scaling", C.c_int),
         ("adaptive_rho", C.c_int), ("adaptive_rho_interval", C.c_int),
         ("warm_start", C.c_int), ("scaled_termination", C.c_int),
+        ("polish", C.c_int), ("polish_refine_iter", C.c_int), ("delta", C.c_double),
     ]
 
 
@@ -85,6 +86,7 @@ def _bind(L):
     L.orc_get_solution.argtypes = [C.c_void_p, dp, dp]
     L.orc_get_info.argtypes = [C.c_void_p, dp]
     L.orc_get_scaling.argtypes = [C.c_void_p, dp, dp, dp]
+    L.orc_get_status_polish.argtypes = [C.c_void_p]
     L.orc_get_scaled_data.argtypes = [C.c_void_p, dp, dp]
     L.orc_get_iterates.argtypes = [C.c_void_p, dp, dp, dp]
     L.orc_solve_batch.restype = C.c_double
@@ -182,6 +184,7 @@ class Solver:
         lib().orc_get_solution(self._h, _p(x), _p(y))
         lib().orc_get_info(self._h, _p(info))
         return dict(rc=rc, x=x, y=y, status=int(info[0]), iter=int(info[1]), rho_updates=int(info[2]),
+                    status_polish=lib().orc_get_status_polish(self._h),
                     rho=info[3], obj=info[4], pri_res=info[5], dua_res=info[6], rho_estimate=info[7])
 
     def scaling(self):

@@ -62,7 +62,7 @@ struct orc_solver {
   double *Ax, *Px, *Aty, *Adelta_x, *Atdelta_y, *Pdelta_x;
   double *tn, *tm; /* temporaries */
   /* info */
-  int status_val, iter, rho_updates;
+  int status_val, iter, rho_updates, status_polish;
   double obj_val, pri_res, dua_res, rho_estimate;
   /* solution (unscaled) */
   double *sol_x, *sol_y;
@@ -76,6 +76,7 @@ void orc_default_settings(orc_settings *s) {
   s->max_iter = 4000; s->check_termination = 25; s->scaling = 10;
   s->adaptive_rho = 1; s->adaptive_rho_interval = 25;
   s->warm_start = 1; s->scaled_termination = 0;
+  s->polish = 0; s->polish_refine_iter = 3; s->delta = 1e-6;
 }
 
 static double *dalloc(size_t k) { return (double *)calloc(k ? k : 1, sizeof(double)); }
@@ -470,6 +471,96 @@ static int adapt_rho(orc_solver *w) {
   return 0;
 }
 
+/* osqp/src/polish.c: polish() -- refine a SOLVED iterate by solving the KKT system of the active set it identifies.
+ *   form_Ared:  row i is lower-active if z_i - l_i < -y_i, upper-active if u_i - z_i < y_i (scaled quantities);
+ *               Ared = [lower-active rows; upper-active rows]
+ *   solve  [P + delta I, Ared'; Ared, -delta I] [x; y_red] = [-q; l_low; u_upp]  (dense LDL', quasi-definite, no pivoting)
+ *   iterative_refinement: polish_refine_iter steps against the UNregularised KKT matrix
+ *   z = A x, y expanded to m rows, (z, y) projected onto the normal cone (project_normalcone); update_info on the polished point; accepted (status_polish = 1) only if it
+ *   improves the residuals as polish.c tests, otherwise the ADMM solution is kept (status_polish = -1). */
+static void polish(orc_solver *w) {
+  int n = w->n, m = w->m;
+  int *act = (int *)calloc(m ? m : 1, sizeof(int));   /* Ared row -> row of A */
+  int *sgn = (int *)calloc(m ? m : 1, sizeof(int));   /* -1 lower-active, +1 upper-active */
+  int k = 0;
+  for (int i = 0; i < m; i++) if (w->z[i] - w->l[i] < -w->y[i]) { act[k] = i; sgn[k] = -1; k++; }
+  for (int i = 0; i < m; i++) if (w->u[i] - w->z[i] < w->y[i]) { act[k] = i; sgn[k] = 1; k++; }
+  int N = n + k;
+  double *K = dalloc((size_t)N * N), *Dk = dalloc(N), *b = dalloc(N), *sol = dalloc(N), *r = dalloc(N);
+  double *px = dalloc(n), *pz = dalloc(m), *py = dalloc(m);
+  const double delta = w->st.delta;
+  for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) K[(size_t)i * N + j] = w->P[(size_t)i * n + j] + (i == j ? delta : 0.0);
+  for (int a = 0; a < k; a++) {
+    for (int j = 0; j < n; j++) { double v = w->A[(size_t)act[a] * n + j]; K[(size_t)(n + a) * N + j] = v; K[(size_t)j * N + n + a] = v; }
+    for (int c = 0; c < k; c++) K[(size_t)(n + a) * N + n + c] = a == c ? -delta : 0.0;
+  }
+  for (int j = 0; j < n; j++) b[j] = -w->q[j];
+  for (int a = 0; a < k; a++) b[n + a] = sgn[a] < 0 ? w->l[act[a]] : w->u[act[a]];
+  /* in-place LDL' (unit lower L below the diagonal of K, D in Dk) */
+  int ok = 1;
+  for (int j = 0; j < N && ok; j++) {
+    double d = K[(size_t)j * N + j];
+    for (int c = 0; c < j; c++) d -= K[(size_t)j * N + c] * K[(size_t)j * N + c] * Dk[c];
+    if (d == 0.0 || d != d) { ok = 0; break; }
+    Dk[j] = d;
+    for (int i = j + 1; i < N; i++) {
+      double s = K[(size_t)i * N + j];
+      for (int c = 0; c < j; c++) s -= K[(size_t)i * N + c] * K[(size_t)j * N + c] * Dk[c];
+      K[(size_t)i * N + j] = s / d;
+    }
+  }
+  w->status_polish = -1;
+  if (ok) {
+#define KKT_SOLVE(v) do { \
+    for (int i = 0; i < N; i++) { double s = (v)[i]; for (int c = 0; c < i; c++) s -= K[(size_t)i * N + c] * (v)[c]; (v)[i] = s; } \
+    for (int i = 0; i < N; i++) (v)[i] /= Dk[i]; \
+    for (int i = N - 1; i >= 0; i--) { double s = (v)[i]; for (int c = i + 1; c < N; c++) s -= K[(size_t)c * N + i] * (v)[c]; (v)[i] = s; } } while (0)
+    memcpy(sol, b, sizeof(double) * N);
+    KKT_SOLVE(sol);
+    for (int it = 0; it < w->st.polish_refine_iter; it++) {
+      /* r = b - [P, Ared'; Ared, 0] sol */
+      for (int i = 0; i < n; i++) {
+        double s = b[i];
+        for (int j = 0; j < n; j++) s -= w->P[(size_t)i * n + j] * sol[j];
+        for (int a = 0; a < k; a++) s -= w->A[(size_t)act[a] * n + i] * sol[n + a];
+        r[i] = s;
+      }
+      for (int a = 0; a < k; a++) { double s = b[n + a]; for (int j = 0; j < n; j++) s -= w->A[(size_t)act[a] * n + j] * sol[j]; r[n + a] = s; }
+      KKT_SOLVE(r);
+      for (int i = 0; i < N; i++) sol[i] += r[i];
+    }
+#undef KKT_SOLVE
+    for (int j = 0; j < n; j++) px[j] = sol[j];
+    for (int i = 0; i < m; i++) py[i] = 0.0;
+    for (int a = 0; a < k; a++) py[act[a]] = sol[n + a];
+    csr_mv(m, w->a_rp, w->a_ci, w->a_v, px, pz);
+    /* project_normalcone (proj.c): z <- proj(z + y), y <- (z + y) - proj(z + y); then update_info on the polished point:
+     * the primal residual is A x - z */
+    double *Ax = dalloc(m), *Px = dalloc(n), *Aty = dalloc(n), *rp = dalloc(m), *rd = dalloc(n);
+    for (int i = 0; i < m; i++) {
+      Ax[i] = pz[i];
+      double zy = pz[i] + py[i];
+      pz[i] = c_min(c_max(zy, w->l[i]), w->u[i]);
+      py[i] = zy - pz[i];
+      rp[i] = Ax[i] - pz[i];
+    }
+    dense_sym_mv(n, w->P, px, Px);
+    csr_mv(n, w->at_rp, w->at_ci, w->at_v, py, Aty);
+    double obj = 0; for (int j = 0; j < n; j++) { obj += 0.5 * px[j] * Px[j] + w->q[j] * px[j]; rd[j] = (w->q[j] + Px[j]) + Aty[j]; }
+    int unscale = w->st.scaling && !w->st.scaled_termination;
+    double pri = m == 0 ? 0.0 : (unscale ? scaled_norm_inf(w->Einv, rp, m) : norm_inf(rp, m));
+    double dua = unscale ? w->cinv * scaled_norm_inf(w->Dinv, rd, n) : norm_inf(rd, n);
+    int success = (pri < w->pri_res && dua < w->dua_res) || (pri < w->pri_res && w->dua_res < 1e-10) || (dua < w->dua_res && w->pri_res < 1e-10);
+    if (success) {
+      memcpy(w->x, px, sizeof(double) * n); memcpy(w->z, pz, sizeof(double) * m); memcpy(w->y, py, sizeof(double) * m);
+      w->obj_val = w->st.scaling ? w->cinv * obj : obj; w->pri_res = pri; w->dua_res = dua;
+      w->status_polish = 1;
+    }
+    free(Ax); free(Px); free(Aty); free(rp); free(rd);
+  }
+  free(act); free(sgn); free(K); free(Dk); free(b); free(sol); free(r); free(px); free(pz); free(py);
+}
+
 /* osqp/src/osqp.c: osqp_solve */
 int orc_solve(orc_solver *w) {
   int n = w->n, m = w->m, iter, can_check = 0;
@@ -512,6 +603,8 @@ int orc_solve(orc_solver *w) {
   if (!can_check) { update_info(w, iter); check_termination(w, 0); }
   if (w->status_val == ORC_UNSOLVED) { if (!check_termination(w, 1)) w->status_val = ORC_MAX_ITER_REACHED; }
   w->rho_estimate = compute_rho_estimate(w);
+  w->status_polish = 0;
+  if (w->st.polish && w->status_val == ORC_SOLVED) polish(w);
   /* store_solution */
   int has_sol = !(w->status_val == ORC_PRIMAL_INFEASIBLE || w->status_val == ORC_PRIMAL_INFEASIBLE_INACCURATE ||
                   w->status_val == ORC_DUAL_INFEASIBLE || w->status_val == ORC_DUAL_INFEASIBLE_INACCURATE);
@@ -534,6 +627,7 @@ void orc_get_info(const orc_solver *w, double *o) {
   o[0] = w->status_val; o[1] = w->iter; o[2] = w->rho_updates; o[3] = w->st.rho;
   o[4] = w->obj_val; o[5] = w->pri_res; o[6] = w->dua_res; o[7] = w->rho_estimate;
 }
+int orc_get_status_polish(const orc_solver *w) { return w->status_polish; }
 void orc_get_scaling(const orc_solver *w, double *D, double *E, double *c) {
   if (D) memcpy(D, w->D, sizeof(double) * w->n);
   if (E) memcpy(E, w->E, sizeof(double) * w->m);

@@ -52,6 +52,9 @@ typedef struct {
                                     port: fixed, default 25 */
   int warm_start;                /* 1     */
   int scaled_termination;        /* 0     */
+  int polish;                    /* 0     (osqp polish.c; the reference leaves it off, cpp:51-52) */
+  int polish_refine_iter;        /* 3     */
+  double delta;                  /* 1e-6  regularisation of the polish KKT system */
 } orc_settings;
 
 typedef struct orc_solver orc_solver;
@@ -81,6 +84,8 @@ void orc_get_solution(const orc_solver *w, double *x, double *y);
 /* info[0]=status_val info[1]=iter info[2]=rho_updates info[3]=rho
  * info[4]=obj_val info[5]=pri_res info[6]=dua_res info[7]=rho_estimate */
 void orc_get_info(const orc_solver *w, double *info8);
+/* polish outcome of the last solve: 0 = not run, 1 = successful, -1 = unsuccessful (osqp info->status_polish) */
+int orc_get_status_polish(const orc_solver *w);
 /* scaling vectors and the scaled data, for parity tests of the device setup */
 void orc_get_scaling(const orc_solver *w, double *D, double *E, double *c);
 void orc_get_scaled_data(const orc_solver *w, double *Pbar, double *Abar);

@@ -76,6 +76,8 @@ SIGNATURES = {
     "smpc_solver_set_scheduling": (_i, [_vp, _i]),
     "smpc_solver_enable_timing": (_i, [_vp, _i]),
     "smpc_solver_kernel_ms": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(_i), _i]),
+    "smpc_solver_set_polish": (_i, [_vp, _i, C.c_double, _i]),
+    "smpc_solver_get_polish_status": (_i, [_vp, _vp, _i]),
     "smpc_solver_solve": (_i, [_vp]),
     "smpc_solver_get_solution": (_i, [_vp, _dp, _dp, _i]),
     "smpc_solver_get_info": (_i, [_vp, _vp, _vp, _dp, _dp, _dp, _dp, _vp, _i]),

@@ -99,7 +99,7 @@ int upload_plan(smpc_solver *s) {
   const smpc::SharedPlan &p = s->plan;
   const size_t n = p.n, m = p.m;
   size_t bytes = 0;
-  for (size_t c : {n * n, m * n, n * m, n * n, n * n, n * n, n * n, m * n, n, n, n, m, m, m, m}) bytes += DeviceBuf::need(c * sizeof(double));
+  for (size_t c : {n * n, m * n, n * m, n * n, n * n, n * n, n * n, m * n, n * n, n, n, n, m, m, m, m}) bytes += DeviceBuf::need(c * sizeof(double));
   bytes += DeviceBuf::need(m);
   CK(s->planbuf.alloc(bytes));
   auto put = [&](const std::vector<double> &v, size_t count, const double **dst) -> cudaError_t {
@@ -118,7 +118,7 @@ int upload_plan(smpc_solver *s) {
   }
   CK(put(p.SG, n * n, &d.SG)); CK(put(p.W, m * n, &d.W)); CK(put(p.WT, n * m, &d.WT));
   CK(put(p.V, n * n, &d.V)); CK(put(p.VT, n * n, &d.VT)); CK(put(p.PVT, n * n, &d.PVT));
-  CK(put(p.VinvT, n * n, &d.VinvT)); CK(put(p.Abar, m * n, &d.Abar));
+  CK(put(p.VinvT, n * n, &d.VinvT)); CK(put(p.Abar, m * n, &d.Abar)); CK(put(p.Pbar, n * n, &d.Pbar));
   CK(put(p.lam, n, &d.lam)); CK(put(p.D, n, &d.D)); CK(put(p.Dinv, n, &d.Dinv));
   CK(put(p.E, m, &d.E)); CK(put(p.Einv, m, &d.Einv));
   std::vector<double> l0(m), u0(m);   // unscaled setup bounds
@@ -483,6 +483,8 @@ int smpc_solver_destroy(smpc_solver *s) {
   cudaSetDevice(s->device);
   cudaStreamSynchronize(s->stream);
   s->planbuf.release(); s->batchbuf.release(); s->packbuf.release(); s->instbuf.release(); s->prepbuf.release(); s->tilebuf.release();
+  if (s->d_polish) cudaFree(s->d_polish);
+  if (s->d_polish_scratch) cudaFree(s->d_polish_scratch);
   delete s;
   return SMPC_OK;
 }
@@ -556,9 +558,9 @@ int smpc_solver_solve(smpc_solver *s) {
   b.x_out = s->d_x; b.y_out = s->d_yout; b.status = s->d_status; b.iter = s->d_iter; b.rho_updates = s->d_rhoup;
   b.obj = s->d_obj; b.pri_res = s->d_pri; b.dua_res = s->d_dua;
   b.fresh = s->cold_solves ? 1 : 0;
-  b.u_apply = (s->regime == 0 && (s->kernel == 2 || s->kernel == 5)) ? s->u_apply : nullptr;
+  b.u_apply = (s->regime == 0 && (s->kernel == 2 || s->kernel == 5) && !s->polish) ? s->u_apply : nullptr;   // polish may still change x
   b.u_export = (s->regime == 0 && s->kernel == 2 && b.u_apply) ? s->u_export : nullptr;
-  b.status_export = (s->regime == 0 && s->kernel == 2) ? s->status_export : nullptr;
+  b.status_export = (s->regime == 0 && s->kernel == 2 && !s->polish) ? s->status_export : nullptr;
   smpc::SettingsDev sd = to_dev(s->st);
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   if (s->timing) {
@@ -573,9 +575,56 @@ int smpc_solver_solve(smpc_solver *s) {
                                    : smpc::launch_admm_shared_generic(s->dplan, b, sd, s->stream);
   if (e != cudaSuccess) return cuda_fail(e, "ADMM kernel launch");
   if (s->timing) { CK(cudaEventRecord(ev1, s->stream)); s->events.emplace_back(ev0, ev1); }
+  if (s->polish) {   // osqp_solve: polish(work) after the ADMM loop when settings->polish and the status is SOLVED
+    smpc::PolishDataDev pd{};
+    pd.n = s->n; pd.m = s->m;
+    if (s->regime == 1) {
+      pd.Pbar = s->dinst.P; pd.Abar = s->dinst.A; pd.D = s->dinst.D; pd.E = s->dinst.E; pd.c_inst = s->dinst.c; pd.c = 1.0;
+      pd.strideP = (size_t)s->n * s->n; pd.strideA = (size_t)s->m * s->n; pd.strideD = s->n; pd.strideE = s->m;
+      pd.l0 = s->dinst.l0; pd.u0 = s->dinst.u0; pd.VinvT = nullptr;
+    } else {
+      pd.Pbar = s->dplan.Pbar; pd.Abar = s->dplan.Abar; pd.D = s->dplan.D; pd.E = s->dplan.E; pd.c = s->dplan.c;
+      pd.l0 = s->dplan.l0; pd.u0 = s->dplan.u0;
+      pd.VinvT = (s->kernel == 4 && s->dtile.xd) ? nullptr : s->dplan.VinvT;
+    }
+    e = smpc::launch_polish(pd, b, sd, s->polish_delta, s->polish_refine, s->d_polish, s->d_polish_scratch, s->num_sms, s->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "polish kernel launch");
+    s->launches++;
+  }
   s->launches += (s->regime == 0 && (s->kernel == 2 || s->kernel == 5) && s->schedule && !s->classified) ? 2 : 1;
   s->classified = false;
   s->solved_once = true;
+  return SMPC_OK;
+}
+
+int smpc_solver_set_polish(smpc_solver *s, int on, double delta, int refine_iter) {
+  if (!s) return fail(SMPC_ERR_ARG, "null handle");
+  if (on && (!(delta > 0) || refine_iter < 0)) return fail(SMPC_ERR_ARG, "polish needs delta > 0 and polish_refine_iter >= 0");
+  if (on && !s->d_polish) {
+    CK(cudaSetDevice(s->device));
+    int sms = 0;
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
+    s->num_sms = sms > 0 ? sms : 148;
+    const size_t scratch = smpc::polish_scratch_doubles(s->n, s->m, s->num_sms);
+    CK(cudaMalloc((void **)&s->d_polish, sizeof(int) * (size_t)s->B));
+    CK(cudaMemset(s->d_polish, 0, sizeof(int) * (size_t)s->B));
+    if (scratch) CK(cudaMalloc((void **)&s->d_polish_scratch, scratch * sizeof(double)));
+  }
+  s->polish = on != 0;
+  if (on) { s->polish_delta = delta; s->polish_refine = refine_iter; }
+  return SMPC_OK;
+}
+int smpc_solver_get_polish_status(smpc_solver *s, int *status_polish, int loc) {
+  if (!s || !status_polish) return fail(SMPC_ERR_ARG, "null argument");
+  if (!s->solved_once) return fail(SMPC_ERR_STATE, "get_polish_status before solve");
+  CK(cudaSetDevice(s->device));
+  if (!s->d_polish) {   // polish never enabled: 0 = not run, as OSQP reports
+    if (loc == SMPC_HOST) { std::memset(status_polish, 0, sizeof(int) * (size_t)s->B); return SMPC_OK; }
+    CK(cudaMemsetAsync(status_polish, 0, sizeof(int) * (size_t)s->B, s->stream));
+    return SMPC_OK;
+  }
+  if (int rc = copy_out(s, status_polish, s->d_polish, (size_t)s->B, loc)) return rc;
+  if (loc == SMPC_HOST) CK(cudaStreamSynchronize(s->stream));
   return SMPC_OK;
 }
 
@@ -916,10 +965,10 @@ int mpc_step_impl(smpc_mpc *M, const double *X, const double *U, const double *r
   M->launches++;
   s->have_q = true; s->have_u = true;
   // cpp:102 solve, cpp:105 U += dU*[0]: inside the small-QP kernels' store_solution, a separate kernel otherwise
-  const bool fused = s->regime == 0 && (s->kernel == 2 || s->kernel == 5);
+  const bool fused = s->regime == 0 && (s->kernel == 2 || s->kernel == 5) && !s->polish;
   // bound result buffers (smpc_mpc_bind_results): written by the one-warp kernel as each instance ends, by an export
   // kernel behind the solve otherwise
-  const bool bound = M->bound_U || M->bound_status, export_fused = bound && s->regime == 0 && s->kernel == 2;
+  const bool bound = M->bound_U || M->bound_status, export_fused = bound && fused && s->kernel == 2;
   s->u_apply = fused ? M->d_U : nullptr;
   s->u_export = export_fused ? M->bound_U : nullptr;
   s->status_export = export_fused ? M->bound_status : nullptr;

@@ -24,6 +24,7 @@ struct SharedPlanDev {
   const double *PVT;    // n*n                    (P̄x)_i = sum_k PVT[k*n+i] xi_k
   const double *VinvT;  // n*n                    xi_i = sum_k VinvT[k*n+i] xbar_k
   const double *Abar;   // m*n   row-major:       (A̅'y)_i = sum_r Abar[r*n+i] y_r
+  const double *Pbar;   // n*n   full symmetric (polish only)
   const double *lam, *D, *Dinv, *E, *Einv;
   const double *l0, *u0;        // UNSCALED setup bounds (used when the batch has none of its own)
   const signed char *ctype;     // m
@@ -87,6 +88,18 @@ struct InstanceDataDev {
   // with, and the ticket queue (2 ints)
   double *pack, *pack_rho;
   int *queue;
+};
+
+// what the polish kernel reads (polish.cu): scaled data and scaling of either regime; strides are 0 when the batch shares them
+struct PolishDataDev {
+  int n, m;
+  const double *Pbar, *Abar;    // n*n full symmetric, m*n row-major
+  const double *D, *E;          // n, m
+  size_t strideP, strideA, strideD, strideE;
+  double c;                     // cost scaling when shared
+  const double *c_inst;         // [B] per-instance cost scaling, or NULL
+  const double *l0, *u0;        // UNSCALED setup bounds (m)
+  const double *VinvT;          // shared-factor kernels that keep xi = V^-1 x̄ as their state; NULL: the state is x̄ itself
 };
 
 // per-instance data and state, [B][len] contiguous

@@ -70,6 +70,11 @@ struct smpc_solver {
   double *u_apply = nullptr;   // MPC layer: U to increment inside the small-QP kernels' store (cpp:105), else NULL
   double *u_export = nullptr;  // MPC layer: bound result buffers (smpc_mpc_bind_results) for this solve, kernel 2 only
   int *status_export = nullptr;
+  bool polish = false;         // smpc_solver_set_polish
+  double polish_delta = 1e-6;
+  int polish_refine = 3;
+  int *d_polish = nullptr;     // [B] status_polish of the last solve
+  double *d_polish_scratch = nullptr;
   bool solved_once = false;
   bool cold_solves = false, timing = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;   // pending kernel timings

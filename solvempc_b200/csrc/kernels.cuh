@@ -51,6 +51,11 @@ size_t instance_pair_pack_doubles(int n);
 cudaError_t launch_admm_instance_pair(const InstanceDataDev &I, const BatchDev &Bt, const SettingsDev &S, int num_sms, cudaStream_t stream,
                                       int prepare);
 
+// polish.cu : OSQP's solution polishing after the ADMM kernel (opt-in), one warp per SOLVED instance
+size_t polish_scratch_doubles(int n, int m, int num_sms);   // global workspace the kernel needs (0: shared memory suffices)
+cudaError_t launch_polish(const PolishDataDev &P, const BatchDev &Bt, const SettingsDev &S, double delta, int refine,
+                          int *status_polish, double *scratch, int num_sms, cudaStream_t stream);
+
 // mpc_assembly.cu
 struct MpcDims { int N, nx, n_state_rows; double Q, R, RD, u_limit; };
 struct MpcMatsDev {   // per plant (index p): all row-major

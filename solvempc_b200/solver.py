@@ -135,6 +135,16 @@ class BatchedSolver:
         L.check(L.lib().smpc_solver_kernel_ms(self._h, C.byref(ms), C.byref(cnt), int(reset)))
         return ms.value, cnt.value
 
+    def set_polish(self, on=True, delta=1e-6, refine_iter=3):
+        """settings()->setPolish / setDelta / setPolishRefineIter (OSQP polish.c); off by default as in the reference."""
+        L.check(L.lib().smpc_solver_set_polish(self._h, int(on), float(delta), int(refine_iter)))
+
+    def polish_status(self):
+        """info->status_polish per instance: 1 polished, -1 unsuccessful, 0 not run."""
+        st = np.empty(self.batch, np.int32)
+        L.check(L.lib().smpc_solver_get_polish_status(self._h, st.ctypes.data, L.HOST))
+        return st
+
     def solve(self):
         """Asynchronous on the handle's stream (osqp-eigen solve())."""
         L.check(L.lib().smpc_solver_solve(self._h))
