@@ -157,6 +157,7 @@ int upload_small_pack(smpc_solver *s) {
   size_t bytes = 0;
   for (size_t c : {M1T.size(), WT.size(), VT.size(), PVT.size(), Ab.size(), V.size(), lam.size(), D.size(), Dinv.size(), E.size(), Einv.size()})
     bytes += DeviceBuf::need(c * sizeof(double));
+  bytes += 5 * DeviceBuf::need(1024 * sizeof(double));   // fused-kernel packs
   bytes += DeviceBuf::need(MP * sizeof(int)) + DeviceBuf::need(sizeof(int) * smpc::small_queue_ints()) +
            DeviceBuf::need(sizeof(int) * (size_t)smpc::small_sched_classes() * s->B);
   CK(s->packbuf.alloc(bytes));
@@ -172,6 +173,41 @@ int upload_small_pack(smpc_solver *s) {
   CK(cudaMemcpy(dct, ct.data(), MP * sizeof(int), cudaMemcpyHostToDevice));
   k.ctype = dct;
   k.mp = (p.pairs > 0 && 2 * p.pairs == p.m && !getenv("SMPC_SMALL_NO_PAIRS")) ? p.pairs : 0;
+  k.M1x = k.WTt = k.C1 = k.C2 = k.cst = nullptr;
+  if (k.mp > 0 && k.mp <= NP) {   // packs of the fused one-phase kernel (device_types.cuh)
+    const int mp = k.mp;
+    std::vector<double> M1x(NP * 32, 0.0), WTt(NP * NP, 0.0), C1(8 * 32 * 2, 0.0), C2(8 * 32 * 2, 0.0), cst(32 * 4, 0.0);
+    for (int kk = 0; kk < n; ++kk) {
+      for (int e = 0; e < n; ++e) M1x[kk * 32 + smpc::small_pos32(e)] = p.SG[(size_t)kk * n + e];
+      for (int j = 0; j < mp; ++j) { M1x[kk * 32 + smpc::small_pos32(16 + j)] = p.W[(size_t)j * n + kk]; WTt[kk * NP + j] = p.W[(size_t)j * n + kk]; }
+    }
+    auto op1 = [&](int r, int c) -> double {   // [V; Wtop]
+      if (c >= n) return 0.0;
+      if (r < 16) return r < n ? p.V[(size_t)r * n + c] : 0.0;
+      return r - 16 < mp ? p.W[(size_t)(r - 16) * n + c] : 0.0;
+    };
+    auto op2 = [&](int r, int c) -> double {   // [P̄V; A̅top']: rows 16 + i take the pair vector y_top - y_bot as input
+      if (r < 16) return (r < n && c < n) ? p.PVT[(size_t)c * n + r] : 0.0;
+      return (r - 16 < n && c < mp) ? p.Abar[(size_t)c * n + (r - 16)] : 0.0;
+    };
+    for (int lane = 0; lane < 32; ++lane) {
+      const int a = lane >> 2, b = lane & 3;
+      for (int l = 0; l < 4; ++l) {
+        const int bt = b ^ smpc::small_rowmix(l), row = (bt < 2 ? 0 : 16) + 2 * a + (bt & 1);
+        for (int c = 0; c < 4; ++c) {
+          const size_t at = ((size_t)(l * 2 + (c >> 1)) * 32 + lane) * 2 + (c & 1);
+          C1[at] = op1(row, 4 * b + c); C2[at] = op2(row, 4 * b + c);
+        }
+      }
+      const int idx = 2 * a + (b & 1);
+      if (b < 2) { cst[lane * 4] = idx < n ? p.D[idx] : 1.0; cst[lane * 4 + 1] = idx < n ? p.Dinv[idx] : 1.0; cst[lane * 4 + 2] = idx < n ? p.lam[idx] : 0.0; }
+      else {
+        cst[lane * 4] = idx < mp ? p.E[idx] : 1.0; cst[lane * 4 + 1] = idx < mp ? p.Einv[idx] : 1.0;
+        cst[lane * 4 + 2] = idx < mp ? p.E[mp + idx] : 1.0; cst[lane * 4 + 3] = idx < mp ? p.Einv[mp + idx] : 1.0;
+      }
+    }
+    CK(put(M1x, &k.M1x)); CK(put(WTt, &k.WTt)); CK(put(C1, &k.C1)); CK(put(C2, &k.C2)); CK(put(cst, &k.cst));
+  }
   s->d_queue = s->packbuf.take<int>(smpc::small_queue_ints());
   s->d_lists = s->packbuf.take<int>((size_t)smpc::small_sched_classes() * s->B);
   if (!s->d_lists) return fail(SMPC_ERR_CUDA, "internal: pack buffer carve-out overflow");
@@ -731,7 +767,7 @@ int smpc_solver_row_pairs(const smpc_solver *s) {
 }
 const char *smpc_solver_kernel_name(const smpc_solver *s) {
   if (!s) return "";
-  return s->regime == 1 ? (s->dinst.pack ? "admm_instance_pair_kernel" : "admm_instance_kernel") : s->kernel == 2 ? "admm_shared_small_kernel"
+  return s->regime == 1 ? (s->dinst.pack ? "admm_instance_pair_kernel" : "admm_instance_kernel") : s->kernel == 2 ? (smpc::small_fused_supports(s->dpack, s->dplan) ? "admm_shared_small_fused_kernel" : "admm_shared_small_kernel")
          : s->kernel == 4 ? (s->dtile.xd ? "admm_shared_tile_kernel<x-space>" : "admm_shared_tile_kernel") : s->kernel == 5 ? "admm_shared_small_mma_kernel" : "admm_shared_generic_kernel";
 }
 

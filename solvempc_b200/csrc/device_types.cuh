@@ -43,7 +43,20 @@ struct SmallPackDev {
   const double *E, *Einv;         // [32]
   const int *ctype;               // [32]
   int mp;                         // > 0: rows are [G; -G] with mp = m / 2 pairs (row mp + i = -row i), else 0
+  // packs of the fused one-phase kernel (admm_shared_small_fused.cu; paired plans with mp <= 16 only, else NULL).  Lane (a, b) =
+  // (lane >> 2, lane & 3) of a warp owns entry idx = 2a + (b & 1) of xi (b < 2, "xi-lane") or pair idx (b >= 2, "pair-lane").
+  const double *M1x;   // [16][32]  M1x[k][small_pos32(e)] = [sigma*G | Wtop'](k, e): column order of the kernel's state s = [xi; wd]
+  const double *WTt;   // [16][16]  WTt[k][i] = Wtop(i, k)
+  const double *C1;    // [8][32][2] 4 x 4 blocks of [V; Wtop] (32 x 16) per lane, chunk-major (layout: upload_small_pack)
+  const double *C2;    // [8][32][2] 4 x 4 blocks of [P̄V; A̅top'] (32 x 16)
+  const double *cst;   // [32][4]   per lane: xi-lane {D, 1/D, lambda, 0} of entry idx; pair-lane {E, 1/E of row idx, E, 1/E of row mp + idx}
 };
+// storage order of a 32-vector read as four 16-byte chunks per lane (lane b reads entries 8b .. 8b+7: the four chunks one
+// LDS.128 touches are contiguous, no bank conflict), and of a 16-vector read as two chunks per lane (entries 4b .. 4b+3)
+__host__ __device__ inline int small_pos32(int e) { return ((((e & 7) >> 1) * 4 + (e >> 3)) * 2) + (e & 1); }
+__host__ __device__ inline int small_pos16(int e) { return ((((e & 3) >> 1) * 4 + (e >> 2)) * 2) + (e & 1); }
+// local row l (0..3) of lane (a, b) in the 2-D block layout is the row finally owned by lane (a, b ^ small_rowmix(l))
+__host__ __device__ inline int small_rowmix(int l) { return ((l & 1) << 1) | (l >> 1); }
 
 // DMMA A-fragment packs of the plan for the tile kernel (admm_shared_tile.cu).  An operator Op (rows x K, both
 // zero-padded to multiples of 8) is stored as [row-block][k-pair][lane][2]:

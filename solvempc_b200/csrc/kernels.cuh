@@ -25,6 +25,11 @@ int small_sched_classes();
 cudaError_t launch_admm_shared_small(const SmallPackDev &K, const SharedPlanDev &P, const BatchDev &Bt,
                                      const SettingsDev &S, int *queue, int *lists, bool classified, int num_sms, cudaStream_t stream);
 
+// admm_shared_small_fused.cu : one-phase kernel for paired rows [G; -G] (mp <= 16); launch_admm_shared_small dispatches to it
+bool small_fused_supports(const SmallPackDev &K, const SharedPlanDev &P);
+cudaError_t launch_admm_shared_small_fused(const SmallPackDev &K, const SharedPlanDev &P, const BatchDev &Bt, const SettingsDev &S,
+                                           int *queue, int *lists, int num_sms, cudaStream_t stream);
+
 // DMMA variant of the small-QP kernel: 8 QPs per CTA of four warps (same packs, same queue / lists)
 cudaError_t launch_admm_shared_small_mma(const SmallPackDev &K, const SharedPlanDev &P, const BatchDev &Bt,
                                          const SettingsDev &S, int *queue, int *lists, bool classified, int num_sms, cudaStream_t stream);

@@ -1,0 +1,68 @@
+// small_common.cuh -- helpers shared by the small-QP kernels (admm_shared_small.cu, admm_shared_small_fused.cu): volatile
+// shared-memory accessors, exact warp reductions, the work-queue layout of the persistent grids and its release protocol.
+#pragma once
+#include <cstdint>
+
+#include "classify.cuh"
+#include "device_types.cuh"
+
+namespace smpc {
+namespace {
+constexpr int NP = 16, MP = 32, KH = (NP + MP) / 2;   // padded sizes; 24 concatenated entries per half-warp
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kClasses = kSchedClasses;   // difficulty classes of the scheduling pre-pass (classify.cuh)
+
+__device__ __forceinline__ double2 lds128(uint32_t addr) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts64(uint32_t addr, double v) {
+  asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
+// exact max over the warp of NON-NEGATIVE doubles: compare the IEEE bit patterns as two 32-bit halves (REDUX)
+__device__ __forceinline__ double wmax_nn(double v) {
+  const unsigned hi = (unsigned)__double2hiint(v);
+  const unsigned mh = __reduce_max_sync(kFull, hi);
+  const unsigned lo = hi == mh ? (unsigned)__double2loint(v) : 0u;
+  const unsigned ml = __reduce_max_sync(kFull, lo);
+  return __hiloint2double((int)mh, (int)ml);
+}
+__device__ __forceinline__ double wsum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+// queue layout: [0] work counter, [1..kClasses] class sizes, [1 + kClasses] warps / CTAs that finished,
+// [kQHard] counter of the hardest class's quiet share, [kQSeen] SMs seen, [kQRank + smid] CTAs arrived on an SM,
+// [kQTicket + smid] 1 + arrival order of the SM (quiet-SM scheduling of admm_shared_small_kernel)
+constexpr int kQHard = 2 + kClasses, kQSeen = 3 + kClasses, kQRank = 16, kSmSlots = 512, kQTicket = kQRank + kSmSlots;
+constexpr int kQueueInts = kQTicket + kSmSlots;
+// the last warp to leave clears the whole queue block (all lanes of the warp call this)
+__device__ __forceinline__ void release_queue_warp(int *queue, int participants, int lane) {
+  int last = 0;
+  if (lane == 0) {
+    __threadfence();
+    last = atomicAdd(queue + 1 + kClasses, 1) == participants - 1;
+  }
+  last = __shfl_sync(kFull, last, 0);
+  if (last) {
+    for (int k = lane; k < kQueueInts; k += 32) queue[k] = 0;
+    __threadfence();
+  }
+}
+__device__ __forceinline__ void release_queue(int *queue, int participants) {
+  __threadfence();
+  if (atomicAdd(queue + 1 + kClasses, 1) == participants - 1) {
+#pragma unroll
+    for (int k = 0; k <= 1 + kClasses; ++k) queue[k] = 0;
+    __threadfence();
+  }
+}
+__device__ __forceinline__ double rho_row(int ct, double rho) {
+  return ct == 0 ? rho : (ct == 1 ? kRhoEqOverIneq * rho : kRhoMin);
+}
+
+
+}  // namespace
+}  // namespace smpc

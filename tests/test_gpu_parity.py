@@ -48,7 +48,9 @@ def cfg_path(repo_root):
     return os.path.join(repo_root, "config", "MPC_API.json")
 
 
-KERNEL_NAMES = {1: "admm_shared_generic_kernel", 2: "admm_shared_small_kernel", 4: "admm_shared_tile_kernel",
+# (kernel 2 on a plan whose rows are [G; -G] pairs -- every MPC plan -- is the fused one-phase kernel when SMPC_SMALL_FUSED=1)
+KERNEL_NAMES = {1: "admm_shared_generic_kernel",
+                2: "admm_shared_small_fused_kernel" if os.environ.get("SMPC_SMALL_FUSED", "0") != "0" else "admm_shared_small_kernel", 4: "admm_shared_tile_kernel",
                 5: "admm_shared_small_mma_kernel"}
 
 
@@ -183,7 +185,7 @@ def _random_qps(n, m, B, kernel):
         r = so.solve()
         xs.append(r["x"]); ys.append(r["y"]); st.append(r["status"]); it.append(r["iter"])
     s = sm.BatchedSolver(P, A, l0, u0, batch=B, kernel=kernel, **EPS)
-    assert s.kernel_name == KERNEL_NAMES[kernel]
+    assert s.kernel_name == ("admm_shared_small_kernel" if kernel == 2 else KERNEL_NAMES[kernel])   # rows are not pairs here
     s.update_gradient(q)
     if m:
         s.update_bounds(l, u)

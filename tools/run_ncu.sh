@@ -6,7 +6,7 @@ A2="--config c2 --steps 3 --warmup 3 --cpu-seconds 0.2"
 python bench.py $A2 > gpurun_out/plain_c2.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_c2.csv python bench.py $A2 > gpurun_out/ncu_launches_c2.log 2>&1
 python bench.py $A2 > gpurun_out/plain_c2b.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:admm_shared_small_kernel -s 3 -c 1 -f -o gpurun_out/prof_c2 python bench.py $A2 > gpurun_out/ncu_c2.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:admm_shared_small -s 3 -c 1 -f -o gpurun_out/prof_c2 python bench.py $A2 > gpurun_out/ncu_c2.log 2>&1
 for c in c3 c4 c5; do
   case $c in c3) K=admm_shared_tile;; c4) K=admm_instance;; c5) K=admm_shared_tile;; esac
   A="--config $c --steps 2 --warmup 3 --cpu-seconds 0.2"

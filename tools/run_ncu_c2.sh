@@ -8,5 +8,5 @@ A2="--config c2 --steps 3 --warmup 3 --cpu-seconds 0.2"
 python bench.py $A2 > gpurun_out/plain_c2.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_c2.csv python bench.py $A2 > gpurun_out/ncu_launches_c2.log 2>&1
 python bench.py $A2 > gpurun_out/plain_c2b.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:admm_shared_small_kernel -s 3 -c 1 -f -o gpurun_out/prof_c2 python bench.py $A2 > gpurun_out/ncu_c2.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:admm_shared_small -s 3 -c 1 -f -o gpurun_out/prof_c2 python bench.py $A2 > gpurun_out/ncu_c2.log 2>&1
 ls -la gpurun_out/*.ncu-rep
