@@ -17,7 +17,11 @@
 // idles on its slowest member (per-problem convergence masking = slot recycling).
 //
 // Panel layout in shared memory: [nb][row][8] doubles (8-slot blocks), so a DMMA B-fragment load (4 k-rows x 8 slots)
-// is 32 consecutive doubles and the C-fragment of a thread is a double2 of the same panel layout.
+// is 32 consecutive doubles and the C-fragment of a thread is a double2 of the same panel layout.  Inside a row the slots are
+// SWIZZLED: slot s of row r sits at position s ^ (4 * ((r >> 1) & 1)).  A 64-bit shared-memory load serves 16 lanes per
+// wavefront; in a B fragment those are k-rows 0..3 x slots 0..3, and unswizzled rows 0 / 2 (and 1 / 3) are 128 bytes apart =
+// the same banks: every B-fragment load took 4 wavefronts instead of 2 (37 % of all shared-memory wavefronts of the kernel,
+// ncu).  With the swizzle the 16 lanes touch 16 distinct 8-byte bank pairs; pairs of slots (2q, 2q + 1) stay adjacent.
 #include <cstdint>
 #include <cstdlib>
 #include <cstdio>
@@ -50,6 +54,7 @@ __device__ __forceinline__ double2 ldg_stream(const double2 *p) {
   asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
   return v;
 }
+__device__ __forceinline__ int swz(int row) { return ((row >> 1) & 1) << 2; }   // panel slot swizzle (see the file header)
 __device__ __forceinline__ double rho_of(int ct, double rho) { return ct == 0 ? rho : (ct == 1 ? kRhoEqOverIneq * rho : kRhoMin); }
 
 // per-tile bookkeeping in shared memory
@@ -183,7 +188,7 @@ admm_shared_tile_kernel(TilePackDev K, SharedPlanDev P, BatchDev Bt, SettingsDev
   const int cvr = n8 + m8;
   double *cv = smem, *Tp = cv + cvr * TB, *qh = Tp + n8 * TB, *dinv = qh + n8 * TB, *Sp = dinv + n8 * TB, *Dp = Sp + n8 * TB;
   double *zp = Dp + n8 * TB, *yp = zp + m8 * TB, *lbp = yp + m8 * TB, *ubp = lbp + m8 * TB;
-  const int bfrag = (lane & 3) * 8 + (lane >> 2);     // this lane's element of a B fragment
+  const int bfrag = (lane & 3) * 8 + ((lane >> 2) ^ swz(lane & 3));   // this lane's element of a B fragment (k-row lane & 3, slot lane >> 2)
   TileCtl<TB, WARPS> &C = *reinterpret_cast<TileCtl<TB, WARPS> *>(ubp + m8 * TB);
   const int NRB = n8 >> 3, MRB = m8 >> 3;
   const int nrb0 = (warp * NRB) / kTileWarps, nrb1 = ((warp + 1) * NRB) / kTileWarps;
@@ -202,7 +207,7 @@ admm_shared_tile_kernel(TilePackDev K, SharedPlanDev P, BatchDev Bt, SettingsDev
 #pragma unroll
       for (int nb = 0; nb < NB; ++nb) acc[r][nb][0] = acc[r][nb][1] = 0.0;
   };
-  auto pidx = [&](int rows, int nb, int row) { return (nb * rows + row) * 8 + q2; };   // this thread's double2 in a panel
+  auto pidx = [&](int rows, int nb, int row) { return (nb * rows + row) * 8 + (q2 ^ swz(row)); };   // this thread's double2 (slots q2, q2 + 1) in a panel
   auto xi_at = [&](int e_n) { const int nb = e_n / (n8 * 8); return e_n + nb * m8 * 8; };            // n-panel index -> cv index (xi part)
   auto w_at = [&](int e_m) { const int nb = e_m / (m8 * 8); return e_m + (nb + 1) * n8 * 8; };        // m-panel index -> cv index (w part)
 
@@ -459,7 +464,7 @@ admm_shared_tile_kernel(TilePackDev K, SharedPlanDev P, BatchDev Bt, SettingsDev
             for (int nb = 0, s8 = tid & 7; nb < NB; ++nb)
 _Pragma("unroll 4")
             for (int i = tid >> 3; i < n8; i += kTileThreads / 8) {
-              const int e = (nb * n8 + i) * 8 + s8, s = nb * 8 + s8;
+              const int e = (nb * n8 + i) * 8 + s8, s = nb * 8 + (s8 ^ swz(i));   // s8 = position in the row
               if (((rho_new & ~done) >> s) & 1) dinv[e] = 1.0 / (1.0 + C.rho[s] * (i < n ? __ldg(P.lam + i) : 0.0));
               if (!((done >> s) & 1)) continue;
               if (i < n) {
@@ -475,7 +480,7 @@ _Pragma("unroll 4")
             for (int nb = 0, s8 = tid & 7; nb < NB; ++nb)
 _Pragma("unroll 4")
             for (int r = tid >> 3; r < m8; r += kTileThreads / 8) {
-              const int e = (nb * m8 + r) * 8 + s8, s = nb * 8 + s8;
+              const int e = (nb * m8 + r) * 8 + s8, s = nb * 8 + (s8 ^ swz(r));
               if (!((done >> s) & 1)) continue;
               if (r < m) {
                 const int b = C.inst[s], st = C.status[s];
@@ -513,7 +518,7 @@ _Pragma("unroll 4")
             for (int nb = 0, s8 = tid & 7; nb < NB; ++nb)
 _Pragma("unroll 4")
             for (int i = tid >> 3; i < n8; i += kTileThreads / 8) {
-              const int e = (nb * n8 + i) * 8 + s8, s = nb * 8 + s8;
+              const int e = (nb * n8 + i) * 8 + s8, s = nb * 8 + (s8 ^ swz(i));   // s8 = position in the row
               if (!((mask >> s) & 1)) continue;
               const int b = C.inst[s];
               const double v = (b >= 0 && i < n && warm) ? Bt.xi[(size_t)b * n + i] : 0.0;
@@ -523,7 +528,7 @@ _Pragma("unroll 4")
             for (int nb = 0, s8 = tid & 7; nb < NB; ++nb)
 _Pragma("unroll 4")
             for (int r = tid >> 3; r < m8; r += kTileThreads / 8) {
-              const int e = (nb * m8 + r) * 8 + s8, s = nb * 8 + s8;
+              const int e = (nb * m8 + r) * 8 + s8, s = nb * 8 + (s8 ^ swz(r));
               if (!((mask >> s) & 1)) continue;
               const int b = C.inst[s];
               double lo = -1.0, hi = 1.0, zz = 0.0, yy = 0.0;
@@ -559,7 +564,7 @@ _Pragma("unroll 4")
             for (int nb = 0, s8 = tid & 7; nb < NB; ++nb)
 _Pragma("unroll 4")
             for (int r = tid >> 3; r < m8; r += kTileThreads / 8) {
-              const int e = (nb * m8 + r) * 8 + s8, s = nb * 8 + s8;
+              const int e = (nb * m8 + r) * 8 + s8, s = nb * 8 + (s8 ^ swz(r));
               if ((again >> s) & 1) { lbp[e] = -1.0; ubp[e] = 1.0; zp[e] = 0.0; yp[e] = 0.0; }
             }
             __syncthreads();
@@ -569,7 +574,7 @@ _Pragma("unroll 4")
             for (int nb = 0, s8 = tid & 7; nb < NB; ++nb)
 _Pragma("unroll 4")
             for (int i = tid >> 3; i < n8; i += kTileThreads / 8) {
-              const int e = (nb * n8 + i) * 8 + s8, s = nb * 8 + s8;
+              const int e = (nb * n8 + i) * 8 + s8, s = nb * 8 + (s8 ^ swz(i));   // s8 = position in the row
               const int b = C.inst[s];
               Sp[e] = (b >= 0 && i < n && Bt.q) ? c * (__ldg(P.D + i) * Bt.q[(size_t)b * n + i]) : 0.0;
             }
@@ -732,15 +737,16 @@ _Pragma("unroll 4")
       // ---- w = rho_vec z - y (the w panel carried delta_y); schedule the next event
       __syncthreads();
       {
-        const int s8 = tid & 7;                      // thread -> slot inside an 8-slot block, rows tid / 8 + 32 j (no divisions)
+        const int s8 = tid & 7;                      // thread -> position inside a row of an 8-slot block, rows tid / 8 + 32 j (no divisions)
 #pragma unroll
         for (int nb = 0; nb < NB; ++nb) {
-          const double rho_s = C.rho[nb * 8 + s8];
           if (XD) {   // rhs = sigma x - q̄ + a .* ((rho_vec z - y)_top - (rho_vec z - y)_bot) into the Sp panel
             for (int r = tid >> 3; r < n8; r += kTileThreads / 8) {
               double v = 0.0;
               if (r < n) {
-                const int e1 = (nb * m8 + r) * 8 + s8, e2 = e1 + mp * 8, en = (nb * n8 + r) * 8 + s8;
+                const int sl = s8 ^ swz(r);              // the slot at this position of row r
+                const double rho_s = C.rho[nb * 8 + sl];
+                const int e1 = (nb * m8 + r) * 8 + s8, e2 = (nb * m8 + r + mp) * 8 + (sl ^ swz(r + mp)), en = (nb * n8 + r) * 8 + s8;
                 const double w1 = rho_of((int)__ldg(P.ctype + r), rho_s) * zp[e1] - yp[e1];
                 const double w2 = rho_of((int)__ldg(P.ctype + r + mp), rho_s) * zp[e2] - yp[e2];
                 v = (S.sigma * cv[xi_at(en)] - qh[en]) + __ldg(K.adiag + r) * (w1 - w2);
@@ -749,7 +755,9 @@ _Pragma("unroll 4")
             }
           } else if (PAIRED) {
             for (int r = tid >> 3; r < mp; r += kTileThreads / 8) {
-              const int e1 = (nb * m8 + r) * 8 + s8, e2 = e1 + mp * 8;
+              const int sl = s8 ^ swz(r);
+              const double rho_s = C.rho[nb * 8 + sl];
+              const int e1 = (nb * m8 + r) * 8 + s8, e2 = (nb * m8 + r + mp) * 8 + (sl ^ swz(r + mp));
               const double w1 = rho_of((int)__ldg(P.ctype + r), rho_s) * zp[e1] - yp[e1];
               const double w2 = rho_of((int)__ldg(P.ctype + r + mp), rho_s) * zp[e2] - yp[e2];
               cv[(nb * cvr + n8 + r) * 8 + s8] = w1 - w2;
@@ -757,6 +765,7 @@ _Pragma("unroll 4")
           } else {
             for (int r = tid >> 3; r < m8; r += kTileThreads / 8) {
               const int e = (nb * m8 + r) * 8 + s8;
+              const double rho_s = C.rho[nb * 8 + (s8 ^ swz(r))];
               const int ct = r < m ? (int)__ldg(P.ctype + r) : 0;
               cv[(nb * cvr + n8 + r) * 8 + s8] = rho_of(ct, rho_s) * zp[e] - yp[e];
             }
