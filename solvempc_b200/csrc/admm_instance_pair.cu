@@ -161,6 +161,7 @@ __global__ void __launch_bounds__(64, CTAS_PER_SM) admm_instance_pair_kernel(Ins
   // first ticket + its G' stage
   if (tid == 0) {
     const int t = atomicAdd(queue, 1);
+    SMPC_DBG(t >= 0, "pair-kernel ticket");
     s_ticket = t;
     if (t < B && !prepare) { fence_proxy_async(); mbar_expect_tx(&mbar[0], gt_bytes); bulk_g2s(Gt0, I.pack + (size_t)t * pack_stride, gt_bytes, &mbar[0]); }
   }
@@ -180,6 +181,7 @@ __global__ void __launch_bounds__(64, CTAS_PER_SM) admm_instance_pair_kernel(Ins
     __syncthreads();                       // everyone has read s_ticket / finished the previous solve
     if (tid == 0) {                        // draw the next ticket now: its operands travel while this QP is solved
       const int t = atomicAdd(queue, 1);
+      SMPC_DBG(t > b, "pair-kernel ticket order");
       s_ticket = t;
       if (t < B && !prepare) {
         const double *pk = I.pack + (size_t)t * pack_stride;

@@ -275,8 +275,10 @@ admm_shared_small_kernel(SmallPackDev K, SharedPlanDev P, BatchDev Bt, SettingsD
   if (quiet_cap > 0 && threadIdx.x == 0) {
     unsigned smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    SMPC_DBG(smid < (unsigned)kSmSlots, "smid slot");
     smid &= kSmSlots - 1;
     const int rank = atomicAdd(queue + kQRank + smid, 1);
+    SMPC_DBG(rank >= 0 && rank < 3, "CTAs per SM in the quiet-SM rank counter");
     int t;
     if (rank == 0) { t = atomicAdd(queue + kQSeen, 1); atomicExch(queue + kQTicket + smid, t + 1); }
     else { do { t = atomicAdd(queue + kQTicket + smid, 0); } while (t == 0); t -= 1; }
@@ -342,6 +344,7 @@ admm_shared_small_kernel(SmallPackDev K, SharedPlanDev P, BatchDev Bt, SettingsD
       b = -1;
       if (quiet_warp) {
         const int qh = atomicAdd(queue + kQHard, 1);
+        SMPC_DBG(qh >= 0 && n_quiet <= Bt.B, "quiet-share counter");
         if (qh < n_quiet) b = lists[qh]; else quiet_warp = false;
       }
       if (b < 0) {
@@ -352,12 +355,14 @@ admm_shared_small_kernel(SmallPackDev K, SharedPlanDev P, BatchDev Bt, SettingsD
 #pragma unroll
             for (int k = 0; k < kClasses; ++k) {
               const int skip = k == 0 ? n_quiet : 0, cnt = queue[1 + k] - skip;
+              SMPC_DBG(cnt >= 0 && cnt + skip <= Bt.B, "class size");
               if (b < 0) { if (q < cnt) b = lists[(size_t)k * Bt.B + skip + q]; else q -= cnt; }
             }
           }
         }
       }
     }
+    SMPC_DBG(b < Bt.B, "instance index from the queue");
     b = __shfl_sync(kFull, b, 0);
     if (b < 0) break;
 #ifdef SMPC_SMALL_TIMELINE

@@ -306,6 +306,7 @@ admm_shared_small_fused_kernel(SmallPackDev K, SharedPlanDev P, BatchDev Bt, Set
       bi = -1;
       if (quiet_warp) {
         const int qh_ = atomicAdd(queue + kQHard, 1);
+        SMPC_DBG(qh_ >= 0 && n_quiet <= Bt.B, "quiet-share counter");
         if (qh_ < n_quiet) bi = lists[qh_]; else quiet_warp = false;
       }
       if (bi < 0) {
@@ -316,12 +317,14 @@ admm_shared_small_fused_kernel(SmallPackDev K, SharedPlanDev P, BatchDev Bt, Set
 #pragma unroll
             for (int k = 0; k < kClasses; ++k) {
               const int skip = k == 0 ? n_quiet : 0, cnt = s_cnt[k] - skip;
+              SMPC_DBG(cnt >= 0 && cnt + skip <= Bt.B, "class size");
               if (bi < 0) { if (q < cnt) bi = lists[(size_t)k * Bt.B + skip + q]; else q -= cnt; }
             }
           }
         }
       }
     }
+    SMPC_DBG(bi < Bt.B, "instance index from the queue");
     bi = __shfl_sync(kFull, bi, 0);
     if (bi < 0) break;
 

@@ -505,6 +505,7 @@ _Pragma("unroll 4")
           while (any_refill) {
             if (tid < TB && ((C.refill_mask >> tid) & 1)) {
               const int b = atomicAdd(queue, 1);
+              SMPC_DBG(b >= 0, "tile queue ticket");
               const bool ok = b < Bt.B;
               C.inst[tid] = ok ? b : -1;
               C.it0[tid] = k; C.rho_up[tid] = 0; C.status[tid] = SMPC_UNSOLVED; C.flags[tid] = 0;

@@ -40,6 +40,7 @@ __device__ __forceinline__ void classify_instance(const SmallPackDev &K, const S
     const double ratio = key / fmax(ref, 1e-300);
     const int cls = !(key > 0.0) ? 4 : (ratio <= 0.02 ? 0 : (ratio <= 0.05 ? 1 : (ratio <= 0.15 ? 2 : 3)));
     const int slot = atomicAdd(counts + cls, 1);
+    SMPC_DBG(slot >= 0 && slot < B, "class list slot");
     if (slot < B) lists[(size_t)cls * B + slot] = b;   // (slot >= B only if stale counters survived a failed step)
   }
 }

@@ -2,6 +2,16 @@
 #pragma once
 #include <cuda_runtime.h>
 
+// -DSMPC_DEBUG_BOUNDS (make NVEXTRA=-DSMPC_DEBUG_BOUNDS): in-kernel checks of the work-queue / ticket protocols and of every
+// index taken from them (compute-sanitizer is not available on the GPU pool); a failed check prints its site and traps, which
+// the host sees as a launch failure.  tools/run_debug_bounds.sh runs the GPU tests against such a build.
+#ifdef SMPC_DEBUG_BOUNDS
+#include <cstdio>
+#define SMPC_DBG(cond, what) do { if (!(cond)) { printf("SMPC_DEBUG_BOUNDS: %s failed (%s:%d)\n", what, __FILE__, __LINE__); __trap(); } } while (0)
+#else
+#define SMPC_DBG(cond, what) do { } while (0)
+#endif
+
 namespace smpc {
 
 constexpr double kRhoMin = 1e-6, kRhoMax = 1e6, kRhoEqOverIneq = 1e3;

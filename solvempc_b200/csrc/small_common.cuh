@@ -43,7 +43,9 @@ __device__ __forceinline__ void release_queue_warp(int *queue, int participants,
   int last = 0;
   if (lane == 0) {
     __threadfence();
-    last = atomicAdd(queue + 1 + kClasses, 1) == participants - 1;
+    const int left = atomicAdd(queue + 1 + kClasses, 1);
+    SMPC_DBG(left >= 0 && left < participants, "warps that left the persistent grid");
+    last = left == participants - 1;
   }
   last = __shfl_sync(kFull, last, 0);
   if (last) {
