@@ -173,12 +173,14 @@ enum PassId { P_XBAR, P_PX, P_ATY, P_AX, P_ATD, P_DX, P_PD, P_ADX, P_QH, P_COUNT
 // two n x n GEMMs (2 n^2 MACs per instance-iteration instead of n^2 + 2 m n = 3 n^2 with pairs), every product with A̅ or A̅' is
 // element-wise in an epilogue, and a check needs ONE panel GEMM (P̄ x) instead of four.  Panels: cv's first n8 rows hold x̄, Sp the
 // right-hand side between events, qh holds q̄.
-template <int NB, bool PAIRED, int WARPS, bool XD = false>
-__global__ void __launch_bounds__(WARPS * 32, 1)
+// CTAS = 2 (with WARPS = 8): two independent tiles share an SM (128 registers per thread, 2 row-blocks per warp at once): their
+// barriers and events are not synchronised, so one tile's check / store / refill overlaps the other's GEMMs on the DMMA pipe.
+template <int NB, bool PAIRED, int WARPS, bool XD = false, int CTAS = 1>
+__global__ void __launch_bounds__(WARPS * 32, CTAS)
 admm_shared_tile_kernel(TilePackDev K, SharedPlanDev P, BatchDev Bt, SettingsDev S, int *queue) {
   static_assert(!XD || PAIRED, "the x-space variant is for paired rows");
   constexpr int TB = 8 * NB;
-  constexpr int kTileWarps = WARPS, kTileThreads = WARPS * 32, kRG = WARPS == 8 ? 4 : 2;   // (shadow the file-level defaults)
+  constexpr int kTileWarps = WARPS, kTileThreads = WARPS * 32, kRG = (WARPS == 8 && CTAS == 1) ? 4 : 2;   // (shadow the file-level defaults)
   extern __shared__ __align__(16) double smem[];
   const int n = P.n, m = P.m, n8 = K.n8, m8 = K.m8;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1001,28 +1003,41 @@ cudaError_t launch_admm_shared_tile(const TilePackDev &K, const SharedPlanDev &P
                                     int *queue, int nb, int num_sms, cudaStream_t stream) {
   if (nb == 0) nb = tile_kernel_nb(P.n, P.m);
   if (nb != 1 && nb != 2) return cudaErrorInvalidValue;
+  const bool paired = K.mp > 0;
+  const size_t cap = 227 * 1024;
+  // Two independent 8-warp tiles per SM (the kernel's CTAS = 2 variant: 128 registers per thread) when two tiles fit shared memory,
+  // if need be with one 8-slot block each instead of two: their barriers and events are not synchronised, so one tile's check /
+  // store / refill overlaps the other's GEMMs (config 5, N = 100: 7.40 -> 6.88 ms per step).  SMPC_TILE_CTAS=1 switches it off.
+  static const int want_ctas = [] { const char *e = getenv("SMPC_TILE_CTAS"); return e ? atoi(e) : 2; }();
+  int ctas = 1;
+  if (want_ctas == 2 && paired && !K.xd) {
+    if (2 * (tile_smem_bytes(P.n, P.m, nb) + 1024) <= cap) ctas = 2;
+    else if (nb == 2 && 2 * (tile_smem_bytes(P.n, P.m, 1) + 1024) <= cap) { nb = 1; ctas = 2; }
+  }
   const size_t smem = tile_smem_bytes(P.n, P.m, nb);
-  if (smem > 227 * 1024) return cudaErrorInvalidValue;
+  if (smem > cap) return cudaErrorInvalidValue;
   cudaError_t e = cudaMemsetAsync(queue, 0, sizeof(int), stream);
   if (e != cudaSuccess) return e;
   const int TB = 8 * nb;
   int grid = (Bt.B + TB - 1) / TB;
   // one CTA per SM when the tile fills shared memory; small problems let several CTAs share an SM
-  int per_sm = (int)((227 * 1024) / (smem + 1024));
+  int per_sm = (int)(cap / (smem + 1024));
   if (per_sm < 1) per_sm = 1;
   if (per_sm > 4) per_sm = 4;
+  if (ctas == 2) per_sm = 2;
   if (grid > num_sms * per_sm) grid = num_sms * per_sm;
   // tiles that own an SM alone run 16 warps (4 per sub-partition cover each other's LDS / L2 / barrier stalls: +11 % at N = 100,
   // +18 % on the quadrotor); smaller tiles keep 8 warps with 4 row-blocks per warp
   int warps = (per_sm == 1 || K.n8 >= 48) ? 16 : 8;   // (with >= 6 row-blocks of n the 16 warps all have work; measured N = 30: 8 warps, N = 50: 16)
   if (const char *env = getenv("SMPC_TILE_WARPS")) warps = atoi(env) == 16 ? 16 : (atoi(env) == 8 ? 8 : warps);   // development knob
+  if (ctas == 2) warps = 8;
   auto go = [&](auto kernel) -> cudaError_t {
     cudaError_t e2 = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e2 != cudaSuccess) return e2;
     kernel<<<grid, warps * 32, smem, stream>>>(K, P, Bt, S, queue);
     return cudaGetLastError();
   };
-  const bool paired = K.mp > 0;
+  if (ctas == 2) return nb == 1 ? go(admm_shared_tile_kernel<1, true, 8, false, 2>) : go(admm_shared_tile_kernel<2, true, 8, false, 2>);
   if (K.xd && paired) {
     if (warps == 16) return nb == 1 ? go(admm_shared_tile_kernel<1, true, 16, true>) : go(admm_shared_tile_kernel<2, true, 16, true>);
     return nb == 1 ? go(admm_shared_tile_kernel<1, true, 8, true>) : go(admm_shared_tile_kernel<2, true, 8, true>);

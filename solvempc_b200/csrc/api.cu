@@ -288,6 +288,7 @@ int upload_tile_pack(smpc_solver *s) {
   CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
   s->num_sms = sms > 0 ? sms : 148;
   s->tile_nb = smpc::tile_kernel_nb(n, m);
+  if (const char *e = getenv("SMPC_TILE_NB")) { if (atoi(e) == 1 && s->tile_nb == 2) s->tile_nb = 1; }   // development knob: one 8-slot block per tile
   return SMPC_OK;
 }
 

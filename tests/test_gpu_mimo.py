@@ -92,3 +92,34 @@ def test_c3_kkt_properties_at_a_larger_batch(quad):
     xs, _ = shard.solver.solution()
     assert np.array_equal(xs, x[lo:hi])
     mpc.close(); shard.close()
+
+
+def test_c3_solution_is_optimal_for_the_rolled_out_plant(quad):
+    """Independent of every assembled matrix (device or oracle): the inputs the GPU returns respect the box, and no feasible
+    perturbation of them lowers the cost accumulated by rolling the plant out stage by stage."""
+    path, cfg, _ = quad
+    B, N, nu = 6, cfg["N"], cfg["Bd"].shape[1]
+    x0, xr = c3_batch(B, seed=5)
+    mpc = sm.BatchedMimoMPC(path, batch=B, **EPS)
+    mpc.set_state(x0=x0, xr=xr)
+    assert mpc.controllerStep()
+    U, _ = mpc.solver.solution()
+    mpc.close()
+    lo, hi = np.tile(cfg["umin"], N), np.tile(cfg["umax"], N)
+
+    def cost(b, z):
+        x, J = x0[b].copy(), 0.0
+        for k in range(N):
+            u = z[k * nu:(k + 1) * nu]
+            x = cfg["Ad"] @ x + cfg["Bd"] @ u
+            J += ((x - xr[b]) ** 2 * cfg["Q"]).sum() + (u ** 2 * cfg["R"]).sum()
+        return J
+    rng = np.random.default_rng(1)
+    for b in range(B):
+        z = U[b]
+        assert (z <= hi + 1e-4).all() and (z >= lo - 1e-4).all()
+        zc = np.clip(z, lo, hi)
+        J0 = cost(b, zc)
+        for _ in range(12):
+            zp = np.clip(zc + 10.0 ** rng.uniform(-4, -1) * rng.standard_normal(z.size), lo, hi)
+            assert cost(b, zp) >= J0 - 1e-6 * max(1.0, abs(J0))
