@@ -534,3 +534,50 @@ def test_pinned_host_buffers_take_the_zero_copy_path(cfg_path):
             out.append((Uo, st))
         mpc.close()
     assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1]) and (out[0][1] == 1).all()
+
+
+def test_fused_small_kernel_opt_in_matches_oracle(repo_root):
+    """The opt-in one-phase small-QP kernel (SMPC_SMALL_FUSED=1, read once per process: hence the subprocess): statuses and
+    iteration counts of the oracle on config-2 instances, cold and warm, and on a plan with infeasible pairs."""
+    import subprocess, sys, textwrap
+    code = textwrap.dedent("""
+        import os, sys
+        import numpy as np
+        sys.path.insert(0, %r); sys.path.insert(0, os.path.join(%r, "tests"))
+        import oracle, solvempc_b200 as sm
+        from problems import c2_batch, random_qp
+        EPS = dict(eps_abs=1e-5, eps_rel=1e-5)
+        cfg = oracle.load_config(os.path.join(%r, "config", "MPC_API.json"))
+        m = oracle.mpc_build(**cfg)
+        B = 777
+        X, U, ref = c2_batch(B, seed=11)
+        f, ub = oracle.mpc_batch_vectors(m, X, U, ref)
+        ora = oracle.solve_batch(m["H"], m["Gbar"], m["lb"], m["W0"], f, ub, nthreads=os.cpu_count() or 1, **EPS)
+        s = sm.BatchedSolver(m["H"], m["Gbar"], m["lb"], m["W0"], batch=B, kernel=2, **EPS)
+        assert s.kernel_name == "admm_shared_small_fused_kernel", s.kernel_name
+        s.update_gradient(f); s.update_upper_bound(ub); s.solve()
+        x, y = s.solution(); info = s.info()
+        assert np.array_equal(info["status"], ora["status"]) and np.array_equal(info["iter"], ora["iter"])
+        sc = np.maximum(np.abs(ora["x"]).max(axis=1), 1e-9)
+        assert (np.abs(x - ora["x"]).max(axis=1) / sc).max() < 1e-9
+        s.solve()                                     # warm: converged iterates, first check ends every solve
+        assert (s.info()["iter"] == 25).all() and (s.info()["status"] == 1).all()
+        s.close()
+        # random pairs [G; -G] with some infeasible instances
+        n, mp = 9, 13
+        P, q0, G, _, _ = random_qp(n, mp, seed=5)
+        A = np.vstack([G, -G]); rng = np.random.default_rng(3)
+        u0 = np.concatenate([1.0 + rng.random(mp), 1.0 + rng.random(mp)]); l0 = np.full(2 * mp, -np.inf)
+        q = q0[None, :] + 0.5 * rng.standard_normal((64, n)); u = u0[None, :] + 0.4 * rng.standard_normal((64, 2 * mp))
+        u[1::7, 0] = -2.0; u[1::7, mp] = -2.0
+        s = sm.BatchedSolver(P, A, l0, u0, batch=64, kernel=2, **EPS)
+        s.update_gradient(q); s.update_upper_bound(u); s.solve()
+        info = s.info()
+        ora = oracle.solve_batch(P, A, l0, u0, q, u, nthreads=4, **EPS)
+        assert np.array_equal(info["status"], ora["status"]) and np.array_equal(info["iter"], ora["iter"])
+        assert (info["status"] == -3).sum() == len(range(1, 64, 7))
+        s.close()
+        print("fused ok")
+    """) % (repo_root, repo_root, repo_root)
+    out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, SMPC_SMALL_FUSED="1"), capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "fused ok" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
