@@ -132,6 +132,9 @@ class Workload:
         return 2.0 * (n * n + 2 * m_exec * n)
 
 
+E2E_DEPTH = 4   # controller batches in flight in the sustained end-to-end pass (tests/dev/dev_e2e_depth.py: 1: 110 us per step, 2: 72, 3: 68, 4: 66, 6: 65)
+
+
 class C2(Workload):
     key, default_batch, flush_l2 = "c2", 4096, True
     l2_note = "flushed with a 256 MB write between timed steps"
@@ -172,40 +175,46 @@ class C2(Workload):
         self.mpc.controller_step_from(self.pin[0], self.pin[1], self.pin[2])   # H2D from pinned memory (read by the step's first kernel)
         self.mpc.sync()
 
-    def pipelined_e2e(self, sm, torch, device, kernel, steps, warmup):
-        """Sustained end-to-end throughput of the public calls: TWO controller batches (this one and a twin with its own pinned
-        buffers and stream) alternate, the host waits for step k - 2 only after it has enqueued step k - 1, so the PCIe reads,
-        the launches and the host wake-up of one batch overlap the solve of the other.  Every step still reads its inputs from
-        pinned host memory and writes control + status back to pinned host memory; the host looks at every step's statuses."""
-        twin = sm.BatchedModelPredictiveControlAPI(self._conf(), batch=self.B, device=device, eps_abs=EPS, eps_rel=EPS, kernel=kernel)
-        twin.solver.set_cold_solves(True)
-        tstream = torch.cuda.Stream()
-        twin.set_stream(tstream.cuda_stream)
-        X, U, ref = self._inputs(self.B, 1000 * self.rank + 500)
-        tpin = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in (X, U, ref)]
-        tout_u, tout_st = torch.empty(self.B, dtype=torch.float64).pin_memory(), torch.empty(self.B, dtype=torch.int32).pin_memory()
-        twin.bind_results(tout_u, tout_st)
-        ctl = [(self.mpc, self.pin, self.out_st.numpy()), (twin, tpin, tout_st.numpy())]
+    def pipelined_e2e(self, sm, torch, device, kernel, steps, warmup, depth=2):
+        """Sustained end-to-end throughput of the public calls: `depth` controller batches (this one and twins with their own
+        pinned buffers and streams) take turns, the host waits for step k - depth only after it has enqueued step k - 1, so the
+        PCIe reads, the launches and the host wake-up of one batch overlap the solves of the others.  Every step still reads its
+        inputs from pinned host memory and writes control + status back to pinned host memory; the host looks at every step's
+        statuses."""
+        ctl = [(self.mpc, self.pin, self.out_st.numpy())]
+        keep = []
+        for t in range(1, depth):
+            twin = sm.BatchedModelPredictiveControlAPI(self._conf(), batch=self.B, device=device, eps_abs=EPS, eps_rel=EPS, kernel=kernel)
+            twin.solver.set_cold_solves(True)
+            tstream = torch.cuda.Stream()
+            twin.set_stream(tstream.cuda_stream)
+            X, U, ref = self._inputs(self.B, 1000 * self.rank + 500 * t)
+            tpin = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in (X, U, ref)]
+            tout_u, tout_st = torch.empty(self.B, dtype=torch.float64).pin_memory(), torch.empty(self.B, dtype=torch.int32).pin_memory()
+            twin.bind_results(tout_u, tout_st)
+            ctl.append((twin, tpin, tout_st.numpy()))
+            keep.append((tstream, tout_u, tout_st))
 
         def run(count):
             solved = True
             for k in range(count):
-                mpc, pin, st = ctl[k & 1]
-                if k >= 2:
-                    mpc.sync()                                   # step k - 2 of this controller: results are in its pinned buffers
+                mpc, pin, st = ctl[k % depth]
+                if k >= depth:
+                    mpc.sync()                                   # step k - depth of this controller: results are in its pinned buffers
                     solved = solved and bool((st == 1).all())
                 mpc.controller_step_from(pin[0], pin[1], pin[2])
             for mpc, _, st in ctl:
                 mpc.sync()
                 solved = solved and bool((st == 1).all())
             return solved
-        run(max(4, warmup))
+        run(max(2 * depth, warmup))
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         ok = run(steps)
         torch.cuda.synchronize()
         ms = 1e3 * (time.perf_counter() - t0) / steps
-        twin.close()
+        for twin, _, _ in ctl[1:]:
+            twin.close()
         assert ok, "a pipelined end-to-end step did not reach SOLVED on every instance"
         return ms
 
@@ -618,11 +627,12 @@ class Bench:
         if key == "c2":
             # sustained throughput of the same calls with two batches in flight (what the CPU arm measures too: all cores busy, no
             # per-step wait); the one-step-at-a-time figure above stays in the line as e2e.sync_*
-            pipe_ms = self.max_over_ranks(wl.pipelined_e2e(self.sm, torch, self.local_rank, args.kernel, max(steps, 20), warmup))
+            pipe_ms = self.max_over_ranks(wl.pipelined_e2e(self.sm, torch, self.local_rank, args.kernel, max(steps, 40), warmup, depth=E2E_DEPTH))
             barrier()
             e2e_extra = {"sync_value": e2e_value, "sync_ms_per_step": e2e_ms,
-                         "mode": "two controller batches of this size in flight on two streams (double-buffered pinned inputs / results, the "
-                                 "host waits for step k-2 after enqueuing step k-1); every step reads its inputs from pinned host memory "
+                         "batches_in_flight": E2E_DEPTH,
+                         "mode": f"{E2E_DEPTH} controller batches of this size take turns on {E2E_DEPTH} streams (each with its own pinned inputs / results; the "
+                                 f"host waits for step k-{E2E_DEPTH} after enqueuing step k-1); every step reads its inputs from pinned host memory "
                                  "and writes control + status to pinned host memory; sync_* = one step at a time, synchronised per step, "
                                  "L2 flushed between steps"}
             e2e_ms, e2e_value = pipe_ms, world * B / (pipe_ms / 1e3)

@@ -127,13 +127,13 @@ __device__ __noinline__ CheckOut check_step(const double *sm, double *cbuf, doub
     __syncwarp();
   }
   const double rp = Ax_r - z_r, rd = (qb_i + apx) + aty;
-  const double s_rp = wmax_nn(fabs(rp)), s_z = wmax_nn(fabs(z_r)), s_Ax = wmax_nn(fabs(Ax_r));
-  const double s_rd = wmax_nn(fabs(rd)), s_q = wmax_nn(fabs(qb_i)), s_Aty = wmax_nn(fabs(aty)), s_Px = wmax_nn(fabs(apx));
+  const double s_rp = wmax_bits(abits(rp)), s_z = wmax_bits(abits(z_r)), s_Ax = wmax_bits(abits(Ax_r));
+  const double s_rd = wmax_bits(abits(rd)), s_q = wmax_bits(abits(qb_i)), s_Aty = wmax_bits(abits(aty)), s_Px = wmax_bits(abits(apx));
   double pri_res, dua_res, nEz, nEAx, nDq, nDAty, nDPx;
   if (unscale) {
-    pri_res = wmax_nn(fabs(L.Einv * rp)); nEz = wmax_nn(fabs(L.Einv * z_r)); nEAx = wmax_nn(fabs(L.Einv * Ax_r));
-    dua_res = cinv * wmax_nn(fabs(L.Dinv * rd)); nDq = wmax_nn(fabs(L.Dinv * qb_i));
-    nDAty = wmax_nn(fabs(L.Dinv * aty)); nDPx = wmax_nn(fabs(L.Dinv * apx));
+    pri_res = wmax_bits(abits(L.Einv * rp)); nEz = wmax_bits(abits(L.Einv * z_r)); nEAx = wmax_bits(abits(L.Einv * Ax_r));
+    dua_res = cinv * wmax_bits(abits(L.Dinv * rd)); nDq = wmax_bits(abits(L.Dinv * qb_i));
+    nDAty = wmax_bits(abits(L.Dinv * aty)); nDPx = wmax_bits(abits(L.Dinv * apx));
   } else {
     pri_res = s_rp; nEz = s_z; nEAx = s_Ax; dua_res = s_rd; nDq = s_q; nDAty = s_Aty; nDPx = s_Px;
   }
@@ -151,7 +151,7 @@ __device__ __noinline__ CheckOut check_step(const double *sm, double *cbuf, doub
       double d = dy_r;
       const bool uinf = ub_r > kInfty * kMinScaling, linf = lb_r < -kInfty * kMinScaling;
       if (uinf) d = linf ? 0.0 : fmin(d, 0.0); else if (linf) d = fmax(d, 0.0);
-      const double nd = wmax_nn(fabs(unscale ? L.E * d : d));
+      const double nd = wmax_bits(abits(unscale ? L.E * d : d));
       if (nd > epi) {
         double lhs = 0.0;
         const double dp = fmax(d, 0.0), dm = fmin(d, 0.0);
@@ -173,7 +173,7 @@ __device__ __noinline__ CheckOut check_step(const double *sm, double *cbuf, doub
             a += __shfl_xor_sync(kFull, a, 16);
           }
           __syncwarp();
-          prim_inf = wmax_nn(fabs(unscale ? L.Dinv * a : a)) < epi * nd;
+          prim_inf = wmax_bits(abits(unscale ? L.Dinv * a : a)) < epi * nd;
         }
       }
     }
@@ -190,7 +190,7 @@ __device__ __noinline__ CheckOut check_step(const double *sm, double *cbuf, doub
         for (int k = 0; k < NP / 2; ++k) dx = fma(sVT[(8 * h + k) * NP + i], sbuf[8 * h + k], dx);
         dx += __shfl_xor_sync(kFull, dx, 16);
       }
-      const double nd = wmax_nn(fabs(unscale ? L.D * dx : dx));
+      const double nd = wmax_bits(abits(unscale ? L.D * dx : dx));
       const double cs = unscale ? c : 1.0;
       if (nd > edi && wsum(h == 0 ? qb_i * dx : 0.0) < -cs * edi * nd) {
         double pd = 0.0;
@@ -200,7 +200,7 @@ __device__ __noinline__ CheckOut check_step(const double *sm, double *cbuf, doub
           for (int k = 0; k < NP / 2; ++k) pd = fma(sPVT[(8 * h + k) * NP + i], sbuf[8 * h + k], pd);
           pd += __shfl_xor_sync(kFull, pd, 16);
         }
-        if (wmax_nn(fabs(unscale ? L.Dinv * pd : pd)) < cs * edi * nd) {
+        if (wmax_bits(abits(unscale ? L.Dinv * pd : pd)) < cs * edi * nd) {
           __syncwarp();
           if (h == 0) sbuf[i] = dx;
           __syncwarp();
@@ -230,9 +230,9 @@ __device__ __noinline__ CheckOut check_step(const double *sm, double *cbuf, doub
   }
   if (do_adapt && o.status == SMPC_UNSOLVED) {
     // compute_rho_estimate / adapt_rho on the SCALED residual norms
-    const double pr = s_rp / (fmax(s_z, s_Ax) + kDivTol);
-    const double dr = s_rd / (fmax(fmax(s_q, s_Aty), s_Px) + kDivTol);
-    const double rn = fmin(fmax(rho * sqrt(pr / (dr + kDivTol)), kRhoMin), kRhoMax);
+    const double pr = fast_div(s_rp, fmax(s_z, s_Ax) + kDivTol);
+    const double dr = fast_div(s_rd, fmax(fmax(s_q, s_Aty), s_Px) + kDivTol);
+    const double rn = fmin(fmax(rho * sqrt(fast_div(pr, dr + kDivTol)), kRhoMin), kRhoMax);
     if (rn > rho * S.rho_tol || rn < rho / S.rho_tol) { o.rho = rn; o.rho_changed = 1; }
   }
   return o;

@@ -28,6 +28,23 @@ __device__ __forceinline__ double wmax_nn(double v) {
   const unsigned ml = __reduce_max_sync(kFull, lo);
   return __hiloint2double((int)mh, (int)ml);
 }
+// |x| as an IEEE bit pattern; for non-negative doubles the order of the patterns is the order of the values (NaN on top, so it
+// propagates like in the oracle's max loops), and max / compare run on the integer pipe instead of DSETP + NaN fix-ups
+typedef unsigned long long ull;
+__device__ __forceinline__ ull abits(double x) { return (ull)__double_as_longlong(x) & 0x7fffffffffffffffULL; }
+__device__ __forceinline__ ull umax2(ull a, ull b) { return a > b ? a : b; }
+__device__ __forceinline__ double wmax_bits(ull v) {
+  const unsigned hi = (unsigned)(v >> 32);
+  const unsigned mh = __reduce_max_sync(kFull, hi);
+  const unsigned lo = hi == mh ? (unsigned)v : 0u;
+  const unsigned ml = __reduce_max_sync(kFull, lo);
+  return __hiloint2double((int)mh, (int)ml);
+}
+// x / y for y > 0 (rho estimate): reciprocal + one correction step, within an ulp of the IEEE quotient
+__device__ __forceinline__ double fast_div(double x, double y) {
+  const double r = __drcp_rn(y), q = x * r;
+  return fma(fma(-y, q, x), r, q);
+}
 __device__ __forceinline__ double wsum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
