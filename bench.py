@@ -240,6 +240,12 @@ class C2(Workload):
 class C3(Workload):
     key, default_batch = "c3", 131072
 
+    def executed_flops(self, n, m_exec):
+        # the x-space variant of the tile kernel multiplies by V' and V only (two n x n GEMMs), the products with A are element-wise
+        if "x-space" in self.solver.kernel_name:
+            return 4.0 * n * n
+        return super().executed_flops(n, m_exec)
+
     def describe(self):
         return (f"config3: 12-state / 4-input quadrotor, N=50, condensed n=200, m=400 (input box as +/- rows), {self.B} random "
                 "x0 / hover references per GPU (= the 1M batch over 8 GPUs) sharing P and A, cold solves")
