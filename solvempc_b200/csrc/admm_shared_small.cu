@@ -462,7 +462,7 @@ admm_shared_small_kernel(SmallPackDev K, SharedPlanDev P, BatchDev Bt, SettingsD
           if constexpr (PAIRED && kSplitZ) zt += __shfl_xor_sync(kFull, zt, 16);   // the same bits in both halves (a + b = b + a)
           // ---- z, y updates (OSQP update_z / update_y re-associated, see the file header)
           const double v = fma(alpha_r, zt, base_r);
-          const double zn = v < lb_r ? lb_r : (v > ub_r ? ub_r : v);
+          const double zn = clip_sel(v, lb_r, ub_r);
           const double dn = v - zn;
           store_w(rv * fma(2.0, zn, -v));   // w' = rho z - y'
           if constexpr (LAST) {

@@ -54,13 +54,6 @@ __device__ __forceinline__ double lds64(uint32_t addr) {
   asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
   return v;
 }
-// v < lo ? lo : (v > hi ? hi : v) as two selects (the compiler otherwise turns the ternaries into divergent branches)
-__device__ __forceinline__ double clip_sel(double v, double lo, double hi) {
-  double r;
-  asm("{\n\t.reg .pred p, q;\n\tsetp.gt.f64 q, %1, %3;\n\tselp.f64 %0, %3, %1, q;\n\tsetp.lt.f64 p, %1, %2;\n\tselp.f64 %0, %2, %0, p;\n\t}"
-      : "=&d"(r) : "d"(v), "d"(lo), "d"(hi));
-  return r;
-}
 // transpose-reduction of four partial sums over the four b-lanes of a row group: returns the lane's own row
 __device__ __forceinline__ double treduce4(double p0, double p1, double p2, double p3) {
   const double q0 = p0 + __shfl_xor_sync(kFull, p2, 1), q1 = p1 + __shfl_xor_sync(kFull, p3, 1);

@@ -45,6 +45,13 @@ __device__ __forceinline__ double fast_div(double x, double y) {
   const double r = __drcp_rn(y), q = x * r;
   return fma(fma(-y, q, x), r, q);
 }
+// v < lo ? lo : (v > hi ? hi : v) as two selects (the compiler otherwise turns the ternaries into divergent branches)
+__device__ __forceinline__ double clip_sel(double v, double lo, double hi) {
+  double r;
+  asm("{\n\t.reg .pred p, q;\n\tsetp.gt.f64 q, %1, %3;\n\tselp.f64 %0, %3, %1, q;\n\tsetp.lt.f64 p, %1, %2;\n\tselp.f64 %0, %2, %0, p;\n\t}"
+      : "=&d"(r) : "d"(v), "d"(lo), "d"(hi));
+  return r;
+}
 __device__ __forceinline__ double wsum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
