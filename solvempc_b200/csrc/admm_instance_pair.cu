@@ -42,6 +42,14 @@ __device__ __forceinline__ double wmax(double v) {   // exact max over the warp 
   const unsigned ml = __reduce_max_sync(kFull, lo);
   return __hiloint2double((int)mh, (int)ml);
 }
+// OSQP's c_min(c_max(v, lo), hi) (a > b ? a : b, then a < b ? a : b: NaN -> lo) as two compare / select pairs: fmin(fmax())
+// compiles to DSETP.MAX / MIN + selects + NaN fix-ups, almost twice the instructions
+__device__ __forceinline__ double clamp_sel(double v, double lo, double hi) {
+  double r;
+  asm("{\n\t.reg .pred p, q;\n\tsetp.gt.f64 p, %1, %2;\n\tselp.f64 %0, %1, %2, p;\n\tsetp.lt.f64 q, %0, %3;\n\tselp.f64 %0, %0, %3, q;\n\t}"
+      : "=&d"(r) : "d"(v), "d"(lo), "d"(hi));
+  return r;
+}
 __device__ __forceinline__ double wsum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
@@ -132,7 +140,7 @@ __host__ __device__ inline int pair_tri2(int n) { return ((n * (n + 1) / 2) + 1)
 // pack of one instance (doubles): G' | M^-1 | K (kPN rows of kPLD each) | S0 | T (packed lower triangles)
 size_t instance_pair_pack_doubles(int n) { return 3 * (size_t)kPN * kPLD + 2 * (size_t)pair_tri2(n); }
 bool instance_pair_supports(int n, int m) { return n >= 1 && n <= kPN && m >= 2 && m % 2 == 0 && m / 2 <= kPN; }
-static size_t pair_smem_bytes(int n) { return ((size_t)3 * n * kPLD + 20 * kPN) * sizeof(double) + 4 * sizeof(uint64_t); }
+static size_t pair_smem_bytes(int n) { return ((size_t)3 * n * kPLD + 21 * kPN) * sizeof(double) + 4 * sizeof(uint64_t); }
 
 template <int CTAS_PER_SM>
 __global__ void __launch_bounds__(64, CTAS_PER_SM) admm_instance_pair_kernel(InstanceDataDev I, BatchDev Bt, SettingsDev S, int *queue, int prepare) {
@@ -148,7 +156,8 @@ __global__ void __launch_bounds__(64, CTAS_PER_SM) admm_instance_pair_kernel(Ins
          *lbb = lbt + kPN, *t0 = lbb + kPN, *t1 = t0 + kPN, *evt = t1 + kPN, *evb = evt + kPN, *dl0 = evb + kPN, *dl1 = dl0 + kPN,
          *dl2 = dl1 + kPN, *rvt = dl2 + kPN, *rvb = rvt + kPN, *rit = rvb + kPN, *rib = rit + kPN, *red = rib + kPN;
   // dl0 / dl1: delta_y (top, bottom), dl2: delta_x of the iteration before a check; rvt .. rib: rho_vec and 1 / rho_vec per row
-  uint64_t *mbar = reinterpret_cast<uint64_t *>(red + kPN);   // [0], [1]: the two G' stages
+  double *zer = red + kPN;                                    // kPN zeros (never written after the initial clear)
+  uint64_t *mbar = reinterpret_cast<uint64_t *>(zer + kPN);   // [0], [1]: the two G' stages
   __shared__ int s_ticket;
 
   const double alpha = S.alpha, sigma = S.sigma;
@@ -156,7 +165,7 @@ __global__ void __launch_bounds__(64, CTAS_PER_SM) admm_instance_pair_kernel(Ins
   const uint32_t gt_bytes = (uint32_t)(n * kPLD * sizeof(double));
 
   if (tid == 0) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); mbar_fence_init(); }
-  for (int e = tid; e < 20 * kPN; e += 64) wd[e] = 0.0;
+  for (int e = tid; e < 21 * kPN; e += 64) wd[e] = 0.0;
   __syncthreads();
   // first ticket + its G' stage
   if (tid == 0) {
@@ -354,16 +363,19 @@ __global__ void __launch_bounds__(64, CTAS_PER_SM) admm_instance_pair_kernel(Ins
         }
         __syncthreads();
         if (live) {                                                         // row_i <- row_i - f * (row_k / d); row_k <- row_k / d
-          const double g = lane == k ? 0.0 : -f;                           // (the pivot row: 0 * x + copy of the scaled row)
+          // the pivot row takes the same FMA with g = 1 on a row of zeros (1 * x + 0 = the scaled row, exactly): no per-entry select
+          const bool piv = lane == k;
+          const double g = piv ? 1.0 : -f;
+          const double *src = piv ? zer : row;
 #pragma unroll
           for (int jj = 0; jj < 16; jj += 2) {
             const double2 p2 = *reinterpret_cast<const double2 *>(prow + jj);
-            double2 r2 = *reinterpret_cast<const double2 *>(row + jj);
-            r2.x = lane == k ? p2.x : fma(g, p2.x, r2.x);
-            r2.y = lane == k ? p2.y : fma(g, p2.y, r2.y);
+            double2 r2 = *reinterpret_cast<const double2 *>(src + jj);
+            r2.x = fma(g, p2.x, r2.x);
+            r2.y = fma(g, p2.y, r2.y);
             *reinterpret_cast<double2 *>(row + jj) = r2;
           }
-          if (w == (k >> 4)) row[k & 15] = lane == k ? pv : g * pv;          // column k: 1 / d on the pivot row, -f / d elsewhere
+          if (w == (k >> 4)) row[k & 15] = piv ? pv : -f * pv;              // column k: 1 / d on the pivot row, -f / d elsewhere
         }
         __syncthreads();
       }
@@ -578,14 +590,14 @@ __global__ void __launch_bounds__(64, CTAS_PER_SM) admm_instance_pair_kernel(Ins
         } else if (lane < mp) {
           {
             const double zr = alpha * acc + (1.0 - alpha) * ZT_;
-            const double zn = fmin(fmax(zr + rit[lane] * YT_, lbt[lane]), ubt[lane]);
+            const double zn = clamp_sel(zr + rit[lane] * YT_, lbt[lane], ubt[lane]);
             const double d = rvt[lane] * (zr - zn);
             ZT_ = zn; YT_ += d;
             if (keep_deltas) dl0[lane] = d;
           }
           {
             const double zr = alpha * (-acc) + (1.0 - alpha) * ZB_;
-            const double zn = fmin(fmax(zr + rib[lane] * YB_, lbb[lane]), ubb[lane]);
+            const double zn = clamp_sel(zr + rib[lane] * YB_, lbb[lane], ubb[lane]);
             const double d = rvb[lane] * (zr - zn);
             ZB_ = zn; YB_ += d;
             if (keep_deltas) dl1[lane] = d;
