@@ -90,14 +90,13 @@ __global__ void __launch_bounds__(256) admm_shared_generic_kernel(SharedPlanDev 
   double rho = Bt.fresh ? fmin(fmax(S.rho0, kRhoMin), kRhoMax) : Bt.rho[b];
   int rho_updates = 0;
   __syncwarp();
-  // osqp_update_bounds refuses l > u; such an instance is left UNSOLVED (iter 0, NaN solution)
-  // ... and so is an instance whose bounds change a row's class (equality / inequality / free): OSQP would
-  // re-classify and refactor for it alone, which the SHARED factor cannot follow (use the per-instance regime)
+  // osqp_update_bounds refuses l > u; such an instance is left UNSOLVED (iter 0, NaN solution).
+  // An instance whose bounds change a row's class (equality / inequality / free) against the SETUP bounds: OSQP would re-classify
+  // the row and refactor for that instance alone, which the shared factor cannot follow.  It is solved with the plan's rho_vec
+  // entries instead -- rho_vec is any positive diagonal for ADMM, the fixed point and every termination test are the same, only
+  // the iterate path (and so the iteration count) can differ from osqp-eigen's for that instance.
   int bad_rows = 0;
-  for (int r = lane; r < m; r += 32) {
-    const int ct = (lb[r] < -kInfty * kMinScaling && ub[r] > kInfty * kMinScaling) ? -1 : ((ub[r] - lb[r] < kRhoTolRow) ? 1 : 0);
-    bad_rows |= (lb[r] > ub[r]) | (ct != P.ctype[r]);
-  }
+  for (int r = lane; r < m; r += 32) bad_rows |= (lb[r] > ub[r]);
   const bool bad_bounds = warp_any(bad_rows);
   for (int i = lane; i < n; i += 32) qh[i] = col_dot(P.V, n, n, i, qb);   // q̂ = V' q̄
   __syncwarp();

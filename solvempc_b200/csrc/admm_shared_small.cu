@@ -382,10 +382,9 @@ admm_shared_small_kernel(SmallPackDev K, SharedPlanDev P, BatchDev Bt, SettingsD
     }
     double rho = Bt.fresh ? fmin(fmax(S.rho0, kRhoMin), kRhoMax) : Bt.rho[b];
     int rho_updates = 0;
-    // l > u (osqp_update_bounds refuses it) or a row whose class (equality / inequality / free) differs from the
-    // shared plan's: the instance is left UNSOLVED (see admm_shared_generic.cu)
-    const int ct_now = (lb_r < -kInfty * kMinScaling && ub_r > kInfty * kMinScaling) ? -1 : ((ub_r - lb_r < kRhoTolRow) ? 1 : 0);
-    const bool bad_bounds = __any_sync(kFull, r < m && (lb_r > ub_r || ct_now != ct_r));
+    // l > u (osqp_update_bounds refuses it): the instance is left UNSOLVED; a row whose class differs from the shared plan's
+    // keeps the plan's rho_vec entry (see admm_shared_generic.cu)
+    const bool bad_bounds = __any_sync(kFull, r < m && lb_r > ub_r);
     // q̂ = V' q̄ ; lanes of the upper half-warp start their partial sum at 0, the lower half at -q̂
     if (h == 0) sbuf[i] = qb_i;
     __syncwarp();
@@ -777,8 +776,7 @@ admm_shared_small_mma_kernel(SmallPackDev K, SharedPlanDev P, BatchDev Bt, Setti
                 if (warm) { z_r = Bt.z[(size_t)b * m + r]; y_r = Bt.y[(size_t)b * m + r]; }
               }
               rho = Bt.fresh ? fmin(fmax(S.rho0, kRhoMin), kRhoMax) : Bt.rho[b];
-              const int ct_now = (lb_r < -kInfty * kMinScaling && ub_r > kInfty * kMinScaling) ? -1 : ((ub_r - lb_r < kRhoTolRow) ? 1 : 0);
-              if (__any_sync(kFull, r < m && (lb_r > ub_r || ct_now != LC.ct))) {
+              if (__any_sync(kFull, r < m && lb_r > ub_r)) {
                 if (h == 0 && i < n) { if (Bt.x_out) Bt.x_out[(size_t)b * n + i] = qnan; Bt.xi[(size_t)b * n + i] = 0.0; }
                 if (r < m) { if (Bt.y_out) Bt.y_out[(size_t)b * m + r] = qnan; Bt.z[(size_t)b * m + r] = 0.0; Bt.y[(size_t)b * m + r] = 0.0; }
                 if (lane == 0) {

@@ -324,13 +324,8 @@ admm_shared_small_fused_kernel(SmallPackDev K, SharedPlanDev P, BatchDev Bt, Set
     }
     double rho = Bt.fresh ? rho0 : Bt.rho[bi];
     int rho_updates = 0;
-    // l > u (osqp_update_bounds refuses it) or a row whose class differs from the shared plan's: left UNSOLVED
-    bool bad_row = false;
-    if (pair_ok) {
-      const int now_t = (lb_t < -kInfty * kMinScaling && ub_t > kInfty * kMinScaling) ? -1 : ((ub_t - lb_t < kRhoTolRow) ? 1 : 0);
-      const int now_b = (lb_b < -kInfty * kMinScaling && ub_b > kInfty * kMinScaling) ? -1 : ((ub_b - lb_b < kRhoTolRow) ? 1 : 0);
-      bad_row = lb_t > ub_t || lb_b > ub_b || now_t != ct_t || now_b != ct_b;
-    }
+    // l > u (osqp_update_bounds refuses it): left UNSOLVED; a row whose class differs from the plan's keeps the plan's rho_vec entry
+    const bool bad_row = pair_ok && (lb_t > ub_t || lb_b > ub_b);
     const bool bad_bounds = __any_sync(kFull, bad_row);
     // q̂ = V' q̄ (the summation order of the two-phase kernel), norms of q̄ for the dual tolerance
     if (is_xi) dv[idx] = qb;

@@ -540,8 +540,7 @@ _Pragma("unroll 4")
                 lo = E * (Bt.l ? Bt.l[(size_t)b * m + r] : __ldg(P.l0 + r));
                 hi = E * (Bt.u ? Bt.u[(size_t)b * m + r] : __ldg(P.u0 + r));
                 if (warm) { zz = Bt.z[(size_t)b * m + r]; yy = Bt.y[(size_t)b * m + r]; }
-                const int ct = (lo < -kInfty * kMinScaling && hi > kInfty * kMinScaling) ? -1 : ((hi - lo < kRhoTolRow) ? 1 : 0);
-                if (lo > hi || ct != (int)__ldg(P.ctype + r)) atomicOr(&C.flags[s], F_BADBOUNDS);
+                if (lo > hi) atomicOr(&C.flags[s], F_BADBOUNDS);   // (a class change keeps the plan's rho_vec entry: admm_shared_generic.cu)
               }
               lbp[e] = lo; ubp[e] = hi; zp[e] = zz; yp[e] = yy;
             }

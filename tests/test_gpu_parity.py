@@ -581,3 +581,32 @@ def test_fused_small_kernel_opt_in_matches_oracle(repo_root):
     """) % (repo_root, repo_root, repo_root)
     out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, SMPC_SMALL_FUSED="1"), capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "fused ok" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
+
+
+@pytest.mark.parametrize("kernel", [1, 2, 4, 5])
+def test_row_class_change_is_solved_with_the_plans_rho_vec(kernel):
+    """Shared-factor regime: instances whose own bounds turn an inequality row into an equality or a free row (OSQP would
+    re-classify and refactor for them) are solved with the setup's rho_vec entries: same status and solution as the oracle within
+    the north star's tolerance; the iteration count may differ for those instances, and must not for the untouched ones."""
+    n, m, B = 8, 12, 6
+    P, q, A, l0, u0 = random_qp(n, m, 21)
+    s = sm.BatchedSolver(P, A, l0, u0, batch=B, kernel=kernel, **EPS)
+    l, u = np.tile(l0, (B, 1)), np.tile(u0, (B, 1))
+    mid = 0.5 * (l0 + u0)
+    l[1, 2] = u[1, 2] = mid[2]                       # equality row
+    l[2, 5], u[2, 5] = -np.inf, np.inf               # free row
+    l[3, 0] = u[3, 0] = mid[0]; l[3, 7], u[3, 7] = -np.inf, np.inf
+    qq = np.tile(q, (B, 1)) + 0.1 * np.arange(B)[:, None]
+    s.update_gradient(qq); s.update_bounds(l, u); s.solve()
+    x, _ = s.solution(); info = s.info()
+    s.close()
+    for b in range(B):
+        so = oracle.Solver(P, np.zeros(n), A, l0, u0, **EPS)
+        so.update_lin_cost(qq[b]); so.update_bounds(l[b], u[b])
+        r = so.solve()
+        assert info["status"][b] == r["status"] == sm.SOLVED
+        assert np.abs(x[b] - r["x"]).max() <= 1e-4 * max(1.0, np.abs(r["x"]).max())
+        if b in (0, 4, 5):
+            assert info["iter"][b] == r["iter"] and np.abs(x[b] - r["x"]).max() <= 1e-9 * max(1.0, np.abs(r["x"]).max())
+        if b in (1, 3):
+            assert abs((A @ x[b])[2 if b == 1 else 0] - (mid[2] if b == 1 else mid[0])) < 1e-3
