@@ -137,8 +137,11 @@ enum { R_SRP, R_SZ, R_SAX, R_URP, R_UZ, R_UAX, R_PIND, R_PILHS, R_SRD, R_SQ, R_S
 }  // namespace
 
 __host__ __device__ inline int pair_tri2(int n) { return ((n * (n + 1) / 2) + 1) & ~1; }
-// pack of one instance (doubles): G' | M^-1 | K (kPN rows of kPLD each) | S0 | T (packed lower triangles)
-size_t instance_pair_pack_doubles(int n) { return 3 * (size_t)kPN * kPLD + 2 * (size_t)pair_tri2(n); }
+// pack of one instance (doubles): G' | M^-1 | K (kPN rows of kPLD each) | S0 | T (packed lower triangles) | V' (kPN rows of kPLD,
+// V'[k][i] = V(i, k)) | lambda (kPN) | flag (2): the generalised eigen-decomposition V' S0 V = I, V' T V = diag(lambda) of the
+// rho-independent split, so that M(rho)^-1 = V diag(1 / (1 + rho lambda)) V' for every rho (flag = 1: valid)
+__host__ __device__ inline size_t pair_pack_stride(int n) { return 4 * (size_t)kPN * kPLD + 2 * (size_t)pair_tri2(n) + kPN + 2; }
+size_t instance_pair_pack_doubles(int n) { return pair_pack_stride(n); }
 bool instance_pair_supports(int n, int m) { return n >= 1 && n <= kPN && m >= 2 && m % 2 == 0 && m / 2 <= kPN; }
 static size_t pair_smem_bytes(int n) { return ((size_t)3 * n * kPLD + 21 * kPN) * sizeof(double) + 4 * sizeof(uint64_t); }
 
@@ -149,7 +152,8 @@ __global__ void __launch_bounds__(64, CTAS_PER_SM) admm_instance_pair_kernel(Ins
   const bool xw = w == 0;
   const int n = I.n, m = I.m, mp = m >> 1, B = Bt.B;
   const int tri = n * (n + 1) / 2, tri2 = pair_tri2(n);
-  const size_t pack_stride = 3 * (size_t)kPN * kPLD + 2 * (size_t)tri2;
+  const size_t pack_stride = pair_pack_stride(n);
+  const size_t oVT = 3 * (size_t)kPN * kPLD + 2 * (size_t)tri2, oLam = oVT + (size_t)kPN * kPLD, oFlag = oLam + kPN;
   double *const Gt0 = smem, *const Gt1 = smem + n * kPLD;
   double *Sc = smem + 2 * n * kPLD;
   double *wd = Sc + n * kPLD, *p1 = wd + kPN, *rhs = p1 + kPN, *xs = rhs + kPN, *ubt = xs + kPN, *ubb = ubt + kPN, *lbt = ubb + kPN,
@@ -198,7 +202,8 @@ __global__ void __launch_bounds__(64, CTAS_PER_SM) admm_instance_pair_kernel(Ins
         mbar_expect_tx(&mbar[stage ^ 1], gt_bytes);
         bulk_g2s(stage ? Gt0 : Gt1, pk, gt_bytes, &mbar[stage ^ 1]);
         bulk_prefetch_l2(pk + kPN * kPLD, (uint32_t)((kPN + n) * kPLD * sizeof(double)));          // M^-1 and the first n rows of K
-        bulk_prefetch_l2(pk + 3 * kPN * kPLD, (uint32_t)(2 * tri2 * sizeof(double)));              // S0, T
+        bulk_prefetch_l2(pk + oVT, (uint32_t)((n * kPLD + 0) * sizeof(double)));                   // V' (rho updates)
+        bulk_prefetch_l2(pk + oLam, (uint32_t)((kPN + 2) * sizeof(double)));                       // lambda, flag
         const uintptr_t pa = reinterpret_cast<uintptr_t>(I.P + (size_t)t * n * n) & ~(uintptr_t)15;
         bulk_prefetch_l2(reinterpret_cast<const void *>(pa), (uint32_t)((n * n * sizeof(double) + 15) & ~(size_t)15));   // P̄ (termination checks)
       }
@@ -258,6 +263,8 @@ __global__ void __launch_bounds__(64, CTAS_PER_SM) admm_instance_pair_kernel(Ins
     __syncthreads();
     const bool bad_bounds = red[R_FLAG0] != 0.0;
     bool split_ok = red[R_FLAG1] == 0.0;     // the pack's S0 / T / M^-1 / K hold for the row classes of the SETUP bounds only
+    static const bool eig_on = true;
+    const bool eig_ok = eig_on && !prepare && pack[oFlag] == 1.0;   // the pack holds the pencil's eigen-decomposition
 
     // ---- operators into registers
     double gt[16], op[kPN];
@@ -295,9 +302,34 @@ __global__ void __launch_bounds__(64, CTAS_PER_SM) admm_instance_pair_kernel(Ins
     // one CTA barrier per sweep) and updates 16 entries per thread; after n sweeps the registers hold M^-1.  All 64 threads
     // work in every sweep and the dependent chain per sweep is one reciprocal + one FMA.  Then rows of M^-1 -> x-warp registers,
     // rows of K = G M^-1 -> z-warp registers.
-    // mode 0: M = S0 + rho T from the pack; 1: assembled from G and this solve's rho_vec; 2 (prepare): also writes S0, T.
+    // mode 0: M = S0 + rho T from the pack; 1: assembled from G and this solve's rho_vec; 2 (prepare): also writes S0, T;
+    // mode 3: no sweeps at all -- M(rho)^-1 = V diag(1 / (1 + rho lambda)) V' from the pack's eigen-decomposition (prepared at
+    // create time by eigen_prepare below): 16 entries per thread, 30 independent FMAs each, no barrier inside.
     auto refactor = [&](int mode) -> bool {
       double *row = Sc + lane * kPLD + 16 * w;      // this thread's 16 entries of M (rows >= n are never touched)
+      if (mode == 3) {
+        const double *VT = pack + oVT, *lam = pack + oLam;
+        if (tid < kPN) t1[tid] = tid < n ? fast_rcp(1.0 + rho * lam[tid]) : 0.0;
+        __syncthreads();
+        if (lane < n) {
+          double acc[16];
+#pragma unroll
+          for (int jj = 0; jj < 16; ++jj) acc[jj] = 0.0;
+          for (int k = 0; k < n; ++k) {
+            const double vik = VT[k * kPLD + lane] * t1[k];
+            const double *vr = VT + k * kPLD + 16 * w;
+#pragma unroll
+            for (int jj = 0; jj < 16; jj += 2) {
+              const double2 v2 = *reinterpret_cast<const double2 *>(vr + jj);
+              acc[jj] = fma(vik, v2.x, acc[jj]); acc[jj + 1] = fma(vik, v2.y, acc[jj + 1]);
+            }
+          }
+#pragma unroll
+          for (int jj = 0; jj < 16; jj += 2) *reinterpret_cast<double2 *>(row + jj) = make_double2(acc[jj], acc[jj + 1]);
+        }
+        __syncthreads();
+        PFI(5)
+      } else {
       if (mode == 0) {
         const double *S0 = pack + 3 * kPN * kPLD, *T = S0 + tri2;
         if (lane < n) {
@@ -381,6 +413,7 @@ __global__ void __launch_bounds__(64, CTAS_PER_SM) admm_instance_pair_kernel(Ins
       }
       PFI(6)
       if (!ok) return false;                                               // (uniform: every thread saw the same pivots)
+      }
       PFI(7)
       if (xw) {
 #pragma unroll
@@ -403,6 +436,102 @@ __global__ void __launch_bounds__(64, CTAS_PER_SM) admm_instance_pair_kernel(Ins
       }
       __syncthreads();
       PFI(9)
+      return true;
+    };
+
+    // Create-time pass (warp 0, after S0 and T are in the pack): generalised eigen-decomposition of the pencil (T, S0) --
+    // Cholesky S0 = L L', C = L^-1 T L^-T, cyclic Jacobi C = Q diag(lambda) Q', V = L^-T Q -- so that rho updates need no
+    // refactorisation sweeps (refactor mode 3).  Work buffers: Sc (L), the idle G' stage (C), this instance's G' stage (Q: G' is
+    // already in the pack and K has been formed).  Returns false when S0 is not positive definite or Jacobi does not settle.
+    auto eigen_prepare = [&]() -> bool {
+      double *Am = Sc, *Bm = stage ? Gt0 : Gt1, *Qm = Gt;
+      const double *S0 = pack + 3 * kPN * kPLD, *T = S0 + tri2;
+      for (int e = lane; e < n * n; e += 32) {
+        const int i = e / n, j = e % n, hi_ = i > j ? i : j, lo_ = i > j ? j : i, t = hi_ * (hi_ + 1) / 2 + lo_;
+        Am[i * kPLD + j] = S0[t]; Bm[i * kPLD + j] = T[t]; Qm[i * kPLD + j] = i == j ? 1.0 : 0.0;
+      }
+      __syncwarp();
+      bool pd = true;
+      for (int k = 0; k < n; ++k) {                       // Cholesky, lower triangle in place
+        const double akk2 = Am[k * kPLD + k];
+        if (!(akk2 > 0.0)) pd = false;
+        const double akk = sqrt(akk2 > 0.0 ? akk2 : 1.0);
+        __syncwarp();
+        if (lane == k) Am[k * kPLD + k] = akk;
+        else if (lane > k && lane < n) Am[lane * kPLD + k] /= akk;
+        __syncwarp();
+        if (lane > k && lane < n) {
+          const double lik = Am[lane * kPLD + k];
+          for (int j = k + 1; j <= lane; ++j) Am[lane * kPLD + j] -= lik * Am[j * kPLD + k];
+        }
+        __syncwarp();
+      }
+      if (!pd) return false;
+      if (lane < n) {                                      // Y = L^-1 T (lane = column), in place
+        for (int i = 0; i < n; ++i) {
+          double sacc = Bm[i * kPLD + lane];
+          for (int k = 0; k < i; ++k) sacc -= Am[i * kPLD + k] * Bm[k * kPLD + lane];
+          Bm[i * kPLD + lane] = sacc / Am[i * kPLD + i];
+        }
+      }
+      __syncwarp();
+      if (lane < n) {                                      // C = Y L^-T (lane = row), in place
+        for (int j = 0; j < n; ++j) {
+          double sacc = Bm[lane * kPLD + j];
+          for (int k = 0; k < j; ++k) sacc -= Am[j * kPLD + k] * Bm[lane * kPLD + k];
+          Bm[lane * kPLD + j] = sacc / Am[j * kPLD + j];
+        }
+      }
+      __syncwarp();
+      for (int e = lane; e < n * n; e += 32) {             // symmetrise
+        const int i = e / n, j = e % n;
+        if (i < j) { const double v = 0.5 * (Bm[i * kPLD + j] + Bm[j * kPLD + i]); Bm[i * kPLD + j] = v; Bm[j * kPLD + i] = v; }
+      }
+      __syncwarp();
+      bool settled = false;
+      for (int sweep = 0; sweep < 30 && !settled; ++sweep) {
+        double off = 0.0, dg = 0.0;
+        if (lane < n)
+          for (int j = 0; j < n; ++j) { const double v = Bm[lane * kPLD + j]; if (j == lane) dg += v * v; else off += v * v; }
+        off = wsum(off); dg = wsum(dg);
+        if (off <= 1e-30 * dg || off == 0.0) { settled = true; break; }
+        for (int p_ = 0; p_ < n - 1; ++p_)
+          for (int q_ = p_ + 1; q_ < n; ++q_) {
+            const double apq = Bm[p_ * kPLD + q_];
+            if (apq == 0.0) continue;                      // (uniform: every lane reads the same entry)
+            const double app = Bm[p_ * kPLD + p_], aqq = Bm[q_ * kPLD + q_];
+            const double theta = (aqq - app) / (2.0 * apq);
+            const double tt = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+            const double cs = 1.0 / sqrt(tt * tt + 1.0), sn = tt * cs;
+            __syncwarp();
+            if (lane < n) {
+              const double ckp = Bm[lane * kPLD + p_], ckq = Bm[lane * kPLD + q_];
+              const double qkp = Qm[lane * kPLD + p_], qkq = Qm[lane * kPLD + q_];
+              Qm[lane * kPLD + p_] = cs * qkp - sn * qkq; Qm[lane * kPLD + q_] = sn * qkp + cs * qkq;
+              if (lane != p_ && lane != q_) {
+                const double np_ = cs * ckp - sn * ckq, nq_ = sn * ckp + cs * ckq;
+                Bm[lane * kPLD + p_] = np_; Bm[lane * kPLD + q_] = nq_; Bm[p_ * kPLD + lane] = np_; Bm[q_ * kPLD + lane] = nq_;
+              }
+            }
+            if (lane == 0) { Bm[p_ * kPLD + p_] = app - tt * apq; Bm[q_ * kPLD + q_] = aqq + tt * apq; Bm[p_ * kPLD + q_] = 0.0; Bm[q_ * kPLD + p_] = 0.0; }
+            __syncwarp();
+          }
+      }
+      if (!settled) return false;
+      if (lane < n) {                                      // V = L^-T Q (lane = column), in place
+        for (int i = n - 1; i >= 0; --i) {
+          double sacc = Qm[i * kPLD + lane];
+          for (int k = i + 1; k < n; ++k) sacc -= Am[k * kPLD + i] * Qm[k * kPLD + lane];
+          Qm[i * kPLD + lane] = sacc / Am[i * kPLD + i];
+        }
+      }
+      __syncwarp();
+      double *VT = pack + oVT, *lam = pack + oLam;
+      for (int e = lane; e < kPN * kPLD; e += 32) {
+        const int k = e / kPLD, i = e % kPLD;
+        VT[e] = (k < n && i < n) ? Qm[i * kPLD + k] : 0.0;
+      }
+      lam[lane] = lane < n ? fmax(Bm[lane * kPLD + lane], 0.0) : 0.0;
       return true;
     };
 
@@ -566,7 +695,7 @@ __global__ void __launch_bounds__(64, CTAS_PER_SM) admm_instance_pair_kernel(Ins
     while (!bad_bounds) {
       if (need_factor) {
         PFI(2)
-        factor_ok = refactor(prepare ? 2 : (split_ok ? 0 : 1));
+        factor_ok = refactor(prepare ? 2 : (split_ok ? (eig_ok ? 3 : 0) : 1));
 #ifdef SMPC_PAIR_PROFILE
         ++pf_refac;
 #endif
@@ -645,6 +774,23 @@ __global__ void __launch_bounds__(64, CTAS_PER_SM) admm_instance_pair_kernel(Ins
       }
       if (tid == 0) I.pack_rho[b] = ok ? rho : -1.0;   // -1: no usable factorisation in the pack
       __syncthreads();
+      bool eig = false;
+      if (ok && xw) eig = eigen_prepare();
+      if (tid == 0) { pack[oFlag] = eig ? 1.0 : 0.0; pack[oFlag + 1] = 0.0; red[R_FLAG0] = eig ? 1.0 : 0.0; }
+      __syncthreads();
+      if (red[R_FLAG0] != 0.0) {
+        // the pack's M(rho0)^-1 and K in the eigen form too, so that a later cold solve (refactor mode 3 at rho0) reproduces the
+        // first one bit for bit; G' comes back from the pack (its stage served as a work buffer)
+        for (int e = tid; e < n * kPLD; e += 64) Gt[e] = pack[e];
+        __syncthreads();
+        refactor(3);
+        if (lane < (xw ? n : mp)) {
+          double *dst = pack + (xw ? 1 : 2) * kPN * kPLD + lane * kPLD;
+#pragma unroll
+          for (int k = 0; k < kPN; k += 2) *reinterpret_cast<double2 *>(dst + k) = make_double2(op[k], op[k + 1]);
+        }
+        __syncthreads();
+      }
       cur = s_ticket;
       continue;
     }
