@@ -309,6 +309,9 @@ __global__ void __launch_bounds__(64, CTAS_PER_SM) admm_instance_pair_kernel(Ins
       double *row = Sc + lane * kPLD + 16 * w;      // this thread's 16 entries of M (rows >= n are never touched)
       if (mode == 3) {
         const double *VT = pack + oVT, *lam = pack + oLam;
+        // every 128-byte line of V' into L1 at once (64 lines at n = 30, one per thread): the k loop below would otherwise take
+        // the L2 latency once per k (its loads of row k + 1 are not issued before the FMAs of row k)
+        for (int e = tid * 16; e < n * kPLD; e += 64 * 16) asm volatile("prefetch.global.L1 [%0];" ::"l"(VT + e));
         if (tid < kPN) t1[tid] = tid < n ? fast_rcp(1.0 + rho * lam[tid]) : 0.0;
         __syncthreads();
         if (lane < n) {
