@@ -593,7 +593,10 @@ _Pragma("unroll 4")
           case P_XBAR: op = reinterpret_cast<const double2 *>(K.Vp);  kpt = kpN; panel = cv;          krows = cvr; rb0 = nrb0; rb1 = nrb1; break;
           case P_PX:   op = reinterpret_cast<const double2 *>(XD ? K.Pp : K.PVp); kpt = kpN; panel = cv; krows = cvr; rb0 = nrb0; rb1 = nrb1; break;
           case P_ATY:  op = reinterpret_cast<const double2 *>(K.ATp); kpt = kpM; panel = yp;          krows = m8;  rb0 = nrb0; rb1 = nrb1; break;
-          case P_AX:   op = reinterpret_cast<const double2 *>(K.Wp);  kpt = kpN; panel = cv;          krows = cvr; rb0 = mrb0; rb1 = mrb1; break;
+          case P_AX:   op = reinterpret_cast<const double2 *>(K.Wp);  kpt = kpN; panel = cv;          krows = cvr; rb0 = mrb0; rb1 = mrb1;
+                       // row pairs: A̅ x̄ of the top half only (row p + mp is its negative): half the DMMAs of this pass
+                       if (PAIRED && !XD) { op = reinterpret_cast<const double2 *>(K.Wtop); rb0 = prb0; rb1 = prb1; }
+                       break;
           case P_ATD:  op = reinterpret_cast<const double2 *>(K.ATp); kpt = kpM; panel = cv + n8 * 8; krows = cvr; rb0 = nrb0; rb1 = nrb1; break;
           case P_DX:   op = reinterpret_cast<const double2 *>(K.Vp);  kpt = kpN; panel = Dp;          krows = n8;  rb0 = nrb0; rb1 = nrb1; break;
           case P_PD:   op = reinterpret_cast<const double2 *>(XD ? K.Pp : K.PVp); kpt = kpN; panel = Dp; krows = n8;  rb0 = nrb0; rb1 = nrb1; break;
@@ -675,6 +678,23 @@ _Pragma("unroll 4")
                   sm[nb][j] += 0.5 * xbj * pxj + qb * xbj;
                 }
               } else if (pass == P_AX) {
+                if (PAIRED && !XD) {   // the accumulator is (A̅ x̄) of top row `row`; the bottom row row + mp has the opposite sign
+                  if (row < mp) {
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                      const int rr = row + half * mp;
+                      const double Einv = __ldg(P.Einv + rr), sg = half ? -1.0 : 1.0;
+                      const double2 zz = *reinterpret_cast<const double2 *>(zp + pidx(m8, nb, rr));
+#pragma unroll
+                      for (int j = 0; j < 2; ++j) {
+                        const double Ax = sg * (j ? a1 : a0), zj = j ? zz.y : zz.x, rp = Ax - zj;
+                        mx[nb][0][j] = fmax(mx[nb][0][j], fabs(rp)); mx[nb][1][j] = fmax(mx[nb][1][j], fabs(zj)); mx[nb][2][j] = fmax(mx[nb][2][j], fabs(Ax));
+                        mx[nb][3][j] = fmax(mx[nb][3][j], fabs(Einv * rp)); mx[nb][4][j] = fmax(mx[nb][4][j], fabs(Einv * zj));
+                        mx[nb][5][j] = fmax(mx[nb][5][j], fabs(Einv * Ax));
+                      }
+                    }
+                  }
+                } else {
                 const double Einv = row < m ? __ldg(P.Einv + row) : 1.0;
                 const double2 zz = *reinterpret_cast<const double2 *>(zp + pidx(m8, nb, row));
 #pragma unroll
@@ -683,6 +703,7 @@ _Pragma("unroll 4")
                   mx[nb][0][j] = fmax(mx[nb][0][j], fabs(rp)); mx[nb][1][j] = fmax(mx[nb][1][j], fabs(zj)); mx[nb][2][j] = fmax(mx[nb][2][j], fabs(Ax));
                   mx[nb][3][j] = fmax(mx[nb][3][j], fabs(Einv * rp)); mx[nb][4][j] = fmax(mx[nb][4][j], fabs(Einv * zj));
                   mx[nb][5][j] = fmax(mx[nb][5][j], fabs(Einv * Ax));
+                }
                 }
               } else if (pass == P_ATD || pass == P_PD) {
                 const double Dinv = (unscale && row < n) ? __ldg(P.Dinv + row) : 1.0;
