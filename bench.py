@@ -305,7 +305,8 @@ class C4(C2):
 
     def describe(self):
         return (f"config4: per-instance linearised plants (distinct P, A per problem; reference dimensions), N=30 (n=30, m=60), "
-                f"{self.B} controllers per GPU, on-device assembly + batched Cholesky path, cold solves")
+                f"{self.B} controllers per GPU, cold solves; the per-plant setup (on-device assembly, scaling, factorisation and "
+                f"pencil eigen-decomposition) runs once at create time, outside the timed step: config.setup_ms")
 
     def setup(self, sm, torch, device, kernel):
         from problems import c4_plants
@@ -314,7 +315,11 @@ class C4(C2):
         conf = dict(Ad=Ad, Bd=Bd, Cd=cfg["Cd"], K=cfg["K"], Q=cfg["Q"], R=cfg["R"], RD=cfg["RD"], horizon=self.N, per_instance=1)
         X, U, ref = self._inputs(self.B, 31 + 1000 * self.rank)
         self.host = [np.ascontiguousarray(a) for a in (X, U, ref)]
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
         self.mpc = sm.BatchedModelPredictiveControlAPI(conf, batch=self.B, device=device, eps_abs=EPS, eps_rel=EPS)
+        torch.cuda.synchronize()
+        self.setup_ms = 1e3 * (time.perf_counter() - t0)   # upload of the plants + every create-time kernel (the CPU arm's constructor)
         self.mpc.solver.set_cold_solves(True)
         self.dev = [torch.from_numpy(a).cuda() for a in self.host]
         self.pin = [torch.from_numpy(a).pin_memory() for a in self.host]
@@ -684,6 +689,11 @@ class Bench:
             }
             if fresh is not None:
                 res["fresh_inputs"] = fresh
+            if getattr(wl, "setup_ms", None) is not None:
+                # the CPU arm of this configuration pays the constructor per plant inside its timed region; the GPU arm pays it once
+                # at create time: both ways of counting, so that nothing hides in the setup
+                res["config"]["setup_ms"] = wl.setup_ms
+                res["config"]["value_with_setup_every_step"] = world * B / ((ms_per_step + wl.setup_ms) / 1e3)
             self._pending_cpu.append((res, wl.__class__, B, cpu_seconds))
         wl.close()
         del wl
