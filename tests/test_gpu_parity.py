@@ -610,3 +610,21 @@ def test_row_class_change_is_solved_with_the_plans_rho_vec(kernel):
             assert info["iter"][b] == r["iter"] and np.abs(x[b] - r["x"]).max() <= 1e-9 * max(1.0, np.abs(r["x"]).max())
         if b in (1, 3):
             assert abs((A @ x[b])[2 if b == 1 else 0] - (mid[2] if b == 1 else mid[0])) < 1e-3
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_c2_more_seeds_match_the_oracle(ref_mats, seed):
+    """Config 2 on other seeded batches (the default small-QP kernel): statuses and iteration counts of the oracle, instance by
+    instance -- a soak for the round-off-level liberties of the kernel's check (bit-pattern norms, reciprocal-based rho estimate)."""
+    m, _ = ref_mats
+    B = 4096
+    X, U, ref = c2_batch(B, seed=seed)
+    f, ub = oracle.mpc_batch_vectors(m, X, U, ref)
+    ora = oracle.solve_batch(m["H"], m["Gbar"], m["lb"], m["W0"], f, ub, nthreads=os.cpu_count() or 1, **EPS)
+    s = sm.BatchedSolver(m["H"], m["Gbar"], m["lb"], m["W0"], batch=B, kernel=2, **EPS)
+    s.update_gradient(f); s.update_upper_bound(ub); s.solve()
+    x, _ = s.solution(); info = s.info()
+    s.close()
+    assert np.array_equal(info["status"], ora["status"]) and np.array_equal(info["iter"], ora["iter"])
+    sc = np.maximum(np.abs(ora["x"]).max(axis=1), 1e-12)
+    assert (np.abs(x - ora["x"]).max(axis=1) / sc).max() < 1e-9
