@@ -628,3 +628,21 @@ def test_c2_more_seeds_match_the_oracle(ref_mats, seed):
     assert np.array_equal(info["status"], ora["status"]) and np.array_equal(info["iter"], ora["iter"])
     sc = np.maximum(np.abs(ora["x"]).max(axis=1), 1e-12)
     assert (np.abs(x - ora["x"]).max(axis=1) / sc).max() < 1e-9
+
+
+@pytest.mark.parametrize("N", [50, 64])
+def test_tile_kernel_two_tiles_per_sm_matches_the_oracle(ref_mats, N):
+    """Horizons whose tiles share an SM pairwise (admm_shared_tile_kernel, CTAS = 2 variant): 2 048 cold MPC QPs, every status and
+    iteration count as the oracle's."""
+    _, cfg = ref_mats
+    B = 2048
+    mats = oracle.mpc_build(**{**cfg, "N": N})
+    X, U, ref = c2_batch(B, seed=40 + N)
+    f, ub = oracle.mpc_batch_vectors(mats, X, U, ref)
+    s = sm.BatchedSolver(mats["H"], mats["Gbar"], mats["lb"], mats["W0"], batch=B, kernel=4, **EPS)
+    s.update_gradient(f); s.update_upper_bound(ub); s.solve()
+    x, _ = s.solution(); info = s.info()
+    s.close()
+    ora = oracle.solve_batch(mats["H"], mats["Gbar"], mats["lb"], mats["W0"], f, ub, nthreads=os.cpu_count() or 1, **EPS)
+    assert np.array_equal(info["status"], ora["status"]) and np.array_equal(info["iter"], ora["iter"])
+    assert (np.abs(x - ora["x"]).max(axis=1) / np.maximum(np.abs(ora["x"]).max(axis=1), 1e-12)).max() < 1e-8
