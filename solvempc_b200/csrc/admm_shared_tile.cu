@@ -405,6 +405,17 @@ admm_shared_tile_kernel(TilePackDev K, SharedPlanDev P, BatchDev Bt, SettingsDev
           }
           run = (any & F_NEED_DINF2) != 0;
         } else if (pass == P_ADX) {
+          // OSQP's third condition, ||P dx|| < eps ||dx||, is known now: a slot that fails it even at the 10 x tolerance of the
+          // approximate check cannot be dual infeasible, and A̅ dx (this pass) is needed by nobody else
+          if (any & F_NEED_DINF2) {
+            __syncthreads();   // the norms of the P̄ dx pass are complete
+            if (tid < TB && (C.flags[tid] & F_NEED_DINF2)) {
+              const double nd = nrm(N_DX, tid), cs = unscale ? c : 1.0;
+              if (!(nrm(N_PD, tid) < cs * 10.0 * S.eps_dual_inf * nd)) C.flags[tid] &= ~F_NEED_DINF2;
+            }
+            __syncthreads();
+            any = any_flags();
+          }
           run = (any & F_NEED_DINF2) != 0;
         } else {   // P_QH: decisions, store, refill, then q̂ for the (re)filled tile
           __syncthreads();
