@@ -36,7 +36,22 @@ namespace {
 constexpr int kTileWarps = 8;
 constexpr int kTileThreads = kTileWarps * 32;
 constexpr int kRG = 4;          // row-blocks (8 operator rows each) a warp accumulates at once
-constexpr int kRing = 3;        // A-fragment prefetch distance in k-pairs (covers the L2 latency)
+// A-fragment prefetch distance in k-pairs.  Measured (round 2, tools/ab_tile.sh, B200): 3 -> 95.4 ms (config 3) / 0.683 s per 100
+// closed-loop steps (config 5); 4 -> 98.6 / 0.705; 5 -> 104.9 / 0.731; 6 -> 105.9 / 0.785; 8 (spills) -> 127.3 / 0.892: the operator
+// stream is bound by L2 -> SM THROUGHPUT, not by latency (SMPC_TILE_PROFILE: a warp with one row-block and a warp with two take
+// the same 8.7 k cycles per n = 200 GEMM and nobody waits at the barriers; 320 KB per GEMM per SM = 37 B / cycle / SM on all
+// 148 SMs, ~86 % of the ~43 B / cycle / SM the L2 delivers chip-wide), and more requests in flight only lengthen its queues.
+#ifndef SMPC_TILE_UNROLL_LD
+#define SMPC_TILE_UNROLL_LD 4
+#endif
+#ifndef SMPC_TILE_UNROLL_ST
+#define SMPC_TILE_UNROLL_ST 4
+#endif
+#ifndef SMPC_TILE_RING
+#define SMPC_TILE_RING 3
+#endif
+constexpr int kRing = SMPC_TILE_RING;
+constexpr int kUnrollLd = SMPC_TILE_UNROLL_LD, kUnrollSt = SMPC_TILE_UNROLL_ST;
 
 enum NormId {
   N_RP_S, N_Z_S, N_AX_S, N_RP_U, N_Z_U, N_AX_U,
@@ -229,7 +244,7 @@ admm_shared_tile_kernel(TilePackDev K, SharedPlanDev P, BatchDev Bt, SettingsDev
   bool event = true, initial = true;
 
 #ifdef SMPC_TILE_PROFILE
-  long long pf_pass[P_COUNT + 3] = {0}, pf_pre[P_COUNT] = {0}, pf_it = 0, pf_t0 = clock64(), pf_c = 0; int pf_nev = 0;
+  long long pf_pass[P_COUNT + 3] = {0}, pf_pre[P_COUNT] = {0}, pf_it = 0, pf_t0 = clock64(), pf_c = 0, pf_x[8] = {0}, pf_i[4] = {0}; int pf_nev = 0;
 #define PFM(arr, i) { const long long tt = clock64(); arr[i] += tt - pf_c; pf_c = tt; }
 #else
 #define PFM(arr, i)
@@ -469,6 +484,7 @@ admm_shared_tile_kernel(TilePackDev K, SharedPlanDev P, BatchDev Bt, SettingsDev
             C.flags[s] = f;
           }
           __syncthreads();
+          PFM(pf_x, 0)
           // ---- store_solution for the QPs that finished; new dinv where rho changed
           int rho_new = 0;
           if (!initial)
@@ -491,7 +507,7 @@ _Pragma("unroll 4")
           }
           if (done) {
             for (int nb = 0, s8 = tid & 7; nb < NB; ++nb)
-_Pragma("unroll 4")
+#pragma unroll kUnrollSt
             for (int r = tid >> 3; r < m8; r += kTileThreads / 8) {
               const int e = (nb * m8 + r) * 8 + s8, s = nb * 8 + (s8 ^ swz(r));
               if (!((done >> s) & 1)) continue;
@@ -512,12 +528,21 @@ _Pragma("unroll 4")
             if (tid == 0) C.refill_mask = done;
           }
           __syncthreads();
+          PFM(pf_x, 1)
           // ---- refill: pull new QPs from the queue into the slots of C.refill_mask.  QPs with invalid bounds (see
           // admm_shared_generic.cu) are stored as UNSOLVED at once and their slot is refilled again.
           const bool any_refill = C.refill_mask != 0;
           while (any_refill) {
-            if (tid < TB && ((C.refill_mask >> tid) & 1)) {
-              const int b = atomicAdd(queue, 1);
+            // one ticket request per tile for all its free slots (the tiles reach their events in waves: per-slot requests
+            // queue several hundred same-address atomics at the L2)
+            int rm = 0, base = 0;
+            if (tid < 32) {
+              rm = C.refill_mask;
+              if (tid == 0) base = atomicAdd(queue, __popc(rm));
+              base = __shfl_sync(0xffffffffu, base, 0);
+            }
+            if (tid < TB && ((rm >> tid) & 1)) {
+              const int b = base + __popc(rm & ((1 << tid) - 1));
               SMPC_DBG(b >= 0, "tile queue ticket");
               const bool ok = b < Bt.B;
               C.inst[tid] = ok ? b : -1;
@@ -527,6 +552,7 @@ _Pragma("unroll 4")
               C.obj[tid] = 0.0; C.pri[tid] = 0.0; C.dua[tid] = 0.0;
             }
             __syncthreads();
+            PFM(pf_x, 2)
             const int mask = C.refill_mask;
             // slot-fast mapping (lane & 7 = slot): conflict-free panel accesses
             for (int nb = 0, s8 = tid & 7; nb < NB; ++nb)
@@ -540,7 +566,7 @@ _Pragma("unroll 4")
               dinv[e] = b >= 0 ? 1.0 / (1.0 + C.rho[s] * (i < n ? __ldg(P.lam + i) : 0.0)) : 1.0;
             }
             for (int nb = 0, s8 = tid & 7; nb < NB; ++nb)
-_Pragma("unroll 4")
+#pragma unroll kUnrollLd
             for (int r = tid >> 3; r < m8; r += kTileThreads / 8) {
               const int e = (nb * m8 + r) * 8 + s8, s = nb * 8 + (s8 ^ swz(r));
               if (!((mask >> s) & 1)) continue;
@@ -556,6 +582,7 @@ _Pragma("unroll 4")
               lbp[e] = lo; ubp[e] = hi; zp[e] = zz; yp[e] = yy;
             }
             __syncthreads();
+            PFM(pf_x, 3)
             int again = 0;
             for (int s = 0; s < TB; ++s) {
               if (!((mask >> s) & 1) || C.inst[s] < 0 || !(C.flags[s] & F_BADBOUNDS)) continue;
@@ -572,6 +599,7 @@ _Pragma("unroll 4")
               }
             }
             __syncthreads();
+            PFM(pf_x, 4)
             if (!again) break;
             if (tid == 0) C.refill_mask = again;
             for (int nb = 0, s8 = tid & 7; nb < NB; ++nb)
@@ -676,10 +704,12 @@ _Pragma("unroll 4")
                 const double Di = row < n ? __ldg(P.D + row) : 1.0, Dinv = row < n ? __ldg(P.Dinv + row) : 1.0;
                 const int pi = pidx(n8, nb, row);
                 const double2 xb = *reinterpret_cast<const double2 *>(Tp + pi), px = *reinterpret_cast<const double2 *>(Sp + pi);
+                double2 qh2 = make_double2(0.0, 0.0);
+                if (XD) qh2 = *reinterpret_cast<const double2 *>(qh + pi);   // x-space: the qh panel holds q̄ = c D q itself (0 for an empty slot)
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
-                  const int b = C.inst[nb * 8 + q2 + j];
-                  const double qb = (b >= 0 && row < n && Bt.q) ? c * (Di * Bt.q[(size_t)b * n + row]) : 0.0;
+                  const int b = XD ? -1 : C.inst[nb * 8 + q2 + j];
+                  const double qb = XD ? (j ? qh2.y : qh2.x) : ((b >= 0 && row < n && Bt.q) ? c * (Di * Bt.q[(size_t)b * n + row]) : 0.0);
                   const double aty = j ? a1 : a0, pxj = j ? px.y : px.x, xbj = j ? xb.y : xb.x;
                   const double rd = (qb + pxj) + aty;
                   mx[nb][0][j] = fmax(mx[nb][0][j], fabs(rd)); mx[nb][1][j] = fmax(mx[nb][1][j], fabs(qb));
@@ -721,10 +751,12 @@ _Pragma("unroll 4")
                 mx[nb][0][0] = fmax(mx[nb][0][0], fabs(Dinv * a0)); mx[nb][0][1] = fmax(mx[nb][0][1], fabs(Dinv * a1));
               } else if (pass == P_DX) {
                 const double Di = row < n ? __ldg(P.D + row) : 1.0;
+                double2 qh2 = make_double2(0.0, 0.0);
+                if (XD) qh2 = *reinterpret_cast<const double2 *>(qh + pidx(n8, nb, row));
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
-                  const int b = C.inst[nb * 8 + q2 + j];
-                  const double qb = (b >= 0 && row < n && Bt.q) ? c * (Di * Bt.q[(size_t)b * n + row]) : 0.0;
+                  const int b = XD ? -1 : C.inst[nb * 8 + q2 + j];
+                  const double qb = XD ? (j ? qh2.y : qh2.x) : ((b >= 0 && row < n && Bt.q) ? c * (Di * Bt.q[(size_t)b * n + row]) : 0.0);
                   const double dx = j ? a1 : a0;
                   mx[nb][0][j] = fmax(mx[nb][0][j], fabs(unscale ? Di * dx : dx));
                   sm[nb][j] += qb * dx;
@@ -825,9 +857,11 @@ _Pragma("unroll 4")
 #ifdef SMPC_TILE_PROFILE
       PFM(pf_pass, P_COUNT + 2)
       pf_t0 = clock64(); ++pf_nev;
-      if (C.active == 0 && blockIdx.x == 0 && tid == 0) {
+      if (C.active == 0 && blockIdx.x == 0 && (tid == 0 || tid == (kTileWarps - 1) * 32)) {
         printf("tile profile: %d events, %d iterations %lld cycles\n  zero/flags %lld  w-rebuild/schedule %lld (gemm-tail %lld)\n", pf_nev, k, pf_it, pf_pass[P_COUNT], pf_pass[P_COUNT + 2], pf_pass[P_COUNT + 1]);
         for (int p = 0; p < P_COUNT; ++p) printf("  pass %d: pre %lld gemm+epilogue %lld\n", p, pf_pre[p], pf_pass[p]);
+        printf("  warp %d iteration: gemm1+epilogue %lld barrier %lld gemm2+epilogue %lld barrier %lld\n", warp, pf_i[0], pf_i[1], pf_i[2], pf_i[3]);
+        printf("  pass 8 pre: decide %lld store %lld tickets %lld load %lld badbounds %lld (rest = q̄)\n", pf_x[0], pf_x[1], pf_x[2], pf_x[3], pf_x[4]);
       }
 #endif
       if (C.active == 0) break;
@@ -854,7 +888,9 @@ _Pragma("unroll 4")
             }
           }
       }
+      PFM(pf_i, 0)
       __syncthreads();
+      PFM(pf_i, 1)
       // ---- GEMM 2: x~ = V u; then, per row i (the owner of x_i also owns constraint rows i and i + mp): x update, z~ = +-a_i x~_i,
       //      z / y updates (OSQP update_z / update_y), next right-hand side
       for (int rb = nrb0; rb < nrb1; rb += kRG) {
@@ -901,7 +937,9 @@ _Pragma("unroll 4")
             }
           }
       }
+      PFM(pf_i, 2)
       __syncthreads();
+      PFM(pf_i, 3)
       continue;
     }
     const double2 *M1l = reinterpret_cast<const double2 *>(PAIRED ? K.M1p : K.M1) + lane;
