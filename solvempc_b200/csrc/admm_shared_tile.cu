@@ -38,11 +38,11 @@ constexpr int kTileThreads = kTileWarps * 32;
 constexpr int kRG = 4;          // row-blocks (8 operator rows each) a warp accumulates at once
 // A-fragment prefetch distance in k-pairs.  Measured (round 2, tools/ab_tile.sh + tools/ab_run.sh, B200; config 3 ms / config 5 s per 100
 // closed-loop steps): 1 -> 96.7 / 0.671, 2 -> 94.2 / 0.686, 3 -> 95.4 / 0.683, 4 -> 98.6 / 0.705, 5 -> 104.9 / 0.731, 6 -> 105.9 / 0.785,
-// 8 (spills) -> 127.3 / 0.892: the GEMMs do not wait for the operator stream.  Diagnostic builds without the operator loads
-// (SMPC_TILE_DIAG_NOLDG), without the B-fragment loads (SMPC_TILE_DIAG_NOLDS) or without both run the n = 200 iteration in the same
-// 18.0-19.1 k cycles as the real kernel (18.0 k): the GEMM phases are bound by DMMA issue (profiles/microbench/tile_gemm_shape.cu: the
-// bare DMMA + barrier skeleton of one n = 200 GEMM takes 6.7 k cycles, 19 cycles per DMMA on the busiest sub-partition against the
-// pipe's 16; the kernel's GEMM + epilogue 8.3-8.7 k), and loading further ahead only costs registers and queue slots.  Also measured and
+// 8 (spills) -> 127.3 / 0.892: the GEMMs do not wait for the operator stream's latency.  Diagnostic builds that replace the operator loads
+// (SMPC_TILE_DIAG_NOLDG), the B-fragment loads (SMPC_TILE_DIAG_NOLDS) or both by register values run the n = 200 iteration in 15.7 / 17.8 /
+// 15.8 k cycles against 18.0 k: the whole operator stream is worth 13 %, the rest of the GEMM phases is DMMA issue
+// (profiles/microbench/tile_gemm_shape.cu: the bare DMMA + barrier skeleton of one n = 200 GEMM takes 6.1 k cycles, 17.4 cycles per DMMA on the
+// busiest sub-partition against the pipe's 16; the kernel's GEMM + epilogue 8.1-8.8 k, 7.1 k without operator loads).  Also measured and
 // not kept: the next GEMM's first fragments loaded before the epilogue and the barrier (+3 % / +4 %), B fragments one k-pair ahead
 // (+-0), separate accumulators for the two k-steps of a pair (+2 % / +3 %), every tile prefetching its own share of the ticket queue
 // into L2 at an event (+-0 / +5 %), deeper unrolling of the refill loads and stores (+-0).
@@ -72,7 +72,7 @@ __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
 __device__ __forceinline__ double2 ldg_stream(const double2 *p) {
   double2 v;
 #ifdef SMPC_TILE_DIAG_NOLDG   // diagnostic only (wrong results): no operator stream, what do the GEMMs cost without it?
-  return make_double2(1e-3 * (double)(((size_t)p >> 4) & 7), 1e-3);
+  return make_double2(__longlong_as_double(0x3F50000000000000LL | (long long)((size_t)p & 0xFF0)), 1e-3);   // (integer ops only: no conversions in the loop)
 #endif
   asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
   return v;
@@ -124,7 +124,7 @@ __device__ __forceinline__ void gemm_run(const double2 *__restrict__ opl, int kp
       double b[NB][2];
 #ifdef SMPC_TILE_DIAG_NOLDS   // diagnostic only (wrong results): no B-fragment loads
 #pragma unroll
-      for (int nb = 0; nb < NB; ++nb) { b[nb][0] = 1e-3 * (double)(kp + d); b[nb][1] = 1e-3; }
+      for (int nb = 0; nb < NB; ++nb) { b[nb][0] = __longlong_as_double(0x3F50000000000000LL | ((long long)(kp + d + nb) << 8)); b[nb][1] = 1e-3; }
 #else
 #pragma unroll
       for (int nb = 0; nb < NB; ++nb) { b[nb][0] = bp[nb * nbs + d * 64]; b[nb][1] = bp[nb * nbs + d * 64 + 32]; }
