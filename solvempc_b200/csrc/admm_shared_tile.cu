@@ -52,10 +52,7 @@ constexpr int kRG = 4;          // row-blocks (8 operator rows each) a warp accu
 #ifndef SMPC_TILE_UNROLL_ST
 #define SMPC_TILE_UNROLL_ST 4
 #endif
-#ifndef SMPC_TILE_RING
-#define SMPC_TILE_RING 3
-#endif
-constexpr int kRing = SMPC_TILE_RING;
+// (per kernel variant, below: kRing; SMPC_TILE_RING overrides it for every variant)
 constexpr int kUnrollLd = SMPC_TILE_UNROLL_LD, kUnrollSt = SMPC_TILE_UNROLL_ST;
 
 enum NormId {
@@ -104,7 +101,7 @@ enum SlotFlag { F_DUE_CHECK = 1, F_DUE_ADAPT = 2, F_AT_MAX = 4, F_PRIM_OK = 8, F
 // operator row-block; bp = panel + (lane&3)*8 + (lane>>2) (+ 64*first k-pair); nbs = doubles between 8-slot blocks.
 // The A fragments run kRing k-pairs ahead of their use in a register ring (covers the L2 latency); the main loop is
 // branch-free (prefetches past the end are clamped to the last k-pair).
-template <int NB, int NR, int RG>
+template <int NB, int NR, int RG, int kRing>
 __device__ __forceinline__ void gemm_run(const double2 *__restrict__ opl, int kpt, int rb, int kp0, int cnt,
                                          const double *bp, int nbs, double (&acc)[RG][NB][2]) {
   const double2 *ap[NR];
@@ -165,16 +162,16 @@ __device__ __forceinline__ void gemm_run(const double2 *__restrict__ opl, int kp
     }
 }
 // nr (1..kRG) row-blocks starting at rb: dispatch to the compile-time variants (nr is warp-uniform)
-template <int NB, int RG>
+template <int NB, int RG, int kRing>
 __device__ __forceinline__ void gemm_seg(const double2 *__restrict__ opl, int kpt, int rb, int nr, int kp0, int cnt,
                                          const double *bp, int nbs, double (&acc)[RG][NB][2]) {
   if (cnt <= 0) return;
   if constexpr (RG >= 4) {
-    if (nr >= 4) { gemm_run<NB, 4, RG>(opl, kpt, rb, kp0, cnt, bp, nbs, acc); return; }
-    if (nr == 3) { gemm_run<NB, 3, RG>(opl, kpt, rb, kp0, cnt, bp, nbs, acc); return; }
+    if (nr >= 4) { gemm_run<NB, 4, RG, kRing>(opl, kpt, rb, kp0, cnt, bp, nbs, acc); return; }
+    if (nr == 3) { gemm_run<NB, 3, RG, kRing>(opl, kpt, rb, kp0, cnt, bp, nbs, acc); return; }
   }
-  if (nr >= 2) gemm_run<NB, 2, RG>(opl, kpt, rb, kp0, cnt, bp, nbs, acc);
-  else gemm_run<NB, 1, RG>(opl, kpt, rb, kp0, cnt, bp, nbs, acc);
+  if (nr >= 2) gemm_run<NB, 2, RG, kRing>(opl, kpt, rb, kp0, cnt, bp, nbs, acc);
+  else gemm_run<NB, 1, RG, kRing>(opl, kpt, rb, kp0, cnt, bp, nbs, acc);
 }
 
 // max over the 8 row-groups of a warp (lanes with equal lane&3 hold the same slot pair)
@@ -209,6 +206,13 @@ admm_shared_tile_kernel(TilePackDev K, SharedPlanDev P, BatchDev Bt, SettingsDev
   static_assert(!XD || PAIRED, "the x-space variant is for paired rows");
   constexpr int TB = 8 * NB;
   constexpr int kTileWarps = WARPS, kTileThreads = WARPS * 32, kRG = (WARPS == 8 && CTAS == 1) ? 4 : 2;   // (shadow the file-level defaults)
+#ifdef SMPC_TILE_RING
+  constexpr int kRing = SMPC_TILE_RING;
+#else
+  // operator prefetch distance in k-pairs (sweep in the file header): 2 for the x-space variant (config 3: 94.2 ms against 95.4 with 3),
+  // 1 with two tiles per SM (config 5: the other tile covers the latency; 0.671 s per 100 steps against 0.683), 3 otherwise
+  constexpr int kRing = XD ? 2 : (CTAS == 2 ? 1 : 3);
+#endif
   extern __shared__ __align__(16) double smem[];
   const int n = P.n, m = P.m, n8 = K.n8, m8 = K.m8;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -693,7 +697,7 @@ _Pragma("unroll 4")
               }
             }
           } else {
-            gemm_seg<NB, kRG>(op + lane, kpt, rb, min(kRG, rb1 - rb), 0, kpt, panel + bfrag, krows * 8, acc);
+            gemm_seg<NB, kRG, kRing>(op + lane, kpt, rb, min(kRG, rb1 - rb), 0, kpt, panel + bfrag, krows * 8, acc);
           }
           double mx[NB][8][2], sm[NB][2];
 #pragma unroll
@@ -889,7 +893,7 @@ _Pragma("unroll 4")
       for (int rb = nrb0; rb < nrb1; rb += kRG) {
         double acc[kRG][NB][2];
         zero_acc(acc);
-        gemm_seg<NB, kRG>(VTl, kpN, rb, min(kRG, nrb1 - rb), 0, kpN, Sp + bfrag, n8 * 8, acc);
+        gemm_seg<NB, kRG, kRing>(VTl, kpN, rb, min(kRG, nrb1 - rb), 0, kpN, Sp + bfrag, n8 * 8, acc);
 #pragma unroll
         for (int r = 0; r < kRG; ++r)
           if (rb + r < nrb1) {
@@ -909,7 +913,7 @@ _Pragma("unroll 4")
       for (int rb = nrb0; rb < nrb1; rb += kRG) {
         double acc[kRG][NB][2];
         zero_acc(acc);
-        gemm_seg<NB, kRG>(Vl, kpN, rb, min(kRG, nrb1 - rb), 0, kpN, Tp + bfrag, n8 * 8, acc);
+        gemm_seg<NB, kRG, kRing>(Vl, kpN, rb, min(kRG, nrb1 - rb), 0, kpN, Tp + bfrag, n8 * 8, acc);
 #pragma unroll
         for (int r = 0; r < kRG; ++r)
           if (rb + r < nrb1) {
@@ -962,7 +966,7 @@ _Pragma("unroll 4")
     for (int rb = nrb0; rb < nrb1; rb += kRG) {
       double acc[kRG][NB][2];
       zero_acc(acc);
-      gemm_seg<NB, kRG>(M1l, kp1, rb, min(kRG, nrb1 - rb), 0, kp1, cv + bfrag, cvr * 8, acc);
+      gemm_seg<NB, kRG, kRing>(M1l, kp1, rb, min(kRG, nrb1 - rb), 0, kp1, cv + bfrag, cvr * 8, acc);
 #pragma unroll
       for (int r = 0; r < kRG; ++r)
         if (rb + r < nrb1) {
@@ -993,7 +997,7 @@ _Pragma("unroll 4")
       for (int rb = prb0; rb < prb1; rb += kRG) {
         double acc[kRG][NB][2];
         zero_acc(acc);
-        gemm_seg<NB, kRG>(Wl, kpN, rb, min(kRG, prb1 - rb), 0, kpN, Tp + bfrag, n8 * 8, acc);
+        gemm_seg<NB, kRG, kRing>(Wl, kpN, rb, min(kRG, prb1 - rb), 0, kpN, Tp + bfrag, n8 * 8, acc);
 #pragma unroll
         for (int r = 0; r < kRG; ++r)
           if (rb + r < prb1) {
@@ -1035,7 +1039,7 @@ _Pragma("unroll 4")
     for (int rb = mrb0; rb < mrb1; rb += kRG) {
       double acc[kRG][NB][2];
       zero_acc(acc);
-      gemm_seg<NB, kRG>(Wl, kpN, rb, min(kRG, mrb1 - rb), 0, kpN, Tp + bfrag, n8 * 8, acc);
+      gemm_seg<NB, kRG, kRing>(Wl, kpN, rb, min(kRG, mrb1 - rb), 0, kpN, Tp + bfrag, n8 * 8, acc);
 #pragma unroll
       for (int r = 0; r < kRG; ++r)
         if (rb + r < mrb1) {
