@@ -687,6 +687,9 @@ class Bench:
                                                 "note": "24(n+2m) B per problem-iteration that a one-launch-per-iteration kernel would stream; "
                                                         "this kernel keeps the iterates on chip and reads/writes HBM once per solve"}},
             }
+            if wl.solver.kernel_name.startswith("admm_shared_tile"):
+                # what bounds this kernel was measured, not assumed (A/B builds, no-load diagnostics, DMMA skeleton, L2 stream): DESIGN 4
+                res["roofline"]["bound_evidence"] = "profiles/r02_tile_kernel_bound_study.json"
             if fresh is not None:
                 res["fresh_inputs"] = fresh
             if getattr(wl, "setup_ms", None) is not None:

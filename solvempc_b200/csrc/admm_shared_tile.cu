@@ -101,9 +101,10 @@ enum SlotFlag { F_DUE_CHECK = 1, F_DUE_ADAPT = 2, F_AT_MAX = 4, F_PRIM_OK = 8, F
 // operator row-block; bp = panel + (lane&3)*8 + (lane>>2) (+ 64*first k-pair); nbs = doubles between 8-slot blocks.
 // The A fragments run kRing k-pairs ahead of their use in a register ring (covers the L2 latency); the main loop is
 // branch-free (prefetches past the end are clamped to the last k-pair).
-template <int NB, int NR, int RG, int kRing>
+// PB ("paired B"): the B operand is the difference of two panel rows, bp[...] - bp2[...] (A̅'y = G'(y_top - y_bot) for row pairs [G; -G]).
+template <int NB, int NR, int RG, int kRing, bool PB = false>
 __device__ __forceinline__ void gemm_run(const double2 *__restrict__ opl, int kpt, int rb, int kp0, int cnt,
-                                         const double *bp, int nbs, double (&acc)[RG][NB][2]) {
+                                         const double *bp, int nbs, double (&acc)[RG][NB][2], const double *bp2 = nullptr, int rowlim = 0) {
   const double2 *ap[NR];
 #pragma unroll
   for (int r = 0; r < NR; ++r) ap[r] = opl + ((size_t)(rb + r) * kpt + kp0) * 32;
@@ -124,7 +125,13 @@ __device__ __forceinline__ void gemm_run(const double2 *__restrict__ opl, int kp
       for (int nb = 0; nb < NB; ++nb) { b[nb][0] = __longlong_as_double(0x3F50000000000000LL | ((long long)(kp + d + nb) << 8)); b[nb][1] = 1e-3; }
 #else
 #pragma unroll
-      for (int nb = 0; nb < NB; ++nb) { b[nb][0] = bp[nb * nbs + d * 64]; b[nb][1] = bp[nb * nbs + d * 64 + 32]; }
+      for (int nb = 0; nb < NB; ++nb) {
+        b[nb][0] = bp[nb * nbs + d * 64]; b[nb][1] = bp[nb * nbs + d * 64 + 32];
+        if constexpr (PB) {   // (rows past the last pair are padding of the operator: keep them finite whatever lies behind the panel)
+          b[nb][0] = 8 * (kp + d) < rowlim ? b[nb][0] - bp2[nb * nbs + d * 64] : 0.0;
+          b[nb][1] = 8 * (kp + d) + 4 < rowlim ? b[nb][1] - bp2[nb * nbs + d * 64 + 32] : 0.0;
+        }
+      }
 #endif
       double2 a[NR];
 #pragma unroll
@@ -144,13 +151,20 @@ __device__ __forceinline__ void gemm_run(const double2 *__restrict__ opl, int kp
         for (int nb = 0; nb < NB; ++nb) dmma(acc[r][nb], a[r].y, b[nb][1]);
     }
     bp += kRing * 64;
+    if constexpr (PB) bp2 += kRing * 64;
   }
 #pragma unroll
   for (int d = 0; d < kRing - 1; ++d)
     if (kp + d < cnt) {
       double b0[NB], b1[NB];
 #pragma unroll
-      for (int nb = 0; nb < NB; ++nb) { b0[nb] = bp[nb * nbs + d * 64]; b1[nb] = bp[nb * nbs + d * 64 + 32]; }
+      for (int nb = 0; nb < NB; ++nb) {
+        b0[nb] = bp[nb * nbs + d * 64]; b1[nb] = bp[nb * nbs + d * 64 + 32];
+        if constexpr (PB) {
+          b0[nb] = 8 * (kp + d) < rowlim ? b0[nb] - bp2[nb * nbs + d * 64] : 0.0;
+          b1[nb] = 8 * (kp + d) + 4 < rowlim ? b1[nb] - bp2[nb * nbs + d * 64 + 32] : 0.0;
+        }
+      }
 #pragma unroll
       for (int nb = 0; nb < NB; ++nb)
 #pragma unroll
@@ -162,16 +176,16 @@ __device__ __forceinline__ void gemm_run(const double2 *__restrict__ opl, int kp
     }
 }
 // nr (1..kRG) row-blocks starting at rb: dispatch to the compile-time variants (nr is warp-uniform)
-template <int NB, int RG, int kRing>
+template <int NB, int RG, int kRing, bool PB = false>
 __device__ __forceinline__ void gemm_seg(const double2 *__restrict__ opl, int kpt, int rb, int nr, int kp0, int cnt,
-                                         const double *bp, int nbs, double (&acc)[RG][NB][2]) {
+                                         const double *bp, int nbs, double (&acc)[RG][NB][2], const double *bp2 = nullptr, int rowlim = 0) {
   if (cnt <= 0) return;
   if constexpr (RG >= 4) {
-    if (nr >= 4) { gemm_run<NB, 4, RG, kRing>(opl, kpt, rb, kp0, cnt, bp, nbs, acc); return; }
-    if (nr == 3) { gemm_run<NB, 3, RG, kRing>(opl, kpt, rb, kp0, cnt, bp, nbs, acc); return; }
+    if (nr >= 4) { gemm_run<NB, 4, RG, kRing, PB>(opl, kpt, rb, kp0, cnt, bp, nbs, acc, bp2, rowlim); return; }
+    if (nr == 3) { gemm_run<NB, 3, RG, kRing, PB>(opl, kpt, rb, kp0, cnt, bp, nbs, acc, bp2, rowlim); return; }
   }
-  if (nr >= 2) gemm_run<NB, 2, RG, kRing>(opl, kpt, rb, kp0, cnt, bp, nbs, acc);
-  else gemm_run<NB, 1, RG, kRing>(opl, kpt, rb, kp0, cnt, bp, nbs, acc);
+  if (nr >= 2) gemm_run<NB, 2, RG, kRing, PB>(opl, kpt, rb, kp0, cnt, bp, nbs, acc, bp2, rowlim);
+  else gemm_run<NB, 1, RG, kRing, PB>(opl, kpt, rb, kp0, cnt, bp, nbs, acc, bp2, rowlim);
 }
 
 // max over the 8 row-groups of a warp (lanes with equal lane&3 hold the same slot pair)
@@ -696,6 +710,11 @@ _Pragma("unroll 4")
                 acc[r][nb][0] = v.x; acc[r][nb][1] = v.y;
               }
             }
+          } else if (PAIRED && !XD && pass == P_ATY) {
+            // row pairs: A̅'y = G'(y_top - y_bot): half the DMMAs and operator bytes of this pass (K = mp instead of m); the B fragment is the
+            // difference of panel rows r and r + mp (the swizzle of a thread's rows does not change from k-step to k-step: 4 rows apart)
+            const int bfrag2 = (mp + (lane & 3)) * 8 + ((lane >> 2) ^ swz(mp + (lane & 3)));
+            gemm_seg<NB, kRG, kRing, true>(reinterpret_cast<const double2 *>(K.ATtop) + lane, kpMp, rb, min(kRG, rb1 - rb), 0, kpMp, yp + bfrag, m8 * 8, acc, yp + bfrag2, mp - (lane & 3));
           } else {
             gemm_seg<NB, kRG, kRing>(op + lane, kpt, rb, min(kRG, rb1 - rb), 0, kpt, panel + bfrag, krows * 8, acc);
           }

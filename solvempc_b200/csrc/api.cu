@@ -245,8 +245,9 @@ int upload_tile_pack(smpc_solver *s) {
   auto ATp = pack(n8, m8, [&](int i, int r) -> double { return (i < n && r < m) ? p.Abar[(size_t)r * n + i] : 0.0; });
   // paired rows [G; -G] (plan.pairs = m / 2): iteration operators on the top half only
   const int mp = p.pairs, mp8 = (mp + 7) & ~7;
-  std::vector<double> M1p, Wtop;
+  std::vector<double> M1p, Wtop, ATtop;
   if (mp > 0) {
+    ATtop = pack(n8, mp8, [&](int i, int r) -> double { return (i < n && r < mp) ? p.Abar[(size_t)r * n + i] : 0.0; });
     M1p = pack(n8, n8 + mp8, [&](int i, int k) -> double {
       if (i >= n) return 0.0;
       if (k < n8) return k < n ? p.SG[(size_t)i * n + k] : 0.0;
@@ -266,7 +267,7 @@ int upload_tile_pack(smpc_solver *s) {
     if (!s->st.scaled_termination) { dmax = 0.0; for (int i = 0; i < n; ++i) dmax = std::max(dmax, p.D[i]); }
   }
   size_t bytes = DeviceBuf::need(sizeof(int) * 4);
-  for (const std::vector<double> *v : {&M1, &Wp, &VTp, &Vp, &PVp, &ATp, &M1p, &Wtop, &Pp, &adiag}) bytes += DeviceBuf::need((v->size() ? v->size() : 1) * sizeof(double));
+  for (const std::vector<double> *v : {&M1, &Wp, &VTp, &Vp, &PVp, &ATp, &M1p, &Wtop, &ATtop, &Pp, &adiag}) bytes += DeviceBuf::need((v->size() ? v->size() : 1) * sizeof(double));
   CK(s->tilebuf.alloc(bytes));
   auto put = [&](const std::vector<double> &v, const double **dst) -> cudaError_t {
     double *d = s->tilebuf.take<double>(v.size() ? v.size() : 1);
@@ -278,7 +279,7 @@ int upload_tile_pack(smpc_solver *s) {
   k.n8 = n8; k.m8 = m8;
   CK(put(M1, &k.M1)); CK(put(Wp, &k.Wp)); CK(put(VTp, &k.VTp)); CK(put(Vp, &k.Vp)); CK(put(PVp, &k.PVp)); CK(put(ATp, &k.ATp));
   k.mp = mp; k.mp8 = mp8;
-  CK(put(M1p, &k.M1p)); CK(put(Wtop, &k.Wtop));
+  CK(put(M1p, &k.M1p)); CK(put(Wtop, &k.Wtop)); CK(put(ATtop, &k.ATtop));
   k.xd = xd ? 1 : 0; k.dmax = dmax;
   CK(put(Pp, &k.Pp)); CK(put(adiag, &k.adiag));
   s->d_queue = s->tilebuf.take<int>(4);

@@ -86,6 +86,7 @@ struct TilePackDev {
   int mp, mp8;
   const double *M1p;   // [sigma*G | Wtop']  n8 x (n8 + mp8)
   const double *Wtop;  // first mp rows of W  mp8 x n8
+  const double *ATtop; // first mp columns of A̅' (= G')  n8 x mp8: A̅'y = G'(y_top - y_bot) in the checks
   // x-space variant (xd != 0): paired rows whose top block is DIAGONAL after scaling, A̅ = [diag(adiag); -diag(adiag)] (mp == n):
   // the iteration multiplies by V' and V only (2 n^2 MACs) and needs P̄ for the checks
   int xd;
